@@ -1,0 +1,393 @@
+"""gphocs-b200: B200-native per-locus likelihood path of G-PhoCS.
+
+The product is csrc/libgphocs_b200.so (hand-written CUDA for sm_100a behind the C ABI of
+include/gphocs_b200.h).  This package is the thin Python binding used by tests and bench.py; it holds
+no arithmetic.  There is no CPU fallback: constructing a store without the built library or without a
+CUDA device raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libgphocs_b200.so")
+
+c_int_p = C.POINTER(C.c_int)
+c_dbl_p = C.POINTER(C.c_double)
+c_ll_p = C.POINTER(C.c_longlong)
+
+OP_ADJUST_AGE, OP_SPR, OP_SCALE_ALL, OP_COMMIT, OP_REVERT, OP_SET_RATE = range(6)
+
+OP_DTYPE = np.dtype([("locus", np.int32), ("type", np.int32), ("a", np.int32), ("b", np.int32), ("x", np.float64)])
+
+
+class GenericBinaryTree(C.Structure):   # layout of src/GenericTree.h:29-39
+    _fields_ = [("numLeaves", C.c_int), ("rootId", C.c_int), ("leafNames", C.c_void_p), ("father", c_int_p),
+                ("leftSon", c_int_p), ("rightSon", c_int_p), ("label1", c_dbl_p), ("label2", c_dbl_p)]
+
+
+_lib = None
+
+
+def lib():
+    """Loads libgphocs_b200.so and declares every entry point of include/gphocs_b200.h."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} is missing — build it with __graft_entry__.build(); there is no CPU fallback")
+    L = C.CDLL(LIB_PATH)
+    vp, ci, cd, cus = C.c_void_p, C.c_int, C.c_double, C.c_ushort
+    sig = {
+        # A. LocusData surface
+        "createLocusData": (vp, [ci, cus]),
+        "initializeLocusData": (ci, [vp, C.POINTER(C.c_char_p), ci, c_int_p, c_int_p]),
+        "freeLocusData": (ci, [vp]),
+        "attachLeaf_UNUSED": (ci, [vp, ci, ci, cd]),
+        "setLocusMutationRate": (None, [vp, cd]),
+        "getLocusMutationRate": (cd, [vp]),
+        "computeAllConditionals": (ci, [vp]),
+        "computeLocusDataLikelihood": (cd, [vp, cus]),
+        "computePatternLogLikelihood": (cd, [vp, ci, c_int_p, c_int_p]),
+        "computeLocusDataLikelihood_deb": (cd, [vp, cus]),
+        "addSitePatterns": (cd, [vp, ci, c_int_p, c_int_p, cus]),
+        "reduceSitePatterns": (cd, [vp, ci, c_int_p, c_int_p, cus]),
+        "checkLocusDataLikelihood": (ci, [vp]),
+        "revertToSaved": (ci, [vp]),
+        "resetSaved": (ci, [vp]),
+        "adjustGenNodeAge": (ci, [vp, ci, cd]),
+        "scaleAllNodeAges": (cd, [vp, cd]),
+        "executeGenSPR": (ci, [vp, ci, ci, cd]),
+        "copyGenericTreeToLocus": (ci, [vp, C.POINTER(GenericBinaryTree)]),
+        "printLocusGenTree": (None, [vp, vp, c_int_p, c_int_p]),
+        "printLocusDataStats": (None, [vp, ci]),
+        "printLocusDataPatterns": (None, [vp, vp]),
+        "computePairwiseLCAs": (ci, [vp, C.POINTER(c_int_p), c_int_p]),
+        "getSortedAges": (ci, [vp, c_dbl_p]),
+        "getLocusDataLikelihood": (cd, [vp]),
+        "getLocusRoot": (ci, [vp]),
+        "getNodeAge": (cd, [vp, ci]),
+        "getNodeFather": (ci, [vp, ci]),
+        "getNodeSon": (ci, [vp, ci, cus]),
+        "gpuLociStore": (vp, []),
+        "gpuLocusIndex": (ci, [vp]),
+        # B. batched engine
+        "gphocsStoreCreate": (vp, [ci, ci, ci, c_ll_p, c_ll_p, C.c_char_p, c_int_p, c_int_p]),
+        "gphocsStoreDestroy": (ci, [vp]),
+        "gphocsStoreSetStream": (ci, [vp, vp]),
+        "gphocsStoreNumLoci": (ci, [vp]),
+        "gphocsStoreNumLeaves": (ci, [vp]),
+        "gphocsStoreNumColumns": (C.c_longlong, [vp]),
+        "gphocsStoreDeviceBytes": (C.c_longlong, [vp]),
+        "gphocsStoreSetTrees": (ci, [vp, ci, c_int_p, c_int_p, c_int_p, c_int_p, c_dbl_p, c_int_p]),
+        "gphocsStoreGetTrees": (ci, [vp, ci, c_int_p, c_int_p, c_int_p, c_int_p, c_dbl_p, c_int_p]),
+        "gphocsStoreSetRates": (ci, [vp, ci, c_int_p, c_dbl_p]),
+        "gphocsStoreApplyOps": (ci, [vp, ci, vp, c_int_p]),
+        "gphocsStoreEvaluate": (ci, [vp, ci, c_int_p, ci, c_dbl_p, c_dbl_p]),
+        "gphocsStoreEvaluateDevice": (ci, [vp, ci, C.POINTER(vp), C.POINTER(vp)]),
+        "gphocsStoreGetLnL": (ci, [vp, ci, c_int_p, c_dbl_p]),
+        "gphocsStoreGetClv": (ci, [vp, ci, ci, ci, c_dbl_p]),
+        "gphocsStoreSync": (ci, [vp]),
+        "gphocsStoreSetDebug": (ci, [vp, ci]),
+        "gphocsStoreCheckMirror": (ci, [vp]),
+        "gphocsKernelLaunchCount": (C.c_longlong, []),
+        # C. genealogy likelihood
+        "gphocsGenCreate": (vp, [ci, ci, ci, ci, ci, c_int_p, c_int_p, c_int_p, c_int_p]),
+        "gphocsGenDestroy": (ci, [vp]),
+        "gphocsGenSetStream": (ci, [vp, vp]),
+        "gphocsGenSetParams": (ci, [vp, c_dbl_p, c_dbl_p]),
+        "gphocsGenSetEvents": (ci, [vp, c_ll_p, c_int_p, c_int_p, c_int_p, c_dbl_p]),
+        "gphocsGenEvaluate": (ci, [vp, c_dbl_p, c_dbl_p, c_int_p, c_dbl_p, c_int_p, c_dbl_p, c_ll_p, c_dbl_p, c_ll_p, c_dbl_p]),
+        "gphocsGenEvaluateDevice": (ci, [vp, C.POINTER(vp), C.POINTER(vp)]),
+        "gphocsGenGetLineages": (ci, [vp, c_int_p]),
+        "gphocsGenSync": (ci, [vp]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)
+        fn.restype = res
+        fn.argtypes = args
+    L._declared = sorted(sig)
+    _lib = L
+    return L
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, np.int32)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, np.float64)
+
+
+def _ip(a):
+    return None if a is None else a.ctypes.data_as(c_int_p)
+
+
+def _dp(a):
+    return None if a is None else a.ctypes.data_as(c_dbl_p)
+
+
+def _lp(a):
+    return None if a is None else a.ctypes.data_as(c_ll_p)
+
+
+class LociStore:
+    """Batched engine (GphocsStore): all loci resident in HBM."""
+
+    def __init__(self, n, patt_start, unph_start, chars, num_phases, counts, device=0, stream=None):
+        self.lib = lib()
+        self.n, self.N = int(n), 2 * int(n) - 1
+        self.L = len(patt_start) - 1
+        ps = np.ascontiguousarray(patt_start, np.int64)
+        us = np.ascontiguousarray(unph_start, np.int64)
+        ch = np.ascontiguousarray(chars, np.uint8)
+        self.h = self.lib.gphocsStoreCreate(device, self.L, self.n, _lp(ps), _lp(us), ch.ctypes.data_as(C.c_char_p),
+                                            _ip(_i32(num_phases)), _ip(_i32(counts)))
+        if not self.h:
+            raise RuntimeError("gphocsStoreCreate failed (no CUDA device? malformed patterns?) — no CPU fallback")
+        self.h = C.c_void_p(self.h)
+        if stream is not None:
+            self.lib.gphocsStoreSetStream(self.h, C.c_void_p(stream))
+
+    @classmethod
+    def from_workload(cls, w, device=0, stream=None):
+        s = cls(w.n, w.patt_start, w.unph_start, w.chars, w.num_phases, w.counts, device, stream)
+        s.set_trees(w.father, w.left, w.right, w.age, w.root)
+        s.set_rates(w.rate)
+        return s
+
+    def close(self):
+        if self.h:
+            self.lib.gphocsStoreDestroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise RuntimeError(f"{what} failed ({rc})")
+
+    def set_trees(self, father, left, right, age, root, ids=None):
+        f, l, r, a, ro = _i32(father), _i32(left), _i32(right), _f64(age), _i32(root)
+        k = len(ro)
+        self._check(self.lib.gphocsStoreSetTrees(self.h, k, _ip(None if ids is None else _i32(ids)), _ip(f), _ip(l),
+                                                 _ip(r), _dp(a), _ip(ro)), "gphocsStoreSetTrees")
+
+    def get_trees(self, ids=None):
+        k = self.L if ids is None else len(ids)
+        f, l, r = (np.zeros((k, self.N), np.int32) for _ in range(3))
+        a = np.zeros((k, self.N))
+        ro = np.zeros(k, np.int32)
+        self._check(self.lib.gphocsStoreGetTrees(self.h, k, _ip(None if ids is None else _i32(ids)), _ip(f), _ip(l),
+                                                 _ip(r), _dp(a), _ip(ro)), "gphocsStoreGetTrees")
+        return f, l, r, a, ro
+
+    def set_rates(self, rates, ids=None):
+        r = _f64(rates)
+        self._check(self.lib.gphocsStoreSetRates(self.h, len(r), _ip(None if ids is None else _i32(ids)), _dp(r)),
+                    "gphocsStoreSetRates")
+
+    def apply_ops(self, ops, want_status=False):
+        ops = np.ascontiguousarray(ops, OP_DTYPE)
+        st = np.zeros(len(ops), np.int32) if want_status else None
+        self._check(self.lib.gphocsStoreApplyOps(self.h, len(ops), ops.ctypes.data_as(C.c_void_p), _ip(st)),
+                    "gphocsStoreApplyOps")
+        return st
+
+    def evaluate(self, use_old, ids=None, want_sum=False, out=None):
+        k = self.L if ids is None else len(ids)
+        out = np.zeros(k) if out is None else out
+        s = C.c_double(0.0)
+        self._check(self.lib.gphocsStoreEvaluate(self.h, k, _ip(None if ids is None else _i32(ids)), int(use_old), _dp(out),
+                                                 C.byref(s) if want_sum else None), "gphocsStoreEvaluate")
+        return (out, s.value) if want_sum else out
+
+    def evaluate_device(self, use_old):
+        """Launch only; returns (device pointer of lnL[L], device pointer of the summed lnL)."""
+        a, b = C.c_void_p(), C.c_void_p()
+        self._check(self.lib.gphocsStoreEvaluateDevice(self.h, int(use_old), C.byref(a), C.byref(b)),
+                    "gphocsStoreEvaluateDevice")
+        return a.value, b.value
+
+    def lnl(self, ids=None):
+        k = self.L if ids is None else len(ids)
+        out = np.zeros(k)
+        self._check(self.lib.gphocsStoreGetLnL(self.h, k, _ip(None if ids is None else _i32(ids)), _dp(out)), "gphocsStoreGetLnL")
+        return out
+
+    def clv(self, locus, node, saved=False, P=None):
+        out = np.zeros(4 * P)
+        self._check(self.lib.gphocsStoreGetClv(self.h, locus, node, int(saved), _dp(out)), "gphocsStoreGetClv")
+        return out.reshape(P, 4)
+
+    def sync(self):
+        self._check(self.lib.gphocsStoreSync(self.h), "gphocsStoreSync")
+
+    def set_debug(self, on=True):
+        self.lib.gphocsStoreSetDebug(self.h, int(on))
+
+    def check_mirror(self):
+        return self.lib.gphocsStoreCheckMirror(self.h)
+
+    @property
+    def num_columns(self):
+        return self.lib.gphocsStoreNumColumns(self.h)
+
+    @property
+    def device_bytes(self):
+        return self.lib.gphocsStoreDeviceBytes(self.h)
+
+
+def make_ops(locus, type_, a=0, b=0, x=0.0):
+    """Edit-record array from broadcastable columns."""
+    locus = np.atleast_1d(np.asarray(locus))
+    ops = np.zeros(len(locus), OP_DTYPE)
+    ops["locus"], ops["type"], ops["a"], ops["b"], ops["x"] = locus, type_, a, b, x
+    return ops
+
+
+class Genealogy:
+    """Genealogy likelihood over flattened event chains (GphocsGenealogy)."""
+
+    def __init__(self, L, pops, device=0, stream=None):
+        self.lib = lib()
+        self.L = int(L)
+        self.Q = len(pops["father"])
+        self.C = len(pops["samples_per_pop"])
+        self.B = len(pops["band_src"])
+        self.h = self.lib.gphocsGenCreate(device, self.L, self.Q, self.C, self.B, _ip(_i32(pops["father"])),
+                                          _ip(_i32(pops["son0"])), _ip(_i32(pops["son1"])), _ip(_i32(pops["samples_per_pop"])))
+        if not self.h:
+            raise RuntimeError("gphocsGenCreate failed — no CPU fallback")
+        self.h = C.c_void_p(self.h)
+        if stream is not None:
+            self.lib.gphocsGenSetStream(self.h, C.c_void_p(stream))
+        self.set_params(pops["theta"], pops["band_rate"])
+        self.E = 0
+
+    def close(self):
+        if self.h:
+            self.lib.gphocsGenDestroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_params(self, theta, mig_rate):
+        m = _f64(mig_rate) if self.B else np.zeros(1)
+        if self.lib.gphocsGenSetParams(self.h, _dp(_f64(theta)), _dp(m)) != 0:
+            raise RuntimeError("gphocsGenSetParams failed")
+
+    def set_events(self, ev_start, pop_start, ev_type, ev_id, ev_time):
+        es = np.ascontiguousarray(ev_start, np.int64)
+        self.E = int(es[-1] - es[0])
+        if self.lib.gphocsGenSetEvents(self.h, _lp(es), _ip(_i32(pop_start)), _ip(_i32(ev_type)), _ip(_i32(ev_id)),
+                                       _dp(_f64(ev_time))) != 0:
+            raise RuntimeError("gphocsGenSetEvents failed")
+
+    def evaluate(self, per_locus_stats=True):
+        L, Q, B = self.L, self.Q, self.B
+        lnl = np.zeros(L)
+        coal = np.zeros((L, Q)) if per_locus_stats else None
+        ncoal = np.zeros((L, Q), np.int32) if per_locus_stats else None
+        mig = np.zeros((L, max(B, 1))) if per_locus_stats else None
+        nmig = np.zeros((L, max(B, 1)), np.int32) if per_locus_stats else None
+        if per_locus_stats and B:
+            mig = np.zeros((L, B))
+            nmig = np.zeros((L, B), np.int32)
+        tc, tm = np.zeros(Q), np.zeros(max(B, 1))
+        tnc, tnm = np.zeros(Q, np.int64), np.zeros(max(B, 1), np.int64)
+        s = C.c_double()
+        rc = self.lib.gphocsGenEvaluate(self.h, _dp(lnl), _dp(coal), _ip(ncoal), _dp(mig), _ip(nmig), _dp(tc), _lp(tnc),
+                                        _dp(tm), _lp(tnm), C.byref(s))
+        if rc != 0:
+            raise RuntimeError("gphocsGenEvaluate failed")
+        return dict(lnl=lnl, coal=coal, num_coals=ncoal, mig=None if mig is None else mig[:, :B],
+                    num_migs=None if nmig is None else nmig[:, :B], total_coal=tc, total_num_coals=tnc,
+                    total_mig=tm[:B], total_num_migs=tnm[:B], sum_lnl=s.value)
+
+    def evaluate_device(self):
+        a, b = C.c_void_p(), C.c_void_p()
+        v = self.lib.gphocsGenEvaluateDevice(self.h, C.byref(a), C.byref(b))
+        if v < 0:
+            raise RuntimeError("gphocsGenEvaluateDevice failed")
+        return a.value, b.value, v
+
+    def lineages(self):
+        out = np.zeros(self.E, np.int32)
+        if self.lib.gphocsGenGetLineages(self.h, _ip(out)) != 0:
+            raise RuntimeError("gphocsGenGetLineages failed")
+        return out
+
+    def sync(self):
+        self.lib.gphocsGenSync(self.h)
+
+
+class ScalarLocus:
+    """One locus driven through the reference's own LocusData entry points exported by the library
+    (createLocusData ... getNodeSon) — the un-modified-caller path of INTEGRATION.md §1."""
+
+    def __init__(self, n, chars, num_phases, counts, rate=1.0):
+        self.lib = lib()
+        self.n, self.N, self.P = n, 2 * n - 1, len(num_phases)
+        self.h = C.c_void_p(self.lib.createLocusData(n, 1))
+        chars = np.ascontiguousarray(chars, np.uint8)
+        rows = (C.c_char_p * max(self.P, 1))(*[chars[p].tobytes() for p in range(self.P)])
+        ph, ct = _i32(num_phases), _i32(counts)
+        if self.lib.initializeLocusData(self.h, rows, self.P, _ip(ph), _ip(ct)) != 0:
+            self.lib.freeLocusData(self.h)
+            raise ValueError("initializeLocusData failed")
+        self.lib.setLocusMutationRate(self.h, rate)
+
+    def set_tree(self, father, left, right, age, root):
+        f, l, r, a = _i32(father).copy(), _i32(left).copy(), _i32(right).copy(), _f64(age).copy()
+        t = GenericBinaryTree(self.n, int(root), None, _ip(f), _ip(l), _ip(r), _dp(a), None)
+        self.lib.copyGenericTreeToLocus(self.h, C.byref(t))
+
+    def tree(self):
+        N = self.N
+        f = np.array([self.lib.getNodeFather(self.h, i) for i in range(N)], np.int32)
+        l = np.array([self.lib.getNodeSon(self.h, i, 0) for i in range(N)], np.int32)
+        r = np.array([self.lib.getNodeSon(self.h, i, 1) for i in range(N)], np.int32)
+        a = np.array([self.lib.getNodeAge(self.h, i) for i in range(N)])
+        return f, l, r, a, self.lib.getLocusRoot(self.h)
+
+    def compute(self, use_old):
+        return self.lib.computeLocusDataLikelihood(self.h, int(use_old))
+
+    def lnl(self):
+        return self.lib.getLocusDataLikelihood(self.h)
+
+    def set_rate(self, r):
+        self.lib.setLocusMutationRate(self.h, r)
+
+    def adjust_age(self, node, age):
+        return self.lib.adjustGenNodeAge(self.h, node, age)
+
+    def scale_all(self, f):
+        return self.lib.scaleAllNodeAges(self.h, f)
+
+    def spr(self, sub, target, age):
+        return self.lib.executeGenSPR(self.h, sub, target, age)
+
+    def revert(self):
+        return self.lib.revertToSaved(self.h)
+
+    def reset(self):
+        return self.lib.resetSaved(self.h)
+
+    def check(self):
+        return self.lib.checkLocusDataLikelihood(self.h)
+
+    def free(self):
+        if self.h:
+            self.lib.freeLocusData(self.h)
+            self.h = None

@@ -1,0 +1,873 @@
+// gphocs_b200.cu — libgphocs_b200.so: device-resident locus store, batched engine, genealogy likelihood
+// and the reference-compatible LocusData C ABI (include/gphocs_b200.h).  sm_100a only, no CPU fallback:
+// every entry point that evaluates a likelihood launches a CUDA kernel or fails loudly.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <atomic>
+#include <mutex>
+#include <vector>
+
+#include "gphocs_b200.h"
+
+#include "clv_kernels.cuh"
+#include "gen_kernels.cuh"
+#include "tree_ops.cuh"
+
+using namespace gphocs;
+
+static_assert(sizeof(GphocsOp) == sizeof(Op), "edit record layout");
+
+static std::atomic<long long> g_launches{0};
+
+#define CUDA_TRY(expr)                                                                                   \
+  do {                                                                                                   \
+    cudaError_t _e = (expr);                                                                             \
+    if (_e != cudaSuccess) {                                                                             \
+      fprintf(stderr, "gphocs_b200: CUDA error %s at %s:%d: %s\n", cudaGetErrorName(_e), __FILE__, __LINE__, \
+              cudaGetErrorString(_e));                                                                   \
+      return -1;                                                                                         \
+    }                                                                                                    \
+  } while (0)
+
+template <typename T>
+static int devAlloc(T** p, size_t count) {
+  *p = nullptr;
+  if (count == 0) count = 1;
+  CUDA_TRY(cudaMalloc((void**)p, count * sizeof(T)));
+  return 0;
+}
+
+// growable pinned host + device buffer pair
+template <typename T>
+struct Staging {
+  T* host = nullptr;
+  T* dev = nullptr;
+  size_t cap = 0;
+  int reserve(size_t n) {
+    if (n <= cap) return 0;
+    size_t nc = std::max(n, cap * 2);
+    if (host) cudaFreeHost(host);
+    if (dev) cudaFree(dev);
+    host = nullptr; dev = nullptr; cap = 0;
+    CUDA_TRY(cudaMallocHost((void**)&host, nc * sizeof(T)));
+    CUDA_TRY(cudaMalloc((void**)&dev, nc * sizeof(T)));
+    cap = nc;
+    return 0;
+  }
+  void release() {
+    if (host) cudaFreeHost(host);
+    if (dev) cudaFree(dev);
+    host = nullptr; dev = nullptr; cap = 0;
+  }
+};
+
+// ======================================================================================= store
+struct GphocsStore {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool ownStream = false;
+  int L = 0, n = 0, N = 0, NI = 0, W = 0;
+  long long Ct = 0;
+  long long deviceBytes = 0;
+  StoreDev d{};
+  uint8_t* dMask = nullptr;
+  Batch* dBatches = nullptr;
+  double* dSum = nullptr;
+  int numBatches = 0;
+  size_t smemBytes = 0;
+  std::vector<Batch> batches;
+  std::vector<int> locusBatch;  // batch index holding each locus (-1: no columns)
+  std::vector<int> colStart;
+  // host mirror (what the reference's getters read)
+  std::vector<int16_t> hFather, hLeft, hRight, hsFather, hsLeft, hsRight;
+  std::vector<double> hAge, hsAge, hRate, hLnL, hSavedLnL;
+  std::vector<uint8_t> hFlags;
+  std::vector<int> hRoot, hSavedRoot;
+  // staging
+  Staging<Op> ops;
+  Staging<int> seg, status, ids;
+  Staging<double> f64;
+  Staging<int16_t> i16;
+  std::vector<Op> pending;  // edits queued by the scalar API, flushed before the next evaluation
+  bool debugMirror = false;  // also mirror SEL/RECALC bits on the host (tests)
+  std::mutex mu;
+
+  TreeView hostView(int l) {
+    TreeView t;
+    const size_t o = (size_t)l * N;
+    t.father = hFather.data() + o; t.left = hLeft.data() + o; t.right = hRight.data() + o;
+    t.svFather = hsFather.data() + o; t.svLeft = hsLeft.data() + o; t.svRight = hsRight.data() + o;
+    t.age = hAge.data() + o; t.svAge = hsAge.data() + o; t.flags = hFlags.data() + o;
+    t.root = &hRoot[l]; t.savedRoot = &hSavedRoot[l];
+    t.lnL = &hLnL[l]; t.savedLnL = &hSavedLnL[l]; t.rate = &hRate[l];
+    t.numLeaves = n;
+    t.numPatterns = colStart[l + 1] - colStart[l];
+    return t;
+  }
+};
+
+static inline unsigned leafCode(char ch) {
+  switch (ch) {  // computeLeafConditionals, LocusDataLikelihood.c:1336-1386
+    case 'T': return 1u;
+    case 'C': return 2u;
+    case 'A': return 4u;
+    case 'G': return 8u;
+    case 'N': return 15u;
+    default: return 0u;
+  }
+}
+
+extern "C" GphocsStore* gphocsStoreCreate(int device, int numLoci, int numLeaves, const long long* pattStart,
+                                          const long long* unphStart, const char* chars, const int* numPhases,
+                                          const int* counts) {
+  if (numLoci <= 0 || numLeaves < 2 || numLeaves > 200) {
+    fprintf(stderr, "gphocs_b200: bad store dimensions (loci %d, leaves %d; leaves must be 2..200)\n", numLoci, numLeaves);
+    return nullptr;
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    fprintf(stderr, "gphocs_b200: no CUDA device visible — this library has no CPU path\n");
+    return nullptr;
+  }
+  if (cudaSetDevice(device) != cudaSuccess) {
+    fprintf(stderr, "gphocs_b200: cannot select CUDA device %d\n", device);
+    return nullptr;
+  }
+  GphocsStore* s = new GphocsStore();
+  s->device = device;
+  s->L = numLoci; s->n = numLeaves; s->N = 2 * numLeaves - 1; s->NI = numLeaves - 1; s->W = (numLeaves + 15) / 16;
+  const int L = s->L, n = s->n, N = s->N, NI = s->NI, W = s->W;
+  const long long Ct = pattStart[L] - pattStart[0];
+  if (Ct >= (1ll << 31) - 256) {
+    fprintf(stderr, "gphocs_b200: too many pattern columns (%lld)\n", Ct);
+    delete s;
+    return nullptr;
+  }
+  s->Ct = Ct;
+  s->colStart.resize(L + 1);
+  for (int l = 0; l <= L; l++) s->colStart[l] = (int)(pattStart[l] - pattStart[0]);
+
+  // ---- host-side packing of leaves and phase groups
+  std::vector<unsigned long long> words((size_t)W * std::max<long long>(Ct, 1), 0ull);
+  std::vector<int> phases(std::max<long long>(Ct, 1), 0), cnt(std::max<long long>(Ct, 1), 0);
+  bool bad = false;
+#pragma omp parallel for schedule(static)
+  for (int l = 0; l < L; l++) {
+    long long u = unphStart[l];
+    for (long long c = pattStart[l]; c < pattStart[l + 1]; c++) {
+      const long long col = c - pattStart[0];
+      const char* row = chars + (size_t)c * n;
+      for (int leaf = 0; leaf < n; leaf++) {
+        const unsigned code = leafCode(row[leaf]);
+        if (!code) bad = true;
+        words[(size_t)(leaf >> 4) * Ct + col] |= (unsigned long long)code << ((leaf & 15) * 4);
+      }
+      phases[col] = numPhases[c];
+      if (numPhases[c] > 0) {
+        cnt[col] = counts ? counts[u] : 0;
+        u++;
+        if (cnt[col] <= 0) bad = true;  // the reference aborts on a dead pattern (.c:450-453)
+      }
+    }
+  }
+  if (bad) {
+    fprintf(stderr, "gphocs_b200: unexpected character in a pattern (only T,C,A,G,N) or non-positive pattern count\n");
+    delete s;
+    return nullptr;
+  }
+  // phase groups must be whole and lie inside their locus
+  for (int l = 0; l < L && !bad; l++)
+    for (int c = s->colStart[l]; c < s->colStart[l + 1];) {
+      const int ph = phases[c];
+      if (ph <= 0 || c + ph > s->colStart[l + 1]) { bad = true; break; }
+      for (int j = 1; j < ph; j++) if (phases[c + j] != 0) bad = true;
+      c += ph;
+    }
+  if (bad) {
+    fprintf(stderr, "gphocs_b200: malformed phase groups (numPhases must be 2^k on the first column, 0 on the rest)\n");
+    delete s;
+    return nullptr;
+  }
+
+  // ---- CTA batches: whole loci packed greedily; an oversized locus gets a CTA of its own
+  long long scratchCols = 0;
+  s->locusBatch.assign(L, -1);
+  {
+    Batch cur{0, 0, 0, 0, -1, 0};
+    auto flush = [&]() { if (cur.numLoci > 0) s->batches.push_back(cur); cur = Batch{0, 0, 0, 0, -1, 0}; };
+    for (int l = 0; l < L; l++) {
+      const int P = s->colStart[l + 1] - s->colStart[l];
+      if (P == 0) { flush(); continue; }  // keeps batches contiguous in locus index
+      if (P > kThreads) {
+        flush();
+        Batch b{l, 1, s->colStart[l], P, (int)scratchCols, 0};
+        scratchCols += P;
+        s->locusBatch[l] = (int)s->batches.size();
+        s->batches.push_back(b);
+        continue;
+      }
+      if (cur.numLoci > 0 && (cur.numCols + P > kThreads || cur.numLoci == kMaxBatchLoci)) flush();
+      if (cur.numLoci == 0) { cur.firstLocus = l; cur.firstCol = s->colStart[l]; }
+      s->locusBatch[l] = (int)s->batches.size();
+      cur.numLoci++;
+      cur.numCols += P;
+    }
+    flush();
+  }
+  s->numBatches = (int)s->batches.size();
+
+  // ---- device allocations
+  StoreDev& d = s->d;
+  d.L = L; d.n = n; d.N = N; d.NI = NI; d.W = W; d.Ct = Ct;
+  int *dColStart = nullptr, *dPh = nullptr, *dCnt = nullptr;
+  unsigned long long* dWords = nullptr;
+  bool ok = true;
+  const size_t LN = (size_t)L * N;
+  ok = ok && devAlloc(&dColStart, L + 1) == 0 && devAlloc(&dWords, words.size()) == 0 && devAlloc(&dPh, phases.size()) == 0 &&
+       devAlloc(&dCnt, cnt.size()) == 0 && devAlloc(&d.clv, (size_t)Ct * NI * 8) == 0 && devAlloc(&d.father, LN) == 0 &&
+       devAlloc(&d.left, LN) == 0 && devAlloc(&d.right, LN) == 0 && devAlloc(&d.svFather, LN) == 0 &&
+       devAlloc(&d.svLeft, LN) == 0 && devAlloc(&d.svRight, LN) == 0 && devAlloc(&d.age, LN) == 0 &&
+       devAlloc(&d.svAge, LN) == 0 && devAlloc(&d.flags, LN) == 0 && devAlloc(&d.root, L) == 0 &&
+       devAlloc(&d.savedRoot, L) == 0 && devAlloc(&d.rate, L) == 0 && devAlloc(&d.lnL, L) == 0 &&
+       devAlloc(&d.savedLnL, L) == 0 && devAlloc(&d.rootScratch, (size_t)scratchCols * 4) == 0 &&
+       devAlloc(&d.ctaSum, s->numBatches) == 0 && devAlloc(&s->dMask, L) == 0 &&
+       devAlloc(&s->dBatches, s->numBatches) == 0 && devAlloc(&s->dSum, 1) == 0;
+  if (!ok) {
+    fprintf(stderr, "gphocs_b200: device allocation failed\n");
+    delete s;
+    return nullptr;
+  }
+  d.colStart = dColStart; d.leafWords = dWords; d.grpPhases = dPh; d.grpCount = dCnt; d.active = nullptr;
+  s->deviceBytes = (long long)((size_t)Ct * NI * 64 + words.size() * 8 + (size_t)Ct * 8 + LN * (6 * 2 + 16 + 1) + (size_t)L * 36);
+  cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
+  s->ownStream = true;
+  cudaMemcpy(dColStart, s->colStart.data(), sizeof(int) * (L + 1), cudaMemcpyHostToDevice);
+  cudaMemcpy(dWords, words.data(), words.size() * 8, cudaMemcpyHostToDevice);
+  cudaMemcpy(dPh, phases.data(), phases.size() * 4, cudaMemcpyHostToDevice);
+  cudaMemcpy(dCnt, cnt.data(), cnt.size() * 4, cudaMemcpyHostToDevice);
+  if (s->numBatches) cudaMemcpy(s->dBatches, s->batches.data(), sizeof(Batch) * s->numBatches, cudaMemcpyHostToDevice);
+  cudaMemset(d.clv, 0, (size_t)Ct * NI * 64);
+  cudaMemset(d.father, 0xff, LN * 2); cudaMemset(d.left, 0xff, LN * 2); cudaMemset(d.right, 0xff, LN * 2);
+  cudaMemset(d.svFather, 0xff, LN * 2); cudaMemset(d.svLeft, 0xff, LN * 2); cudaMemset(d.svRight, 0xff, LN * 2);
+  cudaMemset(d.age, 0, LN * 8); cudaMemset(d.svAge, 0, LN * 8); cudaMemset(d.flags, 0, LN);
+  cudaMemset(d.root, 0xff, (size_t)L * 4); cudaMemset(d.savedRoot, 0xff, (size_t)L * 4);
+  cudaMemset(d.lnL, 0, (size_t)L * 8); cudaMemset(d.savedLnL, 0, (size_t)L * 8);
+  cudaMemset(s->dMask, 0, L);
+  {
+    std::vector<double> ones(L, 1.0);
+    cudaMemcpy(d.rate, ones.data(), (size_t)L * 8, cudaMemcpyHostToDevice);
+  }
+  s->smemBytes = evalSmemBytes(n);
+  if (cudaFuncSetAttribute(k_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smemBytes) != cudaSuccess ||
+      cudaDeviceSynchronize() != cudaSuccess) {
+    fprintf(stderr, "gphocs_b200: device initialisation failed: %s\n", cudaGetErrorString(cudaGetLastError()));
+    delete s;
+    return nullptr;
+  }
+  // ---- host mirror
+  s->hFather.assign(LN, -1); s->hLeft.assign(LN, -1); s->hRight.assign(LN, -1);
+  s->hsFather.assign(LN, -1); s->hsLeft.assign(LN, -1); s->hsRight.assign(LN, -1);
+  s->hAge.assign(LN, 0.0); s->hsAge.assign(LN, 0.0); s->hFlags.assign(LN, 0);
+  s->hRoot.assign(L, -1); s->hSavedRoot.assign(L, -1);
+  s->hRate.assign(L, 1.0); s->hLnL.assign(L, 0.0); s->hSavedLnL.assign(L, 0.0);
+  return s;
+}
+
+extern "C" int gphocsStoreDestroy(GphocsStore* s) {
+  if (!s) return 0;
+  cudaSetDevice(s->device);
+  cudaDeviceSynchronize();
+  StoreDev& d = s->d;
+  void* ptrs[] = {(void*)d.colStart, (void*)d.leafWords, (void*)d.grpPhases, (void*)d.grpCount, d.clv, d.father, d.left,
+                  d.right, d.svFather, d.svLeft, d.svRight, d.age, d.svAge, d.flags, d.root, d.savedRoot, d.rate, d.lnL,
+                  d.savedLnL, d.rootScratch, d.ctaSum, s->dMask, s->dBatches, s->dSum};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  s->ops.release(); s->seg.release(); s->status.release(); s->ids.release(); s->f64.release(); s->i16.release();
+  if (s->ownStream && s->stream) cudaStreamDestroy(s->stream);
+  delete s;
+  return 0;
+}
+
+extern "C" int gphocsStoreSetStream(GphocsStore* s, void* cudaStream) {
+  cudaSetDevice(s->device);
+  cudaStreamSynchronize(s->stream);
+  if (s->ownStream && s->stream) cudaStreamDestroy(s->stream);
+  if (cudaStream) { s->stream = (cudaStream_t)cudaStream; s->ownStream = false; }
+  else { cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking); s->ownStream = true; }
+  return 0;
+}
+extern "C" int gphocsStoreNumLoci(const GphocsStore* s) { return s->L; }
+extern "C" int gphocsStoreNumLeaves(const GphocsStore* s) { return s->n; }
+extern "C" long long gphocsStoreNumColumns(const GphocsStore* s) { return s->Ct; }
+extern "C" long long gphocsStoreDeviceBytes(const GphocsStore* s) { return s->deviceBytes; }
+extern "C" long long gphocsKernelLaunchCount(void) { return g_launches.load(); }
+extern "C" int gphocsStoreSync(GphocsStore* s) {
+  cudaSetDevice(s->device);
+  CUDA_TRY(cudaStreamSynchronize(s->stream));
+  return 0;
+}
+
+// ---- genealogies
+static int setTreesLocked(GphocsStore* s, int nLoci, const int* locusIds, const int* father, const int* left,
+                          const int* right, const double* age, const int* root) {
+  const int N = s->N;
+  cudaSetDevice(s->device);
+  for (int k = 0; k < nLoci; k++) {
+    const int l = locusIds ? locusIds[k] : k;
+    if (l < 0 || l >= s->L) { fprintf(stderr, "gphocs_b200: locus %d out of range\n", l); return -1; }
+    const size_t o = (size_t)l * N, in = (size_t)k * N;
+    for (int i = 0; i < N; i++) {
+      s->hFather[o + i] = (int16_t)father[in + i];
+      s->hLeft[o + i] = (int16_t)left[in + i];
+      s->hRight[o + i] = (int16_t)right[in + i];
+      s->hAge[o + i] = age[in + i];
+    }
+    s->hRoot[l] = root[k];
+  }
+  StoreDev& d = s->d;
+  if (!locusIds) {  // contiguous prefix: one copy per array
+    const size_t cnt = (size_t)nLoci * N;
+    CUDA_TRY(cudaMemcpyAsync(d.father, s->hFather.data(), cnt * 2, cudaMemcpyHostToDevice, s->stream));
+    CUDA_TRY(cudaMemcpyAsync(d.left, s->hLeft.data(), cnt * 2, cudaMemcpyHostToDevice, s->stream));
+    CUDA_TRY(cudaMemcpyAsync(d.right, s->hRight.data(), cnt * 2, cudaMemcpyHostToDevice, s->stream));
+    CUDA_TRY(cudaMemcpyAsync(d.age, s->hAge.data(), cnt * 8, cudaMemcpyHostToDevice, s->stream));
+    CUDA_TRY(cudaMemcpyAsync(d.root, s->hRoot.data(), (size_t)nLoci * 4, cudaMemcpyHostToDevice, s->stream));
+  } else {
+    for (int k = 0; k < nLoci; k++) {
+      const int l = locusIds[k];
+      const size_t o = (size_t)l * N;
+      CUDA_TRY(cudaMemcpyAsync(d.father + o, s->hFather.data() + o, (size_t)N * 2, cudaMemcpyHostToDevice, s->stream));
+      CUDA_TRY(cudaMemcpyAsync(d.left + o, s->hLeft.data() + o, (size_t)N * 2, cudaMemcpyHostToDevice, s->stream));
+      CUDA_TRY(cudaMemcpyAsync(d.right + o, s->hRight.data() + o, (size_t)N * 2, cudaMemcpyHostToDevice, s->stream));
+      CUDA_TRY(cudaMemcpyAsync(d.age + o, s->hAge.data() + o, (size_t)N * 8, cudaMemcpyHostToDevice, s->stream));
+      CUDA_TRY(cudaMemcpyAsync(d.root + l, s->hRoot.data() + l, 4, cudaMemcpyHostToDevice, s->stream));
+    }
+  }
+  CUDA_TRY(cudaStreamSynchronize(s->stream));  // the mirror vectors are pageable: finish before returning
+  return 0;
+}
+
+extern "C" int gphocsStoreSetTrees(GphocsStore* s, int nLoci, const int* locusIds, const int* father, const int* left,
+                                   const int* right, const double* age, const int* root) {
+  std::lock_guard<std::mutex> lk(s->mu);
+  return setTreesLocked(s, nLoci, locusIds, father, left, right, age, root);
+}
+
+extern "C" int gphocsStoreGetTrees(GphocsStore* s, int nLoci, const int* locusIds, int* father, int* left, int* right,
+                                   double* age, int* root) {
+  std::lock_guard<std::mutex> lk(s->mu);
+  const int N = s->N;
+  for (int k = 0; k < nLoci; k++) {
+    const int l = locusIds ? locusIds[k] : k;
+    if (l < 0 || l >= s->L) return -1;
+    const size_t o = (size_t)l * N, out = (size_t)k * N;
+    for (int i = 0; i < N; i++) {
+      father[out + i] = s->hFather[o + i];
+      left[out + i] = s->hLeft[o + i];
+      right[out + i] = s->hRight[o + i];
+      age[out + i] = s->hAge[o + i];
+    }
+    root[k] = s->hRoot[l];
+  }
+  return 0;
+}
+
+// ---- edits
+static int launchOps(GphocsStore* s, const Op* ops, int nOps, int* outStatus) {
+  if (nOps <= 0) return 0;
+  cudaSetDevice(s->device);
+  if (s->ops.reserve(nOps) || s->seg.reserve(nOps + 1) || s->status.reserve(nOps)) return -1;
+  // stable grouping by locus so one device thread replays a locus' records in call order
+  std::vector<int> order(nOps);
+  bool sorted = true;
+  for (int i = 0; i < nOps; i++) {
+    order[i] = i;
+    if (i && ops[i].locus < ops[i - 1].locus) sorted = false;
+  }
+  if (!sorted) std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return ops[a].locus < ops[b].locus; });
+  int nSegs = 0;
+  for (int i = 0; i < nOps; i++) {
+    s->ops.host[i] = ops[order[i]];
+    if (i == 0 || s->ops.host[i].locus != s->ops.host[i - 1].locus) s->seg.host[nSegs++] = i;
+  }
+  s->seg.host[nSegs] = nOps;
+  CUDA_TRY(cudaMemcpyAsync(s->ops.dev, s->ops.host, sizeof(Op) * nOps, cudaMemcpyHostToDevice, s->stream));
+  CUDA_TRY(cudaMemcpyAsync(s->seg.dev, s->seg.host, sizeof(int) * (nSegs + 1), cudaMemcpyHostToDevice, s->stream));
+  k_apply_ops<<<(nSegs + 127) / 128, 128, 0, s->stream>>>(s->d, s->ops.dev, s->seg.dev, nSegs, s->status.dev);
+  g_launches++;
+  CUDA_TRY(cudaGetLastError());
+  if (outStatus) {
+    CUDA_TRY(cudaMemcpyAsync(s->status.host, s->status.dev, sizeof(int) * nOps, cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    for (int i = 0; i < nOps; i++) outStatus[order[i]] = s->status.host[i];
+  } else {
+    // staging buffers are reused by the next call
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+  }
+  return 0;
+}
+
+static int flushPending(GphocsStore* s) {
+  if (s->pending.empty()) return 0;
+  std::vector<Op> ops;
+  ops.swap(s->pending);
+  return launchOps(s, ops.data(), (int)ops.size(), nullptr);
+}
+
+extern "C" int gphocsStoreApplyOps(GphocsStore* s, int nOps, const GphocsOp* ops_, int* outStatus) {
+  std::lock_guard<std::mutex> lk(s->mu);
+  const Op* ops = reinterpret_cast<const Op*>(ops_);
+  if (flushPending(s)) return -1;
+  // host mirror first (getters must see the proposal immediately); statuses come from here as well and are
+  // cross-checked against the device's in debug builds of the tests
+  for (int i = 0; i < nOps; i++) {
+    if (ops[i].locus < 0 || ops[i].locus >= s->L) { fprintf(stderr, "gphocs_b200: locus %d out of range\n", ops[i].locus); return -1; }
+    applyOp(s->hostView(ops[i].locus), ops[i]);
+  }
+  return launchOps(s, ops, nOps, outStatus);
+}
+
+extern "C" int gphocsStoreSetRates(GphocsStore* s, int nLoci, const int* locusIds, const double* rates) {
+  std::vector<GphocsOp> ops(nLoci);
+  for (int k = 0; k < nLoci; k++) ops[k] = GphocsOp{locusIds ? locusIds[k] : k, GPHOCS_OP_SET_RATE, 0, 0, rates[k]};
+  return gphocsStoreApplyOps(s, nLoci, ops.data(), nullptr);
+}
+
+// ---- evaluation
+static int launchEval(GphocsStore* s, int useOld, int onlyLocus, bool masked) {
+  cudaSetDevice(s->device);
+  StoreDev d = s->d;
+  d.active = masked ? s->dMask : nullptr;
+  if (onlyLocus >= 0) {
+    const int b = s->locusBatch[onlyLocus];
+    if (b < 0) return 0;
+    k_eval<<<1, kThreads, s->smemBytes, s->stream>>>(d, s->dBatches, b, useOld, onlyLocus);
+    g_launches++;
+  } else if (s->numBatches > 0) {
+    k_eval<<<s->numBatches, kThreads, s->smemBytes, s->stream>>>(d, s->dBatches, 0, useOld, -1);
+    g_launches++;
+  }
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int gphocsStoreEvaluateDevice(GphocsStore* s, int useOld, void** devLnL, void** devSum) {
+  std::lock_guard<std::mutex> lk(s->mu);
+  if (flushPending(s)) return -1;
+  if (launchEval(s, useOld, -1, false)) return -1;
+  k_reduce_sum<<<1, 1024, 0, s->stream>>>(s->d.ctaSum, s->numBatches, s->dSum);
+  g_launches++;
+  CUDA_TRY(cudaGetLastError());
+  if (devLnL) *devLnL = s->d.lnL;
+  if (devSum) *devSum = s->dSum;
+  return 0;
+}
+
+static int readLnL(GphocsStore* s, int nLoci, const int* locusIds, double* outLnL, bool refreshMirror) {
+  // device -> pinned staging -> caller; keeps the host mirror of lnL current
+  const int L = s->L;
+  if (s->f64.reserve(L + 1)) return -1;
+  if (!locusIds) {
+    CUDA_TRY(cudaMemcpyAsync(s->f64.host, s->d.lnL, sizeof(double) * L, cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    if (refreshMirror) memcpy(s->hLnL.data(), s->f64.host, sizeof(double) * L);
+    if (outLnL) memcpy(outLnL, s->f64.host, sizeof(double) * nLoci);
+  } else {
+    if (s->ids.reserve(nLoci)) return -1;
+    memcpy(s->ids.host, locusIds, sizeof(int) * nLoci);
+    CUDA_TRY(cudaMemcpyAsync(s->ids.dev, s->ids.host, sizeof(int) * nLoci, cudaMemcpyHostToDevice, s->stream));
+    k_gather_f64<<<(nLoci + 255) / 256, 256, 0, s->stream>>>(s->d.lnL, s->ids.dev, nLoci, s->f64.dev);
+    g_launches++;
+    CUDA_TRY(cudaMemcpyAsync(s->f64.host, s->f64.dev, sizeof(double) * nLoci, cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    for (int k = 0; k < nLoci; k++) {
+      if (refreshMirror) s->hLnL[locusIds[k]] = s->f64.host[k];
+      if (outLnL) outLnL[k] = s->f64.host[k];
+    }
+  }
+  return 0;
+}
+
+// Host replay of the buffer flips an evaluation performs on the device (debug / mirror-check mode only):
+// exactly the dirty nodes and their ancestors, or every internal node for a full evaluation.
+static void replayFlipsOnMirror(GphocsStore* s, int l, int useOld) {
+  const int n = s->n, N = s->N;
+  if (s->colStart[l + 1] == s->colStart[l] || s->hRoot[l] < 0) return;
+  TreeView t = s->hostView(l);
+  if (!useOld) {
+    for (int i = n; i < N; i++) flipClv(t, i);
+    return;
+  }
+  for (int i = 0; i < N; i++) {
+    if (!(t.flags[i] & F_RECALC) || (t.flags[i] & 0x80)) continue;
+    int u = i < n ? t.father[i] : i;
+    while (u >= 0 && !(t.flags[u] & 0x80)) {  // 0x80: visited in this replay
+      flipClv(t, u);
+      t.flags[u] |= 0x80;
+      u = t.father[u];
+    }
+  }
+  for (int i = 0; i < N; i++) t.flags[i] &= 0x7f;
+}
+
+extern "C" int gphocsStoreEvaluate(GphocsStore* s, int nLoci, const int* locusIds, int useOld, double* outLnL,
+                                   double* outSum) {
+  std::lock_guard<std::mutex> lk(s->mu);
+  if (flushPending(s)) return -1;
+  cudaSetDevice(s->device);
+  const bool all = (locusIds == nullptr);
+  if (all && nLoci != s->L) { fprintf(stderr, "gphocs_b200: locusIds == NULL requires nLoci == numLoci\n"); return -1; }
+  if (s->f64.reserve((size_t)s->L + 1)) return -1;
+  // mirror: savedLnL <- lnL for every evaluated locus (.c:440; loci without patterns or tree hold 0 in both)
+  if (all) {
+    memcpy(s->hSavedLnL.data(), s->hLnL.data(), sizeof(double) * s->L);
+  } else {
+    for (int k = 0; k < nLoci; k++) {
+      const int l = locusIds[k];
+      if (l < 0 || l >= s->L) { fprintf(stderr, "gphocs_b200: locus %d out of range\n", l); return -1; }
+      s->hSavedLnL[l] = s->hLnL[l];
+    }
+  }
+  if (!all && nLoci == 1) {
+    if (launchEval(s, useOld, locusIds[0], false)) return -1;
+  } else if (all) {
+    if (launchEval(s, useOld, -1, false)) return -1;
+  } else {
+    if (s->ids.reserve(nLoci)) return -1;
+    memcpy(s->ids.host, locusIds, sizeof(int) * nLoci);
+    CUDA_TRY(cudaMemsetAsync(s->dMask, 0, s->L, s->stream));
+    CUDA_TRY(cudaMemcpyAsync(s->ids.dev, s->ids.host, sizeof(int) * nLoci, cudaMemcpyHostToDevice, s->stream));
+    k_set_mask<<<(nLoci + 255) / 256, 256, 0, s->stream>>>(s->dMask, s->ids.dev, nLoci);
+    g_launches++;
+    if (launchEval(s, useOld, -1, true)) return -1;
+  }
+  if (outSum && all) {
+    k_reduce_sum<<<1, 1024, 0, s->stream>>>(s->d.ctaSum, s->numBatches, s->dSum);
+    g_launches++;
+    CUDA_TRY(cudaMemcpyAsync(s->f64.host + s->L, s->dSum, sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+  }
+  if (s->debugMirror)
+    for (int k = 0; k < nLoci; k++) replayFlipsOnMirror(s, all ? k : locusIds[k], useOld);
+  if (readLnL(s, nLoci, locusIds, outLnL, true)) return -1;  // synchronises the stream
+  if (outSum) {
+    if (all) {
+      *outSum = s->f64.host[s->L];
+    } else {
+      double v = 0.0;
+      for (int k = 0; k < nLoci; k++) v += s->hLnL[locusIds[k]];
+      *outSum = v;
+    }
+  }
+  return 0;
+}
+
+// Compares the host mirror with the device copy; returns the number of mismatching entries (tree fields,
+// roots, SAVED bits; with debug mirroring on also SEL/RECALC bits and lnL/savedLnL), or -1 on error.
+extern "C" int gphocsStoreCheckMirror(GphocsStore* s) {
+  std::lock_guard<std::mutex> lk(s->mu);
+  if (flushPending(s)) return -1;
+  cudaSetDevice(s->device);
+  CUDA_TRY(cudaStreamSynchronize(s->stream));
+  const size_t LN = (size_t)s->L * s->N;
+  std::vector<int16_t> f(LN), l(LN), r(LN);
+  std::vector<double> a(LN), lnl(s->L), sv(s->L), rate(s->L);
+  std::vector<uint8_t> fl(LN);
+  std::vector<int> root(s->L), sroot(s->L);
+  CUDA_TRY(cudaMemcpy(f.data(), s->d.father, LN * 2, cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(l.data(), s->d.left, LN * 2, cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(r.data(), s->d.right, LN * 2, cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(a.data(), s->d.age, LN * 8, cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(fl.data(), s->d.flags, LN, cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(root.data(), s->d.root, (size_t)s->L * 4, cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(sroot.data(), s->d.savedRoot, (size_t)s->L * 4, cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(lnl.data(), s->d.lnL, (size_t)s->L * 8, cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(sv.data(), s->d.savedLnL, (size_t)s->L * 8, cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(rate.data(), s->d.rate, (size_t)s->L * 8, cudaMemcpyDeviceToHost));
+  int bad = 0;
+  const uint8_t mask = s->debugMirror ? (F_SEL | F_RECALC | F_SAVED) : F_SAVED;
+  for (size_t i = 0; i < LN; i++) {
+    bad += f[i] != s->hFather[i];
+    bad += l[i] != s->hLeft[i];
+    bad += r[i] != s->hRight[i];
+    bad += a[i] != s->hAge[i];
+    bad += (fl[i] & mask) != (s->hFlags[i] & mask);
+  }
+  for (int i = 0; i < s->L; i++) {
+    bad += root[i] != s->hRoot[i];
+    bad += sroot[i] != s->hSavedRoot[i];
+    bad += rate[i] != s->hRate[i];
+    if (s->debugMirror) {
+      bad += lnl[i] != s->hLnL[i];
+      bad += sv[i] != s->hSavedLnL[i];
+    }
+  }
+  return bad;
+}
+
+extern "C" int gphocsStoreSetDebug(GphocsStore* s, int on) {
+  s->debugMirror = on != 0;
+  return 0;
+}
+
+extern "C" int gphocsStoreGetLnL(GphocsStore* s, int nLoci, const int* locusIds, double* outLnL) {
+  std::lock_guard<std::mutex> lk(s->mu);
+  if (flushPending(s)) return -1;
+  cudaSetDevice(s->device);
+  return readLnL(s, nLoci, locusIds, outLnL, false);
+}
+
+extern "C" int gphocsStoreGetClv(GphocsStore* s, int locus, int node, int saved, double* out) {
+  std::lock_guard<std::mutex> lk(s->mu);
+  if (flushPending(s)) return -1;
+  cudaSetDevice(s->device);
+  if (locus < 0 || locus >= s->L || node < 0 || node >= s->N) return -1;
+  const int P = s->colStart[locus + 1] - s->colStart[locus];
+  if (node < s->n) {  // leaves are stored as base masks; expand on request
+    std::vector<unsigned long long> w(P);
+    CUDA_TRY(cudaMemcpy(w.data(), s->d.leafWords + (size_t)(node >> 4) * s->Ct + s->colStart[locus], sizeof(unsigned long long) * P,
+                        cudaMemcpyDeviceToHost));
+    for (int p = 0; p < P; p++) {
+      const unsigned code = (unsigned)(w[p] >> ((node & 15) * 4)) & 15u;
+      for (int b = 0; b < 4; b++) out[p * 4 + b] = (code >> b) & 1u ? 1.0 : 0.0;
+    }
+    return 0;
+  }
+  uint8_t f;
+  CUDA_TRY(cudaStreamSynchronize(s->stream));
+  CUDA_TRY(cudaMemcpy(&f, s->d.flags + (size_t)locus * s->N + node, 1, cudaMemcpyDeviceToHost));
+  const int buf = (f & F_SEL) ^ (saved ? 1 : 0);
+  const double* src = s->d.clv + (size_t)s->colStart[locus] * s->NI * 8 + (size_t)((node - s->n) * 2 + buf) * P * 4;
+  CUDA_TRY(cudaMemcpy(out, src, sizeof(double) * P * 4, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+// ======================================================================================= genealogy likelihood
+struct GphocsGenealogy {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool ownStream = false;
+  int L = 0, Q = 0, C = 0, B = 0, V = 0;
+  long long totalEvents = 0;
+  int maxTileEvents = 0, numCtas = 0;
+  GenParams hp{};
+  GenDev d{};
+  GenParams* dParams = nullptr;
+  int* dEvStart = nullptr;
+  uint16_t* dPopStart = nullptr;
+  double* dEvTime = nullptr;
+  uint16_t* dEvCode = nullptr;
+  uint8_t* dLineages = nullptr;
+  double* dTotals = nullptr;
+  size_t evCap = 0;
+  Staging<double> out;
+  std::vector<int> postOrder;
+};
+
+static int genPostOrder(const int* son0, const int* son1, int C, int pop, int* out) {
+  if (pop < C) { out[0] = pop; return 1; }
+  int size = genPostOrder(son0, son1, C, son0[pop], out);
+  size += genPostOrder(son0, son1, C, son1[pop], out + size);
+  out[size] = pop;
+  return size + 1;
+}
+
+extern "C" GphocsGenealogy* gphocsGenCreate(int device, int numLoci, int numPops, int numCurPops, int numBands,
+                                            const int* popFather, const int* popSon0, const int* popSon1,
+                                            const int* samplesPerPop) {
+  if (numLoci <= 0 || numPops != 2 * numCurPops - 1 || numPops > kMaxPops || numBands < 0 || numBands > kMaxBands) {
+    fprintf(stderr, "gphocs_b200: bad genealogy dimensions (pops %d, current %d, bands %d)\n", numPops, numCurPops, numBands);
+    return nullptr;
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || cudaSetDevice(device) != cudaSuccess) {
+    fprintf(stderr, "gphocs_b200: no usable CUDA device — this library has no CPU path\n");
+    return nullptr;
+  }
+  GphocsGenealogy* g = new GphocsGenealogy();
+  g->device = device; g->L = numLoci; g->Q = numPops; g->C = numCurPops; g->B = numBands;
+  g->V = genTotalsLen(numPops, numBands);
+  GenParams& p = g->hp;
+  memset(&p, 0, sizeof(p));
+  p.Q = numPops; p.C = numCurPops; p.B = numBands; p.rootPop = -1;
+  for (int i = 0; i < numPops; i++) {
+    p.son0[i] = popSon0[i]; p.son1[i] = popSon1[i];
+    p.samplesPerPop[i] = i < numCurPops ? samplesPerPop[i] : 0;
+    if (popFather[i] < 0) p.rootPop = i;
+    p.theta[i] = 1.0;
+  }
+  if (p.rootPop < 0 || genPostOrder(p.son0, p.son1, numCurPops, p.rootPop, p.postOrder) != numPops) {
+    fprintf(stderr, "gphocs_b200: malformed population tree\n");
+    delete g;
+    return nullptr;
+  }
+  g->numCtas = (numLoci + kGenTile - 1) / kGenTile;
+  const size_t LQ = (size_t)numLoci * numPops, LB = (size_t)numLoci * std::max(numBands, 1);
+  bool ok = devAlloc(&g->dParams, 1) == 0 && devAlloc(&g->dEvStart, numLoci + 1) == 0 &&
+            devAlloc(&g->dPopStart, (size_t)numLoci * (numPops + 1)) == 0 && devAlloc(&g->d.lnL, numLoci) == 0 &&
+            devAlloc(&g->d.coal, LQ) == 0 && devAlloc(&g->d.numCoals, LQ) == 0 && devAlloc(&g->d.mig, LB) == 0 &&
+            devAlloc(&g->d.numMigs, LB) == 0 && devAlloc(&g->d.ctaTotals, (size_t)g->numCtas * g->V) == 0 &&
+            devAlloc(&g->dTotals, g->V) == 0;
+  if (!ok) { delete g; return nullptr; }
+  cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking);
+  g->ownStream = true;
+  cudaMemcpy(g->dParams, &g->hp, sizeof(GenParams), cudaMemcpyHostToDevice);
+  return g;
+}
+
+extern "C" int gphocsGenDestroy(GphocsGenealogy* g) {
+  if (!g) return 0;
+  cudaSetDevice(g->device);
+  cudaDeviceSynchronize();
+  void* ptrs[] = {g->dParams, g->dEvStart, g->dPopStart, g->dEvTime, g->dEvCode, g->dLineages, g->dTotals, g->d.lnL,
+                  g->d.coal, g->d.numCoals, g->d.mig, g->d.numMigs, g->d.ctaTotals};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  g->out.release();
+  if (g->ownStream && g->stream) cudaStreamDestroy(g->stream);
+  delete g;
+  return 0;
+}
+
+extern "C" int gphocsGenSetStream(GphocsGenealogy* g, void* cudaStream) {
+  cudaSetDevice(g->device);
+  cudaStreamSynchronize(g->stream);
+  if (g->ownStream && g->stream) cudaStreamDestroy(g->stream);
+  if (cudaStream) { g->stream = (cudaStream_t)cudaStream; g->ownStream = false; }
+  else { cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking); g->ownStream = true; }
+  return 0;
+}
+
+extern "C" int gphocsGenSetParams(GphocsGenealogy* g, const double* theta, const double* migRate) {
+  cudaSetDevice(g->device);
+  for (int p = 0; p < g->Q; p++) {
+    g->hp.theta[p] = theta[p];
+    g->hp.log2OverTheta[p] = log(2 / theta[p]);  // same expression as patch.c:2712, evaluated by the host libm
+  }
+  for (int b = 0; b < g->B; b++) {
+    g->hp.migRate[b] = migRate[b];
+    g->hp.logMigRate[b] = migRate[b] > 0.0 ? log(migRate[b]) : 0.0;
+  }
+  CUDA_TRY(cudaStreamSynchronize(g->stream));
+  CUDA_TRY(cudaMemcpyAsync(g->dParams, &g->hp, sizeof(GenParams), cudaMemcpyHostToDevice, g->stream));
+  CUDA_TRY(cudaStreamSynchronize(g->stream));
+  return 0;
+}
+
+extern "C" int gphocsGenSetEvents(GphocsGenealogy* g, const long long* evStart, const int* popStart, const int* evType,
+                                  const int* evId, const double* evTime) {
+  cudaSetDevice(g->device);
+  const int L = g->L, Q = g->Q;
+  const long long E = evStart[L] - evStart[0];
+  if (E <= 0 || E >= (1ll << 31)) { fprintf(stderr, "gphocs_b200: bad event count %lld\n", E); return -1; }
+  if ((size_t)E > g->evCap) {
+    if (g->dEvTime) cudaFree(g->dEvTime);
+    if (g->dEvCode) cudaFree(g->dEvCode);
+    if (g->dLineages) cudaFree(g->dLineages);
+    g->evCap = (size_t)E + (size_t)E / 8;
+    if (devAlloc(&g->dEvTime, g->evCap) || devAlloc(&g->dEvCode, g->evCap) || devAlloc(&g->dLineages, g->evCap)) return -1;
+  }
+  g->totalEvents = E;
+  std::vector<int> es(L + 1);
+  std::vector<uint16_t> ps((size_t)L * (Q + 1)), code(E);
+  int maxTile = 0;
+  bool bad = false;
+#pragma omp parallel for schedule(static)
+  for (int l = 0; l < L; l++) {
+    es[l] = (int)(evStart[l] - evStart[0]);
+    const long long nEv = evStart[l + 1] - evStart[l];
+    if (nEv > 65535) bad = true;
+    for (int p = 0; p <= Q; p++) ps[(size_t)l * (Q + 1) + p] = (uint16_t)popStart[(size_t)l * (Q + 1) + p];
+    for (long long e = evStart[l]; e < evStart[l + 1]; e++) {
+      const int t = evType[e], id = evId[e];
+      const bool needsBand = (t == EV_IN_MIG || t == EV_BAND_START || t == EV_BAND_END);
+      if (t < 0 || t > EV_DUMMY || (needsBand && (id < 0 || id >= g->B))) bad = true;
+      code[e - evStart[0]] = (uint16_t)(t | ((needsBand ? id : 0) << 3));
+    }
+  }
+  es[L] = (int)E;
+  if (bad) { fprintf(stderr, "gphocs_b200: malformed event snapshot\n"); return -1; }
+  for (int l0 = 0; l0 < L; l0 += kGenTile) maxTile = std::max(maxTile, es[std::min(L, l0 + kGenTile)] - es[l0]);
+  g->maxTileEvents = maxTile;
+  CUDA_TRY(cudaStreamSynchronize(g->stream));
+  CUDA_TRY(cudaMemcpyAsync(g->dEvStart, es.data(), sizeof(int) * (L + 1), cudaMemcpyHostToDevice, g->stream));
+  CUDA_TRY(cudaMemcpyAsync(g->dPopStart, ps.data(), sizeof(uint16_t) * ps.size(), cudaMemcpyHostToDevice, g->stream));
+  CUDA_TRY(cudaMemcpyAsync(g->dEvCode, code.data(), sizeof(uint16_t) * E, cudaMemcpyHostToDevice, g->stream));
+  CUDA_TRY(cudaMemcpyAsync(g->dEvTime, evTime + evStart[0], sizeof(double) * E, cudaMemcpyHostToDevice, g->stream));
+  CUDA_TRY(cudaStreamSynchronize(g->stream));
+  const size_t smem = genSmemBytes(g->Q, g->B, g->maxTileEvents);
+  if (smem > 200 * 1024) { fprintf(stderr, "gphocs_b200: event tile too large for shared memory (%zu bytes)\n", smem); return -1; }
+  CUDA_TRY(cudaFuncSetAttribute(k_gen_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  return 0;
+}
+
+static int genLaunch(GphocsGenealogy* g, bool wantLineages) {
+  cudaSetDevice(g->device);
+  if (g->totalEvents <= 0) { fprintf(stderr, "gphocs_b200: gphocsGenSetEvents has not been called\n"); return -1; }
+  GenDev d = g->d;
+  d.L = g->L; d.Q = g->Q; d.B = g->B;
+  d.evStart = g->dEvStart; d.popStart = g->dPopStart; d.evTime = g->dEvTime; d.evCode = g->dEvCode;
+  d.evLineages = wantLineages ? g->dLineages : nullptr;
+  d.params = g->dParams;
+  const size_t smem = genSmemBytes(g->Q, g->B, g->maxTileEvents);
+  k_gen_eval<<<g->numCtas, kGenThreads, smem, g->stream>>>(d, g->maxTileEvents);
+  k_gen_reduce<<<g->V, 256, 0, g->stream>>>(g->d.ctaTotals, g->numCtas, g->V, g->dTotals);
+  g_launches += 2;
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int gphocsGenEvaluateDevice(GphocsGenealogy* g, void** devLnL, void** devTotals) {
+  if (genLaunch(g, false)) return -1;
+  if (devLnL) *devLnL = g->d.lnL;
+  if (devTotals) *devTotals = g->dTotals;
+  return g->V;
+}
+
+extern "C" int gphocsGenEvaluate(GphocsGenealogy* g, double* lnL, double* coal, int* numCoals, double* mig, int* numMigs,
+                                 double* totalCoal, long long* totalNumCoals, double* totalMig, long long* totalNumMigs,
+                                 double* sumLnL) {
+  if (genLaunch(g, false)) return -1;
+  const int L = g->L, Q = g->Q, B = g->B;
+  if (g->out.reserve((size_t)L + g->V)) return -1;
+  if (lnL) CUDA_TRY(cudaMemcpyAsync(g->out.host, g->d.lnL, sizeof(double) * L, cudaMemcpyDeviceToHost, g->stream));
+  CUDA_TRY(cudaMemcpyAsync(g->out.host + L, g->dTotals, sizeof(double) * g->V, cudaMemcpyDeviceToHost, g->stream));
+  if (coal) CUDA_TRY(cudaMemcpyAsync(coal, g->d.coal, sizeof(double) * L * Q, cudaMemcpyDeviceToHost, g->stream));
+  if (numCoals) CUDA_TRY(cudaMemcpyAsync(numCoals, g->d.numCoals, sizeof(int) * L * Q, cudaMemcpyDeviceToHost, g->stream));
+  if (mig && B) CUDA_TRY(cudaMemcpyAsync(mig, g->d.mig, sizeof(double) * L * B, cudaMemcpyDeviceToHost, g->stream));
+  if (numMigs && B) CUDA_TRY(cudaMemcpyAsync(numMigs, g->d.numMigs, sizeof(int) * L * B, cudaMemcpyDeviceToHost, g->stream));
+  CUDA_TRY(cudaStreamSynchronize(g->stream));
+  if (lnL) memcpy(lnL, g->out.host, sizeof(double) * L);
+  const double* t = g->out.host + L;
+  if (sumLnL) *sumLnL = t[0];
+  for (int p = 0; p < Q; p++) {
+    if (totalCoal) totalCoal[p] = t[1 + p];
+    if (totalNumCoals) totalNumCoals[p] = (long long)llround(t[1 + Q + p]);
+  }
+  for (int b = 0; b < B; b++) {
+    if (totalMig) totalMig[b] = t[1 + 2 * Q + b];
+    if (totalNumMigs) totalNumMigs[b] = (long long)llround(t[1 + 2 * Q + B + b]);
+  }
+  return 0;
+}
+
+extern "C" int gphocsGenGetLineages(GphocsGenealogy* g, int* numLineages) {
+  if (genLaunch(g, true)) return -1;
+  std::vector<uint8_t> tmp(g->totalEvents);
+  CUDA_TRY(cudaStreamSynchronize(g->stream));
+  CUDA_TRY(cudaMemcpy(tmp.data(), g->dLineages, g->totalEvents, cudaMemcpyDeviceToHost));
+  for (long long e = 0; e < g->totalEvents; e++) numLineages[e] = tmp[e];
+  return 0;
+}
+
+extern "C" int gphocsGenSync(GphocsGenealogy* g) {
+  cudaSetDevice(g->device);
+  CUDA_TRY(cudaStreamSynchronize(g->stream));
+  return 0;
+}
+
+#include "locus_api.inc"

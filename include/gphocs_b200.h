@@ -1,0 +1,192 @@
+/*
+ * gphocs_b200.h — C ABI of libgphocs_b200.so, the B200-native (sm_100a) per-locus likelihood path
+ * of G-PhoCS.  Plain pointers and sizes only; no CUDA or torch types cross this boundary
+ * (a CUDA stream is passed as void*).
+ *
+ * Three groups of entry points:
+ *
+ *  A. The reference's LocusData call surface, same names and signatures as
+ *     /root/reference/src/LocusDataLikelihood.h:54-341, so GPhoCS.c / patch.c link against this
+ *     library instead of LocusDataLikelihood.o without source changes.
+ *     Tree getters are host-memory reads; everything that touches conditional likelihoods runs
+ *     on the GPU.  There is no CPU fallback: without a CUDA device these calls fail loudly.
+ *
+ *  B. The batched engine (GphocsStore): all loci resident in HBM, proposals shipped as 24-byte edit
+ *     records, one launch evaluates every locus.  This is what the MCMC update steps of GPhoCS.c
+ *     (:2287-4916) call after loop interchange and what bench.py measures.
+ *
+ *  C. The genealogy likelihood: computeGenetreeStats + recalcStats + gtreeLnLikelihood +
+ *     computeTotalStats (/root/reference/src/patch.c:2330,2387,2702,2134) for all loci in one launch
+ *     over a flattened snapshot of the host's event chains (patch.h:159-172).
+ */
+#ifndef GPHOCS_B200_H
+#define GPHOCS_B200_H
+
+#include <stdio.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ===================================================================================== A. LocusData
+ * Replaces src/LocusDataLikelihood.{h,c}.  Line numbers cite LocusDataLikelihood.h. */
+
+typedef struct LOCUS_LIKELIHOOD LocusData; /* opaque, :35 */
+
+/* layout-compatible with src/GenericTree.h:29-39 (only used by copyGenericTreeToLocus) */
+#ifndef GPHOCS_B200_NO_GENERIC_TREE
+typedef struct GENERIC_BINARY_TREE {
+  int numLeaves;
+  int rootId;
+  char **leafNames;
+  int *father;
+  int *leftSon;
+  int *rightSon;
+  double *label1;
+  double *label2;
+} GenericBinaryTree;
+#endif
+
+LocusData *createLocusData(int numLeaves, unsigned short hetMode);                           /* :54  */
+int initializeLocusData(LocusData *locusData, char **patternArray, int numPatterns,
+                        int *numPhases, int *patternCounts);                                 /* :65  */
+int freeLocusData(LocusData *locusData);                                                     /* :74  */
+int attachLeaf_UNUSED(LocusData *locusData, int leafId, int target, double age);             /* :87  */
+void setLocusMutationRate(LocusData *locusData, double newRate);                             /* :95  */
+double getLocusMutationRate(LocusData *locusData);                                           /* :103 */
+int computeAllConditionals(LocusData *locusData);                                            /* :114 */
+double computeLocusDataLikelihood(LocusData *locusData, unsigned short useOldConditionals);  /* :127 */
+double computePatternLogLikelihood(LocusData *locusData, int numPatterns, int *patternIds,
+                                   int *patternCounts);                                      /* :137 */
+double computeLocusDataLikelihood_deb(LocusData *locusData, unsigned short useOldConditionals); /* :144 */
+double addSitePatterns(LocusData *locusData, int numPatterns, int *patternIds, int *patternCounts,
+                       unsigned short revertToSaved);                                        /* :155 */
+double reduceSitePatterns(LocusData *locusData, int numPatterns, int *patternIds, int *patternCounts,
+                          unsigned short revertToSaved);                                     /* :166 */
+int checkLocusDataLikelihood(LocusData *locusData);                                          /* :177 */
+int revertToSaved(LocusData *locusData);                                                     /* :186 */
+int resetSaved(LocusData *locusData);                                                        /* :195 */
+int adjustGenNodeAge(LocusData *locusData, int nodeId, double age);                          /* :205 */
+double scaleAllNodeAges(LocusData *locusData, double factor);                                /* :215 */
+int executeGenSPR(LocusData *locusData, int subtreeRoot, int targetBranch, double age);      /* :228 */
+int copyGenericTreeToLocus(LocusData *locusData, GenericBinaryTree *genericTree);            /* :239 */
+void printLocusGenTree(LocusData *locusData, FILE *stream, int *nodePops, int *nodeEvents);  /* :250 */
+void printLocusDataStats(LocusData *locusData, int maxLogPhases);                            /* :264 */
+void printLocusDataPatterns(LocusData *locusData, FILE *outFile);                            /* :276 */
+int computePairwiseLCAs(LocusData *locusData, int **lcaMatrix, int *leafArray_aux);          /* :286 */
+int getSortedAges(LocusData *locusData, double *ageArray);                                   /* :297 */
+double getLocusDataLikelihood(LocusData *locusData);                                         /* :309 */
+int getLocusRoot(LocusData *locusData);                                                      /* :317 */
+double getNodeAge(LocusData *locusData, int nodeId);                                         /* :325 */
+int getNodeFather(LocusData *locusData, int nodeId);                                         /* :333 */
+int getNodeSon(LocusData *locusData, int nodeId, unsigned short son);                        /* :341 */
+
+/* Additive: the store that backs every LocusData created so far (built lazily on first use), so a host
+ * that has been loop-interchanged can drive the batched engine over the loci it created through A.
+ * Locus index = creation order = `gen` of dataState.lociData[gen] (GPhoCS.c:354). */
+struct GphocsStore *gpuLociStore(void);
+int gpuLocusIndex(LocusData *locusData);
+
+/* ===================================================================================== B. batched engine */
+
+typedef struct GphocsStore GphocsStore;
+
+/* edit record; `type` values below.  One record = one call of the named reference function on `locus`. */
+typedef struct GphocsOp {
+  int locus;
+  int type;
+  int a, b;
+  double x;
+} GphocsOp;
+enum {
+  GPHOCS_OP_ADJUST_AGE = 0, /* adjustGenNodeAge(locus, a, x)                                   */
+  GPHOCS_OP_SPR = 1,        /* executeGenSPR(locus, a, b, x) -> status 0/1/2                    */
+  GPHOCS_OP_SCALE_ALL = 2,  /* scaleAllNodeAges(locus, x) without its evaluation               */
+  GPHOCS_OP_COMMIT = 3,     /* resetSaved(locus)                                               */
+  GPHOCS_OP_REVERT = 4,     /* revertToSaved(locus)                                            */
+  GPHOCS_OP_SET_RATE = 5    /* setLocusMutationRate(locus, x)                                  */
+};
+
+/* Builds the device-resident store: `numLoci` loci of `numLeaves` leaves; phased patterns in CSR form
+ * (pattStart[numLoci+1] rows of `chars`/`numPhases`, unphStart[numLoci+1] rows of `counts`), same
+ * meaning as initializeLocusData's arguments.  Returns NULL (and prints why) on error. */
+GphocsStore *gphocsStoreCreate(int device, int numLoci, int numLeaves, const long long *pattStart,
+                               const long long *unphStart, const char *chars, const int *numPhases,
+                               const int *counts);
+int gphocsStoreDestroy(GphocsStore *s);
+/* all work of the store is enqueued on this CUDA stream (cudaStream_t as void*; NULL = own stream) */
+int gphocsStoreSetStream(GphocsStore *s, void *cudaStream);
+int gphocsStoreNumLoci(const GphocsStore *s);
+int gphocsStoreNumLeaves(const GphocsStore *s);
+long long gphocsStoreNumColumns(const GphocsStore *s);
+long long gphocsStoreDeviceBytes(const GphocsStore *s);
+
+/* genealogies host -> device.  locusIds NULL = loci 0..nLoci-1.  Arrays are [nLoci][2*numLeaves-1]. */
+int gphocsStoreSetTrees(GphocsStore *s, int nLoci, const int *locusIds, const int *father, const int *left,
+                        const int *right, const double *age, const int *root);
+int gphocsStoreGetTrees(GphocsStore *s, int nLoci, const int *locusIds, int *father, int *left, int *right,
+                        double *age, int *root);
+int gphocsStoreSetRates(GphocsStore *s, int nLoci, const int *locusIds, const double *rates);
+
+/* proposals / accept / reject: applied to the host mirror at once and to the device copy in order.
+ * Several records may target one locus (they apply in array order).  outStatus[nOps] may be NULL. */
+int gphocsStoreApplyOps(GphocsStore *s, int nOps, const GphocsOp *ops, int *outStatus);
+
+/* computeLocusDataLikelihood(locus, useOld) for every listed locus (NULL = all) in one launch.
+ * outLnL[nLoci] (host) receives the per-locus values, *outSum their sum; either may be NULL. */
+int gphocsStoreEvaluate(GphocsStore *s, int nLoci, const int *locusIds, int useOldConditionals,
+                        double *outLnL, double *outSum);
+/* same, results left on the device: *devLnL = device pointer to lnL[numLoci], *devSum = device pointer
+ * to the summed lnL (one double).  For callers that chain a collective on the same stream. */
+int gphocsStoreEvaluateDevice(GphocsStore *s, int useOldConditionals, void **devLnL, void **devSum);
+int gphocsStoreGetLnL(GphocsStore *s, int nLoci, const int *locusIds, double *outLnL);
+/* current (saved=0) / saved (saved=1) conditional likelihoods of one node: out[numPatterns*4] */
+int gphocsStoreGetClv(GphocsStore *s, int locus, int node, int saved, double *out);
+int gphocsStoreSync(GphocsStore *s);
+/* test hooks: with debug on the host mirror also tracks buffer-select / dirty bits and lnL, and
+ * gphocsStoreCheckMirror returns the number of entries in which host mirror and device copy differ */
+int gphocsStoreSetDebug(GphocsStore *s, int on);
+int gphocsStoreCheckMirror(GphocsStore *s);
+/* timing hooks for benchmarks: number of kernels this library has launched so far */
+long long gphocsKernelLaunchCount(void);
+
+/* ===================================================================================== C. genealogy likelihood */
+
+typedef struct GphocsGenealogy GphocsGenealogy;
+
+/* event types, numerically equal to the reference's enum event_type (patch.h:159) */
+enum { GPHOCS_EV_COAL = 0, GPHOCS_EV_IN_MIG, GPHOCS_EV_OUT_MIG, GPHOCS_EV_MIG_BAND_START,
+       GPHOCS_EV_MIG_BAND_END, GPHOCS_EV_SAMPLES_START, GPHOCS_EV_END_CHAIN, GPHOCS_EV_DUMMY };
+
+/* population tree: father/son0/son1 [numPops] (-1 where absent), samplesPerPop[numCurPops] haploid leaves */
+GphocsGenealogy *gphocsGenCreate(int device, int numLoci, int numPops, int numCurPops, int numBands,
+                                 const int *popFather, const int *popSon0, const int *popSon1,
+                                 const int *samplesPerPop);
+int gphocsGenDestroy(GphocsGenealogy *g);
+int gphocsGenSetStream(GphocsGenealogy *g, void *cudaStream);
+/* model parameters (change every UpdateTheta / UpdateMigRates): theta[numPops], migRate[numBands] */
+int gphocsGenSetParams(GphocsGenealogy *g, const double *theta, const double *migRate);
+/* flattened snapshot of event_chains[gen] for all loci: evStart[numLoci+1]; popStart[numLoci][numPops+1]
+ * relative to the locus' first event; per event type, id (migration band for mig/band events, as
+ * recalcStats resolves it at patch.c:2425) and elapsed_time. */
+int gphocsGenSetEvents(GphocsGenealogy *g, const long long *evStart, const int *popStart, const int *evType,
+                       const int *evId, const double *evTime);
+/* computeGenetreeStats + gtreeLnLikelihood for every locus, computeTotalStats over them.
+ * Host outputs (any may be NULL): lnL[numLoci]; per-locus stats coal[numLoci][numPops],
+ * numCoals[numLoci][numPops], mig[numLoci][numBands], numMigs[numLoci][numBands];
+ * totals: totalCoal[numPops], totalNumCoals[numPops], totalMig[numBands], totalNumMigs[numBands], *sumLnL */
+int gphocsGenEvaluate(GphocsGenealogy *g, double *lnL, double *coal, int *numCoals, double *mig, int *numMigs,
+                      double *totalCoal, long long *totalNumCoals, double *totalMig, long long *totalNumMigs,
+                      double *sumLnL);
+/* device-resident variant: *devTotals points at a packed vector
+ * [sumLnL, totalCoal[numPops], totalNumCoals[numPops] (as exact doubles), totalMig[numBands], totalNumMigs[numBands]]
+ * = the all-reduce payload of SURVEY.md §8e. Returns its length in doubles. */
+int gphocsGenEvaluateDevice(GphocsGenealogy *g, void **devLnL, void **devTotals);
+/* num_lineages per event as recalcStats leaves it (patch.c:2405); host array [total events] */
+int gphocsGenGetLineages(GphocsGenealogy *g, int *numLineages);
+int gphocsGenSync(GphocsGenealogy *g);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPHOCS_B200_H */

@@ -1,0 +1,322 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the oracle and the golden vectors
+dumped from the reference.  Tolerance: north_star's 1e-10 relative on every per-locus log-likelihood
+(observed ~1e-15: device exp/log are within 1 ulp of glibc's); genealogy statistics and log-density
+are bit-exact; genealogy edits (trees, roots, flags) are exact."""
+import importlib
+
+import numpy as np
+import pytest
+import torch
+
+import golden_io
+import ops
+from oracle import bindings as ob
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not torch.cuda.is_available(), reason="needs a CUDA device")]
+
+gp = importlib.import_module("g-phocs_b200")
+synth = importlib.import_module("g-phocs_b200.synth")
+RTOL = 1e-10
+
+
+def rel(a, b):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    return np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300)) if a.size else 0.0
+
+
+def oracle_loci(w, ids=None):
+    out = []
+    for l in (range(w.L) if ids is None else ids):
+        p0, p1 = int(w.patt_start[l]), int(w.patt_start[l + 1])
+        u0, u1 = int(w.unph_start[l]), int(w.unph_start[l + 1])
+        lc = ob.OracleLocus(w.n, w.chars[p0:p1], w.num_phases[p0:p1], w.counts[u0:u1], float(w.rate[l]))
+        lc.set_tree(w.father[l], w.left[l], w.right[l], w.age[l], int(w.root[l]))
+        out.append(lc)
+    return out
+
+
+# ------------------------------------------------------------------------------------- golden vectors
+@pytest.mark.parametrize("name", golden_io.CASES)
+def test_data_lnl_against_reference_golden(name):
+    g = golden_io.load(name)
+    st = gp.LociStore(int(g["n"]), g["patt_start"], g["unph_start"], g["chars"], g["num_phases"], g["counts"])
+    st.set_trees(g["father"], g["left"], g["right"], g["age"], g["root"])
+    st.set_rates(g["rate"])
+    lnl, total = st.evaluate(0, want_sum=True)
+    assert rel(lnl, g["data_lnl_full"]) < RTOL
+    assert abs(total - g["data_lnl_full"].sum()) <= RTOL * abs(total)
+    # conditional likelihood vectors of every internal node against the oracle
+    n = int(g["n"])
+    for l in range(0, int(g["L"]), 5):
+        (p0, p1), (u0, u1), _, _ = golden_io.locus_slices(g, l)
+        lc = ob.OracleLocus(n, g["chars"][p0:p1], g["num_phases"][p0:p1], g["counts"][u0:u1], float(g["rate"][l]))
+        lc.set_tree(g["father"][l], g["left"][l], g["right"][l], g["age"][l], int(g["root"][l]))
+        lc.compute(0)
+        for node in range(2 * n - 1):
+            got = st.clv(l, node, P=p1 - p0)
+            assert np.allclose(got, lc.clv(node), rtol=1e-12, atol=0.0), (l, node)
+    st.close()
+
+
+@pytest.mark.parametrize("name", golden_io.CASES)
+def test_genealogy_against_reference_golden(name):
+    g = golden_io.load(name)
+    pops = golden_io.pops_of(g)
+    L, Q, B = int(g["L"]), int(g["Q"]), int(g["B"])
+    gen = gp.Genealogy(L, pops)
+    gen.set_events(g["ev_start"], g["pop_start"], g["ev_type"], g["ev_id"], g["ev_time"])
+    r = gen.evaluate()
+    pt, keep = ob.make_poptree(pops, g["band_start"], g["band_end"])
+    lineages = gen.lineages()
+    for l in range(L):
+        _, _, (e0, e1), _ = golden_io.locus_slices(g, l)
+        nl, cs, nc, ms, nm, lnl = ob.oracle_gen_locus(pt, g["pop_start"][l], g["ev_type"][e0:e1], g["ev_id"][e0:e1],
+                                                      g["ev_time"][e0:e1])
+        # same elapsed times, same order of operations, no FMA: bit-exact against the oracle
+        assert np.array_equal(r["coal"][l], cs)
+        assert np.array_equal(r["num_coals"][l], nc)
+        assert np.array_equal(r["mig"][l], ms)
+        assert np.array_equal(r["num_migs"][l], nm)
+        assert r["lnl"][l] == lnl
+        assert np.array_equal(lineages[e0:e1], nl)
+        assert np.array_equal(lineages[e0:e1], g["ev_lineages"][e0:e1])
+    # against the reference's own (incrementally maintained) numbers
+    assert rel(r["lnl"], g["gen_lnl"]) < RTOL
+    assert np.allclose(r["coal"], g["coal_stats"], rtol=RTOL, atol=1e-13)
+    assert np.array_equal(r["num_coals"], g["num_coals"])
+    assert np.array_equal(r["num_migs"], g["num_migs"])
+    # computeTotalStats
+    assert np.array_equal(r["total_num_coals"], g["total_num_coals"])
+    assert np.array_equal(r["total_num_migs"], g["total_num_migs"])
+    assert np.allclose(r["total_coal"], g["total_coal_stats"], rtol=1e-9)
+    assert np.allclose(r["total_mig"], g["total_mig_stats"], rtol=1e-9, atol=1e-12)
+    assert abs(r["sum_lnl"] - r["lnl"].sum()) <= 1e-12 * abs(r["sum_lnl"])
+    gen.close()
+
+
+# ------------------------------------------------------------------------------------- scalar (drop-in) API
+def test_scalar_api_replays_reference_traces():
+    """The reference's LocusData entry points, exported by the CUDA library, replay the proposal traces
+    recorded from the reference (adjust age / SPR / rescale / ancient-sample / rate moves, accept & reject)."""
+    z = np.load(golden_io.os.path.join(golden_io.HERE, "golden", "ops_reference.npz"))
+    cases = []
+    for i in range(int(z["num_cases"])):
+        cases.append({k[len(f"c{i}_"):]: z[k] for k in z.files if k.startswith(f"c{i}_")})
+    # all loci of one process must share the leaf count: group traces by n
+    by_n = {}
+    for c in cases:
+        by_n.setdefault(int(c["n"]), []).append(c)
+    for n, group in by_n.items():
+        loci = []
+        for c in group:
+            lc = gp.ScalarLocus(n, c["chars"], c["num_phases"], c["counts"], float(c["rate"]))
+            lc.set_tree(c["father"], c["left"], c["right"], c["age"], int(c["root"]))
+            loci.append(lc)
+        for c, lc in zip(group, loci):
+            tr = ops.run_ops(lc, n, int(c["seed"]), int(c["steps"]), allow_leaf_age=bool(c["leaf"]), rate_moves=bool(c["ratem"]))
+            lnls, trees = [], []
+            for e in tr:
+                if e[0] in ("init", "final-full", "rate"):
+                    lnls.append([e[1], np.nan])
+                else:
+                    lnls.append([e[1], e[3]])
+                    trees.append(np.concatenate([e[4], e[5], e[6], [e[8]]]).astype(np.float64).tolist() + e[7].tolist())
+            lnls = np.array(lnls)
+            ok = ~np.isnan(c["lnls"])
+            assert rel(lnls[ok], c["lnls"][ok]) < RTOL
+            assert np.array_equal(np.array(trees), c["trees"])     # genealogy edits are exact
+            assert lc.check() == 1
+        store_mismatch = gp.lib().gphocsStoreCheckMirror(gp.lib().gpuLociStore())
+        assert store_mismatch == 0
+        for lc in loci:
+            lc.free()
+
+
+# ------------------------------------------------------------------------------------- batched engine
+@pytest.mark.parametrize("cfg,L", [("hap16", 300), ("dip8mig", 200), ("pop6mig4", 150), ("ancient", 200)])
+def test_batched_proposals_against_oracle(cfg, L):
+    """One proposal per locus per round for all loci at once (the loop-interchanged Shape A / Shape B
+    traffic of GPhoCS.c:2287-4916), random accept/reject masks, against per-locus oracle instances."""
+    w = synth.generate(synth.config(cfg), L, seed=11, missing_frac=0.05 if cfg == "dip8mig" else 0.0)
+    st = gp.LociStore.from_workload(w)
+    st.set_debug(True)
+    orc = oracle_loci(w)
+    want = np.array([o.compute(0) for o in orc])
+    got = st.evaluate(0)
+    assert rel(got, want) < RTOL
+    for o in orc:
+        o.reset()
+    st.apply_ops(gp.make_ops(np.arange(L), gp.OP_COMMIT))
+    rng = np.random.default_rng(3)
+    n = w.n
+
+    class Rec:
+        """records the edits a proposal makes so they can be sent as one batch"""
+        def __init__(self, o, l):
+            self.o, self.l, self.ops = o, l, []
+        def tree(self): return self.o.tree()
+        def adjust_age(self, node, age):
+            self.ops.append((self.l, gp.OP_ADJUST_AGE, node, 0, age)); return self.o.adjust_age(node, age)
+        def spr(self, s, t, age):
+            self.ops.append((self.l, gp.OP_SPR, s, t, age)); return self.o.spr(s, t, age)
+        def scale_all(self, f):
+            self.ops.append((self.l, gp.OP_SCALE_ALL, 0, 0, f)); return self.o.scale_all(f)
+
+    for rnd in range(12):
+        recs, spr_status = [], {}
+        for l in range(L):
+            r = Rec(orc[l], l)
+            d = ops.propose(r, rng, n, allow_leaf_age=(cfg == "ancient"))
+            if d[0] == "spr":
+                spr_status[l] = d[4]
+            recs += r.ops
+        batch = np.array(recs, dtype=gp.OP_DTYPE)
+        status = st.apply_ops(batch, want_status=True)
+        for i, rec in enumerate(recs):
+            if rec[1] == gp.OP_SPR:
+                assert status[i] == spr_status[rec[0]]
+        got, total = st.evaluate(1, want_sum=True)
+        want = np.array([o.compute(1) if not any(r[0] == l and r[1] == gp.OP_SCALE_ALL for r in recs) else o.lnl()
+                         for l, o in enumerate(orc)]) if False else None
+        scaled = {r[0] for r in recs if r[1] == gp.OP_SCALE_ALL}
+        want = np.array([o.lnl() if l in scaled else o.compute(1) for l, o in enumerate(orc)])
+        assert rel(got, want) < RTOL, rnd
+        assert abs(total - want.sum()) <= RTOL * abs(total)
+        accept = rng.random(L) < 0.5
+        for l, o in enumerate(orc):
+            o.reset() if accept[l] else o.revert()
+        st.apply_ops(gp.make_ops(np.arange(L), np.where(accept, gp.OP_COMMIT, gp.OP_REVERT)))
+        f, lf, rt, a, root = st.get_trees()
+        for l, o in enumerate(orc):
+            of, ol, orr, oa, oroot = o.tree()
+            assert np.array_equal(f[l], of) and np.array_equal(lf[l], ol) and np.array_equal(rt[l], orr)
+            assert np.array_equal(a[l], oa) and root[l] == oroot
+        assert rel(st.lnl(), [o.lnl() for o in orc]) < RTOL
+        assert st.check_mirror() == 0
+    # the incrementally maintained state equals a from-scratch evaluation (the reference's checkAll invariant)
+    inc = st.lnl()
+    full = st.evaluate(0)
+    assert rel(full, inc) < 1e-9
+    assert rel(full, [o.compute(0) for o in orc]) < RTOL
+    st.close()
+
+
+def test_oversized_and_ragged_loci():
+    """Loci wider than one CTA (P > 128), single-column loci, loci without live patterns, missing data."""
+    rng = np.random.default_rng(8)
+    n = 10
+    Ps = [300, 1, 0, 129, 128, 2, 517, 0, 7]
+    chars, phases, counts, ps, us = [], [], [], [0], [0]
+    for P in Ps:
+        c, ph, ct = ops.random_patterns(n, P, rng, diploid_pairs=5, missing=0.1) if P else (
+            np.zeros((0, n), np.uint8), np.zeros(0, np.int32), np.zeros(0, np.int32))
+        chars.append(c); phases.append(ph); counts.append(ct)
+        ps.append(ps[-1] + len(ph)); us.append(us[-1] + len(ct))
+    st = gp.LociStore(n, ps, us, np.concatenate(chars), np.concatenate(phases), np.concatenate(counts))
+    trees = [ops.random_tree(n, rng) for _ in Ps]
+    st.set_trees(*[np.array([t[k] for t in trees]) for k in range(4)], np.array([t[4] for t in trees]))
+    got, total = st.evaluate(0, want_sum=True)
+    want = []
+    for i, P in enumerate(Ps):
+        lc = ob.OracleLocus(n, chars[i], phases[i], counts[i], 1.0)
+        lc.set_tree(*trees[i])
+        want.append(lc.compute(0))
+    assert rel(got, want) < RTOL
+    assert got[2] == 0.0 and got[7] == 0.0
+    assert abs(total - sum(want)) <= RTOL * abs(total)
+    st.close()
+
+
+def test_subset_evaluation_touches_only_listed_loci():
+    w = synth.generate(synth.config("hap16"), 64, seed=2)
+    st = gp.LociStore.from_workload(w)
+    full = st.evaluate(0).copy()
+    st.apply_ops(gp.make_ops(np.arange(64), gp.OP_COMMIT))
+    ids = np.array([3, 17, 40], np.int32)
+    node = w.n + 2
+    st.apply_ops(gp.make_ops(np.arange(64), gp.OP_ADJUST_AGE, a=node, x=w.age[:, node] * 1.01))
+    part = st.evaluate(1, ids=ids)
+    now = st.lnl()
+    untouched = np.setdiff1d(np.arange(64), ids)
+    assert np.array_equal(now[untouched], full[untouched])
+    assert np.all(now[ids] != full[ids]) and np.array_equal(part, now[ids])
+    st.close()
+
+
+def test_rejects_bad_input():
+    with pytest.raises(RuntimeError):
+        gp.LociStore(3, [0, 1], [0, 1], np.frombuffer(b"TXT", np.uint8).reshape(1, 3), [1], [5])     # bad character
+    with pytest.raises(RuntimeError):
+        gp.LociStore(3, [0, 2], [0, 1], np.frombuffer(b"TCTTCA", np.uint8).reshape(2, 3), [4, 0], [5])  # phase group overruns
+
+
+# ------------------------------------------------------------------------------------- BASELINE sizes: properties
+@pytest.mark.parametrize("cfg", ["hap16", "dip8mig"])
+def test_full_size_properties(cfg):
+    """10k loci (BASELINE.json configs[1], [2]): size-independent properties — a sampled oracle check,
+    revert restores bit-identical likelihoods, rescaling by f then 1/f returns to the start, the incremental
+    path equals the full path, and the device-side sum equals the sum of the per-locus values."""
+    L = synth.CONFIG_LOCI[cfg]
+    w = synth.generate(synth.config(cfg), L, seed=1000)
+    st = gp.LociStore.from_workload(w)
+    base, total = st.evaluate(0, want_sum=True)
+    assert abs(total - base.sum()) <= 1e-12 * abs(total)
+    ids = np.random.default_rng(0).choice(L, 200, replace=False)
+    orc = oracle_loci(w, ids)
+    assert rel(base[ids], [o.compute(0) for o in orc]) < RTOL
+    st.apply_ops(gp.make_ops(np.arange(L), gp.OP_COMMIT))
+    # move one internal node in every locus, evaluate incrementally, reject: bit-identical restore
+    node = w.n + 1
+    st.apply_ops(gp.make_ops(np.arange(L), gp.OP_ADJUST_AGE, a=node, x=w.age[:, node] * (1 + 1e-3)))
+    moved = st.evaluate(1)
+    assert np.all(moved != base)
+    st.apply_ops(gp.make_ops(np.arange(L), gp.OP_REVERT))
+    assert np.array_equal(st.lnl(), base)
+    assert np.array_equal(st.evaluate(1), base)          # nothing dirty: stored values come back
+    # accept the same move: incremental == from scratch
+    st.apply_ops(gp.make_ops(np.arange(L), gp.OP_ADJUST_AGE, a=node, x=w.age[:, node] * (1 + 1e-3)))
+    inc = st.evaluate(1).copy()
+    st.apply_ops(gp.make_ops(np.arange(L), gp.OP_COMMIT))
+    assert rel(st.evaluate(0), inc) < 1e-12
+    st.apply_ops(gp.make_ops(np.arange(L), gp.OP_COMMIT))
+    # mixing-style rescale (scaleAllNodeAges on every locus) and its inverse
+    st.apply_ops(gp.make_ops(np.arange(L), gp.OP_SCALE_ALL, x=1.25))
+    st.evaluate(1)
+    st.apply_ops(gp.make_ops(np.arange(L), gp.OP_COMMIT))
+    st.apply_ops(gp.make_ops(np.arange(L), gp.OP_SCALE_ALL, x=0.8))
+    back = st.evaluate(1)
+    assert rel(back, inc) < 1e-9
+    st.close()
+
+
+def test_full_size_genealogy_properties():
+    """100k-locus shape of configs[3] at 20k loci: totals equal the sums of per-locus statistics, counts
+    are exact integers, theta-rescaling moves lnL by the closed form UpdateTheta uses (GPhoCS.c:3068-3070)."""
+    m = synth.config("pop6mig4")
+    L = 20000
+    w = synth.generate(m, L, seed=77)
+    gen = gp.Genealogy(L, w.pops)
+    gen.set_events(w.ev_start, w.pop_start, w.ev_type, w.ev_id, w.ev_time)
+    r = gen.evaluate()
+    assert np.array_equal(r["total_num_coals"], r["num_coals"].sum(0))
+    assert r["total_num_coals"].sum() == L * (w.n - 1)
+    assert np.array_equal(r["total_num_migs"], r["num_migs"].sum(0))
+    assert r["total_num_migs"].sum() == len(w.mig_age)
+    assert np.allclose(r["total_coal"], r["coal"].sum(0), rtol=1e-11)
+    assert np.allclose(r["total_mig"], r["mig"].sum(0), rtol=1e-11)
+    assert abs(r["sum_lnl"] - r["lnl"].sum()) <= 1e-11 * abs(r["sum_lnl"])
+    # oracle on a sample
+    pt, keep = ob.make_poptree(w.pops, w.band_start, w.band_end)
+    for l in np.random.default_rng(1).choice(L, 100, replace=False):
+        e0, e1 = int(w.ev_start[l]), int(w.ev_start[l + 1])
+        nl, cs, nc, ms, nm, lnl = ob.oracle_gen_locus(pt, w.pop_start[l], w.ev_type[e0:e1], w.ev_id[e0:e1], w.ev_time[e0:e1])
+        assert r["lnl"][l] == lnl and np.array_equal(r["coal"][l], cs) and np.array_equal(r["mig"][l], ms)
+    # UpdateTheta's closed form
+    theta2 = w.pops["theta"].copy()
+    theta2[3] *= 1.1
+    gen.set_params(theta2, w.pops["band_rate"])
+    r2 = gen.evaluate(per_locus_stats=False)
+    lnc = np.log(1.1)
+    delta = -(lnc * r["total_num_coals"][3] + (1 / theta2[3] - 1 / w.pops["theta"][3]) * r["total_coal"][3])
+    assert abs((r2["sum_lnl"] - r["sum_lnl"]) - delta) <= 1e-9 * abs(delta)
+    gen.close()
