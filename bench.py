@@ -1,0 +1,421 @@
+#!/usr/bin/env python
+"""bench.py — locus log-likelihood evaluations/s of the G-PhoCS hot path on B200 (BASELINE.json metric).
+
+One *step* = one pass of the hot path over every resident locus: the full Felsenstein data likelihood
+(computeLocusDataLikelihood(locus, 0) semantics: every internal conditional vector recomputed and left
+resident, phase-averaged root reduction) + the genealogy likelihood (computeGenetreeStats + gtreeLnLikelihood
++ computeTotalStats) + the packed [sum data lnL, sum genealogy lnL, coal/mig totals] vector, all-reduced over
+ranks when N > 1.  One evaluation = data + genealogy log-likelihood of one locus.
+
+    python bench.py --gpus 1 --steps 20 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+           bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...     # the reference's own CPU implementation on the host cores
+
+Workload (config.workload): BASELINE.json configs[3] — 100k loci x 1 kb, 6-population tree + 4 migration
+bands, 2 unphased diploids per population (24 leaves) — per GPU (weak scaling, loci sharded by rank with no
+data-path collective).  Synthetic alignments from g-phocs_b200/synth.py; per-step HBM working set is
+several GB (>> 126 MB L2), so no explicit L2 flush is needed.
+"""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+PASSES_PER_STEP = 200      # reference arm: passes over the bounded sample that make up one timed step
+METRIC = "locus_lnL_evals_per_sec"
+UNIT = "locus-evals/s"
+
+
+def algorithmic_bytes_data(n, P):
+    """bytes_full = 32*P*(2n-1) + 24*(2n-1) + 8*P + 8 per locus (P live phased patterns)."""
+    return 32.0 * P * (2 * n - 1) + 24.0 * (2 * n - 1) + 8.0 * P + 8.0
+
+
+def algorithmic_bytes_gen(E, Q, B):
+    """bytes_gen = 32*E + 16*(Q+B) + 8 per locus."""
+    return 32.0 * E + 16.0 * (Q + B) + 8.0
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.index, self.proc, self.rows = index, None, []
+
+    def start(self):
+        q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------- reference arm
+def reference_sample(cfg, sample_loci, seed, reps, threads, quiet=True):
+    """Times the reference's own CPU implementation (oracle/_ref, all host threads) on a bounded sample of
+    the workload: OpenMP loop over loci of computeLocusDataLikelihood(locus,0)+resetSaved and
+    computeGenetreeStats+gtreeLnLikelihood (ref_harness.c: refh_time_both_once).  Runs in THIS process
+    (call it from a subprocess: the reference keeps global state).  Returns per-rep seconds."""
+    import ctypes as C
+    import tempfile
+    synth = importlib.import_module("g-phocs_b200.synth")
+    from oracle import bindings as ob
+    model = synth.config(cfg)
+    with tempfile.TemporaryDirectory() as tmp:
+        seq, ctl = os.path.join(tmp, "seqs.txt"), os.path.join(tmp, "run.ctl")
+        synth.generate(model, sample_loci, seed=seed, seqfile=seq)
+        synth.write_control_file(model, ctl, seq, os.path.join(tmp, "trace.log"), iterations=1, seed=4242)
+        lib = ob.ref()
+        if quiet:
+            sys.stdout.flush()
+            devnull = os.open(os.devnull, os.O_WRONLY)
+            saved = os.dup(1)
+            os.dup2(devnull, 1)
+        try:
+            rc = lib.refh_setup(ctl.encode(), threads, 0)
+            assert rc == 0, f"reference set-up failed ({rc})"
+            lib.refh_init_only()
+        finally:
+            if quiet:
+                sys.stdout.flush()
+                os.dup2(saved, 1)
+                os.close(devnull)
+    lib.refh_set_threads(threads)
+    times = []
+    sd, sg = C.c_double(), C.c_double()
+    for _ in range(reps):
+        t = 0.0
+        for _p in range(PASSES_PER_STEP):
+            t += lib.refh_time_both_once(C.byref(sd), C.byref(sg))
+        times.append(t)
+    return times, lib.refh_num_loci() * PASSES_PER_STEP, sd.value, sg.value
+
+
+def port_sample(cfg, sample_loci, seed, reps):
+    """Fallback when oracle/_ref is absent: the oracle C port, one thread."""
+    synth = importlib.import_module("g-phocs_b200.synth")
+    from oracle import bindings as ob
+    w = synth.generate(synth.config(cfg), sample_loci, seed=seed)
+    loci = []
+    for l in range(w.L):
+        p0, p1, u0, u1 = int(w.patt_start[l]), int(w.patt_start[l + 1]), int(w.unph_start[l]), int(w.unph_start[l + 1])
+        lc = ob.OracleLocus(w.n, w.chars[p0:p1], w.num_phases[p0:p1], w.counts[u0:u1], float(w.rate[l]))
+        lc.set_tree(w.father[l], w.left[l], w.right[l], w.age[l], int(w.root[l]))
+        loci.append(lc)
+    pt, keep = ob.make_poptree(w.pops, w.band_start, w.band_end)
+    times = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        for l, lc in enumerate(loci):
+            lc.compute(0)
+            lc.reset()
+            e0, e1 = int(w.ev_start[l]), int(w.ev_start[l + 1])
+            ob.oracle_gen_locus(pt, w.pop_start[l], w.ev_type[e0:e1], w.ev_id[e0:e1], w.ev_time[e0:e1])
+        times.append(time.perf_counter() - t0)
+    return times, w.L, 0.0, 0.0
+
+
+def cpu_baseline_subprocess(cfg, sample_loci, reps):
+    """cpu_baseline leg: run the reference sample in a child process, parse its JSON."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", str(reps), "--warmup", "1",
+           "--config", cfg, "--sample-loci", str(sample_loci), "--gpus", "1"]
+    env = dict(os.environ)
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE"):
+        env.pop(k, None)
+    try:
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
+        line = [x for x in out.stdout.splitlines() if x.startswith("{")][-1]
+        return json.loads(line)["cpu_baseline"]
+    except Exception as e:   # the baseline is reported, never required
+        return {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": f"failed: {e}"[:200]}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import bindings as ob
+    threads = os.cpu_count() or 1
+    t_all0 = time.perf_counter()
+    if ob.have_ref():
+        kind = "reference"
+        times, L, sd, sg = reference_sample(args.config, args.sample_loci, 4242, args.steps + args.warmup, threads)
+    else:
+        kind, threads = "port", 1
+        times, L, sd, sg = port_sample(args.config, min(args.sample_loci, 500), 4242, args.steps + args.warmup)
+    timed = times[args.warmup:]
+    total = float(sum(timed))
+    value = L * len(timed) / total
+    sample = (f"{L // PASSES_PER_STEP if kind == 'reference' else L} loci of workload {args.config} (same generator, seed 4242), "
+              f"{len(timed)} steps x {PASSES_PER_STEP if kind == 'reference' else 1} passes of "
+              f"computeLocusDataLikelihood(locus,0)+resetSaved and computeGenetreeStats+gtreeLnLikelihood over all loci, "
+              f"OpenMP static schedule, {threads} threads; wall {time.perf_counter() - t_all0:.1f}s incl. ingest")
+    cb = {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample}
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(timed),
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / len(timed), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(args.config, args.loci) + " per GPU", "sample": sample},
+        "cpu_baseline": cb,
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def workload_name(cfg, L):
+    synth = importlib.import_module("g-phocs_b200.synth")
+    m = synth.config(cfg)
+    return (f"{cfg}: {L} loci x {m.sites} bp, {m.numLeaves} leaves ({'unphased diploids' if m.diploid else 'haploid'}), "
+            f"{m.numCurPops}-population tree, {len(m.bands)} migration bands")
+
+
+# --------------------------------------------------------------------------------------- B200 arm
+def run_b200(args):
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    gp = importlib.import_module("g-phocs_b200")
+    synth = importlib.import_module("g-phocs_b200.synth")
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: libgphocs_b200 has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    L = args.loci
+    model = synth.config(args.config)
+    w = synth.generate(model, L, seed=1000 + 17 * rank)     # each rank owns its own shard of loci
+    n, Q, B = w.n, model.numPops, len(model.bands)
+    P = np.diff(w.patt_start).astype(np.float64)
+    E = np.diff(w.ev_start).astype(np.float64)
+    bytes_data = float(algorithmic_bytes_data(n, P).sum())
+    bytes_gen = float(algorithmic_bytes_gen(E, Q, B).sum())
+
+    stream = torch.cuda.Stream(device=dev)
+    st = gp.LociStore.from_workload(w, device=local_rank, stream=stream.cuda_stream)
+    gen = gp.Genealogy(L, w.pops, device=local_rank, stream=stream.cuda_stream)
+    gen.set_events(w.ev_start, w.pop_start, w.ev_type, w.ev_id, w.ev_time)
+    lib = gp.lib()
+    V = 1 + 2 * Q + 2 * B
+    payload = torch.zeros(1 + V, dtype=torch.float64, device=dev)   # [sum data lnL | sum gen lnL, totals...]
+
+    def step(record=None):
+        """device-resident pass; `record` = list to append (start, mid, end) events to"""
+        with torch.cuda.stream(stream):
+            if record is not None:
+                e0 = torch.cuda.Event(enable_timing=True); e0.record(stream)
+            _, dsum = st.evaluate_device(0)
+            if record is not None:
+                e1 = torch.cuda.Event(enable_timing=True); e1.record(stream)
+            _, dtot, v = gen.evaluate_device()
+            if record is not None:
+                e2 = torch.cuda.Event(enable_timing=True); e2.record(stream)
+                record.append((e0, e1, e2))
+            lib.gphocsCopyDeviceAsync(C.c_void_p(payload.data_ptr()), C.c_void_p(dsum), 8, C.c_void_p(stream.cuda_stream))
+            lib.gphocsCopyDeviceAsync(C.c_void_p(payload.data_ptr() + 8), C.c_void_p(dtot), 8 * V, C.c_void_p(stream.cuda_stream))
+            if world > 1:
+                dist.all_reduce(payload)          # the only cross-GPU traffic: < 1 KB per step
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = lib.gphocsKernelLaunchCount()
+    rec = []
+    t_start = torch.cuda.Event(enable_timing=True)
+    t_end = torch.cuda.Event(enable_timing=True)
+    barrier()
+    with torch.cuda.stream(stream):
+        t_start.record(stream)
+    for _ in range(args.steps):
+        step(rec)
+    with torch.cuda.stream(stream):
+        t_end.record(stream)
+    barrier()
+    launches = lib.gphocsKernelLaunchCount() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = t_start.elapsed_time(t_end)
+    ms_data = sum(a.elapsed_time(b) for a, b, _ in rec) / len(rec)
+    ms_gen = sum(b.elapsed_time(c) for _, b, c in rec) / len(rec)
+    if world > 1:
+        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    total_data_lnl, total_gen_lnl = float(payload[0].item()), float(payload[1].item())
+
+    # ---- e2e: the same pass through the C ABI with HOST buffers (H2D of genealogies + event snapshots, D2H of
+    # per-locus log-likelihoods and totals inside the timed region)
+    lnl_host = np.zeros(L)
+    e2e_steps = max(3, min(args.steps, 10))
+    h2d = L * w.father.shape[1] * (3 * 2 + 8) + 4 * L + int(E.sum()) * 10 + L * (Q + 1) * 2 + 4 * (L + 1)
+    d2h = 8 * L + 8 + 8 * L + 8 * V
+
+    def e2e_step():
+        st.set_trees(w.father, w.left, w.right, w.age, w.root)
+        _, sdata = st.evaluate(0, want_sum=True, out=lnl_host)
+        gen.set_events(w.ev_start, w.pop_start, w.ev_type, w.ev_id, w.ev_time)
+        r = gen.evaluate(per_locus_stats=False)
+        return sdata, r["sum_lnl"]
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        sdata, sgen = e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = world * L * e2e_steps / e2e_s
+
+    # ---- MCMC-style cycle (extra): one node-age proposal per locus -> incremental evaluation -> accept/reject
+    node = n + 2
+    prop = gp.make_ops(np.arange(L), gp.OP_ADJUST_AGE, a=node, x=w.age[:, node] * 1.001)
+    rej = gp.make_ops(np.arange(L), gp.OP_REVERT)
+    st.apply_ops(gp.make_ops(np.arange(L), gp.OP_COMMIT))
+    for _ in range(2):
+        st.apply_ops(prop); st.evaluate(1, out=lnl_host); st.apply_ops(rej)
+    cyc = 5
+    t0 = time.perf_counter()
+    for _ in range(cyc):
+        st.apply_ops(prop); st.evaluate(1, out=lnl_host); st.apply_ops(rej)
+    cyc_s = time.perf_counter() - t0
+    with torch.cuda.stream(stream):
+        a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+        st.apply_ops(prop)
+        a.record(stream)
+        st.evaluate_device(1)
+        b.record(stream)
+    torch.cuda.synchronize()
+    inc_ms = a.elapsed_time(b)
+    st.apply_ops(rej)
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        achieved = bytes_data / (ms_data * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            tj = json.load(open(tp))
+            if tj.get("workload") == f"{args.config}:{L}":
+                traffic = tj.get("k_eval_dram_bytes_per_launch")
+        value = world * L * args.steps / (ms_total * 1e-3)
+        cb = cpu_baseline_subprocess(args.config, args.sample_loci, 3) if (world == 1 and not args.no_cpu_baseline) else None
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(args.config, L) + " per GPU", "loci_per_gpu": L, "leaves": n,
+                       "mean_phased_patterns": float(P.mean()), "mean_events": float(E.mean()),
+                       "l2": "per-step HBM working set %.2f GB >> 126 MB L2 (no flush needed)" % (bytes_data / 2e9),
+                       "parallelism": f"loci sharded over {world} GPU(s), all-reduce of a {8 * (1 + V)}-byte vector per step"},
+            "roofline": {"bound": "hbm", "kernel": "k_eval (full data-likelihood evaluation, all loci)",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                         "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_data,
+                         "ms_per_launch": ms_data, "genealogy_kernel_ms": ms_gen,
+                         "genealogy_achieved_gbs": bytes_gen / (ms_gen * 1e-3) / 1e9},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "steps": e2e_steps},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "extra": {"sum_data_lnl": total_data_lnl, "sum_gen_lnl": total_gen_lnl,
+                      "mcmc_cycle_proposals_per_sec_e2e": world * L * cyc / cyc_s,
+                      "incremental_eval_ms_device": inc_ms,
+                      "incremental_evals_per_sec_device": L / (inc_ms * 1e-3),
+                      "device_bytes_store": st.device_bytes},
+        }
+        if cb is not None:
+            line["cpu_baseline"] = cb
+        print(json.dumps(line))
+    st.close()
+    gen.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="pop6mig4")
+    ap.add_argument("--loci", type=int, default=100_000, help="loci per GPU")
+    ap.add_argument("--sample-loci", type=int, default=2000, help="loci in the CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

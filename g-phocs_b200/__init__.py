@@ -92,6 +92,7 @@ def lib():
         "gphocsStoreSetDebug": (ci, [vp, ci]),
         "gphocsStoreCheckMirror": (ci, [vp]),
         "gphocsKernelLaunchCount": (C.c_longlong, []),
+        "gphocsCopyDeviceAsync": (ci, [vp, vp, C.c_longlong, vp]),
         # C. genealogy likelihood
         "gphocsGenCreate": (vp, [ci, ci, ci, ci, ci, c_int_p, c_int_p, c_int_p, c_int_p]),
         "gphocsGenDestroy": (ci, [vp]),

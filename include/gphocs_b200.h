@@ -149,6 +149,8 @@ int gphocsStoreSetDebug(GphocsStore *s, int on);
 int gphocsStoreCheckMirror(GphocsStore *s);
 /* timing hooks for benchmarks: number of kernels this library has launched so far */
 long long gphocsKernelLaunchCount(void);
+/* stream-ordered device-to-device copy (gathers device-resident results into a caller's buffer) */
+int gphocsCopyDeviceAsync(void *dst, const void *src, long long bytes, void *cudaStream);
 
 /* ===================================================================================== C. genealogy likelihood */
 
