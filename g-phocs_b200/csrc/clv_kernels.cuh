@@ -11,16 +11,22 @@
 //   internal  clv[colStart[l]*NI*8 + (((node-n)*2 + buf)*P_l + p)*4 + base]  (fp64) — for one
 //             (locus,node,buffer) the P_l columns are contiguous 32-byte records, so a warp of
 //             column-threads issues fully used 32-byte sectors whatever the tree shape
-//   trees     father/left/right int16, age fp64, flag byte per node (tree_ops.cuh), locus-major
+//   trees     one 8-byte record {father,left,right:int16, flags:u8} + one fp64 age per node, locus-major
 //
 // Execution: one CTA of 128 threads owns a host-packed batch of whole loci whose columns fit the CTA
-// (or one oversized locus, walked in 128-column chunks).  The CTA stages the batch's topology in
-// shared memory, marks dirty nodes and their ancestors, orders them (post-order DFS restricted to the
-// marked set), computes the JC69 edge probabilities of exactly those nodes once per locus into shared
-// memory, then every thread walks its locus' schedule for its own column: children come from the
-// leaf mask, from registers (the node computed just before), or from HBM; the new vector goes to the
-// node's *other* buffer, so accept/reject never copies.  The root step sums 4*phases conditionals per
-// phase group, takes count*log, and reduces per locus in shared memory.
+// (or one oversized locus, walked in 128-column chunks).
+//   A  stage the batch's node records and ages in shared memory (coalesced 8-byte loads)
+//   B  mark dirty nodes and their ancestors
+//   C  flip the destination buffers of marked nodes; count marked nodes per subtree (shared atomics)
+//   D  every marked node finds its own position in a post-order that visits the heavier child first by
+//      walking up its ancestors (no serial traversal), and writes its schedule entry: destination,
+//      where each child's vector comes from, JC69 edge terms
+//   E  every thread walks its locus' schedule for its own column.  Results are pushed on a per-column
+//      stack in shared memory (depth <= log2(n)+1 because the heavier child goes first), so in a full
+//      evaluation a child is never re-read from HBM: leaves come from a 16-entry table, computed
+//      children from the stack, clean children (incremental evaluation) from HBM.  The new vector is
+//      written to the node's *other* buffer, so accept/reject never copies.
+//   F  root: sum 4*phases conditionals per phase group, count*log, per-locus sum in shared memory.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -30,7 +36,9 @@
 namespace gphocs {
 
 constexpr int kThreads = 128;      // threads (= columns) per CTA
+constexpr int kWarps = kThreads / 32;
 constexpr int kMaxBatchLoci = 16;  // loci per CTA batch
+constexpr int kStack = 3;          // on-chip result slots per column; deeper results are re-read from HBM
 
 struct Batch {
   int firstLocus, numLoci;
@@ -47,9 +55,8 @@ struct StoreDev {
   const int* grpPhases;
   const int* grpCount;
   double* clv;
-  int16_t *father, *left, *right, *svFather, *svLeft, *svRight;
+  NodeRec *node, *saved;
   double *age, *svAge;
-  uint8_t* flags;
   int *root, *savedRoot;
   double *rate, *lnL, *savedLnL;
   double* rootScratch;
@@ -57,28 +64,60 @@ struct StoreDev {
   double* ctaSum;         // one partial sum per batch
 };
 
-struct SchedEntry {
-  int16_t node, left, right;
-  uint16_t info;  // bit0 dst buffer, bit1 left-child buffer, bit2 right-child buffer
-  double e0L, e0R;
+// One schedule entry = one node to (re)compute; entries are ordered so that children precede parents.
+enum : uint32_t { SRC_LEAF = 0, SRC_STACK = 1, SRC_GLOBAL = 2 };
+constexpr uint32_t kRow = kThreads * 16;       // bytes per stack row (one double2 per column)
+constexpr uint32_t kHi = kStack * kRow + 256;  // distance from the lo half of a vector to its hi half
+struct __align__(16) SchedEntry {
+  double e0A, e1A, e0B, e1B;  // JC69 edge terms of the two children: p and 1-4p (.c:1596-1602)
+  // where a child's vector comes from, ready to use by the column threads:
+  //   leaf    byte offset of its 32-bit code word row | bit shift << 16
+  //   stack   (slot * row bytes) << 16
+  //   global  byte offset of the source record from the column's base
+  uint32_t offA, offB;
+  uint32_t dstOff;            // byte offset of the destination record from the column's base
+  uint32_t ctl;               // bits 0-1 kind of A, 2-3 kind of B, bits 16-31 stack byte offset to push to (0xffff: none)
 };
+static_assert(sizeof(SchedEntry) == 48, "schedule entry layout");
 
-__host__ __device__ inline size_t evalSmemBytes(int n) {
+struct EvalSmem {
+  size_t perScratch, offAge, offNode, offSize, offWalk, offNeed;  // per-locus scheduling scratch
+  size_t perSched;                                                // per-locus schedule
+  size_t offStack, offSched, offWords, offTerm, offMeta, total;   // CTA regions
+  int W32;
+};
+// Shared-memory plan for a CTA that holds up to `maxLoci` loci of `n` leaves.
+__host__ __device__ inline EvalSmem evalSmemLayout(int n, int maxLoci) {
   const int N = 2 * n - 1, NI = n - 1;
-  size_t perLocus = (size_t)3 * N * sizeof(int16_t)  // father,left,right
-                    + 2 * N                          // flags, need
-                    + (size_t)(NI + 1) * sizeof(int16_t) * 2  // schedule node list + DFS stack
-                    + (size_t)NI * sizeof(SchedEntry);
-  perLocus = (perLocus + 15) & ~(size_t)15;
-  return perLocus * kMaxBatchLoci + kMaxBatchLoci * 48 + (size_t)kThreads * 5 * sizeof(double) + 64;
+  EvalSmem m;
+  m.W32 = (n + 7) / 8;
+  m.offAge = 0;                                            // [N] double
+  m.offNode = m.offAge + (size_t)N * sizeof(double);       // [N] NodeRec
+  m.offSize = m.offNode + (size_t)N * sizeof(NodeRec);     // [NI] int: marked nodes per subtree
+  m.offWalk = m.offSize + (size_t)NI * sizeof(int);        // [N] uint32: father+1 | contribution << 16
+  m.offNeed = m.offWalk + (size_t)N * sizeof(uint32_t);    // [N] uint8
+  m.perScratch = (m.offNeed + (size_t)N + 15) & ~(size_t)15;
+  m.perSched = (size_t)NI * sizeof(SchedEntry);
+  // Region 0 is used twice: first as the scheduling scratch of the batch's loci, then (phase E) as the
+  // per-column stack: lo halves [kStack][kThreads] double2 + 16-entry leaf table, then the hi halves.
+  // The root vectors reuse its first rows after the walk.
+  const size_t stackBytes = 2 * (size_t)kHi, scratchBytes = m.perScratch * (size_t)maxLoci;
+  m.offStack = 0;
+  m.offSched = stackBytes > scratchBytes ? stackBytes : scratchBytes;
+  m.offWords = m.offSched + m.perSched * (size_t)maxLoci;           // [W32][kThreads] uint32 leaf codes
+  m.offTerm = m.offWords;                                           // [kThreads] double, after the walk
+  const size_t wordBytes = (size_t)m.W32 * kThreads * 4, termBytes = (size_t)kThreads * 8;
+  m.offMeta = m.offWords + (wordBytes > termBytes ? wordBytes : termBytes);
+  m.total = m.offMeta + (size_t)kMaxBatchLoci * 48;
+  return m;
 }
+__host__ __device__ inline size_t evalSmemBytes(int n, int maxLoci = kMaxBatchLoci) { return evalSmemLayout(n, maxLoci).total; }
 
 __device__ __forceinline__ TreeView deviceView(const StoreDev& d, int l) {
   TreeView t;
   const size_t o = (size_t)l * d.N;
-  t.father = d.father + o; t.left = d.left + o; t.right = d.right + o;
-  t.svFather = d.svFather + o; t.svLeft = d.svLeft + o; t.svRight = d.svRight + o;
-  t.age = d.age + o; t.svAge = d.svAge + o; t.flags = d.flags + o;
+  t.node = d.node + o; t.saved = d.saved + o;
+  t.age = d.age + o; t.svAge = d.svAge + o;
   t.root = d.root + l; t.savedRoot = d.savedRoot + l;
   t.lnL = d.lnL + l; t.savedLnL = d.savedLnL + l; t.rate = d.rate + l;
   t.numLeaves = d.n;
@@ -97,219 +136,341 @@ __global__ void k_apply_ops(StoreDev d, const Op* __restrict__ ops, const int* _
   for (int o = o0; o < o1; o++) status[o] = applyOp(t, ops[o]);
 }
 
+// genealogies host -> device: topology fields, ages and roots of the listed loci; flag bytes (buffer
+// selectors, dirty marks) stay as they are on the device
+__global__ void k_set_trees(StoreDev d, const int* __restrict__ ids, const int16_t* __restrict__ topo,
+                            const double* __restrict__ age, const int* __restrict__ root, int nLoci) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)nLoci * d.N) return;
+  const int k = (int)(i / d.N), v = (int)(i - (size_t)k * d.N);
+  const int l = ids[k];
+  const size_t o = (size_t)l * d.N + v;
+  NodeRec r = d.node[o];
+  r.father = topo[i * 3]; r.left = topo[i * 3 + 1]; r.right = topo[i * 3 + 2];
+  d.node[o] = r;
+  d.age[o] = age[i];
+  if (v == 0) d.root[l] = root[k];
+}
+
 // computeEdgeConditionalJC (.c:1831-1848): off-diagonal JC69 transition probability
 __device__ __forceinline__ double edgeProb(double edgeLength) {
   if (edgeLength < 1e-100) return 0.0;
   return (1.0 - exp(-4.0 * edgeLength / 3.0)) / 4.0;
 }
 
-// computeSubtreeConditionals_new (.c:1650-1673)
-__device__ __forceinline__ void foldChild(const double (&son)[4], double (&parent)[4], double e0) {
-  const double s = ((son[0] + son[1]) + son[2]) + son[3];
-  if (s >= 4.0) return;  // all-missing subtree
-  const double e1 = 1.0 - 4.0 * e0;
-  const double q = s * e0;
-#pragma unroll
-  for (int b = 0; b < 4; b++) parent[b] *= (q + son[b] * e1);
+__device__ __forceinline__ uint32_t smemAddr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ double2 ldsD2(uint32_t a) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void stsD2(uint32_t a, double x, double y) {
+  asm volatile("st.shared.v2.f64 [%0], {%1,%2};" ::"r"(a), "d"(x), "d"(y) : "memory");
 }
 
-__device__ __forceinline__ void loadClv(const double* p, double (&v)[4]) {
-  const double2 a = *reinterpret_cast<const double2*>(p);
-  const double2 b = *reinterpret_cast<const double2*>(p + 2);
-  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+__device__ __forceinline__ uint32_t ldsU32(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
 }
-__device__ __forceinline__ void storeClv(double* p, const double (&v)[4]) {
-  *reinterpret_cast<double2*>(p) = make_double2(v[0], v[1]);
-  *reinterpret_cast<double2*>(p + 2) = make_double2(v[2], v[3]);
+__device__ __forceinline__ void stsU32(uint32_t a, uint32_t v) {
+  asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint4 ldsU4(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+  return v;
+}
+// rare path of the column walk
+__device__ __forceinline__ void missingSubtree(const double (&a)[4], const double (&b)[4], double sA, double sB, double qA,
+                                            double qB, double e1A, double e1B, double (&v)[4]) {
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    const double fa = sA >= 4.0 ? 1.0 : (qA + a[q] * e1A);
+    const double fb = sB >= 4.0 ? 1.0 : (qB + b[q] * e1B);
+    v[q] = fa * fb;
+  }
 }
 
 __global__ void __launch_bounds__(kThreads)
-k_eval(StoreDev d, const Batch* __restrict__ batches, int batchBase, int useOld, int onlyLocus) {
+k_eval(StoreDev d, const Batch* __restrict__ batches, int batchBase, int useOld, int onlyLocus, int maxLoci) {
   extern __shared__ __align__(16) unsigned char smem[];
   const Batch b = batches[batchBase + blockIdx.x];
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n = d.n, N = d.N, NI = d.NI, nl = b.numLoci;
+  const EvalSmem lay = evalSmemLayout(n, maxLoci);
 
   // ---- carve shared memory
-  size_t perLocus = (size_t)3 * N * sizeof(int16_t) + 2 * N + (size_t)(NI + 1) * sizeof(int16_t) * 2 +
-                    (size_t)NI * sizeof(SchedEntry);
-  perLocus = (perLocus + 15) & ~(size_t)15;
-  unsigned char* base = smem;
-  double* sRoot = reinterpret_cast<double*>(base);              // [kThreads][4]
-  double* sTerm = sRoot + kThreads * 4;                         // [kThreads]
-  base += (size_t)kThreads * 5 * sizeof(double);
-  int* mColStart = reinterpret_cast<int*>(base);                // per-slot metadata
+  const uint32_t stackBase = smemAddr(smem + lay.offStack);
+  double* sRoot = reinterpret_cast<double*>(smem + lay.offStack);        // [kThreads][4], after the walk
+  double* sTerm = reinterpret_cast<double*>(smem + lay.offTerm);         // [kThreads]
+  int* mColStart = reinterpret_cast<int*>(smem + lay.offMeta);           // per-slot metadata
   int* mP = mColStart + kMaxBatchLoci;
   int* mK = mP + kMaxBatchLoci;
   int* mRoot = mK + kMaxBatchLoci;
   int* mActive = mRoot + kMaxBatchLoci;
   double* mRate = reinterpret_cast<double*>(mActive + kMaxBatchLoci);
   double* mLnL = mRate + kMaxBatchLoci;
-  base += kMaxBatchLoci * 48;
-  auto slotBase = [&](int s) { return base + perLocus * s; };
-  auto sSched = [&](int s) { return reinterpret_cast<SchedEntry*>(slotBase(s)); };
-  auto sFather = [&](int s) { return reinterpret_cast<int16_t*>(slotBase(s) + (size_t)NI * sizeof(SchedEntry)); };
-  auto sLeft = [&](int s) { return sFather(s) + N; };
-  auto sRight = [&](int s) { return sFather(s) + 2 * N; };
-  auto sList = [&](int s) { return sFather(s) + 3 * N; };            // [NI+1] post-order node list
-  auto sStack = [&](int s) { return sFather(s) + 3 * N + NI + 1; };  // [NI+1]
-  auto sFlags = [&](int s) { return reinterpret_cast<uint8_t*>(sFather(s) + 3 * N + 2 * (NI + 1)); };
-  auto sNeed = [&](int s) { return sFlags(s) + N; };
+  auto sSched = [&](int s) { return reinterpret_cast<SchedEntry*>(smem + lay.offSched + lay.perSched * s); };
+  auto sAge = [&](int s) { return reinterpret_cast<double*>(smem + lay.perScratch * s + lay.offAge); };
+  auto sNode = [&](int s) { return reinterpret_cast<NodeRec*>(smem + lay.perScratch * s + lay.offNode); };
+  auto sSize = [&](int s) { return reinterpret_cast<int*>(smem + lay.perScratch * s + lay.offSize); };
+  auto sWalk = [&](int s) { return reinterpret_cast<uint32_t*>(smem + lay.perScratch * s + lay.offWalk); };
+  auto sNeed = [&](int s) { return reinterpret_cast<uint8_t*>(smem + lay.perScratch * s + lay.offNeed); };
 
-  // ---- phase 0: per-locus metadata
+  // ---- early loads: what the column walk and the root step need from HBM depends only on the batch
+  //      descriptor, so it is requested now and arrives while the schedule is being built
+  const bool oversized = b.scratchOff >= 0;
+  unsigned long long w0 = 0ull, w1 = 0ull;
+  int ph = 0, cnt = 0;
+  if (tid < b.numCols) {
+    const int c = b.firstCol + tid;
+    w0 = d.leafWords[c];
+    if (d.W > 1) w1 = d.leafWords[(size_t)d.Ct + c];
+    if (!oversized) { ph = d.grpPhases[c]; cnt = d.grpCount[c]; }
+  }
+  // ---- phase A: per-locus metadata; node records and ages staged with coalesced loads
   if (tid < nl) {
     const int l = b.firstLocus + tid;
     const int c0 = d.colStart[l];
     mColStart[tid] = c0;
     mP[tid] = d.colStart[l + 1] - c0;
-    mRoot[tid] = d.root[l];
+    const int root = d.root[l];
+    mRoot[tid] = root;
     mRate[tid] = d.rate[l];
-    int act = (mP[tid] > 0) && (d.root[l] >= 0);
+    int act = (mP[tid] > 0) && (root >= n);
     if (d.active && !d.active[l]) act = 0;
     if (onlyLocus >= 0 && l != onlyLocus) act = 0;
     mActive[tid] = act;
     mK[tid] = 0;
-    mLnL[tid] = 0.0;
+    const double cur = d.lnL[l];
+    mLnL[tid] = cur;
+    if (act) d.savedLnL[l] = cur;  // always, even when nothing is recomputed (.c:440)
   }
-  // ---- phase 1: stage topology + flags (contiguous in HBM across the batch's loci -> coalesced)
-  {
-    const size_t g0 = (size_t)b.firstLocus * N;
-    for (int i = tid; i < nl * N; i += kThreads) {
-      const int s = i / N, v = i - s * N;
-      sFather(s)[v] = d.father[g0 + i];
-      sLeft(s)[v] = d.left[g0 + i];
-      sRight(s)[v] = d.right[g0 + i];
-      sFlags(s)[v] = d.flags[g0 + i];
-      sNeed(s)[v] = 0;
-    }
-  }
-  __syncthreads();
-  // ---- phase 2: mark dirty nodes and their ancestors (computeConditionalJC_new's recursion condition, .c:1583)
-  for (int i = tid; i < nl * N; i += kThreads) {
-    const int s = i / N, v = i - s * N;
-    if (!mActive[s]) continue;
-    if (!useOld) {
-      if (v >= n) sNeed(s)[v] = 1;
-    } else if (sFlags(s)[v] & F_RECALC) {
-      int u = v < n ? sFather(s)[v] : v;  // a moved leaf dirties its father (.c:1569-1575)
-      uint8_t* need = sNeed(s);
-      const int16_t* fa = sFather(s);
-      while (u >= 0 && !need[u]) {
-        need[u] = 1;
-        u = fa[u];
-      }
-    }
-  }
-  __syncthreads();
-  // ---- phase 3: per locus, post-order over the marked set; flip buffers of scheduled nodes
-  if (tid < nl && mActive[tid]) {
-    const int s = tid, l = b.firstLocus + s;
+  for (int s = warp; s < nl; s += kWarps) {
+    const size_t g0 = (size_t)(b.firstLocus + s) * N;
+    NodeRec* nd = sNode(s);
+    double* age = sAge(s);
     uint8_t* need = sNeed(s);
-    uint8_t* fl = sFlags(s);
-    int16_t* list = sList(s);
-    int16_t* stack = sStack(s);
-    const int16_t *le = sLeft(s), *ri = sRight(s);
-    int k = 0, sp = 0;
-    const int root = mRoot[s];
-    if (root >= n && need[root]) stack[sp++] = (int16_t)root;
-    while (sp > 0) {
-      const int v = stack[sp - 1];
-      if (need[v] == 1) {
-        need[v] = 2;
-        const int r = ri[v], lf = le[v];
-        if (r >= n && need[r] == 1) stack[sp++] = (int16_t)r;
-        if (lf >= n && need[lf] == 1) stack[sp++] = (int16_t)lf;
-      } else {
-        sp--;
-        list[k++] = (int16_t)v;
-      }
+    int* size = sSize(s);
+    for (int v = lane; v < N; v += 32) {
+      nd[v] = d.node[g0 + v];
+      age[v] = d.age[g0 + v];
+      need[v] = 0;
+      if (v < NI) size[v] = 0;
     }
-    uint8_t* gflags = d.flags + (size_t)l * N;
-    for (int e = 0; e < k; e++) {
-      const int v = list[e];
-      uint8_t f = fl[v];
-      if (!(f & F_RECALC)) {  // copyNodeConditionals: flip once per proposal
-        f = (uint8_t)((f ^ F_SEL) | F_RECALC);
-        fl[v] = f;
-        gflags[v] = f;
-      }
-    }
-    d.savedLnL[l] = d.lnL[l];  // always, even when nothing is recomputed (.c:440)
-    mLnL[s] = d.lnL[l];
-    mK[s] = k;
   }
   __syncthreads();
-  // ---- phase 4: edge probabilities, once per (locus, scheduled node)
-  for (int i = tid; i < nl * NI; i += kThreads) {
-    const int s = i / NI, e = i - s * NI;
-    if (e >= mK[s]) continue;
-    const int v = sList(s)[e];
-    const int lf = sLeft(s)[v], r = sRight(s)[v];
-    const double* age = d.age + (size_t)(b.firstLocus + s) * N;
-    const double av = age[v], rate = mRate[s];
-    SchedEntry en;
-    en.node = (int16_t)v; en.left = (int16_t)lf; en.right = (int16_t)r;
-    const uint8_t* fl = sFlags(s);
-    en.info = (uint16_t)((fl[v] & 1) | ((fl[lf] & 1) << 1) | ((fl[r] & 1) << 2));
-    en.e0L = edgeProb(rate * (av - age[lf]));
-    en.e0R = edgeProb(rate * (av - age[r]));
-    sSched(s)[e] = en;
+  // ---- phase B: mark dirty nodes and their ancestors (computeConditionalJC_new's recursion condition, .c:1583)
+  for (int s = warp; s < nl; s += kWarps) {
+    if (!mActive[s]) continue;
+    const NodeRec* nd = sNode(s);
+    uint8_t* need = sNeed(s);
+    for (int v = lane; v < N; v += 32) {
+      if (!useOld) {
+        if (v >= n) need[v] = 1;
+      } else if (nd[v].flags & F_RECALC) {
+        int u = v < n ? nd[v].father : v;  // a moved leaf dirties its father (.c:1569-1575)
+        for (int it = 0; u >= 0 && !need[u] && it < N; it++) {
+          need[u] = 1;
+          u = nd[u].father;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  // ---- phase C: flip the buffers of the nodes to compute (copyNodeConditionals: once per proposal);
+  //      count the marked nodes of every subtree
+  for (int s = warp; s < nl; s += kWarps) {
+    if (!mActive[s]) continue;
+    NodeRec* nd = sNode(s);
+    const uint8_t* need = sNeed(s);
+    int* size = sSize(s);
+    for (int v = n + lane; v < N; v += 32) {
+      if (!need[v]) continue;
+      uint8_t f = nd[v].flags;
+      if (!(f & F_RECALC)) {
+        f = (uint8_t)((f ^ F_SEL) | F_RECALC);
+        nd[v].flags = f;
+        d.node[(size_t)(b.firstLocus + s) * N + v].flags = f;
+      }
+      int a = v;
+      for (int it = 0; a >= 0 && it < N; it++) {
+        atomicAdd(&size[a - n], 1);
+        a = nd[a].father;
+      }
+    }
+  }
+  __syncthreads();
+  // ---- phase D1: what a node contributes to the post-order start of everything below it.  The heavier
+  //      child of a node is visited first; a node visited second starts after its sibling's subtree.
+  for (int s = warp; s < nl; s += kWarps) {
+    if (!mActive[s]) continue;
+    const NodeRec* nd = sNode(s);
+    const uint8_t* need = sNeed(s);
+    const int* size = sSize(s);
+    uint32_t* walk = sWalk(s);
+    for (int v = n + lane; v < N; v += 32) {
+      if (!need[v]) continue;
+      const int a = nd[v].father;
+      uint32_t contrib = 0;
+      if (a >= 0) {
+        const int l = nd[a].left, r = nd[a].right;
+        const int wl = (l >= n && need[l]) ? size[l - n] : 0;
+        const int wr = (r >= n && need[r]) ? size[r - n] : 0;
+        const int first = wl >= wr ? l : r;
+        if (v != first) contrib = (uint32_t)(v == l ? wr : wl);
+      }
+      walk[v] = (uint32_t)(a + 1) | (contrib << 16);
+    }
+  }
+  __syncthreads();
+  // ---- phase D2: position and stack depth of every marked node, sources of its children, JC69 edge terms
+  for (int s = warp; s < nl; s += kWarps) {
+    if (!mActive[s]) continue;
+    const NodeRec* nd = sNode(s);
+    const uint8_t* need = sNeed(s);
+    const int* size = sSize(s);
+    const uint32_t* walk = sWalk(s);
+    const double* age = sAge(s);
+    const double rate = mRate[s];
+    for (int v = n + lane; v < N; v += 32) {
+      if (!need[v]) continue;
+      int start = 0, depth = 0;  // depth = results parked on the stack when v's subtree is entered
+      {
+        uint32_t w = walk[v];
+        for (int it = 0; it < N; it++) {
+          const uint32_t c = w >> 16;
+          start += c;
+          depth += c != 0;
+          const int a = (int)(w & 0xffffu) - 1;
+          if (a < 0) break;
+          w = walk[a];
+        }
+      }
+      const int l = nd[v].left, r = nd[v].right;
+      const int wl = (l >= n && need[l]) ? size[l - n] : 0;
+      const int wr = (r >= n && need[r]) ? size[r - n] : 0;
+      const bool leftFirst = wl >= wr;
+      const int A = leftFirst ? l : r, B = leftFirst ? r : l;  // visiting order
+      const int wA = leftFirst ? wl : wr, wB = leftFirst ? wr : wl;
+      const uint32_t strideBytes = (uint32_t)mP[s] * 32u;  // one (node, buffer) record of this locus
+      auto record = [&](int x) { return (uint32_t)((x - n) * 2 + (nd[x].flags & F_SEL)) * strideBytes; };
+      auto leafRef = [&](int x) { return (uint32_t)(x >> 3) * (kThreads * 4u) | ((uint32_t)(x & 7) * 4u) << 16; };
+      // a computed child sits on the stack at the depth its own subtree was entered with
+      const int slotA = depth, slotB = depth + (wA > 0);
+      uint32_t kindA, kindB, offA, offB;
+      if (A < n) { kindA = SRC_LEAF; offA = leafRef(A); }
+      else if (wA > 0 && slotA < kStack) { kindA = SRC_STACK; offA = ((uint32_t)slotA * kRow) << 16; }
+      else { kindA = SRC_GLOBAL; offA = record(A); }  // clean child, or a result the thread parked in HBM
+      if (B < n) { kindB = SRC_LEAF; offB = leafRef(B); }
+      else if (wB > 0 && slotB < kStack) { kindB = SRC_STACK; offB = ((uint32_t)slotB * kRow) << 16; }
+      else { kindB = SRC_GLOBAL; offB = record(B); }
+      SchedEntry en;
+      const double av = age[v];
+      en.e0A = edgeProb(rate * (av - age[A]));
+      en.e1A = 1.0 - 4.0 * en.e0A;
+      en.e0B = edgeProb(rate * (av - age[B]));
+      en.e1B = 1.0 - 4.0 * en.e0B;
+      en.offA = offA; en.offB = offB;
+      en.dstOff = record(v);
+      const uint32_t push = (v != mRoot[s] && depth < kStack) ? (uint32_t)depth * kRow : 0xffffu;
+      en.ctl = kindA | (kindB << 2) | (push << 16);
+      sSched(s)[start + size[v - n] - 1] = en;
+      if (v == mRoot[s]) mK[s] = size[v - n];
+    }
   }
   __syncthreads();
 
-  // ---- phase 5: every thread walks its locus' schedule for its own column
+  // ---- phase E: every thread walks its locus' schedule for its own column.  The scheduling scratch is dead;
+  //      its space becomes the per-column stack and the leaf table.
+  if (tid < 16) {  // conditional vectors of a leaf by base mask (computeLeafConditionals, .c:1336-1386)
+    stsD2(stackBase + kStack * kRow + tid * 16, (tid & 1) ? 1.0 : 0.0, (tid & 2) ? 1.0 : 0.0);
+    stsD2(stackBase + kStack * kRow + kHi + tid * 16, (tid & 4) ? 1.0 : 0.0, (tid & 8) ? 1.0 : 0.0);
+  }
+  __syncthreads();
   const int numChunks = (b.numCols + kThreads - 1) / kThreads;
-  const bool oversized = b.scratchOff >= 0;
+  const uint32_t myStack = stackBase + tid * 16;
+  const uint32_t leafRel = kStack * kRow - tid * 16;  // leaf table relative to this column's stack
+  const uint32_t myWords = smemAddr(smem + lay.offWords) + tid * 4;
+  int s = 0, k = 0;
   for (int chunk = 0; chunk < numChunks; chunk++) {
     const int colInBatch = chunk * kThreads + tid;
     const bool live = colInBatch < b.numCols;
     const int c = b.firstCol + colInBatch;
-    int s = 0;
+    s = 0;
     if (live) {
       while (s + 1 < nl && c >= mColStart[s + 1]) s++;
     }
     double pv[4] = {0.0, 0.0, 0.0, 0.0};
-    int k = 0;
-    if (live && mActive[s]) {
-      k = mK[s];
-      const int P = mP[s], p = c - mColStart[s];
-      const unsigned long long w0 = d.leafWords[c];
-      const unsigned long long w1 = d.W > 1 ? d.leafWords[(size_t)d.Ct + c] : 0ull;
-      double* clvL = d.clv + (size_t)mColStart[s] * NI * 8;
-      const SchedEntry* sched = sSched(s);
-      int prevNode = -1;
-      auto childValue = [&](int child, int buf, double (&v)[4]) {
-        if (child < n) {
-          const int w = child >> 4;
-          const unsigned long long word = w == 0 ? w0 : (w == 1 ? w1 : d.leafWords[(size_t)w * d.Ct + c]);
-          const unsigned code = (unsigned)(word >> ((child & 15) * 4)) & 15u;
-#pragma unroll
-          for (int q = 0; q < 4; q++) v[q] = (code >> q) & 1u ? 1.0 : 0.0;
-        } else if (child == prevNode) {
-#pragma unroll
-          for (int q = 0; q < 4; q++) v[q] = pv[q];
+    k = (live && mActive[s]) ? mK[s] : 0;
+    if (chunk > 0 && live) {
+      w0 = d.leafWords[c];
+      w1 = d.W > 1 ? d.leafWords[(size_t)d.Ct + c] : 0ull;
+    }
+    if (k > 0) {
+      const int p = c - mColStart[s];
+      // this column's leaf masks, 8 leaves per 32-bit word
+      stsU32(myWords, (uint32_t)w0);
+      if (lay.W32 > 1) stsU32(myWords + kThreads * 4, (uint32_t)(w0 >> 32));
+      if (lay.W32 > 2) stsU32(myWords + 2 * kThreads * 4, (uint32_t)w1);
+      if (lay.W32 > 3) stsU32(myWords + 3 * kThreads * 4, (uint32_t)(w1 >> 32));
+      for (int w = 2; w < d.W; w++) {
+        const unsigned long long word = d.leafWords[(size_t)w * d.Ct + c];
+        stsU32(myWords + (2 * w) * kThreads * 4, (uint32_t)word);
+        if (2 * w + 1 < lay.W32) stsU32(myWords + (2 * w + 1) * kThreads * 4, (uint32_t)(word >> 32));
+      }
+      char* clvCol = reinterpret_cast<char*>(d.clv + (size_t)mColStart[s] * NI * 8 + (size_t)p * 4);
+      uint32_t entry = smemAddr(sSched(s));
+      auto childValue = [&](uint32_t kind, uint32_t off, double (&v)[4]) {
+        if (kind == SRC_GLOBAL) {
+          const double2* g = reinterpret_cast<const double2*>(clvCol + off);
+          const double2 x = g[0], y = g[1];
+          v[0] = x.x; v[1] = x.y; v[2] = y.x; v[3] = y.y;
         } else {
-          loadClv(clvL + ((size_t)((child - n) * 2 + buf) * P + p) * 4, v);
+          // leaf: table row picked by the 4-bit mask of this column; stack: this column's slot
+          const uint32_t word = ldsU32(myWords + (off & 0xffffu));
+          const uint32_t hi = off >> 16;
+          const uint32_t a = myStack + (kind == SRC_LEAF ? leafRel + (((word >> hi) & 15u) << 4) : hi);
+          const double2 x = ldsD2(a), y = ldsD2(a + kHi);
+          v[0] = x.x; v[1] = x.y; v[2] = y.x; v[3] = y.y;
         }
       };
-      for (int e = 0; e < k; e++) {
-        const SchedEntry en = sched[e];
-        double a[4], bb[4], v[4] = {1.0, 1.0, 1.0, 1.0};
-        childValue(en.left, (en.info >> 1) & 1, a);
-        childValue(en.right, (en.info >> 2) & 1, bb);
-        foldChild(a, v, en.e0L);
-        foldChild(bb, v, en.e0R);
-        storeClv(clvL + ((size_t)((en.node - n) * 2 + (en.info & 1)) * P + p) * 4, v);
-        prevNode = en.node;
+      for (int e = 0; e < k; e++, entry += sizeof(SchedEntry)) {
+        const double2 eA = ldsD2(entry), eB = ldsD2(entry + 16);   // (e0A,e1A), (e0B,e1B)
+        const uint4 ix = ldsU4(entry + 32);                        // offA, offB, dstOff, ctl
+        double a[4], bb[4], v[4];
+        childValue(ix.w & 3u, ix.x, a);
+        childValue((ix.w >> 2) & 3u, ix.y, bb);
+        // computeSubtreeConditionals_new (.c:1650-1673) for both children
+        const double sA = ((a[0] + a[1]) + a[2]) + a[3];
+        const double sB = ((bb[0] + bb[1]) + bb[2]) + bb[3];
+        const double qA = sA * eA.x, qB = sB * eB.x;
+#pragma unroll
+        for (int q = 0; q < 4; q++) v[q] = (qA + a[q] * eA.y) * (qB + bb[q] * eB.y);
+        // sums are positive, so s >= 4.0 can be read off the high word (4.0 = 0x40100000'00000000)
+        if (__builtin_expect((__double2hiint(sA) >= 0x40100000) | (__double2hiint(sB) >= 0x40100000), 0)) {
+          // a child whose conditionals sum to 4 is an all-missing subtree and contributes exactly 1 (.c:1660-1663)
+          missingSubtree(a, bb, sA, sB, qA, qB, eA.y, eB.y, v);
+        }
+        double2* dst = reinterpret_cast<double2*>(clvCol + ix.z);
+        dst[0] = make_double2(v[0], v[1]);
+        dst[1] = make_double2(v[2], v[3]);
+        const uint32_t push = ix.w >> 16;
+        if (push != 0xffffu) {
+          stsD2(myStack + push, v[0], v[1]);
+          stsD2(myStack + push + kHi, v[2], v[3]);
+        }
 #pragma unroll
         for (int q = 0; q < 4; q++) pv[q] = v[q];
       }
     }
-    // ---- phase 6: root conditionals -> shared (or scratch for an oversized locus)
+    // ---- root conditionals -> shared (or scratch for an oversized locus)
     if (!oversized) {
+      __syncthreads();  // the stack is dead from here on; its space takes the root vectors
 #pragma unroll
       for (int q = 0; q < 4; q++) sRoot[tid * 4 + q] = pv[q];
-    } else if (live && k > 0) {
+    } else if (k > 0) {
       double* dst = d.rootScratch + ((size_t)b.scratchOff + colInBatch) * 4;
 #pragma unroll
       for (int q = 0; q < 4; q++) dst[q] = pv[q];
@@ -317,32 +478,25 @@ k_eval(StoreDev d, const Batch* __restrict__ batches, int batchBase, int useOld,
   }
   __syncthreads();
 
+  // ---- phase F
   if (!oversized) {
     // sum over the 4*phases root conditionals of each phase group, in the reference's order (.c:470-479)
-    const bool live = tid < b.numCols;
-    const int c = b.firstCol + tid;
-    int s = 0;
-    if (live) while (s + 1 < nl && c >= mColStart[s + 1]) s++;
     double term = 0.0;
-    if (live && mActive[s] && mK[s] > 0) {
-      const int ph = d.grpPhases[c];
-      if (ph > 0) {
-        double prob = 0.0;
-        const int numConds = 4 * ph;
-        for (int j = 0; j < numConds; j++) prob += sRoot[tid * 4 + j];
-        term = log(prob / numConds) * d.grpCount[c];
-      }
+    if (k > 0 && ph > 0) {
+      double prob = 0.0;
+      const int numConds = 4 * ph;
+      for (int j = 0; j < numConds; j++) prob += sRoot[tid * 4 + j];
+      term = log(prob / numConds) * cnt;
     }
-    sTerm[tid] = term;
+    sTerm[tid] = term;  // 0.0 for the other members of a phase group: adding it below is exact
     __syncthreads();
-    if (live && mActive[s] && mK[s] > 0 && c == mColStart[s]) {
-      const int P = mP[s];
-      const int* ph = d.grpPhases + c;
+    if (tid < nl && mActive[tid] && mK[tid] > 0) {
+      const int P = mP[tid];
+      const double* t = sTerm + (mColStart[tid] - b.firstCol);
       double lnl = 0.0;
-      for (int j = 0; j < P; j++)
-        if (ph[j] > 0) lnl += sTerm[tid + j];
-      d.lnL[b.firstLocus + s] = lnl;
-      mLnL[s] = lnl;
+      for (int j = 0; j < P; j++) lnl += t[j];
+      d.lnL[b.firstLocus + tid] = lnl;
+      mLnL[tid] = lnl;
     }
     __syncthreads();
     if (tid == 0) {
@@ -359,10 +513,10 @@ k_eval(StoreDev d, const Batch* __restrict__ batches, int batchBase, int useOld,
       const int P = mP[0], c0 = mColStart[0];
       const double* src = d.rootScratch + (size_t)b.scratchOff * 4;
       for (int p = tid; p < P; p += kThreads) {
-        const int ph = d.grpPhases[c0 + p];
-        if (ph > 0) {
+        const int phs = d.grpPhases[c0 + p];
+        if (phs > 0) {
           double prob = 0.0;
-          const int numConds = 4 * ph;
+          const int numConds = 4 * phs;
           for (int j = 0; j < numConds; j++) prob += src[(size_t)p * 4 + j];
           acc += log(prob / numConds) * d.grpCount[c0 + p];
         }

@@ -80,14 +80,14 @@ struct GphocsStore {
   Batch* dBatches = nullptr;
   double* dSum = nullptr;
   int numBatches = 0;
+  int maxBatchLoci = 1;  // most loci any CTA batch holds (sizes the kernel's shared memory)
   size_t smemBytes = 0;
   std::vector<Batch> batches;
   std::vector<int> locusBatch;  // batch index holding each locus (-1: no columns)
   std::vector<int> colStart;
   // host mirror (what the reference's getters read)
-  std::vector<int16_t> hFather, hLeft, hRight, hsFather, hsLeft, hsRight;
+  std::vector<NodeRec> hNode, hsNode;
   std::vector<double> hAge, hsAge, hRate, hLnL, hSavedLnL;
-  std::vector<uint8_t> hFlags;
   std::vector<int> hRoot, hSavedRoot;
   // staging
   Staging<Op> ops;
@@ -101,9 +101,8 @@ struct GphocsStore {
   TreeView hostView(int l) {
     TreeView t;
     const size_t o = (size_t)l * N;
-    t.father = hFather.data() + o; t.left = hLeft.data() + o; t.right = hRight.data() + o;
-    t.svFather = hsFather.data() + o; t.svLeft = hsLeft.data() + o; t.svRight = hsRight.data() + o;
-    t.age = hAge.data() + o; t.svAge = hsAge.data() + o; t.flags = hFlags.data() + o;
+    t.node = hNode.data() + o; t.saved = hsNode.data() + o;
+    t.age = hAge.data() + o; t.svAge = hsAge.data() + o;
     t.root = &hRoot[l]; t.savedRoot = &hSavedRoot[l];
     t.lnL = &hLnL[l]; t.savedLnL = &hSavedLnL[l]; t.rate = &hRate[l];
     t.numLeaves = n;
@@ -198,6 +197,10 @@ extern "C" GphocsStore* gphocsStoreCreate(int device, int numLoci, int numLeaves
   // ---- CTA batches: whole loci packed greedily; an oversized locus gets a CTA of its own
   long long scratchCols = 0;
   s->locusBatch.assign(L, -1);
+  // loci per batch are also capped so that the per-locus staging area fits a 64 KB shared-memory budget
+  // (keeps several CTAs resident per SM whatever the number of leaves)
+  int lociCap = kMaxBatchLoci;
+  while (lociCap > 1 && evalSmemBytes(n, lociCap) > 64 * 1024) lociCap--;
   {
     Batch cur{0, 0, 0, 0, -1, 0};
     auto flush = [&]() { if (cur.numLoci > 0) s->batches.push_back(cur); cur = Batch{0, 0, 0, 0, -1, 0}; };
@@ -212,7 +215,7 @@ extern "C" GphocsStore* gphocsStoreCreate(int device, int numLoci, int numLeaves
         s->batches.push_back(b);
         continue;
       }
-      if (cur.numLoci > 0 && (cur.numCols + P > kThreads || cur.numLoci == kMaxBatchLoci)) flush();
+      if (cur.numLoci > 0 && (cur.numCols + P > kThreads || cur.numLoci == lociCap)) flush();
       if (cur.numLoci == 0) { cur.firstLocus = l; cur.firstCol = s->colStart[l]; }
       s->locusBatch[l] = (int)s->batches.size();
       cur.numLoci++;
@@ -221,6 +224,7 @@ extern "C" GphocsStore* gphocsStoreCreate(int device, int numLoci, int numLeaves
     flush();
   }
   s->numBatches = (int)s->batches.size();
+  for (const Batch& bt : s->batches) s->maxBatchLoci = std::max(s->maxBatchLoci, bt.numLoci);
 
   // ---- device allocations
   StoreDev& d = s->d;
@@ -230,10 +234,9 @@ extern "C" GphocsStore* gphocsStoreCreate(int device, int numLoci, int numLeaves
   bool ok = true;
   const size_t LN = (size_t)L * N;
   ok = ok && devAlloc(&dColStart, L + 1) == 0 && devAlloc(&dWords, words.size()) == 0 && devAlloc(&dPh, phases.size()) == 0 &&
-       devAlloc(&dCnt, cnt.size()) == 0 && devAlloc(&d.clv, (size_t)Ct * NI * 8) == 0 && devAlloc(&d.father, LN) == 0 &&
-       devAlloc(&d.left, LN) == 0 && devAlloc(&d.right, LN) == 0 && devAlloc(&d.svFather, LN) == 0 &&
-       devAlloc(&d.svLeft, LN) == 0 && devAlloc(&d.svRight, LN) == 0 && devAlloc(&d.age, LN) == 0 &&
-       devAlloc(&d.svAge, LN) == 0 && devAlloc(&d.flags, LN) == 0 && devAlloc(&d.root, L) == 0 &&
+       devAlloc(&dCnt, cnt.size()) == 0 && devAlloc(&d.clv, (size_t)Ct * NI * 8) == 0 && devAlloc(&d.node, LN) == 0 &&
+       devAlloc(&d.saved, LN) == 0 && devAlloc(&d.age, LN) == 0 &&
+       devAlloc(&d.svAge, LN) == 0 && devAlloc(&d.root, L) == 0 &&
        devAlloc(&d.savedRoot, L) == 0 && devAlloc(&d.rate, L) == 0 && devAlloc(&d.lnL, L) == 0 &&
        devAlloc(&d.savedLnL, L) == 0 && devAlloc(&d.rootScratch, (size_t)scratchCols * 4) == 0 &&
        devAlloc(&d.ctaSum, s->numBatches) == 0 && devAlloc(&s->dMask, L) == 0 &&
@@ -244,7 +247,7 @@ extern "C" GphocsStore* gphocsStoreCreate(int device, int numLoci, int numLeaves
     return nullptr;
   }
   d.colStart = dColStart; d.leafWords = dWords; d.grpPhases = dPh; d.grpCount = dCnt; d.active = nullptr;
-  s->deviceBytes = (long long)((size_t)Ct * NI * 64 + words.size() * 8 + (size_t)Ct * 8 + LN * (6 * 2 + 16 + 1) + (size_t)L * 36);
+  s->deviceBytes = (long long)((size_t)Ct * NI * 64 + words.size() * 8 + (size_t)Ct * 8 + LN * (2 * 8 + 16) + (size_t)L * 36);
   cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
   s->ownStream = true;
   cudaMemcpy(dColStart, s->colStart.data(), sizeof(int) * (L + 1), cudaMemcpyHostToDevice);
@@ -253,9 +256,7 @@ extern "C" GphocsStore* gphocsStoreCreate(int device, int numLoci, int numLeaves
   cudaMemcpy(dCnt, cnt.data(), cnt.size() * 4, cudaMemcpyHostToDevice);
   if (s->numBatches) cudaMemcpy(s->dBatches, s->batches.data(), sizeof(Batch) * s->numBatches, cudaMemcpyHostToDevice);
   cudaMemset(d.clv, 0, (size_t)Ct * NI * 64);
-  cudaMemset(d.father, 0xff, LN * 2); cudaMemset(d.left, 0xff, LN * 2); cudaMemset(d.right, 0xff, LN * 2);
-  cudaMemset(d.svFather, 0xff, LN * 2); cudaMemset(d.svLeft, 0xff, LN * 2); cudaMemset(d.svRight, 0xff, LN * 2);
-  cudaMemset(d.age, 0, LN * 8); cudaMemset(d.svAge, 0, LN * 8); cudaMemset(d.flags, 0, LN);
+  cudaMemset(d.age, 0, LN * 8); cudaMemset(d.svAge, 0, LN * 8);
   cudaMemset(d.root, 0xff, (size_t)L * 4); cudaMemset(d.savedRoot, 0xff, (size_t)L * 4);
   cudaMemset(d.lnL, 0, (size_t)L * 8); cudaMemset(d.savedLnL, 0, (size_t)L * 8);
   cudaMemset(s->dMask, 0, L);
@@ -263,7 +264,12 @@ extern "C" GphocsStore* gphocsStoreCreate(int device, int numLoci, int numLeaves
     std::vector<double> ones(L, 1.0);
     cudaMemcpy(d.rate, ones.data(), (size_t)L * 8, cudaMemcpyHostToDevice);
   }
-  s->smemBytes = evalSmemBytes(n);
+  s->smemBytes = evalSmemBytes(n, s->maxBatchLoci);
+  if (s->smemBytes > 220 * 1024) {
+    fprintf(stderr, "gphocs_b200: %d leaves need %zu bytes of shared memory per locus batch\n", n, s->smemBytes);
+    delete s;
+    return nullptr;
+  }
   if (cudaFuncSetAttribute(k_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smemBytes) != cudaSuccess ||
       cudaDeviceSynchronize() != cudaSuccess) {
     fprintf(stderr, "gphocs_b200: device initialisation failed: %s\n", cudaGetErrorString(cudaGetLastError()));
@@ -271,9 +277,10 @@ extern "C" GphocsStore* gphocsStoreCreate(int device, int numLoci, int numLeaves
     return nullptr;
   }
   // ---- host mirror
-  s->hFather.assign(LN, -1); s->hLeft.assign(LN, -1); s->hRight.assign(LN, -1);
-  s->hsFather.assign(LN, -1); s->hsLeft.assign(LN, -1); s->hsRight.assign(LN, -1);
-  s->hAge.assign(LN, 0.0); s->hsAge.assign(LN, 0.0); s->hFlags.assign(LN, 0);
+  s->hNode.assign(LN, NodeRec{-1, -1, -1, 0, 0}); s->hsNode.assign(LN, NodeRec{-1, -1, -1, 0, 0});
+  s->hAge.assign(LN, 0.0); s->hsAge.assign(LN, 0.0);
+  cudaMemcpy(d.node, s->hNode.data(), LN * sizeof(NodeRec), cudaMemcpyHostToDevice);
+  cudaMemcpy(d.saved, s->hsNode.data(), LN * sizeof(NodeRec), cudaMemcpyHostToDevice);
   s->hRoot.assign(L, -1); s->hSavedRoot.assign(L, -1);
   s->hRate.assign(L, 1.0); s->hLnL.assign(L, 0.0); s->hSavedLnL.assign(L, 0.0);
   return s;
@@ -284,8 +291,8 @@ extern "C" int gphocsStoreDestroy(GphocsStore* s) {
   cudaSetDevice(s->device);
   cudaDeviceSynchronize();
   StoreDev& d = s->d;
-  void* ptrs[] = {(void*)d.colStart, (void*)d.leafWords, (void*)d.grpPhases, (void*)d.grpCount, d.clv, d.father, d.left,
-                  d.right, d.svFather, d.svLeft, d.svRight, d.age, d.svAge, d.flags, d.root, d.savedRoot, d.rate, d.lnL,
+  void* ptrs[] = {(void*)d.colStart, (void*)d.leafWords, (void*)d.grpPhases, (void*)d.grpCount, d.clv, d.node, d.saved,
+                  d.age, d.svAge, d.root, d.savedRoot, d.rate, d.lnL,
                   d.savedLnL, d.rootScratch, d.ctaSum, s->dMask, s->dBatches, s->dSum};
   for (void* p : ptrs) if (p) cudaFree(p);
   s->ops.release(); s->seg.release(); s->status.release(); s->ids.release(); s->f64.release(); s->i16.release();
@@ -327,35 +334,49 @@ static int setTreesLocked(GphocsStore* s, int nLoci, const int* locusIds, const 
   for (int k = 0; k < nLoci; k++) {
     const int l = locusIds ? locusIds[k] : k;
     if (l < 0 || l >= s->L) { fprintf(stderr, "gphocs_b200: locus %d out of range\n", l); return -1; }
+  }
+#pragma omp parallel for schedule(static)
+  for (int k = 0; k < nLoci; k++) {
+    const int l = locusIds ? locusIds[k] : k;
     const size_t o = (size_t)l * N, in = (size_t)k * N;
     for (int i = 0; i < N; i++) {
-      s->hFather[o + i] = (int16_t)father[in + i];
-      s->hLeft[o + i] = (int16_t)left[in + i];
-      s->hRight[o + i] = (int16_t)right[in + i];
+      NodeRec& r = s->hNode[o + i];   // flag bits (buffer selectors) are kept
+      r.father = (int16_t)father[in + i];
+      r.left = (int16_t)left[in + i];
+      r.right = (int16_t)right[in + i];
       s->hAge[o + i] = age[in + i];
     }
     s->hRoot[l] = root[k];
   }
-  StoreDev& d = s->d;
-  if (!locusIds) {  // contiguous prefix: one copy per array
-    const size_t cnt = (size_t)nLoci * N;
-    CUDA_TRY(cudaMemcpyAsync(d.father, s->hFather.data(), cnt * 2, cudaMemcpyHostToDevice, s->stream));
-    CUDA_TRY(cudaMemcpyAsync(d.left, s->hLeft.data(), cnt * 2, cudaMemcpyHostToDevice, s->stream));
-    CUDA_TRY(cudaMemcpyAsync(d.right, s->hRight.data(), cnt * 2, cudaMemcpyHostToDevice, s->stream));
-    CUDA_TRY(cudaMemcpyAsync(d.age, s->hAge.data(), cnt * 8, cudaMemcpyHostToDevice, s->stream));
-    CUDA_TRY(cudaMemcpyAsync(d.root, s->hRoot.data(), (size_t)nLoci * 4, cudaMemcpyHostToDevice, s->stream));
-  } else {
-    for (int k = 0; k < nLoci; k++) {
-      const int l = locusIds[k];
-      const size_t o = (size_t)l * N;
-      CUDA_TRY(cudaMemcpyAsync(d.father + o, s->hFather.data() + o, (size_t)N * 2, cudaMemcpyHostToDevice, s->stream));
-      CUDA_TRY(cudaMemcpyAsync(d.left + o, s->hLeft.data() + o, (size_t)N * 2, cudaMemcpyHostToDevice, s->stream));
-      CUDA_TRY(cudaMemcpyAsync(d.right + o, s->hRight.data() + o, (size_t)N * 2, cudaMemcpyHostToDevice, s->stream));
-      CUDA_TRY(cudaMemcpyAsync(d.age + o, s->hAge.data() + o, (size_t)N * 8, cudaMemcpyHostToDevice, s->stream));
-      CUDA_TRY(cudaMemcpyAsync(d.root + l, s->hRoot.data() + l, 4, cudaMemcpyHostToDevice, s->stream));
+  // the device keeps the authoritative flag bytes: only topology fields are overwritten there
+  if (s->i16.reserve((size_t)nLoci * N * 3) || s->ids.reserve(nLoci)) return -1;
+#pragma omp parallel for schedule(static)
+  for (int k = 0; k < nLoci; k++) {
+    const int l = locusIds ? locusIds[k] : k;
+    s->ids.host[k] = l;
+    for (int i = 0; i < N; i++) {
+      const NodeRec& r = s->hNode[(size_t)l * N + i];
+      int16_t* o3 = s->i16.host + ((size_t)k * N + i) * 3;
+      o3[0] = r.father; o3[1] = r.left; o3[2] = r.right;
     }
   }
-  CUDA_TRY(cudaStreamSynchronize(s->stream));  // the mirror vectors are pageable: finish before returning
+  StoreDev& d = s->d;
+  const size_t cnt = (size_t)nLoci * N;
+  if (s->f64.reserve(cnt) || s->seg.reserve(nLoci)) return -1;
+#pragma omp parallel for schedule(static)
+  for (int k = 0; k < nLoci; k++) {
+    const int l = s->ids.host[k];
+    memcpy(s->f64.host + (size_t)k * N, s->hAge.data() + (size_t)l * N, sizeof(double) * N);
+    s->seg.host[k] = s->hRoot[l];
+  }
+  CUDA_TRY(cudaMemcpyAsync(s->ids.dev, s->ids.host, sizeof(int) * nLoci, cudaMemcpyHostToDevice, s->stream));
+  CUDA_TRY(cudaMemcpyAsync(s->seg.dev, s->seg.host, sizeof(int) * nLoci, cudaMemcpyHostToDevice, s->stream));
+  CUDA_TRY(cudaMemcpyAsync(s->i16.dev, s->i16.host, sizeof(int16_t) * cnt * 3, cudaMemcpyHostToDevice, s->stream));
+  CUDA_TRY(cudaMemcpyAsync(s->f64.dev, s->f64.host, sizeof(double) * cnt, cudaMemcpyHostToDevice, s->stream));
+  k_set_trees<<<(unsigned)((cnt + 255) / 256), 256, 0, s->stream>>>(d, s->ids.dev, s->i16.dev, s->f64.dev, s->seg.dev, nLoci);
+  g_launches++;
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaStreamSynchronize(s->stream));  // the staging buffers are reused by the next call
   return 0;
 }
 
@@ -374,9 +395,9 @@ extern "C" int gphocsStoreGetTrees(GphocsStore* s, int nLoci, const int* locusId
     if (l < 0 || l >= s->L) return -1;
     const size_t o = (size_t)l * N, out = (size_t)k * N;
     for (int i = 0; i < N; i++) {
-      father[out + i] = s->hFather[o + i];
-      left[out + i] = s->hLeft[o + i];
-      right[out + i] = s->hRight[o + i];
+      father[out + i] = s->hNode[o + i].father;
+      left[out + i] = s->hNode[o + i].left;
+      right[out + i] = s->hNode[o + i].right;
       age[out + i] = s->hAge[o + i];
     }
     root[k] = s->hRoot[l];
@@ -453,10 +474,10 @@ static int launchEval(GphocsStore* s, int useOld, int onlyLocus, bool masked) {
   if (onlyLocus >= 0) {
     const int b = s->locusBatch[onlyLocus];
     if (b < 0) return 0;
-    k_eval<<<1, kThreads, s->smemBytes, s->stream>>>(d, s->dBatches, b, useOld, onlyLocus);
+    k_eval<<<1, kThreads, s->smemBytes, s->stream>>>(d, s->dBatches, b, useOld, onlyLocus, s->maxBatchLoci);
     g_launches++;
   } else if (s->numBatches > 0) {
-    k_eval<<<s->numBatches, kThreads, s->smemBytes, s->stream>>>(d, s->dBatches, 0, useOld, -1);
+    k_eval<<<s->numBatches, kThreads, s->smemBytes, s->stream>>>(d, s->dBatches, 0, useOld, -1, s->maxBatchLoci);
     g_launches++;
   }
   CUDA_TRY(cudaGetLastError());
@@ -511,15 +532,15 @@ static void replayFlipsOnMirror(GphocsStore* s, int l, int useOld) {
     return;
   }
   for (int i = 0; i < N; i++) {
-    if (!(t.flags[i] & F_RECALC) || (t.flags[i] & 0x80)) continue;
-    int u = i < n ? t.father[i] : i;
-    while (u >= 0 && !(t.flags[u] & 0x80)) {  // 0x80: visited in this replay
+    if (!(t.node[i].flags & F_RECALC) || (t.node[i].flags & 0x80)) continue;
+    int u = i < n ? t.node[i].father : i;
+    while (u >= 0 && !(t.node[u].flags & 0x80)) {  // 0x80: visited in this replay
       flipClv(t, u);
-      t.flags[u] |= 0x80;
-      u = t.father[u];
+      t.node[u].flags |= 0x80;
+      u = t.node[u].father;
     }
   }
-  for (int i = 0; i < N; i++) t.flags[i] &= 0x7f;
+  for (int i = 0; i < N; i++) t.node[i].flags &= 0x7f;
 }
 
 extern "C" int gphocsStoreEvaluate(GphocsStore* s, int nLoci, const int* locusIds, int useOld, double* outLnL,
@@ -581,15 +602,11 @@ extern "C" int gphocsStoreCheckMirror(GphocsStore* s) {
   cudaSetDevice(s->device);
   CUDA_TRY(cudaStreamSynchronize(s->stream));
   const size_t LN = (size_t)s->L * s->N;
-  std::vector<int16_t> f(LN), l(LN), r(LN);
+  std::vector<NodeRec> nd(LN);
   std::vector<double> a(LN), lnl(s->L), sv(s->L), rate(s->L);
-  std::vector<uint8_t> fl(LN);
   std::vector<int> root(s->L), sroot(s->L);
-  CUDA_TRY(cudaMemcpy(f.data(), s->d.father, LN * 2, cudaMemcpyDeviceToHost));
-  CUDA_TRY(cudaMemcpy(l.data(), s->d.left, LN * 2, cudaMemcpyDeviceToHost));
-  CUDA_TRY(cudaMemcpy(r.data(), s->d.right, LN * 2, cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(nd.data(), s->d.node, LN * sizeof(NodeRec), cudaMemcpyDeviceToHost));
   CUDA_TRY(cudaMemcpy(a.data(), s->d.age, LN * 8, cudaMemcpyDeviceToHost));
-  CUDA_TRY(cudaMemcpy(fl.data(), s->d.flags, LN, cudaMemcpyDeviceToHost));
   CUDA_TRY(cudaMemcpy(root.data(), s->d.root, (size_t)s->L * 4, cudaMemcpyDeviceToHost));
   CUDA_TRY(cudaMemcpy(sroot.data(), s->d.savedRoot, (size_t)s->L * 4, cudaMemcpyDeviceToHost));
   CUDA_TRY(cudaMemcpy(lnl.data(), s->d.lnL, (size_t)s->L * 8, cudaMemcpyDeviceToHost));
@@ -598,11 +615,11 @@ extern "C" int gphocsStoreCheckMirror(GphocsStore* s) {
   int bad = 0;
   const uint8_t mask = s->debugMirror ? (F_SEL | F_RECALC | F_SAVED) : F_SAVED;
   for (size_t i = 0; i < LN; i++) {
-    bad += f[i] != s->hFather[i];
-    bad += l[i] != s->hLeft[i];
-    bad += r[i] != s->hRight[i];
+    bad += nd[i].father != s->hNode[i].father;
+    bad += nd[i].left != s->hNode[i].left;
+    bad += nd[i].right != s->hNode[i].right;
     bad += a[i] != s->hAge[i];
-    bad += (fl[i] & mask) != (s->hFlags[i] & mask);
+    bad += (nd[i].flags & mask) != (s->hNode[i].flags & mask);
   }
   for (int i = 0; i < s->L; i++) {
     bad += root[i] != s->hRoot[i];
@@ -644,10 +661,10 @@ extern "C" int gphocsStoreGetClv(GphocsStore* s, int locus, int node, int saved,
     }
     return 0;
   }
-  uint8_t f;
+  NodeRec rec;
   CUDA_TRY(cudaStreamSynchronize(s->stream));
-  CUDA_TRY(cudaMemcpy(&f, s->d.flags + (size_t)locus * s->N + node, 1, cudaMemcpyDeviceToHost));
-  const int buf = (f & F_SEL) ^ (saved ? 1 : 0);
+  CUDA_TRY(cudaMemcpy(&rec, s->d.node + (size_t)locus * s->N + node, sizeof(NodeRec), cudaMemcpyDeviceToHost));
+  const int buf = (rec.flags & F_SEL) ^ (saved ? 1 : 0);
   const double* src = s->d.clv + (size_t)s->colStart[locus] * s->NI * 8 + (size_t)((node - s->n) * 2 + buf) * P * 4;
   CUDA_TRY(cudaMemcpy(out, src, sizeof(double) * P * 4, cudaMemcpyDeviceToHost));
   return 0;

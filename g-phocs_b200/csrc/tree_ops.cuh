@@ -40,12 +40,18 @@ struct Op {
   double x;
 };
 
-// View over one locus' slice of the structure-of-arrays genealogy store.
+// One genealogy node: topology + flag byte in a single 8-byte record (one load per node on the device).
+struct NodeRec {
+  int16_t father, left, right;
+  uint8_t flags;
+  uint8_t pad;
+};
+
+// View over one locus' slice of the genealogy store.
 struct TreeView {
-  int16_t *father, *left, *right;        // current
-  int16_t *svFather, *svLeft, *svRight;  // saved
+  NodeRec *node;   // current [2n-1]
+  NodeRec *saved;  // saved copies (their flag bytes are unused)
   double *age, *svAge;
-  uint8_t *flags;
   int *root, *savedRoot;
   double *lnL, *savedLnL, *rate;
   int numLeaves;
@@ -54,18 +60,16 @@ struct TreeView {
 
 // copyNodeConditionals (.c:1889-1906)
 GP_HD void flipClv(const TreeView& t, int node) {
-  if (t.numPatterns <= 0 || (t.flags[node] & F_RECALC)) return;
-  t.flags[node] = (uint8_t)((t.flags[node] ^ F_SEL) | F_RECALC);
+  if (t.numPatterns <= 0 || (t.node[node].flags & F_RECALC)) return;
+  t.node[node].flags = (uint8_t)((t.node[node].flags ^ F_SEL) | F_RECALC);
 }
 
 // copyNodeToSaved (.c:1864-1876)
 GP_HD void saveNode(const TreeView& t, int node, bool recalc) {
   if (recalc) flipClv(t, node);
-  t.flags[node] |= F_SAVED;
+  t.node[node].flags |= F_SAVED;
   t.svAge[node] = t.age[node];
-  t.svFather[node] = t.father[node];
-  t.svLeft[node] = t.left[node];
-  t.svRight[node] = t.right[node];
+  t.saved[node] = t.node[node];
 }
 
 GP_HD void adjustAge(const TreeView& t, int node, double age) {
@@ -80,24 +84,25 @@ GP_HD void scaleAll(const TreeView& t, double factor) {
 
 // executeGenSPR (.c:931-1012)
 GP_HD int spr(const TreeView& t, int sub, int target, double age) {
-  const int targetFather = t.father[target];
-  const int father = t.father[sub];
-  const int grandpa = t.father[father];
-  const int sibling = t.left[father] + t.right[father] - sub;
+  NodeRec* nd = t.node;
+  const int targetFather = nd[target].father;
+  const int father = nd[sub].father;
+  const int grandpa = nd[father].father;
+  const int sibling = nd[father].left + nd[father].right - sub;
   adjustAge(t, father, age);
   if (target == sibling || target == father) return 0;
   saveNode(t, sibling, false);
-  t.father[sibling] = (int16_t)grandpa;
+  nd[sibling].father = (int16_t)grandpa;
   if (grandpa >= 0) {
     saveNode(t, grandpa, true);
-    if (t.left[grandpa] == father) t.left[grandpa] = (int16_t)sibling;
-    else t.right[grandpa] = (int16_t)sibling;
+    if (nd[grandpa].left == father) nd[grandpa].left = (int16_t)sibling;
+    else nd[grandpa].right = (int16_t)sibling;
   }
-  t.father[father] = (int16_t)targetFather;
-  t.left[father] = (int16_t)sub;
-  t.right[father] = (int16_t)target;
+  nd[father].father = (int16_t)targetFather;
+  nd[father].left = (int16_t)sub;
+  nd[father].right = (int16_t)target;
   if (target != grandpa) saveNode(t, target, false);
-  t.father[target] = (int16_t)father;
+  nd[target].father = (int16_t)father;
   if (targetFather < 0) {
     *t.savedRoot = target;
     *t.root = father;
@@ -105,8 +110,8 @@ GP_HD int spr(const TreeView& t, int sub, int target, double age) {
   }
   if (targetFather == sibling) flipClv(t, targetFather);
   else if (targetFather != grandpa) saveNode(t, targetFather, true);
-  if (t.left[targetFather] == target) t.left[targetFather] = (int16_t)father;
-  else t.right[targetFather] = (int16_t)father;
+  if (nd[targetFather].left == target) nd[targetFather].left = (int16_t)father;
+  else nd[targetFather].right = (int16_t)father;
   if (grandpa < 0) {
     *t.savedRoot = father;
     *t.root = sibling;
@@ -118,7 +123,7 @@ GP_HD int spr(const TreeView& t, int sub, int target, double age) {
 // resetSaved (.c:852-864)
 GP_HD void commit(const TreeView& t) {
   const int N = 2 * t.numLeaves - 1;
-  for (int i = 0; i < N; i++) t.flags[i] &= F_SEL;
+  for (int i = 0; i < N; i++) t.node[i].flags &= F_SEL;
   *t.savedRoot = -1;
   *t.savedLnL = *t.lnL;
 }
@@ -133,15 +138,15 @@ GP_HD void revert(const TreeView& t) {
     *t.savedRoot = -1;
   }
   for (int i = 0; i < N; i++) {
-    uint8_t f = t.flags[i];
+    NodeRec r = t.node[i];
+    uint8_t f = r.flags;
     if (f & F_SAVED) {
       t.age[i] = t.svAge[i];
-      t.father[i] = t.svFather[i];
-      t.left[i] = t.svLeft[i];
-      t.right[i] = t.svRight[i];
+      r = t.saved[i];
     }
     if (f & F_RECALC) f ^= F_SEL;
-    t.flags[i] = f & F_SEL;
+    r.flags = f & F_SEL;
+    t.node[i] = r;
   }
 }
 
