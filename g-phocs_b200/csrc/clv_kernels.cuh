@@ -168,6 +168,7 @@ __device__ __forceinline__ void stsD2(uint32_t a, double x, double y) {
   asm volatile("st.shared.v2.f64 [%0], {%1,%2};" ::"r"(a), "d"(x), "d"(y) : "memory");
 }
 
+__device__ __forceinline__ void prefetchL2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ uint32_t ldsU32(uint32_t a) {
   uint32_t v;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
@@ -193,7 +194,8 @@ __device__ __forceinline__ void missingSubtree(const double (&a)[4], const doubl
 }
 
 __global__ void __launch_bounds__(kThreads)
-k_eval(StoreDev d, const Batch* __restrict__ batches, int batchBase, int useOld, int onlyLocus, int maxLoci) {
+k_eval(StoreDev d, const Batch* __restrict__ batches, int batchBase, int useOld, int onlyLocus, int maxLoci,
+       int prefetchAhead) {
   extern __shared__ __align__(16) unsigned char smem[];
   const Batch b = batches[batchBase + blockIdx.x];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -261,6 +263,28 @@ k_eval(StoreDev d, const Batch* __restrict__ batches, int batchBase, int useOld,
     }
   }
   __syncthreads();
+  // Pull the inputs of the batch that the CTA taking this one's place will own into L2 (128-byte lines,
+  // spread over the CTA), so that CTA does not start with a chain of HBM round trips.
+  if (prefetchAhead > 0 && onlyLocus < 0 && (int)blockIdx.x + prefetchAhead < (int)gridDim.x) {
+    const Batch ahead = batches[batchBase + blockIdx.x + prefetchAhead];   // in L2: prefetched by an earlier CTA
+    if (tid == 0) prefetchL2(batches + batchBase + blockIdx.x + 2 * prefetchAhead);
+    const char* p0 = reinterpret_cast<const char*>(d.node + (size_t)ahead.firstLocus * N);
+    const char* p1 = reinterpret_cast<const char*>(d.age + (size_t)ahead.firstLocus * N);
+    const int recBytes = ahead.numLoci * N * 8;
+    for (int o = tid * 128; o < recBytes; o += kThreads * 128) { prefetchL2(p0 + o); prefetchL2(p1 + o); }
+    const int cols = min(ahead.numCols, kThreads);
+    if (tid * 16 < cols) {   // 16 columns of 8 bytes per line
+      for (int w = 0; w < d.W; w++) prefetchL2(d.leafWords + (size_t)w * d.Ct + ahead.firstCol + tid * 16);
+    }
+    if (tid * 32 < cols) {   // 32 columns of 4 bytes per line
+      prefetchL2(d.grpPhases + ahead.firstCol + tid * 32);
+      prefetchL2(d.grpCount + ahead.firstCol + tid * 32);
+    }
+    if (tid == 0) {
+      prefetchL2(d.colStart + ahead.firstLocus); prefetchL2(d.root + ahead.firstLocus);
+      prefetchL2(d.rate + ahead.firstLocus); prefetchL2(d.lnL + ahead.firstLocus);
+    }
+  }
   // ---- phase B: mark dirty nodes and their ancestors (computeConditionalJC_new's recursion condition, .c:1583)
   for (int s = warp; s < nl; s += kWarps) {
     if (!mActive[s]) continue;
@@ -490,20 +514,27 @@ k_eval(StoreDev d, const Batch* __restrict__ batches, int batchBase, int useOld,
     }
     sTerm[tid] = term;  // 0.0 for the other members of a phase group: adding it below is exact
     __syncthreads();
-    if (tid < nl && mActive[tid] && mK[tid] > 0) {
-      const int P = mP[tid];
-      const double* t = sTerm + (mColStart[tid] - b.firstCol);
+    if (warp == 0) {
+      // per-locus sums in pattern order, then the CTA's partial sum in locus order (both fixed, deterministic)
       double lnl = 0.0;
-      for (int j = 0; j < P; j++) lnl += t[j];
-      d.lnL[b.firstLocus + tid] = lnl;
-      mLnL[tid] = lnl;
-    }
-    __syncthreads();
-    if (tid == 0) {
+      const bool mine = lane < nl && mActive[lane];
+      if (mine) {
+        lnl = mLnL[lane];
+        if (mK[lane] > 0) {
+          const int P = mP[lane];
+          const double* t = sTerm + (mColStart[lane] - b.firstCol);
+          lnl = 0.0;
+          for (int j = 0; j < P; j++) lnl += t[j];
+          d.lnL[b.firstLocus + lane] = lnl;
+        }
+      }
       double sum = 0.0;
-      for (int j = 0; j < nl; j++)
-        if (mActive[j]) sum += mLnL[j];
-      d.ctaSum[batchBase + blockIdx.x] = sum;
+      for (int j = 0; j < nl; j++) {
+        const double x = __shfl_sync(0xffffffffu, lnl, j);
+        const int on = __shfl_sync(0xffffffffu, (int)mine, j);
+        if (on) sum += x;
+      }
+      if (lane == 0) d.ctaSum[batchBase + blockIdx.x] = sum;
     }
   } else {
     // oversized locus: groups may straddle chunks; reduce from scratch with a fixed-order block tree

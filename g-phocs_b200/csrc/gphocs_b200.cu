@@ -81,6 +81,7 @@ struct GphocsStore {
   double* dSum = nullptr;
   int numBatches = 0;
   int maxBatchLoci = 1;  // most loci any CTA batch holds (sizes the kernel's shared memory)
+  int prefetchAhead = 0; // CTAs resident on the whole GPU at once = how far ahead a CTA prefetches into L2
   size_t smemBytes = 0;
   std::vector<Batch> batches;
   std::vector<int> locusBatch;  // batch index holding each locus (-1: no columns)
@@ -275,6 +276,12 @@ extern "C" GphocsStore* gphocsStoreCreate(int device, int numLoci, int numLeaves
     fprintf(stderr, "gphocs_b200: device initialisation failed: %s\n", cudaGetErrorString(cudaGetLastError()));
     delete s;
     return nullptr;
+  }
+  {
+    int perSm = 0, sms = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_eval, kThreads, s->smemBytes);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    s->prefetchAhead = std::max(1, perSm) * std::max(1, sms);
   }
   // ---- host mirror
   s->hNode.assign(LN, NodeRec{-1, -1, -1, 0, 0}); s->hsNode.assign(LN, NodeRec{-1, -1, -1, 0, 0});
@@ -474,10 +481,10 @@ static int launchEval(GphocsStore* s, int useOld, int onlyLocus, bool masked) {
   if (onlyLocus >= 0) {
     const int b = s->locusBatch[onlyLocus];
     if (b < 0) return 0;
-    k_eval<<<1, kThreads, s->smemBytes, s->stream>>>(d, s->dBatches, b, useOld, onlyLocus, s->maxBatchLoci);
+    k_eval<<<1, kThreads, s->smemBytes, s->stream>>>(d, s->dBatches, b, useOld, onlyLocus, s->maxBatchLoci, 0);
     g_launches++;
   } else if (s->numBatches > 0) {
-    k_eval<<<s->numBatches, kThreads, s->smemBytes, s->stream>>>(d, s->dBatches, 0, useOld, -1, s->maxBatchLoci);
+    k_eval<<<s->numBatches, kThreads, s->smemBytes, s->stream>>>(d, s->dBatches, 0, useOld, -1, s->maxBatchLoci, s->prefetchAhead);
     g_launches++;
   }
   CUDA_TRY(cudaGetLastError());

@@ -41,7 +41,7 @@ struct Op {
 };
 
 // One genealogy node: topology + flag byte in a single 8-byte record (one load per node on the device).
-struct NodeRec {
+struct alignas(8) NodeRec {
   int16_t father, left, right;
   uint8_t flags;
   uint8_t pad;
