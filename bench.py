@@ -41,6 +41,12 @@ def algorithmic_bytes_data(n, P):
     return 32.0 * P * (2 * n - 1) + 24.0 * (2 * n - 1) + 8.0 * P + 8.0
 
 
+def layout_bytes_data(n, P):
+    """What this layout must move per full evaluation of one locus: internal vectors written once (32*P*(n-1));
+    leaf masks (8 B per 16 leaves per column), phase/count words, node records + ages, lnL/savedLnL read or written."""
+    return 32.0 * P * (n - 1) + 8.0 * P * ((n + 15) // 16) + 8.0 * P + 16.0 * (2 * n - 1) + 24.0
+
+
 def algorithmic_bytes_gen(E, Q, B):
     """bytes_gen = 32*E + 16*(Q+B) + 8 per locus."""
     return 32.0 * E + 16.0 * (Q + B) + 8.0
@@ -132,12 +138,15 @@ def reference_sample(cfg, sample_loci, seed, reps, threads, quiet=True):
     lib.refh_set_threads(threads)
     times = []
     sd, sg = C.c_double(), C.c_double()
+    # bounded sample: passes per step sized from two calibration passes so that the whole run is ~20 s of CPU work
+    t_pass = min(lib.refh_time_both_once(C.byref(sd), C.byref(sg)) for _ in range(2))
+    passes = int(max(1, min(PASSES_PER_STEP, round(20.0 / max(reps * t_pass, 1e-9)))))
     for _ in range(reps):
         t = 0.0
-        for _p in range(PASSES_PER_STEP):
+        for _p in range(passes):
             t += lib.refh_time_both_once(C.byref(sd), C.byref(sg))
         times.append(t)
-    return times, lib.refh_num_loci() * PASSES_PER_STEP, sd.value, sg.value
+    return times, lib.refh_num_loci() * passes, sd.value, sg.value, passes
 
 
 def port_sample(cfg, sample_loci, seed, reps):
@@ -161,7 +170,7 @@ def port_sample(cfg, sample_loci, seed, reps):
             e0, e1 = int(w.ev_start[l]), int(w.ev_start[l + 1])
             ob.oracle_gen_locus(pt, w.pop_start[l], w.ev_type[e0:e1], w.ev_id[e0:e1], w.ev_time[e0:e1])
         times.append(time.perf_counter() - t0)
-    return times, w.L, 0.0, 0.0
+    return times, w.L, 0.0, 0.0, 1
 
 
 def cpu_baseline_subprocess(cfg, sample_loci, reps):
@@ -188,15 +197,15 @@ def run_reference(args):
     t_all0 = time.perf_counter()
     if ob.have_ref():
         kind = "reference"
-        times, L, sd, sg = reference_sample(args.config, args.sample_loci, 4242, args.steps + args.warmup, threads)
+        times, L, sd, sg, passes = reference_sample(args.config, args.sample_loci, 4242, args.steps + args.warmup, threads)
     else:
         kind, threads = "port", 1
-        times, L, sd, sg = port_sample(args.config, min(args.sample_loci, 500), 4242, args.steps + args.warmup)
+        times, L, sd, sg, passes = port_sample(args.config, min(args.sample_loci, 500), 4242, args.steps + args.warmup)
     timed = times[args.warmup:]
     total = float(sum(timed))
     value = L * len(timed) / total
-    sample = (f"{L // PASSES_PER_STEP if kind == 'reference' else L} loci of workload {args.config} (same generator, seed 4242), "
-              f"{len(timed)} steps x {PASSES_PER_STEP if kind == 'reference' else 1} passes of "
+    sample = (f"{L // passes} loci of workload {args.config} (same generator, seed 4242), "
+              f"{len(timed)} steps x {passes} passes of "
               f"computeLocusDataLikelihood(locus,0)+resetSaved and computeGenetreeStats+gtreeLnLikelihood over all loci, "
               f"OpenMP static schedule, {threads} threads; wall {time.perf_counter() - t_all0:.1f}s incl. ingest")
     cb = {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample}
@@ -225,6 +234,7 @@ def run_b200(args):
     import torch.distributed as dist
     gp = importlib.import_module("g-phocs_b200")
     synth = importlib.import_module("g-phocs_b200.synth")
+    shard = importlib.import_module("g-phocs_b200.shard")
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -248,6 +258,7 @@ def run_b200(args):
     E = np.diff(w.ev_start).astype(np.float64)
     bytes_data = float(algorithmic_bytes_data(n, P).sum())
     bytes_gen = float(algorithmic_bytes_gen(E, Q, B).sum())
+    bytes_layout = float(layout_bytes_data(n, P).sum())
 
     stream = torch.cuda.Stream(device=dev)
     st = gp.LociStore.from_workload(w, device=local_rank, stream=stream.cuda_stream)
@@ -255,6 +266,7 @@ def run_b200(args):
     gen.set_events(w.ev_start, w.pop_start, w.ev_type, w.ev_id, w.ev_time)
     lib = gp.lib()
     V = 1 + 2 * Q + 2 * B
+    assert 1 + V == shard.payload_len(Q, B)
     payload = torch.zeros(1 + V, dtype=torch.float64, device=dev)   # [sum data lnL | sum gen lnL, totals...]
 
     def step(record=None):
@@ -271,8 +283,7 @@ def run_b200(args):
                 record.append((e0, e1, e2))
             lib.gphocsCopyDeviceAsync(C.c_void_p(payload.data_ptr()), C.c_void_p(dsum), 8, C.c_void_p(stream.cuda_stream))
             lib.gphocsCopyDeviceAsync(C.c_void_p(payload.data_ptr() + 8), C.c_void_p(dtot), 8 * V, C.c_void_p(stream.cuda_stream))
-            if world > 1:
-                dist.all_reduce(payload)          # the only cross-GPU traffic: < 1 KB per step
+            shard.all_reduce_payload(payload)     # the only cross-GPU traffic: < 1 KB per step
 
     def barrier():
         if world > 1:
@@ -298,7 +309,6 @@ def run_b200(args):
         t_end.record(stream)
     barrier()
     launches = lib.gphocsKernelLaunchCount() - launches0
-    clocks = sampler.stop() if rank == 0 else None
     ms_total = t_start.elapsed_time(t_end)
     ms_data = sum(a.elapsed_time(b) for a, b, _ in rec) / len(rec)
     ms_gen = sum(b.elapsed_time(c) for _, b, c in rec) / len(rec)
@@ -310,15 +320,19 @@ def run_b200(args):
 
     # ---- e2e: the same pass through the C ABI with HOST buffers (H2D of genealogies + event snapshots, D2H of
     # per-locus log-likelihoods and totals inside the timed region)
-    lnl_host = np.zeros(L)
-    e2e_steps = max(3, min(args.steps, 10))
-    h2d = L * w.father.shape[1] * (3 * 2 + 8) + 4 * L + int(E.sum()) * 10 + L * (Q + 1) * 2 + 4 * (L + 1)
+    lnl_host = gp.pinned_like(np.zeros(L))
+    hw = {k: gp.pinned_like(getattr(w, k)) for k in ("father", "left", "right", "age", "root", "ev_start", "pop_start",
+                                                       "ev_type", "ev_id", "ev_time")}   # inputs in page-locked host memory
+    e2e_steps = max(3, min(args.steps, 20))
+    # bytes that cross PCIe per step, counted from the buffers the library copies: int16 topology + fp64 ages +
+    # roots + locus ids; 10 bytes per event + chain offsets; back: per-locus data lnL + its sum, genealogy lnL + totals
+    h2d = L * w.father.shape[1] * (3 * 2 + 8) + 8 * L + int(E.sum()) * 10 + L * (Q + 1) * 2 + 4 * (L + 1)
     d2h = 8 * L + 8 + 8 * L + 8 * V
 
     def e2e_step():
-        st.set_trees(w.father, w.left, w.right, w.age, w.root)
+        st.set_trees(hw["father"], hw["left"], hw["right"], hw["age"], hw["root"])
         _, sdata = st.evaluate(0, want_sum=True, out=lnl_host)
-        gen.set_events(w.ev_start, w.pop_start, w.ev_type, w.ev_id, w.ev_time)
+        gen.set_events(hw["ev_start"], hw["pop_start"], hw["ev_type"], hw["ev_id"], hw["ev_time"])
         r = gen.evaluate(per_locus_stats=False)
         return sdata, r["sum_lnl"]
 
@@ -356,6 +370,7 @@ def run_b200(args):
     torch.cuda.synchronize()
     inc_ms = a.elapsed_time(b)
     st.apply_ops(rej)
+    clocks = sampler.stop() if rank == 0 else None
 
     if rank == 0:
         peak, peak_src = measured_peak()
@@ -365,7 +380,7 @@ def run_b200(args):
         if os.path.exists(tp):
             tj = json.load(open(tp))
             if tj.get("workload") == f"{args.config}:{L}":
-                traffic = tj.get("k_eval_dram_bytes_per_launch")
+                traffic = tj.get("k_eval_dram_bytes_per_launch")   # ncu --set full: dram__bytes_read.sum + dram__bytes_write.sum
         value = world * L * args.steps / (ms_total * 1e-3)
         cb = cpu_baseline_subprocess(args.config, args.sample_loci, 3) if (world == 1 and not args.no_cpu_baseline) else None
         line = {
@@ -379,6 +394,11 @@ def run_b200(args):
             "roofline": {"bound": "hbm", "kernel": "k_eval (full data-likelihood evaluation, all loci)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_data,
+                         "algorithmic_bytes_formula": "SURVEY.md 8d: 32*P*(2n-1) + 24*(2n-1) + 8*P + 8 per locus, summed over loci",
+                         "layout_min_bytes_per_launch": bytes_layout,
+                         "frac_of_layout_min": bytes_layout / (ms_data * 1e-3) / 1e9 / peak,
+                         "note": "leaves are stored as 4-bit masks, not fp64 vectors, so the layout moves fewer bytes than "
+                                 "the survey formula counts; frac uses the formula, frac_of_layout_min the bytes this layout must move",
                          "ms_per_launch": ms_data, "genealogy_kernel_ms": ms_gen,
                          "genealogy_achieved_gbs": bytes_gen / (ms_gen * 1e-3) / 1e9},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
@@ -403,7 +423,7 @@ def run_b200(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=500)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="pop6mig4")

@@ -93,6 +93,8 @@ def lib():
         "gphocsStoreCheckMirror": (ci, [vp]),
         "gphocsKernelLaunchCount": (C.c_longlong, []),
         "gphocsCopyDeviceAsync": (ci, [vp, vp, C.c_longlong, vp]),
+        "gphocsHostAlloc": (vp, [C.c_longlong]),
+        "gphocsHostFree": (ci, [vp]),
         # C. genealogy likelihood
         "gphocsGenCreate": (vp, [ci, ci, ci, ci, ci, c_int_p, c_int_p, c_int_p, c_int_p]),
         "gphocsGenDestroy": (ci, [vp]),
@@ -242,6 +244,32 @@ class LociStore:
     @property
     def device_bytes(self):
         return self.lib.gphocsStoreDeviceBytes(self.h)
+
+
+def pinned_like(a):
+    """Copy of array `a` in page-locked host memory (gphocsHostAlloc); keeps the allocation alive with the array."""
+    a = np.ascontiguousarray(a)
+    if a.nbytes == 0:
+        return a
+    L = lib()
+    p = L.gphocsHostAlloc(a.nbytes)
+    if not p:
+        raise MemoryError("gphocsHostAlloc failed")
+    buf = (C.c_char * a.nbytes).from_address(p)
+    out = np.frombuffer(buf, dtype=a.dtype).reshape(a.shape)
+    out[...] = a
+    _PINNED.append((p, buf))
+    return out
+
+
+_PINNED = []
+
+
+def free_pinned():
+    L = lib()
+    while _PINNED:
+        p, _ = _PINNED.pop()
+        L.gphocsHostFree(C.c_void_p(p))
 
 
 def make_ops(locus, type_, a=0, b=0, x=0.0):

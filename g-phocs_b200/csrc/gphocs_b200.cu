@@ -327,6 +327,19 @@ extern "C" int gphocsCopyDeviceAsync(void* dst, const void* src, long long bytes
   CUDA_TRY(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)cudaStream));
   return 0;
 }
+// page-locked host memory for callers that want their input/output arrays to move at full PCIe speed
+extern "C" void* gphocsHostAlloc(long long bytes) {
+  void* p = nullptr;
+  if (bytes <= 0 || cudaMallocHost(&p, (size_t)bytes) != cudaSuccess) {
+    fprintf(stderr, "gphocs_b200: cannot allocate %lld bytes of page-locked host memory\n", bytes);
+    return nullptr;
+  }
+  return p;
+}
+extern "C" int gphocsHostFree(void* p) {
+  if (p) CUDA_TRY(cudaFreeHost(p));
+  return 0;
+}
 extern "C" int gphocsStoreSync(GphocsStore* s) {
   cudaSetDevice(s->device);
   CUDA_TRY(cudaStreamSynchronize(s->stream));
@@ -338,48 +351,42 @@ static int setTreesLocked(GphocsStore* s, int nLoci, const int* locusIds, const 
                           const int* right, const double* age, const int* root) {
   const int N = s->N;
   cudaSetDevice(s->device);
-  for (int k = 0; k < nLoci; k++) {
-    const int l = locusIds ? locusIds[k] : k;
-    if (l < 0 || l >= s->L) { fprintf(stderr, "gphocs_b200: locus %d out of range\n", l); return -1; }
-  }
-#pragma omp parallel for schedule(static)
-  for (int k = 0; k < nLoci; k++) {
-    const int l = locusIds ? locusIds[k] : k;
-    const size_t o = (size_t)l * N, in = (size_t)k * N;
-    for (int i = 0; i < N; i++) {
-      NodeRec& r = s->hNode[o + i];   // flag bits (buffer selectors) are kept
-      r.father = (int16_t)father[in + i];
-      r.left = (int16_t)left[in + i];
-      r.right = (int16_t)right[in + i];
-      s->hAge[o + i] = age[in + i];
-    }
-    s->hRoot[l] = root[k];
-  }
-  // the device keeps the authoritative flag bytes: only topology fields are overwritten there
-  if (s->i16.reserve((size_t)nLoci * N * 3) || s->ids.reserve(nLoci)) return -1;
-#pragma omp parallel for schedule(static)
-  for (int k = 0; k < nLoci; k++) {
-    const int l = locusIds ? locusIds[k] : k;
-    s->ids.host[k] = l;
-    for (int i = 0; i < N; i++) {
-      const NodeRec& r = s->hNode[(size_t)l * N + i];
-      int16_t* o3 = s->i16.host + ((size_t)k * N + i) * 3;
-      o3[0] = r.father; o3[1] = r.left; o3[2] = r.right;
-    }
-  }
-  StoreDev& d = s->d;
+  if (nLoci <= 0) return 0;
+  if (locusIds)
+    for (int k = 0; k < nLoci; k++)
+      if (locusIds[k] < 0 || locusIds[k] >= s->L) { fprintf(stderr, "gphocs_b200: locus %d out of range\n", locusIds[k]); return -1; }
+  if (!locusIds && nLoci > s->L) { fprintf(stderr, "gphocs_b200: %d genealogies for %d loci\n", nLoci, s->L); return -1; }
   const size_t cnt = (size_t)nLoci * N;
-  if (s->f64.reserve(cnt) || s->seg.reserve(nLoci)) return -1;
+  if (s->i16.reserve(cnt * 3) || s->f64.reserve(cnt) || s->ids.reserve(nLoci) || s->seg.reserve(nLoci)) return -1;
+  StoreDev& d = s->d;
+  // Loci are converted in chunks by all host threads straight into page-locked staging (int16 topology, fp64 ages,
+  // roots, ids) and each chunk's copies are enqueued at once, so PCIe transfers overlap the conversion of the next
+  // chunk.  The host mirror is updated in the same pass; flag bytes (buffer selectors) are kept on both sides.
+  const int numChunks = nLoci >= 8192 ? 8 : 1;
+  for (int c = 0; c < numChunks; c++) {
+    const int k0 = (int)((long long)nLoci * c / numChunks), k1 = (int)((long long)nLoci * (c + 1) / numChunks);
 #pragma omp parallel for schedule(static)
-  for (int k = 0; k < nLoci; k++) {
-    const int l = s->ids.host[k];
-    memcpy(s->f64.host + (size_t)k * N, s->hAge.data() + (size_t)l * N, sizeof(double) * N);
-    s->seg.host[k] = s->hRoot[l];
+    for (int k = k0; k < k1; k++) {
+      const int l = locusIds ? locusIds[k] : k;
+      const size_t o = (size_t)l * N, in = (size_t)k * N;
+      int16_t* o3 = s->i16.host + in * 3;
+      double* oa = s->f64.host + in;
+      for (int i = 0; i < N; i++) {
+        NodeRec& r = s->hNode[o + i];
+        r.father = o3[3 * i] = (int16_t)father[in + i];
+        r.left = o3[3 * i + 1] = (int16_t)left[in + i];
+        r.right = o3[3 * i + 2] = (int16_t)right[in + i];
+        s->hAge[o + i] = oa[i] = age[in + i];
+      }
+      s->hRoot[l] = s->seg.host[k] = root[k];
+      s->ids.host[k] = l;
+    }
+    const size_t n0 = (size_t)k0 * N, nn = (size_t)(k1 - k0) * N;
+    CUDA_TRY(cudaMemcpyAsync(s->ids.dev + k0, s->ids.host + k0, sizeof(int) * (k1 - k0), cudaMemcpyHostToDevice, s->stream));
+    CUDA_TRY(cudaMemcpyAsync(s->seg.dev + k0, s->seg.host + k0, sizeof(int) * (k1 - k0), cudaMemcpyHostToDevice, s->stream));
+    CUDA_TRY(cudaMemcpyAsync(s->i16.dev + n0 * 3, s->i16.host + n0 * 3, sizeof(int16_t) * nn * 3, cudaMemcpyHostToDevice, s->stream));
+    CUDA_TRY(cudaMemcpyAsync(s->f64.dev + n0, s->f64.host + n0, sizeof(double) * nn, cudaMemcpyHostToDevice, s->stream));
   }
-  CUDA_TRY(cudaMemcpyAsync(s->ids.dev, s->ids.host, sizeof(int) * nLoci, cudaMemcpyHostToDevice, s->stream));
-  CUDA_TRY(cudaMemcpyAsync(s->seg.dev, s->seg.host, sizeof(int) * nLoci, cudaMemcpyHostToDevice, s->stream));
-  CUDA_TRY(cudaMemcpyAsync(s->i16.dev, s->i16.host, sizeof(int16_t) * cnt * 3, cudaMemcpyHostToDevice, s->stream));
-  CUDA_TRY(cudaMemcpyAsync(s->f64.dev, s->f64.host, sizeof(double) * cnt, cudaMemcpyHostToDevice, s->stream));
   k_set_trees<<<(unsigned)((cnt + 255) / 256), 256, 0, s->stream>>>(d, s->ids.dev, s->i16.dev, s->f64.dev, s->seg.dev, nLoci);
   g_launches++;
   CUDA_TRY(cudaGetLastError());
@@ -413,36 +420,62 @@ extern "C" int gphocsStoreGetTrees(GphocsStore* s, int nLoci, const int* locusId
 }
 
 // ---- edits
-static int launchOps(GphocsStore* s, const Op* ops, int nOps, int* outStatus) {
+// Ships edit records to the device (grouped by locus, call order kept within a locus) and, while the copy and
+// the kernel run, applies the same records to the host mirror with all host threads (loci are independent).
+// `mirror` = false when the caller has already applied them to the mirror (scalar API).
+static int launchOps(GphocsStore* s, const Op* ops, int nOps, int* outStatus, bool mirror) {
   if (nOps <= 0) return 0;
   cudaSetDevice(s->device);
   if (s->ops.reserve(nOps) || s->seg.reserve(nOps + 1) || s->status.reserve(nOps)) return -1;
-  // stable grouping by locus so one device thread replays a locus' records in call order
-  std::vector<int> order(nOps);
   bool sorted = true;
-  for (int i = 0; i < nOps; i++) {
-    order[i] = i;
-    if (i && ops[i].locus < ops[i - 1].locus) sorted = false;
+  for (int i = 1; i < nOps; i++)
+    if (ops[i].locus < ops[i - 1].locus) { sorted = false; break; }
+  std::vector<int> order;
+  if (!sorted) {  // stable grouping by locus so one device thread replays a locus' records in call order
+    order.resize(nOps);
+    for (int i = 0; i < nOps; i++) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return ops[a].locus < ops[b].locus; });
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < nOps; i++) s->ops.host[i] = ops[order[i]];
+  } else {
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < nOps; i++) s->ops.host[i] = ops[i];
   }
-  if (!sorted) std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return ops[a].locus < ops[b].locus; });
   int nSegs = 0;
-  for (int i = 0; i < nOps; i++) {
-    s->ops.host[i] = ops[order[i]];
+  for (int i = 0; i < nOps; i++)
     if (i == 0 || s->ops.host[i].locus != s->ops.host[i - 1].locus) s->seg.host[nSegs++] = i;
-  }
   s->seg.host[nSegs] = nOps;
   CUDA_TRY(cudaMemcpyAsync(s->ops.dev, s->ops.host, sizeof(Op) * nOps, cudaMemcpyHostToDevice, s->stream));
   CUDA_TRY(cudaMemcpyAsync(s->seg.dev, s->seg.host, sizeof(int) * (nSegs + 1), cudaMemcpyHostToDevice, s->stream));
   k_apply_ops<<<(nSegs + 127) / 128, 128, 0, s->stream>>>(s->d, s->ops.dev, s->seg.dev, nSegs, s->status.dev);
   g_launches++;
   CUDA_TRY(cudaGetLastError());
-  if (outStatus) {
+  const bool wantDeviceStatus = outStatus && (s->debugMirror || !mirror);
+  if (wantDeviceStatus)
     CUDA_TRY(cudaMemcpyAsync(s->status.host, s->status.dev, sizeof(int) * nOps, cudaMemcpyDeviceToHost, s->stream));
-    CUDA_TRY(cudaStreamSynchronize(s->stream));
-    for (int i = 0; i < nOps; i++) outStatus[order[i]] = s->status.host[i];
-  } else {
-    // staging buffers are reused by the next call
-    CUDA_TRY(cudaStreamSynchronize(s->stream));
+  if (mirror) {
+    // host mirror (getters must see the proposal when this call returns); statuses come from the same code
+    const Op* hops = s->ops.host;
+    const int* seg = s->seg.host;
+#pragma omp parallel for schedule(static)
+    for (int g = 0; g < nSegs; g++) {
+      const TreeView t = s->hostView(hops[seg[g]].locus);
+      for (int o = seg[g]; o < seg[g + 1]; o++) {
+        const int st = applyOp(t, hops[o]);
+        if (outStatus) outStatus[sorted ? o : order[o]] = st;
+      }
+    }
+  }
+  CUDA_TRY(cudaStreamSynchronize(s->stream));  // staging buffers are reused by the next call
+  if (wantDeviceStatus) {
+    for (int i = 0; i < nOps; i++) {
+      int& dst = outStatus[sorted ? i : order[i]];
+      if (mirror && dst != s->status.host[i]) {
+        fprintf(stderr, "gphocs_b200: host mirror and device disagree on the status of edit %d\n", i);
+        return -1;
+      }
+      dst = s->status.host[i];
+    }
   }
   return 0;
 }
@@ -451,20 +484,16 @@ static int flushPending(GphocsStore* s) {
   if (s->pending.empty()) return 0;
   std::vector<Op> ops;
   ops.swap(s->pending);
-  return launchOps(s, ops.data(), (int)ops.size(), nullptr);
+  return launchOps(s, ops.data(), (int)ops.size(), nullptr, false);
 }
 
 extern "C" int gphocsStoreApplyOps(GphocsStore* s, int nOps, const GphocsOp* ops_, int* outStatus) {
   std::lock_guard<std::mutex> lk(s->mu);
   const Op* ops = reinterpret_cast<const Op*>(ops_);
   if (flushPending(s)) return -1;
-  // host mirror first (getters must see the proposal immediately); statuses come from here as well and are
-  // cross-checked against the device's in debug builds of the tests
-  for (int i = 0; i < nOps; i++) {
+  for (int i = 0; i < nOps; i++)
     if (ops[i].locus < 0 || ops[i].locus >= s->L) { fprintf(stderr, "gphocs_b200: locus %d out of range\n", ops[i].locus); return -1; }
-    applyOp(s->hostView(ops[i].locus), ops[i]);
-  }
-  return launchOps(s, ops, nOps, outStatus);
+  return launchOps(s, ops, nOps, outStatus, true);
 }
 
 extern "C" int gphocsStoreSetRates(GphocsStore* s, int nLoci, const int* locusIds, const double* rates) {
@@ -696,6 +725,8 @@ struct GphocsGenealogy {
   double* dTotals = nullptr;
   size_t evCap = 0;
   Staging<double> out;
+  Staging<int> sEs;
+  Staging<uint16_t> sPs, sCode;
   std::vector<int> postOrder;
 };
 
@@ -757,7 +788,7 @@ extern "C" int gphocsGenDestroy(GphocsGenealogy* g) {
   void* ptrs[] = {g->dParams, g->dEvStart, g->dPopStart, g->dEvTime, g->dEvCode, g->dLineages, g->dTotals, g->d.lnL,
                   g->d.coal, g->d.numCoals, g->d.mig, g->d.numMigs, g->d.ctaTotals};
   for (void* p : ptrs) if (p) cudaFree(p);
-  g->out.release();
+  g->out.release(); g->sEs.release(); g->sPs.release(); g->sCode.release();
   if (g->ownStream && g->stream) cudaStreamDestroy(g->stream);
   delete g;
   return 0;
@@ -802,32 +833,43 @@ extern "C" int gphocsGenSetEvents(GphocsGenealogy* g, const long long* evStart, 
     if (devAlloc(&g->dEvTime, g->evCap) || devAlloc(&g->dEvCode, g->evCap) || devAlloc(&g->dLineages, g->evCap)) return -1;
   }
   g->totalEvents = E;
-  std::vector<int> es(L + 1);
-  std::vector<uint16_t> ps((size_t)L * (Q + 1)), code(E);
+  if (g->sEs.reserve(L + 1) || g->sPs.reserve((size_t)L * (Q + 1)) || g->sCode.reserve((size_t)E)) return -1;
+  int* es = g->sEs.host;            // pinned staging: conversions land where the DMA engine reads them
+  uint16_t* ps = g->sPs.host;
+  uint16_t* code = g->sCode.host;
   int maxTile = 0;
   bool bad = false;
+  CUDA_TRY(cudaStreamSynchronize(g->stream));
+  // chunks of loci are converted by all host threads into page-locked staging and their copies enqueued at once,
+  // so PCIe transfers overlap the conversion of the next chunk
+  const int numChunks = L >= 8192 ? 8 : 1;
+  for (int c = 0; c < numChunks && !bad; c++) {
+    const int l0 = (int)((long long)L * c / numChunks), l1 = (int)((long long)L * (c + 1) / numChunks);
 #pragma omp parallel for schedule(static)
-  for (int l = 0; l < L; l++) {
-    es[l] = (int)(evStart[l] - evStart[0]);
-    const long long nEv = evStart[l + 1] - evStart[l];
-    if (nEv > 65535) bad = true;
-    for (int p = 0; p <= Q; p++) ps[(size_t)l * (Q + 1) + p] = (uint16_t)popStart[(size_t)l * (Q + 1) + p];
-    for (long long e = evStart[l]; e < evStart[l + 1]; e++) {
-      const int t = evType[e], id = evId[e];
-      const bool needsBand = (t == EV_IN_MIG || t == EV_BAND_START || t == EV_BAND_END);
-      if (t < 0 || t > EV_DUMMY || (needsBand && (id < 0 || id >= g->B))) bad = true;
-      code[e - evStart[0]] = (uint16_t)(t | ((needsBand ? id : 0) << 3));
+    for (int l = l0; l < l1; l++) {
+      es[l] = (int)(evStart[l] - evStart[0]);
+      const long long nEv = evStart[l + 1] - evStart[l];
+      if (nEv > 65535 || nEv < 0) { bad = true; continue; }
+      for (int p = 0; p <= Q; p++) ps[(size_t)l * (Q + 1) + p] = (uint16_t)popStart[(size_t)l * (Q + 1) + p];
+      for (long long e = evStart[l]; e < evStart[l + 1]; e++) {
+        const int t = evType[e], id = evId[e];
+        const bool needsBand = (t == EV_IN_MIG || t == EV_BAND_START || t == EV_BAND_END);
+        if (t < 0 || t > EV_DUMMY || (needsBand && (id < 0 || id >= g->B))) bad = true;
+        code[e - evStart[0]] = (uint16_t)(t | ((needsBand ? id : 0) << 3));
+      }
     }
+    if (bad) break;
+    const long long e0 = evStart[l0] - evStart[0], e1 = evStart[l1] - evStart[0];
+    CUDA_TRY(cudaMemcpyAsync(g->dPopStart + (size_t)l0 * (Q + 1), ps + (size_t)l0 * (Q + 1),
+                             sizeof(uint16_t) * (size_t)(l1 - l0) * (Q + 1), cudaMemcpyHostToDevice, g->stream));
+    CUDA_TRY(cudaMemcpyAsync(g->dEvCode + e0, code + e0, sizeof(uint16_t) * (size_t)(e1 - e0), cudaMemcpyHostToDevice, g->stream));
+    CUDA_TRY(cudaMemcpyAsync(g->dEvTime + e0, evTime + evStart[0] + e0, sizeof(double) * (size_t)(e1 - e0), cudaMemcpyHostToDevice, g->stream));
   }
   es[L] = (int)E;
-  if (bad) { fprintf(stderr, "gphocs_b200: malformed event snapshot\n"); return -1; }
+  if (bad) { cudaStreamSynchronize(g->stream); fprintf(stderr, "gphocs_b200: malformed event snapshot\n"); return -1; }
   for (int l0 = 0; l0 < L; l0 += kGenTile) maxTile = std::max(maxTile, es[std::min(L, l0 + kGenTile)] - es[l0]);
   g->maxTileEvents = maxTile;
-  CUDA_TRY(cudaStreamSynchronize(g->stream));
-  CUDA_TRY(cudaMemcpyAsync(g->dEvStart, es.data(), sizeof(int) * (L + 1), cudaMemcpyHostToDevice, g->stream));
-  CUDA_TRY(cudaMemcpyAsync(g->dPopStart, ps.data(), sizeof(uint16_t) * ps.size(), cudaMemcpyHostToDevice, g->stream));
-  CUDA_TRY(cudaMemcpyAsync(g->dEvCode, code.data(), sizeof(uint16_t) * E, cudaMemcpyHostToDevice, g->stream));
-  CUDA_TRY(cudaMemcpyAsync(g->dEvTime, evTime + evStart[0], sizeof(double) * E, cudaMemcpyHostToDevice, g->stream));
+  CUDA_TRY(cudaMemcpyAsync(g->dEvStart, es, sizeof(int) * (L + 1), cudaMemcpyHostToDevice, g->stream));
   CUDA_TRY(cudaStreamSynchronize(g->stream));
   const size_t smem = genSmemBytes(g->Q, g->B, g->maxTileEvents);
   if (smem > 200 * 1024) { fprintf(stderr, "gphocs_b200: event tile too large for shared memory (%zu bytes)\n", smem); return -1; }

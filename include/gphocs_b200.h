@@ -149,6 +149,10 @@ int gphocsStoreSetDebug(GphocsStore *s, int on);
 int gphocsStoreCheckMirror(GphocsStore *s);
 /* timing hooks for benchmarks: number of kernels this library has launched so far */
 long long gphocsKernelLaunchCount(void);
+/* page-locked host memory (cudaMallocHost) for callers' input/output arrays, so host<->device copies of the
+ * batched calls run at full PCIe speed; plain malloc'd arrays work too, slower */
+void *gphocsHostAlloc(long long bytes);
+int gphocsHostFree(void *p);
 /* stream-ordered device-to-device copy (gathers device-resident results into a caller's buffer) */
 int gphocsCopyDeviceAsync(void *dst, const void *src, long long bytes, void *cudaStream);
 
