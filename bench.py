@@ -265,6 +265,7 @@ def run_b200(args):
     gen = gp.Genealogy(L, w.pops, device=local_rank, stream=stream.cuda_stream)
     gen.set_events(w.ev_start, w.pop_start, w.ev_type, w.ev_id, w.ev_time)
     lib = gp.lib()
+    host_threads = lib.gphocsSetHostThreads(max(1, (os.cpu_count() or 1) // world))   # torchrun pins OMP_NUM_THREADS=1
     V = 1 + 2 * Q + 2 * B
     assert 1 + V == shard.payload_len(Q, B)
     payload = torch.zeros(1 + V, dtype=torch.float64, device=dev)   # [sum data lnL | sum gen lnL, totals...]
@@ -402,7 +403,7 @@ def run_b200(args):
                          "ms_per_launch": ms_data, "genealogy_kernel_ms": ms_gen,
                          "genealogy_achieved_gbs": bytes_gen / (ms_gen * 1e-3) / 1e9},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "steps": e2e_steps},
+                    "steps": e2e_steps, "host_threads_per_rank": host_threads},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "extra": {"sum_data_lnl": total_data_lnl, "sum_gen_lnl": total_gen_lnl,

@@ -93,6 +93,8 @@ def lib():
         "gphocsStoreCheckMirror": (ci, [vp]),
         "gphocsKernelLaunchCount": (C.c_longlong, []),
         "gphocsCopyDeviceAsync": (ci, [vp, vp, C.c_longlong, vp]),
+        "gphocsSetHostThreads": (ci, [ci]),
+        "gphocsFiberSelfTest": (C.c_longlong, [ci, ci, ci, ci]),
         "gphocsHostAlloc": (vp, [C.c_longlong]),
         "gphocsHostFree": (ci, [vp]),
         # C. genealogy likelihood

@@ -10,10 +10,12 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <mutex>
 #include <vector>
 
 #include "gphocs_b200.h"
+#include "host_runtime.h"
 
 #include "clv_kernels.cuh"
 #include "gen_kernels.cuh"
@@ -67,6 +69,25 @@ struct Staging {
   }
 };
 
+// growable device-only buffer
+template <typename T>
+struct DevBuf {
+  T* dev = nullptr;
+  size_t cap = 0;
+  int reserve(size_t n) {
+    if (n <= cap) return 0;
+    if (dev) cudaFree(dev);
+    dev = nullptr; cap = 0;
+    CUDA_TRY(cudaMalloc((void**)&dev, n * sizeof(T)));
+    cap = n;
+    return 0;
+  }
+  void release() {
+    if (dev) cudaFree(dev);
+    dev = nullptr; cap = 0;
+  }
+};
+
 // ======================================================================================= store
 struct GphocsStore {
   int device = 0;
@@ -97,6 +118,7 @@ struct GphocsStore {
   Staging<int16_t> i16;
   std::vector<Op> pending;  // edits queued by the scalar API, flushed before the next evaluation
   bool debugMirror = false;  // also mirror SEL/RECALC bits on the host (tests)
+  bool opsInFlight = false;  // an edit batch was enqueued without a stream synchronisation
   std::mutex mu;
 
   TreeView hostView(int l) {
@@ -157,8 +179,8 @@ extern "C" GphocsStore* gphocsStoreCreate(int device, int numLoci, int numLeaves
   std::vector<unsigned long long> words((size_t)W * std::max<long long>(Ct, 1), 0ull);
   std::vector<int> phases(std::max<long long>(Ct, 1), 0), cnt(std::max<long long>(Ct, 1), 0);
   bool bad = false;
-#pragma omp parallel for schedule(static)
-  for (int l = 0; l < L; l++) {
+  parallelFor(0, L, [&](long long lo_, long long hi_) {
+  for (int l = (int)lo_; l < (int)hi_; l++) {
     long long u = unphStart[l];
     for (long long c = pattStart[l]; c < pattStart[l + 1]; c++) {
       const long long col = c - pattStart[0];
@@ -176,6 +198,7 @@ extern "C" GphocsStore* gphocsStoreCreate(int device, int numLoci, int numLeaves
       }
     }
   }
+  });
   if (bad) {
     fprintf(stderr, "gphocs_b200: unexpected character in a pattern (only T,C,A,G,N) or non-positive pattern count\n");
     delete s;
@@ -327,6 +350,11 @@ extern "C" int gphocsCopyDeviceAsync(void* dst, const void* src, long long bytes
   CUDA_TRY(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)cudaStream));
   return 0;
 }
+// host threads used for staging conversions and the host mirror (defaults to OpenMP's choice, which launchers
+// such as torchrun pin to 1 through OMP_NUM_THREADS)
+extern "C" int gphocsSetHostThreads(int n) {
+  return setHostThreads(n);
+}
 // page-locked host memory for callers that want their input/output arrays to move at full PCIe speed
 extern "C" void* gphocsHostAlloc(long long bytes) {
   void* p = nullptr;
@@ -357,6 +385,10 @@ static int setTreesLocked(GphocsStore* s, int nLoci, const int* locusIds, const 
       if (locusIds[k] < 0 || locusIds[k] >= s->L) { fprintf(stderr, "gphocs_b200: locus %d out of range\n", locusIds[k]); return -1; }
   if (!locusIds && nLoci > s->L) { fprintf(stderr, "gphocs_b200: %d genealogies for %d loci\n", nLoci, s->L); return -1; }
   const size_t cnt = (size_t)nLoci * N;
+  if (s->opsInFlight) {   // an edit batch may still be reading the shared staging buffers
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    s->opsInFlight = false;
+  }
   if (s->i16.reserve(cnt * 3) || s->f64.reserve(cnt) || s->ids.reserve(nLoci) || s->seg.reserve(nLoci)) return -1;
   StoreDev& d = s->d;
   // Loci are converted in chunks by all host threads straight into page-locked staging (int16 topology, fp64 ages,
@@ -365,8 +397,8 @@ static int setTreesLocked(GphocsStore* s, int nLoci, const int* locusIds, const 
   const int numChunks = nLoci >= 8192 ? 8 : 1;
   for (int c = 0; c < numChunks; c++) {
     const int k0 = (int)((long long)nLoci * c / numChunks), k1 = (int)((long long)nLoci * (c + 1) / numChunks);
-#pragma omp parallel for schedule(static)
-    for (int k = k0; k < k1; k++) {
+    parallelFor(k0, k1, [&](long long lo_, long long hi_) {
+    for (int k = (int)lo_; k < (int)hi_; k++) {
       const int l = locusIds ? locusIds[k] : k;
       const size_t o = (size_t)l * N, in = (size_t)k * N;
       int16_t* o3 = s->i16.host + in * 3;
@@ -381,6 +413,7 @@ static int setTreesLocked(GphocsStore* s, int nLoci, const int* locusIds, const 
       s->hRoot[l] = s->seg.host[k] = root[k];
       s->ids.host[k] = l;
     }
+    }, 256);
     const size_t n0 = (size_t)k0 * N, nn = (size_t)(k1 - k0) * N;
     CUDA_TRY(cudaMemcpyAsync(s->ids.dev + k0, s->ids.host + k0, sizeof(int) * (k1 - k0), cudaMemcpyHostToDevice, s->stream));
     CUDA_TRY(cudaMemcpyAsync(s->seg.dev + k0, s->seg.host + k0, sizeof(int) * (k1 - k0), cudaMemcpyHostToDevice, s->stream));
@@ -426,6 +459,10 @@ extern "C" int gphocsStoreGetTrees(GphocsStore* s, int nLoci, const int* locusId
 static int launchOps(GphocsStore* s, const Op* ops, int nOps, int* outStatus, bool mirror) {
   if (nOps <= 0) return 0;
   cudaSetDevice(s->device);
+  if (s->opsInFlight) {   // the previous batch may still be reading the staging buffers
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    s->opsInFlight = false;
+  }
   if (s->ops.reserve(nOps) || s->seg.reserve(nOps + 1) || s->status.reserve(nOps)) return -1;
   bool sorted = true;
   for (int i = 1; i < nOps; i++)
@@ -435,11 +472,13 @@ static int launchOps(GphocsStore* s, const Op* ops, int nOps, int* outStatus, bo
     order.resize(nOps);
     for (int i = 0; i < nOps; i++) order[i] = i;
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return ops[a].locus < ops[b].locus; });
-#pragma omp parallel for schedule(static)
-    for (int i = 0; i < nOps; i++) s->ops.host[i] = ops[order[i]];
+    parallelFor(0, nOps, [&](long long lo_, long long hi_) {
+    for (int i = (int)lo_; i < (int)hi_; i++) s->ops.host[i] = ops[order[i]];
+    }, 32768);
   } else {
-#pragma omp parallel for schedule(static)
-    for (int i = 0; i < nOps; i++) s->ops.host[i] = ops[i];
+    parallelFor(0, nOps, [&](long long lo_, long long hi_) {
+    for (int i = (int)lo_; i < (int)hi_; i++) s->ops.host[i] = ops[i];
+    }, 32768);
   }
   int nSegs = 0;
   for (int i = 0; i < nOps; i++)
@@ -457,16 +496,21 @@ static int launchOps(GphocsStore* s, const Op* ops, int nOps, int* outStatus, bo
     // host mirror (getters must see the proposal when this call returns); statuses come from the same code
     const Op* hops = s->ops.host;
     const int* seg = s->seg.host;
-#pragma omp parallel for schedule(static)
-    for (int g = 0; g < nSegs; g++) {
+    parallelFor(0, nSegs, [&](long long lo_, long long hi_) {
+    for (int g = (int)lo_; g < (int)hi_; g++) {
       const TreeView t = s->hostView(hops[seg[g]].locus);
       for (int o = seg[g]; o < seg[g + 1]; o++) {
         const int st = applyOp(t, hops[o]);
         if (outStatus) outStatus[sorted ? o : order[o]] = st;
       }
     }
+    });
   }
-  CUDA_TRY(cudaStreamSynchronize(s->stream));  // staging buffers are reused by the next call
+  if (mirror || wantDeviceStatus) {
+    CUDA_TRY(cudaStreamSynchronize(s->stream));  // staging buffers are reused by the next call
+  } else {
+    s->opsInFlight = true;   // scalar / fiber path: the evaluation that follows synchronises the stream
+  }
   if (wantDeviceStatus) {
     for (int i = 0; i < nOps; i++) {
       int& dst = outStatus[sorted ? i : order[i]];
@@ -503,11 +547,15 @@ extern "C" int gphocsStoreSetRates(GphocsStore* s, int nLoci, const int* locusId
 }
 
 // ---- evaluation
-static int launchEval(GphocsStore* s, int useOld, int onlyLocus, bool masked) {
+// masked: evaluate only loci whose mask byte is set; [bLo, bHi] restricts the launch to that range of CTA batches
+static int launchEval(GphocsStore* s, int useOld, int onlyLocus, bool masked, int bLo = 0, int bHi = -1) {
   cudaSetDevice(s->device);
   StoreDev d = s->d;
   d.active = masked ? s->dMask : nullptr;
-  if (onlyLocus >= 0) {
+  if (bHi >= bLo && onlyLocus < 0) {
+    k_eval<<<bHi - bLo + 1, kThreads, s->smemBytes, s->stream>>>(d, s->dBatches, bLo, useOld, -1, s->maxBatchLoci, s->prefetchAhead);
+    g_launches++;
+  } else if (onlyLocus >= 0) {
     const int b = s->locusBatch[onlyLocus];
     if (b < 0) return 0;
     k_eval<<<1, kThreads, s->smemBytes, s->stream>>>(d, s->dBatches, b, useOld, onlyLocus, s->maxBatchLoci, 0);
@@ -579,9 +627,15 @@ static void replayFlipsOnMirror(GphocsStore* s, int l, int useOld) {
   for (int i = 0; i < N; i++) t.node[i].flags &= 0x7f;
 }
 
+static int evaluateLocked(GphocsStore* s, int nLoci, const int* locusIds, int useOld, double* outLnL, double* outSum);
+
 extern "C" int gphocsStoreEvaluate(GphocsStore* s, int nLoci, const int* locusIds, int useOld, double* outLnL,
                                    double* outSum) {
   std::lock_guard<std::mutex> lk(s->mu);
+  return evaluateLocked(s, nLoci, locusIds, useOld, outLnL, outSum);
+}
+
+static int evaluateLocked(GphocsStore* s, int nLoci, const int* locusIds, int useOld, double* outLnL, double* outSum) {
   if (flushPending(s)) return -1;
   cudaSetDevice(s->device);
   const bool all = (locusIds == nullptr);
@@ -604,11 +658,21 @@ extern "C" int gphocsStoreEvaluate(GphocsStore* s, int nLoci, const int* locusId
   } else {
     if (s->ids.reserve(nLoci)) return -1;
     memcpy(s->ids.host, locusIds, sizeof(int) * nLoci);
-    CUDA_TRY(cudaMemsetAsync(s->dMask, 0, s->L, s->stream));
-    CUDA_TRY(cudaMemcpyAsync(s->ids.dev, s->ids.host, sizeof(int) * nLoci, cudaMemcpyHostToDevice, s->stream));
-    k_set_mask<<<(nLoci + 255) / 256, 256, 0, s->stream>>>(s->dMask, s->ids.dev, nLoci);
-    g_launches++;
-    if (launchEval(s, useOld, -1, true)) return -1;
+    // only the CTA batches that cover the listed loci are launched; the mask keeps their other loci untouched
+    int lMin = s->L, lMax = -1, bLo = s->numBatches, bHi = -1;
+    for (int k = 0; k < nLoci; k++) {
+      const int l = locusIds[k], b = s->locusBatch[l];
+      lMin = std::min(lMin, l); lMax = std::max(lMax, l);
+      if (b >= 0) { bLo = std::min(bLo, b); bHi = std::max(bHi, b); }
+    }
+    if (bHi >= bLo) {
+      const int mLo = s->batches[bLo].firstLocus, mHi = s->batches[bHi].firstLocus + s->batches[bHi].numLoci;
+      CUDA_TRY(cudaMemsetAsync(s->dMask + mLo, 0, mHi - mLo, s->stream));
+      CUDA_TRY(cudaMemcpyAsync(s->ids.dev, s->ids.host, sizeof(int) * nLoci, cudaMemcpyHostToDevice, s->stream));
+      k_set_mask<<<(nLoci + 255) / 256, 256, 0, s->stream>>>(s->dMask, s->ids.dev, nLoci);
+      g_launches++;
+      if (launchEval(s, useOld, -1, true, bLo, bHi)) return -1;
+    }
   }
   if (outSum && all) {
     k_reduce_sum<<<1, 1024, 0, s->stream>>>(s->d.ctaSum, s->numBatches, s->dSum);
@@ -845,8 +909,8 @@ extern "C" int gphocsGenSetEvents(GphocsGenealogy* g, const long long* evStart, 
   const int numChunks = L >= 8192 ? 8 : 1;
   for (int c = 0; c < numChunks && !bad; c++) {
     const int l0 = (int)((long long)L * c / numChunks), l1 = (int)((long long)L * (c + 1) / numChunks);
-#pragma omp parallel for schedule(static)
-    for (int l = l0; l < l1; l++) {
+    parallelFor(l0, l1, [&](long long lo_, long long hi_) {
+    for (int l = (int)lo_; l < (int)hi_; l++) {
       es[l] = (int)(evStart[l] - evStart[0]);
       const long long nEv = evStart[l + 1] - evStart[l];
       if (nEv > 65535 || nEv < 0) { bad = true; continue; }
@@ -858,6 +922,7 @@ extern "C" int gphocsGenSetEvents(GphocsGenealogy* g, const long long* evStart, 
         code[e - evStart[0]] = (uint16_t)(t | ((needsBand ? id : 0) << 3));
       }
     }
+    });
     if (bad) break;
     const long long e0 = evStart[l0] - evStart[0], e1 = evStart[l1] - evStart[0];
     CUDA_TRY(cudaMemcpyAsync(g->dPopStart + (size_t)l0 * (Q + 1), ps + (size_t)l0 * (Q + 1),

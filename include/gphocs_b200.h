@@ -149,6 +149,13 @@ int gphocsStoreSetDebug(GphocsStore *s, int on);
 int gphocsStoreCheckMirror(GphocsStore *s);
 /* timing hooks for benchmarks: number of kernels this library has launched so far */
 long long gphocsKernelLaunchCount(void);
+/* number of host threads the library uses for staging conversions and the host mirror (one rank per GPU:
+ * give each rank its share of the cores); returns the value in effect */
+int gphocsSetHostThreads(int n);
+/* CPU-only self-test of the fiber scheduler behind the OpenMP entry points this library exports for the reference
+ * host (GOMP_parallel, omp_get_thread_num, omp_get_num_threads, omp_get_max_threads, omp_set_num_threads — the
+ * libgomp symbols GPhoCS.o/patch.o reference): sum over fibers of (id+1)*parks, or -1 on inconsistency */
+long long gphocsFiberSelfTest(int numFibers, int parks, int threads, int useFibers);
 /* page-locked host memory (cudaMallocHost) for callers' input/output arrays, so host<->device copies of the
  * batched calls run at full PCIe speed; plain malloc'd arrays work too, slower */
 void *gphocsHostAlloc(long long bytes);
