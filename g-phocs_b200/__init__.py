@@ -107,6 +107,16 @@ def lib():
         "gphocsGenEvaluateDevice": (ci, [vp, C.POINTER(vp), C.POINTER(vp)]),
         "gphocsGenGetLineages": (ci, [vp, c_int_p]),
         "gphocsGenSync": (ci, [vp]),
+        # D. device-resident MCMC steps
+        "gphocsSamplerCreate": (vp, [vp, ci, ci, c_int_p, c_int_p, c_int_p, c_int_p, c_dbl_p, c_dbl_p, c_dbl_p, c_dbl_p,
+                                     c_dbl_p, c_dbl_p, c_int_p, C.c_ulonglong]),
+        "gphocsSamplerDestroy": (ci, [vp]),
+        "gphocsSamplerSetFinetunes": (ci, [vp, cd, cd, cd, cd]),
+        "gphocsSamplerIterate": (ci, [vp, ci, c_dbl_p]),
+        "gphocsSamplerTraceWidth": (ci, [vp]),
+        "gphocsSamplerGetState": (ci, [vp, c_dbl_p, c_dbl_p, c_ll_p, c_ll_p]),
+        "gphocsSamplerCheck": (ci, [vp, c_dbl_p, c_dbl_p]),
+        "gphocsSamplerDownload": (ci, [vp, c_int_p]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -421,4 +431,61 @@ class ScalarLocus:
     def free(self):
         if self.h:
             self.lib.freeLocusData(self.h)
+            self.h = None
+
+
+class Sampler:
+    """Device-resident MCMC update steps (GphocsSampler) over the loci of a LociStore."""
+    MOVES = ("coal_time", "spr", "theta", "tau", "mixing")
+
+    def __init__(self, store, pops, node_pop, theta_prior=(1.0, 1000.0), tau_prior=None, seed=1, finetunes=None):
+        self.lib = lib()
+        self.store = store
+        self.Q = len(pops["father"])
+        self.C = len(pops["samples_per_pop"])
+        Q = self.Q
+        ta = np.full(Q, float(theta_prior[0]))
+        tb = np.full(Q, float(theta_prior[1]))
+        if tau_prior is None:        # the control files written by synth.write_control_file: alpha 1, beta 1/tau-initial
+            aa = np.full(Q, 1.0)
+            ab = np.array([1.0 / t if t > 0 else 1.0 for t in pops["age"]])
+        else:
+            aa, ab = (np.ascontiguousarray(x, np.float64) for x in tau_prior)
+        self.h = self.lib.gphocsSamplerCreate(store.h, Q, self.C, _ip(_i32(pops["father"])), _ip(_i32(pops["son0"])),
+                                              _ip(_i32(pops["son1"])), _ip(_i32(pops["samples_per_pop"])),
+                                              _dp(_f64(pops["theta"])), _dp(_f64(pops["age"])), _dp(ta), _dp(tb), _dp(aa), _dp(ab),
+                                              _ip(_i32(node_pop)), int(seed))
+        if not self.h:
+            raise RuntimeError("gphocsSamplerCreate failed")
+        self.h = C.c_void_p(self.h)
+        self.width = self.lib.gphocsSamplerTraceWidth(self.h)
+        if finetunes is not None:
+            self.lib.gphocsSamplerSetFinetunes(self.h, *[float(x) for x in finetunes])
+
+    def iterate(self, iterations, trace=True):
+        out = np.zeros((iterations, self.width)) if trace else None
+        if self.lib.gphocsSamplerIterate(self.h, int(iterations), _dp(out)) != 0:
+            raise RuntimeError("gphocsSamplerIterate failed")
+        return out
+
+    def state(self):
+        th, ta = np.zeros(self.Q), np.zeros(self.Q)
+        acc, prop = np.zeros(5, np.int64), np.zeros(5, np.int64)
+        self.lib.gphocsSamplerGetState(self.h, _dp(th), _dp(ta), _lp(acc), _lp(prop))
+        return dict(theta=th, tau=ta, accepted=dict(zip(self.MOVES, acc)), proposed=dict(zip(self.MOVES, prop)))
+
+    def check(self):
+        a, b = C.c_double(), C.c_double()
+        v = self.lib.gphocsSamplerCheck(self.h, C.byref(a), C.byref(b))
+        return v, a.value, b.value
+
+    def download(self):
+        out = np.zeros((self.store.L, self.store.N), np.int32)
+        if self.lib.gphocsSamplerDownload(self.h, _ip(out)) != 0:
+            raise RuntimeError("gphocsSamplerDownload failed")
+        return out
+
+    def close(self):
+        if self.h:
+            self.lib.gphocsSamplerDestroy(self.h)
             self.h = None

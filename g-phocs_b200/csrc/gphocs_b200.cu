@@ -19,6 +19,7 @@
 
 #include "clv_kernels.cuh"
 #include "gen_kernels.cuh"
+#include "sampler_kernels.cuh"
 #include "tree_ops.cuh"
 
 using namespace gphocs;
@@ -1008,3 +1009,4 @@ extern "C" int gphocsGenSync(GphocsGenealogy* g) {
 }
 
 #include "locus_api.inc"
+#include "sampler.inc"

@@ -195,17 +195,22 @@ def sample_names(model: Model):
     return out
 
 
+FINETUNES = dict(coal_time=0.01, mig_time=0.3, theta=0.04, mig_rate=0.02, tau=0.0000008, mixing=0.003)
+
+
 def write_control_file(model: Model, path: str, seqfile: str, tracefile: str, iterations: int = 0,
-                       seed: int = 4242, iterations_per_log: int = 10):
+                       seed: int = 4242, iterations_per_log: int = 10, finetunes: dict = None):
     """Control file for the reference program, SURVEY.md Appendix C layout."""
+    ft = dict(FINETUNES)
+    ft.update(finetunes or {})
     lines = ["GENERAL-INFO-START",
              f"\tseq-file\t{seqfile}", f"\ttrace-file\t{tracefile}",
              f"\tlocus-mut-rate\t{'VAR 1.0' if model.rate_shape > 0 else 'CONST'}",
              f"\trandom-seed\t{seed}", f"\tmcmc-iterations\t{iterations}",
              f"\titerations-per-log\t{iterations_per_log}", "\tlogs-per-line\t10",
-             "\tfind-finetunes\tFALSE", "\tfinetune-coal-time\t0.01", "\tfinetune-mig-time\t0.3",
-             "\tfinetune-theta\t0.04", "\tfinetune-mig-rate\t0.02", "\tfinetune-tau\t0.0000008",
-             "\tfinetune-mixing\t0.003"]
+             "\tfind-finetunes\tFALSE", f"\tfinetune-coal-time\t{ft['coal_time']}", f"\tfinetune-mig-time\t{ft['mig_time']}",
+             f"\tfinetune-theta\t{ft['theta']}", f"\tfinetune-mig-rate\t{ft['mig_rate']}", f"\tfinetune-tau\t{ft['tau']:.10f}",
+             f"\tfinetune-mixing\t{ft['mixing']}"]
     if model.rate_shape > 0:
         lines.append("\tfinetune-locus-rate\t0.3")
     lines += ["\ttau-theta-print\t10000.0", "\ttau-theta-alpha\t1.0", f"\ttau-theta-beta\t{1.0 / model.theta:.1f}",

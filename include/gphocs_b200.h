@@ -199,6 +199,35 @@ int gphocsGenEvaluateDevice(GphocsGenealogy *g, void **devLnL, void **devTotals)
 int gphocsGenGetLineages(GphocsGenealogy *g, int *numLineages);
 int gphocsGenSync(GphocsGenealogy *g);
 
+/* ===================================================================================== D. device-resident MCMC steps
+ * the update steps of GPhoCS.c run for all loci per launch with no host round trip inside a sweep —
+ * UpdateGB_InternalNode (:2287), UpdateGB_MigSPR (:2598), UpdateTheta (:3035), UpdateTau (:3224), mixing (:4688).
+ * This version covers population trees without migration bands, samples of age 0 and constant locus rates.
+ * The sampler edits the device copy of the store's genealogies; call gphocsSamplerDownload before reading them
+ * through the store or the LocusData getters. */
+typedef struct GphocsSampler GphocsSampler;
+/* population tree as in gphocsGenCreate; theta[numPops], tau[numPops] (ancestral entries used); Gamma(alpha, beta)
+ * priors per population (thetaPrior / agePrior of PopulationTree.h:80-101); nodePop[numLoci][2n-1] = nodePops
+ * (patch.h:123).  The store must hold the genealogies (gphocsStoreSetTrees). */
+GphocsSampler *gphocsSamplerCreate(GphocsStore *s, int numPops, int numCurPops, const int *popFather, const int *popSon0,
+                                   const int *popSon1, const int *samplesPerPop, const double *theta, const double *tau,
+                                   const double *thetaAlpha, const double *thetaBeta, const double *tauAlpha,
+                                   const double *tauBeta, const int *nodePop, unsigned long long seed);
+int gphocsSamplerDestroy(GphocsSampler *sm);
+/* finetune-coal-time, finetune-theta, finetune-tau, finetune-mixing of the control file (MCMCcontrol.c:575-787) */
+int gphocsSamplerSetFinetunes(GphocsSampler *sm, double coalTime, double theta, double tau, double mixing);
+/* `iterations` MCMC iterations; trace (may be NULL): one row per iteration of gphocsSamplerTraceWidth() doubles =
+ * [theta (numPops), tau of ancestral populations, sum of data lnL, sum of genealogy lnL] */
+int gphocsSamplerIterate(GphocsSampler *sm, int iterations, double *trace);
+int gphocsSamplerTraceWidth(const GphocsSampler *sm);
+/* accepted[5], proposed[5] for {coalescence time, SPR, theta, tau, mixing} */
+int gphocsSamplerGetState(GphocsSampler *sm, double *theta, double *tau, long long *accepted, long long *proposed);
+/* checkAll (patch.c:2745) on the device: returns structural violations; largest relative deviation of the
+ * incrementally maintained statistics / data log-likelihoods from a recomputation from scratch */
+int gphocsSamplerCheck(GphocsSampler *sm, double *maxStatErr, double *maxLnLErr);
+/* brings the store's host mirror up to date and returns nodePop[numLoci][2n-1] (may be NULL) */
+int gphocsSamplerDownload(GphocsSampler *sm, int *nodePop);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,109 @@
+"""GPU: device-resident MCMC update steps (include/gphocs_b200.h group D).
+
+The chains use their own random streams, so parity with the reference is statistical:
+  * with uninformative data (every base missing) the chain must sample the PRIOR: thetas and the root split time
+    come out Gamma(alpha, beta) — a check of every move's acceptance ratio that needs no reference at all;
+  * on real synthetic alignments the posterior means of every theta and tau must agree with the reference's own
+    chain (oracle/_ref/G-PhoCS-ref, same control file) within Monte-Carlo error;
+  * after any number of iterations the device state passes the reference's checkAll invariants (patch.c:2745):
+    incrementally maintained statistics and log-likelihoods equal a recomputation from scratch."""
+import importlib
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not torch.cuda.is_available(), reason="needs a CUDA device")]
+
+gp = importlib.import_module("g-phocs_b200")
+synth = importlib.import_module("g-phocs_b200.synth")
+from test_gpu_dropin import REF, read_trace  # noqa: E402
+
+
+def batch_se(x, batches=20):
+    """Monte-Carlo standard error of the mean of a correlated series by batch means."""
+    x = np.asarray(x, float)
+    k = len(x) // batches
+    means = x[:k * batches].reshape(batches, k).mean(1)
+    return means.std(ddof=1) / np.sqrt(batches)
+
+
+def test_state_stays_consistent_on_real_data():
+    w = synth.generate(synth.config("hap16"), 400, seed=31)
+    st = gp.LociStore.from_workload(w)
+    sm = gp.Sampler(st, w.pops, w.node_pop, seed=5)
+    v, es, el = sm.check()
+    assert v == 0 and es < 1e-10 and el < 1e-12
+    tr = sm.iterate(30)
+    assert np.all(np.isfinite(tr))
+    v, es, el = sm.check()
+    assert v == 0, v
+    assert es < 1e-9 and el < 1e-9, (es, el)
+    s = sm.state()
+    for move in ("coal_time", "spr", "theta", "tau"):
+        assert 0 < s["accepted"][move] <= s["proposed"][move], (move, s)
+    # the genealogy log-density in the trace equals the kernels' from-scratch value for the downloaded state
+    node_pop = sm.download()
+    f, l, r, a, root = st.get_trees()
+    assert node_pop.shape == f.shape and np.all(a[np.arange(len(root)), root] >= s["tau"][len(w.pops["father"]) - 1] - 1e-12)
+    sm.close()
+    st.close()
+
+
+def test_uninformative_data_recovers_the_prior():
+    """Two current populations (3 haploids each) + root; every base missing => likelihood 1 => posterior = prior.
+    theta_A, theta_B, theta_root ~ Gamma(3, 3000) and tau_root ~ Gamma(3, 3000) marginally (sum over genealogies of
+    P(G | theta, tau) is 1), whatever the number of loci."""
+    m = synth.Model("prior", [("A", 3), ("B", 3)], [("root", "A", "B", 1e-3)])
+    L = 3
+    w = synth.generate(m, L, seed=3)
+    n = w.n
+    chars = np.full((L, n), ord("N"), np.uint8)
+    st = gp.LociStore(n, np.arange(L + 1), np.arange(L + 1), chars, np.ones(L, np.int32), np.ones(L, np.int32))
+    st.set_trees(w.father, w.left, w.right, w.age, w.root)
+    alpha, beta = 3.0, 3000.0
+    Q = 3
+    sm = gp.Sampler(st, w.pops, w.node_pop, theta_prior=(alpha, beta), tau_prior=(np.full(Q, alpha), np.full(Q, beta)), seed=11,
+                    finetunes=(0.01, 0.6, 0.0008, 0.3))
+    sm.iterate(2000, trace=False)                       # burn-in
+    tr = sm.iterate(40000)
+    assert sm.check()[0] == 0
+    mean, sd = alpha / beta, np.sqrt(alpha) / beta
+    for col, name in [(0, "theta_A"), (1, "theta_B"), (2, "theta_root"), (3, "tau_root")]:
+        x = tr[:, col]
+        se = batch_se(x)
+        assert abs(x.mean() - mean) < 4.5 * se + 0.01 * mean, (name, x.mean(), mean, se)
+        assert abs(x.std() - sd) < 0.12 * sd, (name, x.std(), sd)
+    assert np.all(tr[:, -2] == 0.0)                     # data log-likelihood is identically zero
+    sm.close()
+    st.close()
+
+
+@pytest.mark.skipif(not os.path.exists(REF), reason="oracle/_ref/G-PhoCS-ref not built")
+def test_posterior_means_match_the_reference_chain(tmp_path):
+    """BASELINE.json configs[1] shape (16 haplotypes, 4 populations, no migration) at 60 loci: posterior means of
+    every theta and tau from the device chain against the reference's own chain on the same alignment."""
+    import subprocess
+    model = synth.config("hap16")
+    L, iters, burn = 60, 12000, 2000
+    seq = str(tmp_path / "seqs.txt")
+    w = synth.generate(model, L, seed=99, seqfile=seq)
+    ft = dict(coal_time=0.01, theta=0.3, tau=0.0002, mixing=0.05)
+    ctl, trace = str(tmp_path / "ref.ctl"), str(tmp_path / "ref.trace")
+    synth.write_control_file(model, ctl, seq, trace, iterations=iters, seed=4242, iterations_per_log=iters, finetunes=ft)
+    r = subprocess.run([REF, ctl, "-n", "4"], capture_output=True, text=True, timeout=1500, cwd=str(tmp_path))
+    assert r.returncode == 0, r.stdout[-2000:]
+    names, ref = read_trace(trace)
+    Q, C = model.numPops, model.numCurPops
+    ref = ref[burn:, 1:1 + 2 * Q - C] / 10000.0        # tau-theta-print factor of the control file
+    st = gp.LociStore.from_workload(w)
+    sm = gp.Sampler(st, w.pops, w.node_pop, seed=2024, finetunes=(ft["coal_time"], ft["theta"], ft["tau"], ft["mixing"]))
+    tr = sm.iterate(iters)[burn:, :2 * Q - C]
+    assert sm.check()[0] == 0
+    for k in range(2 * Q - C):
+        a, b = ref[:, k], tr[:, k]
+        se = np.hypot(batch_se(a), batch_se(b))
+        assert abs(a.mean() - b.mean()) < 4.5 * se + 0.02 * abs(a.mean()), (names[1 + k], a.mean(), b.mean(), se)
+    sm.close()
+    st.close()
