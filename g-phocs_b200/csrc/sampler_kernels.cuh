@@ -49,8 +49,9 @@ struct SmpDev {
   int L, Q;
   uint8_t* nodePop;    // [L][N] population of every genealogy node (nodePops, patch.h:123)
   double* coal;        // [L][Q] coal_stats per locus
-  double* coalT;       // [L][Q] tentative statistics of a pending global proposal
+  double* coalT;       // [L][Q] statistics of the pending proposal
   int* ncoal;          // [L][Q] num_coals per locus
+  int* ncoalT;         // [L][Q] coalescence counts of the pending proposal
   SmpProposal* prop;   // [L]
   unsigned long long* accepted;  // [8] acceptance counters per move kind
   double* partial;     // [blocks][kSmpPartials] block partial sums
@@ -95,260 +96,368 @@ __device__ inline double smpPopEnd(const SmpModel& m, int pop, int ovPop, double
   return m.father[pop] >= 0 ? smpTau(m, m.father[pop], ovPop, ovTau) : kOldAge;
 }
 
-// coal statistic of one population: sum over the intervals between its coalescence events of n(n-1)*length
-// (recalcStats, patch.c:2403-2413), events visited in age order by repeated selection (no scratch memory).
-// nStart = lineages entering the population.  Returns the number of coalescences through *numCoals.
-__device__ inline double smpPopCoalStat(const SmpModel& m, const double* age, const uint8_t* nodePop, int pop, int nStart,
-                                        int ovPop, double ovTau, int* numCoals) {
-  const int n = m.n, N = 2 * n - 1;
-  double t = smpTau(m, pop, ovPop, ovTau);
-  const double tEnd = smpPopEnd(m, pop, ovPop, ovTau);
-  double stat = 0.0;
-  int lin = nStart, prev = -1, count = 0;
-  double prevAge = -1.0;
-  for (;;) {
-    // next coalescence of this population after (prevAge, prev) in (age, id) order
-    int best = -1;
-    double bestAge = 0.0;
-    for (int x = n; x < N; x++) {
-      if (nodePop[x] != pop) continue;
-      const double a = age[x];
-      if (a < prevAge || (a == prevAge && x <= prev)) continue;
-      if (best < 0 || a < bestAge || (a == bestAge && x < best)) { best = x; bestAge = a; }
+// ------------------------------------------------------------------------------------------ a locus held by a warp
+// Every sampler kernel gives one WARP to a locus: lane i holds nodes i, i+32, ... (R per lane) in registers, so the
+// O(N^2) work of a proposal is spread over the lanes and no per-locus scratch memory is needed.
+constexpr int kSmpLociPerCta = kSmpThreads / 32;
+constexpr double kSmpInf = 1e300;
+
+template <int R>
+struct WarpLocus {
+  double age[R];
+  int pop[R];      // population of the node; -1 for slots beyond the last node
+  int father[R];
+};
+
+template <int R>
+__device__ inline void wlLoad(WarpLocus<R>& w, const StoreDev& d, const SmpDev& sd, int l, int lane) {
+#pragma unroll
+  for (int r = 0; r < R; r++) {
+    const int x = lane + 32 * r;
+    if (x < d.N) {
+      const size_t o = (size_t)l * d.N + x;
+      w.age[r] = d.age[o];
+      w.pop[r] = sd.nodePop[o];
+      w.father[r] = d.node[o].father;
+    } else {
+      w.age[r] = kSmpInf; w.pop[r] = -1; w.father[r] = -1;
     }
-    if (best < 0) break;
-    stat += (double)(lin * (lin - 1)) * (bestAge - t);
-    t = bestAge;
-    lin--;
-    count++;
-    prev = best;
-    prevAge = bestAge;
-  }
-  stat += (double)(lin * (lin - 1)) * (tEnd - t);
-  if (numCoals) *numCoals = count;
-  return stat;
-}
-
-// lineages entering a population, from the coalescence counts of the populations below it
-__device__ inline int smpLineagesEntering(const SmpModel& m, const int* ncoal, int pop) {
-  int lin = m.leavesBelow[pop];
-  for (int q = 0; q < m.Q; q++)
-    if (q != pop && ((m.below[pop] >> q) & 1ull)) lin -= ncoal[q];
-  return lin;
-}
-
-// all statistics of a locus from its genealogy (computeGenetreeStats, patch.c:2330-2354)
-__device__ inline void smpLocusStats(const SmpModel& m, const double* age, const uint8_t* nodePop, int ovPop, double ovTau,
-                                     double* coal, int* ncoal) {
-  int nEnd[kSmpMaxPops];
-  for (int i = 0; i < m.Q; i++) {
-    const int p = m.postOrder[i];
-    const int nStart = p < m.C ? m.samplesPerPop[p] : nEnd[m.son0[p]] + nEnd[m.son1[p]];
-    int nc = 0;
-    coal[p] = smpPopCoalStat(m, age, nodePop, p, nStart, ovPop, ovTau, &nc);
-    ncoal[p] = nc;
-    nEnd[p] = nStart - nc;
   }
 }
 
-// population in which a lineage that started in `pop` lives at time s
-__device__ inline int smpPopAt(const SmpModel& m, int pop, double s) {
-  while (m.father[pop] >= 0 && m.tau[m.father[pop]] <= s) pop = m.father[pop];
-  return pop;
+__device__ inline double warpSumD(double v) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+  return v;
+}
+
+// Statistics of the locus (computeGenetreeStats + recalcStats, patch.c:2330-2513): coal[p] = sum over the
+// intervals of population p of n(n-1)*length, ncoal[p] = coalescences in p.  For every coalescence x the lanes find,
+// in one all-pairs pass over shuffled (age, population) pairs, how many coalescences of the same population precede
+// it and the age of the latest one; its interval then contributes n_x(n_x - 1)(age_x - previous).  Sums per
+// population are fixed-order shuffle trees (deterministic).  scratch: per-warp shared ints [2*Q].
+template <int R>
+__device__ inline void wlStats(const SmpModel& m, const WarpLocus<R>& w, int n, int N, int lane, int ovPop, double ovTau,
+                               int* scratch, double* coalOut, int* ncoalOut) {
+  const int Q = m.Q;
+  int* sNcoal = scratch;
+  int* sNstart = scratch + Q;
+  int ev[R];   // population of the node if it is a coalescence, else -1
+#pragma unroll
+  for (int r = 0; r < R; r++) ev[r] = (lane + 32 * r >= n && lane + 32 * r < N) ? w.pop[r] : -1;
+  for (int p = 0; p < Q; p++) {
+    int c = 0;
+#pragma unroll
+    for (int r = 0; r < R; r++) c += __popc(__ballot_sync(0xffffffffu, ev[r] == p));
+    if (lane == 0) sNcoal[p] = c;
+  }
+  __syncwarp();
+  for (int p = lane; p < Q; p += 32) {   // lineages entering p = samples below it minus coalescences strictly below it
+    int lin = m.leavesBelow[p];
+    for (int q = 0; q < Q; q++)
+      if (q != p && ((m.below[p] >> q) & 1ull)) lin -= sNcoal[q];
+    sNstart[p] = lin;
+  }
+  __syncwarp();
+  int cnt[R];
+  double prev[R];
+#pragma unroll
+  for (int r = 0; r < R; r++) { cnt[r] = 0; prev[r] = ev[r] >= 0 ? smpTau(m, ev[r], ovPop, ovTau) : 0.0; }
+#pragma unroll
+  for (int r2 = 0; r2 < R; r2++) {
+    for (int src = 0; src < 32; src++) {
+      const int y = src + 32 * r2;
+      if (y < n) continue;
+      if (y >= N) break;
+      const double ay = __shfl_sync(0xffffffffu, w.age[r2], src);
+      const int py = __shfl_sync(0xffffffffu, ev[r2], src);
+#pragma unroll
+      for (int r = 0; r < R; r++) {
+        const int x = lane + 32 * r;
+        if (py == ev[r] && (ay < w.age[r] || (ay == w.age[r] && y < x))) {
+          cnt[r]++;
+          prev[r] = fmax(prev[r], ay);
+        }
+      }
+    }
+  }
+  double term[R];
+#pragma unroll
+  for (int r = 0; r < R; r++) {
+    term[r] = 0.0;
+    if (ev[r] >= 0) {
+      const int lin = sNstart[ev[r]] - cnt[r];
+      term[r] = (double)(lin * (lin - 1)) * (w.age[r] - prev[r]);
+      if (cnt[r] == sNcoal[ev[r]] - 1) {   // last coalescence of its population: the interval up to the population's end
+        const int rest = lin - 1;
+        term[r] += (double)(rest * (rest - 1)) * (smpPopEnd(m, ev[r], ovPop, ovTau) - w.age[r]);
+      }
+    }
+  }
+  for (int p = 0; p < Q; p++) {
+    double v = 0.0;
+#pragma unroll
+    for (int r = 0; r < R; r++) v += ev[r] == p ? term[r] : 0.0;
+    v = warpSumD(v);
+    if (lane == 0) {
+      if (sNcoal[p] == 0) {
+        const int lin = sNstart[p];
+        v = (double)(lin * (lin - 1)) * (smpPopEnd(m, p, ovPop, ovTau) - smpTau(m, p, ovPop, ovTau));
+      }
+      coalOut[p] = v;
+      ncoalOut[p] = sNcoal[p];
+    }
+  }
+  __syncwarp();
+}
+
+// change of the genealogy log-density between the stored and the tentative statistics of a locus (lane 0's value)
+__device__ inline double smpGenDelta(const SmpModel& m, const double* coalOld, const double* coalNew, const int* ncoalOld,
+                                     const int* ncoalNew) {
+  double delta = 0.0;
+  for (int p = 0; p < m.Q; p++) {
+    delta -= (coalNew[p] - coalOld[p]) / m.theta[p];
+    if (ncoalNew[p] != ncoalOld[p]) delta += (double)(ncoalNew[p] - ncoalOld[p]) * log(2.0 / m.theta[p]);
+  }
+  return delta;
+}
+
+#define SMP_WARP_PROLOGUE                                                       \
+  extern __shared__ int smpScratch[];                                           \
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;                    \
+  const int l = blockIdx.x * kSmpLociPerCta + wid;                              \
+  if (l >= d.L) return;                                                         \
+  const SmpModel& m = *mp;                                                      \
+  int* scratch = smpScratch + wid * 2 * kSmpMaxPops;                            \
+  const TreeView t = deviceView(d, l);                                          \
+  const int n = d.n, N = d.N;                                                   \
+  (void)scratch; (void)n; (void)N; (void)lane; (void)m;
+
+__device__ inline SmpProposal smpNoProposal() {
+  SmpProposal pr;
+  pr.genDelta = 0.0; pr.aux = 0.0; pr.pop = 0; pr.node = -1; pr.valid = 0; pr.ntj0 = 0; pr.ntj1 = 0;
+  return pr;
 }
 
 // ------------------------------------------------------------------------------------------ coalescence-time move
+template <int R>
 __global__ void __launch_bounds__(kSmpThreads)
 k_smp_age_propose(StoreDev d, SmpDev sd, const SmpModel* __restrict__ mp, int inode, double finetune, unsigned long long seed,
                   unsigned long long step) {
-  const int l = blockIdx.x * blockDim.x + threadIdx.x;
-  if (l >= d.L) return;
-  const SmpModel& m = *mp;
-  SmpProposal pr;
-  pr.genDelta = 0.0; pr.aux = 0.0; pr.pop = 0; pr.node = inode; pr.valid = 0; pr.ntj0 = 0; pr.ntj1 = 0;
-  const TreeView t = deviceView(d, l);
+  SMP_WARP_PROLOGUE
+  SmpProposal pr = smpNoProposal();
+  pr.node = inode;
   const int root = *t.root;
-  if (root >= d.n && t.numPatterns >= 0) {
-    const uint8_t* np = sd.nodePop + (size_t)l * d.N;
+  if (root < n) { if (lane == 0) sd.prop[l] = pr; return; }
+  WarpLocus<R> w;
+  wlLoad(w, d, sd, l, lane);
+  double tnew = 0.0;
+  int valid = 0;
+  if (lane == 0) {
+    const uint8_t* np = sd.nodePop + (size_t)l * N;
     const int pop = np[inode];
     const double told = t.age[inode];
     const NodeRec rec = t.node[inode];
-    double lo = fmax(m.tau[pop], fmax(t.age[rec.left], t.age[rec.right]));
+    const double lo = fmax(m.tau[pop], fmax(t.age[rec.left], t.age[rec.right]));
     double hi = m.father[pop] >= 0 ? m.tau[m.father[pop]] : kOldAge;
     if (inode != root) hi = fmin(hi, t.age[rec.father]);
     SmpRng rng(seed, (unsigned long long)l, step);
-    const double tnew = smpReflect(told + finetune * rng.normal2(), lo, hi);
-    if (fabs(tnew - told) >= 1e-15) {   // GPhoCS.c:2354-2358
-      const int* nc = sd.ncoal + (size_t)l * m.Q;
-      const int nStart = smpLineagesEntering(m, nc, pop);
-      adjustAge(t, inode, tnew);
-      const double coalNew = smpPopCoalStat(m, t.age, np, pop, nStart, -1, 0.0, nullptr);
-      pr.genDelta = -(coalNew - sd.coal[(size_t)l * m.Q + pop]) / m.theta[pop];
-      pr.aux = coalNew;
-      pr.pop = pop;
+    tnew = smpReflect(told + finetune * rng.normal2(), lo, hi);
+    valid = fabs(tnew - told) >= 1e-15;   // GPhoCS.c:2354-2358
+    if (valid) adjustAge(t, inode, tnew);
+  }
+  valid = __shfl_sync(0xffffffffu, valid, 0);
+  tnew = __shfl_sync(0xffffffffu, tnew, 0);
+  if (valid) {
+#pragma unroll
+    for (int r = 0; r < R; r++)
+      if (lane + 32 * r == inode) w.age[r] = tnew;
+    double* cT = sd.coalT + (size_t)l * m.Q;
+    int* nT = sd.ncoalT + (size_t)l * m.Q;
+    wlStats<R>(m, w, n, N, lane, -1, 0.0, scratch, cT, nT);
+    if (lane == 0) {
+      pr.genDelta = smpGenDelta(m, sd.coal + (size_t)l * m.Q, cT, sd.ncoal + (size_t)l * m.Q, nT);
       pr.valid = 1;
     }
   }
-  sd.prop[l] = pr;
+  if (lane == 0) sd.prop[l] = pr;
 }
 
 // ------------------------------------------------------------------------------------------ subtree prune and regraft
-// The pruned lineage is re-attached by simulating the coalescent conditional on the rest of the genealogy: in
-// population p with k other lineages it coalesces at rate 2k/theta_p, moves to the parent population at its
-// end, and picks its target uniformly among the k lineages.  The proposal is the conditional prior, so the
-// acceptance ratio is the data-likelihood ratio alone (GPhoCS.c:2702-2706).
+// The pruned lineage is re-attached by the coalescent conditional on the rest of the genealogy: while it shares
+// a population with another lineage it coalesces with it at rate 2/theta of that population.  These are
+// independent competing clocks, so every lane draws the first ring of its own lineages' clocks (integrating the
+// piecewise-constant rate along the populations the pruned lineage passes through) and the earliest ring over
+// the warp gives the new coalescence time, its population and the target branch — the same law as walking the
+// intervals of the event chain (traceLineage, patch.c:886-1331, without migration).  The proposal is the
+// conditional prior, so the acceptance ratio is the data-likelihood ratio alone (GPhoCS.c:2702-2706).
+template <int R>
 __global__ void __launch_bounds__(kSmpThreads)
 k_smp_spr_propose(StoreDev d, SmpDev sd, const SmpModel* __restrict__ mp, int node, unsigned long long seed,
                   unsigned long long step) {
-  const int l = blockIdx.x * blockDim.x + threadIdx.x;
-  if (l >= d.L) return;
-  const SmpModel& m = *mp;
-  SmpProposal pr;
-  pr.genDelta = 0.0; pr.aux = 0.0; pr.pop = 0; pr.node = -1; pr.valid = 0; pr.ntj0 = 0; pr.ntj1 = 0;
-  const TreeView t = deviceView(d, l);
-  const int root = *t.root, n = d.n, N = d.N;
-  if (root >= n && node != root) {
-    uint8_t* np = sd.nodePop + (size_t)l * N;
-    const int F = t.node[node].father;
-    const int S = t.node[F].left + t.node[F].right - node;
-    const int G = t.node[F].father;
-    SmpRng rng(seed, (unsigned long long)l, step);
-    double now = t.age[node];
-    int pop = smpPopAt(m, np[node], now);
+  SMP_WARP_PROLOGUE
+  SmpProposal pr = smpNoProposal();
+  const int root = *t.root;
+  if (root < n || node == root) { if (lane == 0) sd.prop[l] = pr; return; }
+  WarpLocus<R> w;
+  wlLoad(w, d, sd, l, lane);
+  const int F = t.node[node].father;
+  const NodeRec recF = t.node[F];
+  const int S = recF.left + recF.right - node;
+  const int G = recF.father;
+  const double t0 = t.age[node];
+  const int pop0 = sd.nodePop[(size_t)l * N + node];
+  const double ageG = G >= 0 ? t.age[G] : kSmpInf;
+  double bestT = kSmpInf;
+  int bestX = -1, bestPop = -1;
+#pragma unroll
+  for (int r = 0; r < R; r++) {
+    const int x = lane + 32 * r;
+    if (x >= N || x == node || x == F) continue;
+    const double endx = x == S ? ageG : (w.father[r] >= 0 ? t.age[w.father[r]] : kSmpInf);
+    int q = w.pop[r];   // first population in which the two lineages can meet: their common ancestor
+    while (!((m.below[q] >> pop0) & 1ull)) q = m.father[q];
+    double sNow = fmax(fmax(t0, w.age[r]), m.tau[q]);
+    if (sNow >= endx) continue;
+    while (m.father[q] >= 0 && m.tau[m.father[q]] <= sNow) q = m.father[q];
+    SmpRng rng(seed, (unsigned long long)l * 512ull + (unsigned long long)x, step);
     double need = rng.exponential();
-    int target = -1;
-    for (int it = 0; it < 4 * N + 4 * kSmpMaxPops && target < 0; it++) {
-      // lineages of the pruned genealogy present in `pop` just after `now`, and the next time anything changes
-      const double popEnd = m.father[pop] >= 0 ? m.tau[m.father[pop]] : kOldAge * 1e6;
-      double next = popEnd;
-      int k = 0;
-      for (int x = 0; x < N; x++) {
-        if (x == node || x == F) continue;
-        const double a = t.age[x];
-        if (a > now) { next = fmin(next, a); continue; }
-        const int par = x == S ? G : t.node[x].father;
-        if (par >= 0 && t.age[par] <= now) continue;
-        if (smpPopAt(m, np[x], now) == pop) k++;
-      }
-      const double rate = 2.0 * k / m.theta[pop];
-      const double span = next - now;
-      if (rate * span >= need) {
-        now += need / rate;
-        int pick = min(k - 1, (int)(rng.uniform() * k));
-        if (pick < 0) pick = 0;
-        for (int x = 0; x < N && target < 0; x++) {   // same enumeration as above, at the same reference time
-          if (x == node || x == F) continue;
-          const double a = t.age[x];
-          if (a > now) continue;
-          const int par = x == S ? G : t.node[x].father;
-          if (par >= 0 && t.age[par] <= now) continue;
-          if (smpPopAt(m, np[x], now) != pop) continue;
-          if (pick-- == 0) target = x;
-        }
+    for (int it = 0; it < kSmpMaxPops; it++) {
+      const double popEnd = m.father[q] >= 0 ? m.tau[m.father[q]] : kSmpInf;
+      const double segEnd = fmin(endx, popEnd);
+      const double rate = 2.0 / m.theta[q];
+      if (rate * (segEnd - sNow) >= need) {
+        const double T = sNow + need / rate;
+        if (T < bestT) { bestT = T; bestX = x; bestPop = q; }
         break;
       }
-      need -= rate * span;
-      now = next;
-      if (next >= popEnd && m.father[pop] >= 0) pop = m.father[pop];
-    }
-    if (target >= 0) {
-      pr.pop = np[F];
-      pr.node = F;
-      spr(t, node, target, now);
-      np[F] = (uint8_t)pop;
-      pr.valid = 1;
+      need -= rate * (segEnd - sNow);
+      sNow = segEnd;
+      if (sNow >= endx) break;
+      q = m.father[q];
     }
   }
-  sd.prop[l] = pr;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {   // earliest ring over the warp (ties: lower node id)
+    const double oT = __shfl_xor_sync(0xffffffffu, bestT, off);
+    const int oX = __shfl_xor_sync(0xffffffffu, bestX, off);
+    const int oP = __shfl_xor_sync(0xffffffffu, bestPop, off);
+    if (oT < bestT || (oT == bestT && oX >= 0 && (bestX < 0 || oX < bestX))) { bestT = oT; bestX = oX; bestPop = oP; }
+  }
+  if (bestX >= 0) {
+    if (lane == 0) {
+      uint8_t* np = sd.nodePop + (size_t)l * N;
+      pr.pop = np[F];
+      pr.node = F;
+      spr(t, node, bestX, bestT);
+      np[F] = (uint8_t)bestPop;
+    }
+#pragma unroll
+    for (int r = 0; r < R; r++)
+      if (lane + 32 * r == F) { w.age[r] = bestT; w.pop[r] = bestPop; }
+    double* cT = sd.coalT + (size_t)l * m.Q;
+    int* nT = sd.ncoalT + (size_t)l * m.Q;
+    wlStats<R>(m, w, n, N, lane, -1, 0.0, scratch, cT, nT);
+    pr.valid = 1;
+  }
+  if (lane == 0) sd.prop[l] = pr;
 }
 
 // ------------------------------------------------------------------------------------------ per-locus accept / reject
-// kind 0: coalescence-time move (likelihood ratio of data and genealogy); kind 1: SPR (data likelihood ratio)
+// kind 0: coalescence-time move (likelihood ratio of data and genealogy); kind 1: SPR (data likelihood ratio).
+// The statistics of the proposed state were left in coalT / ncoalT by the proposal kernel.
 __global__ void __launch_bounds__(kSmpThreads)
 k_smp_accept(StoreDev d, SmpDev sd, const SmpModel* __restrict__ mp, int kind, unsigned long long seed, unsigned long long step) {
-  const int l = blockIdx.x * blockDim.x + threadIdx.x;
-  unsigned long long acc = 0;
-  if (l < d.L) {
-    const SmpModel& m = *mp;
-    const SmpProposal pr = sd.prop[l];
-    if (pr.valid) {
-      const TreeView t = deviceView(d, l);
+  SMP_WARP_PROLOGUE
+  const SmpProposal pr = sd.prop[l];
+  int ok = 0;
+  if (pr.valid) {
+    if (lane == 0) {
       const double lnacc = (*t.lnL - *t.savedLnL) + pr.genDelta;
-      SmpRng rng(seed, (unsigned long long)l, step);
-      bool ok = lnacc >= 0.0;
-      if (!ok) ok = rng.uniform() < exp(lnacc);
-      if (ok) {
-        commit(t);
-        if (kind == 0) {
-          sd.coal[(size_t)l * m.Q + pr.pop] = pr.aux;
-        } else {
-          smpLocusStats(m, t.age, sd.nodePop + (size_t)l * d.N, -1, 0.0, sd.coal + (size_t)l * m.Q, sd.ncoal + (size_t)l * m.Q);
-        }
-        acc = 1;
-      } else {
-        revert(t);
-        if (kind == 1) sd.nodePop[(size_t)l * d.N + pr.node] = (uint8_t)pr.pop;
+      ok = lnacc >= 0.0;
+      if (!ok) {
+        SmpRng rng(seed, (unsigned long long)l, step);
+        ok = rng.uniform() < exp(lnacc);
       }
-    } else if (kind == 0) {
-      acc = 1;   // an unchanged age counts as accepted (GPhoCS.c:2354-2358)
     }
+    ok = __shfl_sync(0xffffffffu, ok, 0);
+    if (ok) {
+      for (int x = lane; x < N; x += 32) commitNode(t, x);
+      for (int p = lane; p < m.Q; p += 32) {
+        sd.coal[(size_t)l * m.Q + p] = sd.coalT[(size_t)l * m.Q + p];
+        sd.ncoal[(size_t)l * m.Q + p] = sd.ncoalT[(size_t)l * m.Q + p];
+      }
+      if (lane == 0) commitLocus(t);
+    } else {
+      for (int x = lane; x < N; x += 32) revertNode(t, x);
+      if (lane == 0) {
+        revertLocus(t);
+        if (kind == 1) sd.nodePop[(size_t)l * N + pr.node] = (uint8_t)pr.pop;
+      }
+    }
+  } else if (kind == 0) {
+    ok = 1;   // an unchanged age counts as accepted (GPhoCS.c:2354-2358)
   }
-  acc = __reduce_add_sync(0xffffffffu, (unsigned)acc);
-  if ((threadIdx.x & 31) == 0 && acc) atomicAdd(sd.accepted + kind, acc);
+  if (lane == 0 && ok) atomicAdd(sd.accepted + kind, 1ull);
 }
 
 // ------------------------------------------------------------------------------------------ split-time move
 // Rubber band (patch.c:596-801) around population A whose split time moves tauOld -> tauNew: coalescences of A
 // in (tauOld, ub) are rescaled towards ub by f1, coalescences of its two sons in (lb, tauOld) towards lb by f0; in
 // the root population everything above tauOld is rescaled from lb by f0 (GPhoCS.c:3749-3785).
+template <int R>
 __global__ void __launch_bounds__(kSmpThreads)
 k_smp_tau_propose(StoreDev d, SmpDev sd, const SmpModel* __restrict__ mp, int A, double tauOld, double tauNew, double lb, double ub,
                   double f0, double f1) {
-  const int l = blockIdx.x * blockDim.x + threadIdx.x;
-  if (l >= d.L) return;
-  const SmpModel& m = *mp;
-  SmpProposal pr;
-  pr.genDelta = 0.0; pr.aux = 0.0; pr.pop = A; pr.node = -1; pr.valid = 0; pr.ntj0 = 0; pr.ntj1 = 0;
-  const TreeView t = deviceView(d, l);
-  if (*t.root >= d.n) {
-    const uint8_t* np = sd.nodePop + (size_t)l * d.N;
-    const bool isRoot = A == m.rootPop;
-    const int s0 = m.son0[A], s1 = m.son1[A];
-    for (int x = d.n; x < d.N; x++) {
-      const int q = np[x];
-      const double a = t.age[x];
-      if (q == A) {
-        if (isRoot) { adjustAge(t, x, lb + (a - lb) * f0); pr.ntj1++; }
-        else if (a > tauOld && a < ub) { adjustAge(t, x, ub + (a - ub) * f1); pr.ntj1++; }
-      } else if ((q == s0 || q == s1) && a > lb && a < tauOld) {
-        adjustAge(t, x, lb + (a - lb) * f0);
-        pr.ntj0++;
-      }
+  SMP_WARP_PROLOGUE
+  SmpProposal pr = smpNoProposal();
+  pr.pop = A;
+  if (*t.root < n) { if (lane == 0) sd.prop[l] = pr; return; }
+  WarpLocus<R> w;
+  wlLoad(w, d, sd, l, lane);
+  const bool isRoot = A == m.rootPop;
+  const int s0 = m.son0[A], s1 = m.son1[A];
+  int n0 = 0, n1 = 0;
+#pragma unroll
+  for (int r = 0; r < R; r++) {
+    const int x = lane + 32 * r;
+    int which = 0;   // 1: lower band, 2: upper band
+    if (x >= n && x < N) {
+      const int q = w.pop[r];
+      const double a = w.age[r];
+      if (q == A) { if (isRoot || (a > tauOld && a < ub)) which = 2; }
+      else if ((q == s0 || q == s1) && a > lb && a < tauOld) which = 1;
     }
-    int nc[kSmpMaxPops];
-    double* cT = sd.coalT + (size_t)l * m.Q;
-    smpLocusStats(m, t.age, np, A, tauNew, cT, nc);
-    const double* c0 = sd.coal + (size_t)l * m.Q;
-    double delta = 0.0;
-    for (int p = 0; p < m.Q; p++) delta -= (cT[p] - c0[p]) / m.theta[p];
-    pr.genDelta = delta;
-    pr.valid = 1;
+    if (which) {
+      const double a = w.age[r];
+      const double an = which == 1 || isRoot ? lb + (a - lb) * f0 : ub + (a - ub) * f1;
+      adjustAge(t, x, an);
+      w.age[r] = an;
+    }
+    n0 += __popc(__ballot_sync(0xffffffffu, which == 1));
+    n1 += __popc(__ballot_sync(0xffffffffu, which == 2));
   }
-  sd.prop[l] = pr;
+  double* cT = sd.coalT + (size_t)l * m.Q;
+  int* nT = sd.ncoalT + (size_t)l * m.Q;
+  wlStats<R>(m, w, n, N, lane, A, tauNew, scratch, cT, nT);
+  if (lane == 0) {
+    pr.genDelta = smpGenDelta(m, sd.coal + (size_t)l * m.Q, cT, sd.ncoal + (size_t)l * m.Q, nT);
+    pr.ntj0 = n0;
+    pr.ntj1 = n1;
+    pr.valid = 1;
+    sd.prop[l] = pr;
+  }
 }
 
 // joint rescaling of every node age by c (scaleAllNodeAges, LocusDataLikelihood.c:895-917, without its evaluation)
-__global__ void __launch_bounds__(kSmpThreads) k_smp_scale_propose(StoreDev d, SmpDev sd, double c) {
-  const int l = blockIdx.x * blockDim.x + threadIdx.x;
-  if (l >= d.L) return;
-  const TreeView t = deviceView(d, l);
-  SmpProposal pr;
-  pr.genDelta = 0.0; pr.aux = 0.0; pr.pop = 0; pr.node = -1; pr.valid = 0; pr.ntj0 = 0; pr.ntj1 = 0;
-  if (*t.root >= d.n) {
-    scaleAll(t, c);
+__global__ void __launch_bounds__(kSmpThreads) k_smp_scale_propose(StoreDev d, SmpDev sd, const SmpModel* __restrict__ mp, double c) {
+  SMP_WARP_PROLOGUE
+  SmpProposal pr = smpNoProposal();
+  if (*t.root >= n) {
+    for (int x = lane; x < N; x += 32) adjustAge(t, x, c * t.age[x]);
     pr.valid = 1;
   }
-  sd.prop[l] = pr;
+  if (lane == 0) sd.prop[l] = pr;
 }
 
 // block partial sums: [0] data delta, [1] genealogy delta, [2] ntj0, [3] ntj1, [4..4+Q) coal totals, [4+Q..4+2Q) ncoal totals
@@ -386,36 +495,32 @@ __global__ void __launch_bounds__(kSmpThreads) k_smp_reduce(StoreDev d, SmpDev s
 }
 
 // one global accept / reject for every locus; how: 0 tau move (statistics <- tentative), 1 rescaling (statistics *= c)
-__global__ void __launch_bounds__(kSmpThreads) k_smp_global_resolve(StoreDev d, SmpDev sd, int accept, int how, double c) {
-  const int l = blockIdx.x * blockDim.x + threadIdx.x;
-  if (l >= d.L) return;
+__global__ void __launch_bounds__(kSmpThreads) k_smp_global_resolve(StoreDev d, SmpDev sd, const SmpModel* __restrict__ mp, int accept,
+                                                                    int how, double c) {
+  SMP_WARP_PROLOGUE
   if (!sd.prop[l].valid) return;
-  const TreeView t = deviceView(d, l);
   if (accept) {
-    commit(t);
-    double* c0 = sd.coal + (size_t)l * sd.Q;
-    if (how == 0) {
-      const double* cT = sd.coalT + (size_t)l * sd.Q;
-      for (int p = 0; p < sd.Q; p++) c0[p] = cT[p];
-    } else {
-      for (int p = 0; p < sd.Q; p++) c0[p] *= c;
+    for (int x = lane; x < N; x += 32) commitNode(t, x);
+    for (int p = lane; p < sd.Q; p += 32) {
+      double* c0 = sd.coal + (size_t)l * sd.Q + p;
+      *c0 = how == 0 ? sd.coalT[(size_t)l * sd.Q + p] : *c0 * c;
     }
+    if (lane == 0) commitLocus(t);
   } else {
-    revert(t);
+    for (int x = lane; x < N; x += 32) revertNode(t, x);
+    if (lane == 0) revertLocus(t);
   }
 }
 
 // statistics of every locus from scratch (initialisation and consistency checks)
-__global__ void __launch_bounds__(kSmpThreads) k_smp_init_stats(StoreDev d, SmpDev sd, const SmpModel* __restrict__ mp, int toTentative,
-                                                                int* __restrict__ ncoalOut) {
-  const int l = blockIdx.x * blockDim.x + threadIdx.x;
-  if (l >= d.L) return;
-  const SmpModel& m = *mp;
-  const TreeView t = deviceView(d, l);
-  if (*t.root < d.n) return;
-  double* dst = (toTentative ? sd.coalT : sd.coal) + (size_t)l * m.Q;
-  int* nc = (toTentative ? ncoalOut : sd.ncoal) + (size_t)l * m.Q;
-  smpLocusStats(m, t.age, sd.nodePop + (size_t)l * d.N, -1, 0.0, dst, nc);
+template <int R>
+__global__ void __launch_bounds__(kSmpThreads) k_smp_init_stats(StoreDev d, SmpDev sd, const SmpModel* __restrict__ mp, int toTentative) {
+  SMP_WARP_PROLOGUE
+  if (*t.root < n) return;
+  WarpLocus<R> w;
+  wlLoad(w, d, sd, l, lane);
+  wlStats<R>(m, w, n, N, lane, -1, 0.0, scratch, (toTentative ? sd.coalT : sd.coal) + (size_t)l * m.Q,
+             (toTentative ? sd.ncoalT : sd.ncoal) + (size_t)l * m.Q);
 }
 
 // consistency of the population assignment: every coalescence lies inside its population's time span and above

@@ -120,34 +120,42 @@ GP_HD int spr(const TreeView& t, int sub, int target, double age) {
   return 0;
 }
 
-// resetSaved (.c:852-864)
-GP_HD void commit(const TreeView& t) {
-  const int N = 2 * t.numLeaves - 1;
-  for (int i = 0; i < N; i++) t.node[i].flags &= F_SEL;
+// resetSaved (.c:852-864), split into its per-node and per-locus parts so device code can spread the nodes over lanes
+GP_HD void commitNode(const TreeView& t, int i) { t.node[i].flags &= F_SEL; }
+GP_HD void commitLocus(const TreeView& t) {
   *t.savedRoot = -1;
   *t.savedLnL = *t.lnL;
+}
+GP_HD void commit(const TreeView& t) {
+  const int N = 2 * t.numLeaves - 1;
+  for (int i = 0; i < N; i++) commitNode(t, i);
+  commitLocus(t);
 }
 
 // revertToSaved (.c:768-841).  The reference's copyAll branch (wholesale array swap after
 // scaleAllNodeAges) is the same thing node by node because scaleAllNodeAges saved every node.
-GP_HD void revert(const TreeView& t) {
-  const int N = 2 * t.numLeaves - 1;
+GP_HD void revertNode(const TreeView& t, int i) {
+  NodeRec r = t.node[i];
+  uint8_t f = r.flags;
+  if (f & F_SAVED) {
+    t.age[i] = t.svAge[i];
+    r = t.saved[i];
+  }
+  if (f & F_RECALC) f ^= F_SEL;
+  r.flags = f & F_SEL;
+  t.node[i] = r;
+}
+GP_HD void revertLocus(const TreeView& t) {
   *t.lnL = *t.savedLnL;
   if (*t.savedRoot >= 0) {
     *t.root = *t.savedRoot;
     *t.savedRoot = -1;
   }
-  for (int i = 0; i < N; i++) {
-    NodeRec r = t.node[i];
-    uint8_t f = r.flags;
-    if (f & F_SAVED) {
-      t.age[i] = t.svAge[i];
-      r = t.saved[i];
-    }
-    if (f & F_RECALC) f ^= F_SEL;
-    r.flags = f & F_SEL;
-    t.node[i] = r;
-  }
+}
+GP_HD void revert(const TreeView& t) {
+  const int N = 2 * t.numLeaves - 1;
+  revertLocus(t);
+  for (int i = 0; i < N; i++) revertNode(t, i);
 }
 
 GP_HD int applyOp(const TreeView& t, const Op& op) {
