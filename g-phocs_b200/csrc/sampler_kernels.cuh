@@ -6,9 +6,9 @@
 //   UpdateTheta            GPhoCS.c:3035-3103   multiplicative theta moves from the total statistics
 //   UpdateTau              GPhoCS.c:3224-3990   split-time moves with the rubber band (patch.c:596-801)
 //   mixing                 GPhoCS.c:4688-4900   joint rescaling of all times and thetas
-// is done here for ALL loci per launch: one thread per locus proposes (its own counter-based Philox stream) and
+// is done here for ALL loci per launch: one warp per locus proposes (its own counter-based random stream) and
 // edits the device-resident genealogy through the same edit protocol the host API uses (tree_ops.cuh); k_eval
-// (clv_kernels.cuh) evaluates every locus incrementally; one thread per locus accepts or rejects.  No host round
+// (clv_kernels.cuh) evaluates every locus incrementally; the same warp accepts or rejects.  No host round
 // trip inside a sweep.  Scope of this version: population trees WITHOUT migration bands, samples of age 0,
 // constant locus rates — the model of BASELINE.json configs[1].  The target density is the reference's:
 //   P(X|G) * prod_pops (2/theta)^ncoal exp(-coal_stats/theta) * Gamma priors on theta and tau
@@ -17,7 +17,6 @@
 // (tests/test_gpu_sampler.py: prior recovery with uninformative data, posterior means against the reference chain).
 #pragma once
 #include <cuda_runtime.h>
-#include <curand_kernel.h>
 #include <stdint.h>
 
 #include "clv_kernels.cuh"
@@ -59,13 +58,28 @@ struct SmpDev {
 constexpr int kSmpPartials = 4 + 2 * kSmpMaxPops;
 constexpr int kSmpThreads = 128;
 
+// Counter-based random numbers: draw k of stream (seed, locus, step) is a SplitMix64-style hash of its coordinates,
+// so kernels need no generator state and every (locus, step) owns an independent stream whatever the launch order.
 struct SmpRng {
-  curandStatePhilox4_32_10_t st;
-  __device__ SmpRng(unsigned long long seed, unsigned long long locus, unsigned long long step) {
-    curand_init(seed, locus, step * 16ull, &st);   // 16 values reserved per (locus, step)
+  unsigned long long key, ctr;
+  __device__ SmpRng(unsigned long long seed, unsigned long long stream, unsigned long long step) {
+    key = mix(seed ^ mix(stream * 0x9E3779B97F4A7C15ull + 0xD1B54A32D192ED03ull) ^ mix(step * 0xBF58476D1CE4E5B9ull + 0x94D049BB133111EBull));
+    ctr = 0;
   }
-  __device__ double uniform() { return curand_uniform_double(&st); }   // (0, 1]
-  __device__ double normal() { return curand_normal_double(&st); }
+  __device__ static unsigned long long mix(unsigned long long z) {
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+  }
+  __device__ unsigned long long next() { return mix(key + (++ctr) * 0x9E3779B97F4A7C15ull); }
+  __device__ double uniform() { return ((double)(next() >> 11) + 0.5) * (1.0 / 9007199254740992.0); }   // (0, 1)
+  // standard normal by Box-Muller in single precision: proposals only need a symmetric, well-spread kernel
+  __device__ double normal() {
+    const unsigned long long r = next();
+    const float u1 = ((float)(unsigned)(r >> 40) + 0.5f) * (1.0f / 16777216.0f);
+    const float u2 = ((float)(unsigned)((r >> 8) & 0xffffffu) + 0.5f) * (1.0f / 16777216.0f);
+    return (double)(sqrtf(-2.0f * __logf(u1)) * __cosf(6.2831853f * u2));
+  }
   // rnd2normal8 (utils.c:482-488): mixture of N(-m, s^2) and N(m, s^2) with m^2 + s^2 = 1, m^2/s^2 = 8
   __device__ double normal2() {
     const double z = 0.94280904158206336 + normal() * (1.0 / 3.0);
@@ -211,6 +225,53 @@ __device__ inline void wlStats(const SmpModel& m, const WarpLocus<R>& w, int n, 
   __syncwarp();
 }
 
+// coal statistic of ONE population (a coalescence-time move changes no other): the all-pairs pass of wlStats
+// restricted to the coalescences of that population, found with a ballot.  nStart = lineages entering it.
+template <int R>
+__device__ inline double wlPopStat(const SmpModel& m, const WarpLocus<R>& w, int n, int N, int lane, int pop, int nStart) {
+  unsigned mask[R];
+  int total = 0;
+#pragma unroll
+  for (int r = 0; r < R; r++) {
+    const int x = lane + 32 * r;
+    mask[r] = __ballot_sync(0xffffffffu, x >= n && x < N && w.pop[r] == pop);
+    total += __popc(mask[r]);
+  }
+  const double tau = m.tau[pop];
+  const double end = m.father[pop] >= 0 ? m.tau[m.father[pop]] : kOldAge;
+  if (total == 0) return (double)(nStart * (nStart - 1)) * (end - tau);
+  int cnt[R];
+  double prev[R];
+#pragma unroll
+  for (int r = 0; r < R; r++) { cnt[r] = 0; prev[r] = tau; }
+#pragma unroll
+  for (int r2 = 0; r2 < R; r2++) {
+    for (unsigned rest = mask[r2]; rest; rest &= rest - 1) {
+      const int src = __ffs(rest) - 1;
+      const int y = src + 32 * r2;
+      const double ay = __shfl_sync(0xffffffffu, w.age[r2], src);
+#pragma unroll
+      for (int r = 0; r < R; r++) {
+        const int x = lane + 32 * r;
+        if (ay < w.age[r] || (ay == w.age[r] && y < x)) { cnt[r]++; prev[r] = fmax(prev[r], ay); }
+      }
+    }
+  }
+  double v = 0.0;
+#pragma unroll
+  for (int r = 0; r < R; r++) {
+    if ((mask[r] >> lane) & 1u) {
+      const int lin = nStart - cnt[r];
+      v += (double)(lin * (lin - 1)) * (w.age[r] - prev[r]);
+      if (cnt[r] == total - 1) {
+        const int restLin = lin - 1;
+        v += (double)(restLin * (restLin - 1)) * (end - w.age[r]);
+      }
+    }
+  }
+  return warpSumD(v);
+}
+
 // change of the genealogy log-density between the stored and the tentative statistics of a locus (lane 0's value)
 __device__ inline double smpGenDelta(const SmpModel& m, const double* coalOld, const double* coalNew, const int* ncoalOld,
                                      const int* ncoalNew) {
@@ -269,14 +330,24 @@ k_smp_age_propose(StoreDev d, SmpDev sd, const SmpModel* __restrict__ mp, int in
   valid = __shfl_sync(0xffffffffu, valid, 0);
   tnew = __shfl_sync(0xffffffffu, tnew, 0);
   if (valid) {
+    int pop = 0, nStart = 0;
+    if (lane == 0) {
+      pop = sd.nodePop[(size_t)l * N + inode];
+      const int* nc = sd.ncoal + (size_t)l * m.Q;
+      nStart = m.leavesBelow[pop];
+      for (int q = 0; q < m.Q; q++)
+        if (q != pop && ((m.below[pop] >> q) & 1ull)) nStart -= nc[q];
+    }
+    pop = __shfl_sync(0xffffffffu, pop, 0);
+    nStart = __shfl_sync(0xffffffffu, nStart, 0);
 #pragma unroll
     for (int r = 0; r < R; r++)
       if (lane + 32 * r == inode) w.age[r] = tnew;
-    double* cT = sd.coalT + (size_t)l * m.Q;
-    int* nT = sd.ncoalT + (size_t)l * m.Q;
-    wlStats<R>(m, w, n, N, lane, -1, 0.0, scratch, cT, nT);
+    const double coalNew = wlPopStat<R>(m, w, n, N, lane, pop, nStart);
     if (lane == 0) {
-      pr.genDelta = smpGenDelta(m, sd.coal + (size_t)l * m.Q, cT, sd.ncoal + (size_t)l * m.Q, nT);
+      pr.genDelta = -(coalNew - sd.coal[(size_t)l * m.Q + pop]) / m.theta[pop];
+      pr.aux = coalNew;
+      pr.pop = pop;
       pr.valid = 1;
     }
   }
@@ -352,20 +423,15 @@ k_smp_spr_propose(StoreDev d, SmpDev sd, const SmpModel* __restrict__ mp, int no
       spr(t, node, bestX, bestT);
       np[F] = (uint8_t)bestPop;
     }
-#pragma unroll
-    for (int r = 0; r < R; r++)
-      if (lane + 32 * r == F) { w.age[r] = bestT; w.pop[r] = bestPop; }
-    double* cT = sd.coalT + (size_t)l * m.Q;
-    int* nT = sd.ncoalT + (size_t)l * m.Q;
-    wlStats<R>(m, w, n, N, lane, -1, 0.0, scratch, cT, nT);
-    pr.valid = 1;
+    pr.valid = 1;   // the statistics of accepted loci are refreshed once, after the sweep (k_smp_init_stats)
   }
   if (lane == 0) sd.prop[l] = pr;
 }
 
 // ------------------------------------------------------------------------------------------ per-locus accept / reject
 // kind 0: coalescence-time move (likelihood ratio of data and genealogy); kind 1: SPR (data likelihood ratio).
-// The statistics of the proposed state were left in coalT / ncoalT by the proposal kernel.
+// A coalescence-time move changes one population's statistic (carried in the proposal record); after an SPR
+// sweep the statistics of all loci are recomputed in one launch.
 __global__ void __launch_bounds__(kSmpThreads)
 k_smp_accept(StoreDev d, SmpDev sd, const SmpModel* __restrict__ mp, int kind, unsigned long long seed, unsigned long long step) {
   SMP_WARP_PROLOGUE
@@ -383,11 +449,10 @@ k_smp_accept(StoreDev d, SmpDev sd, const SmpModel* __restrict__ mp, int kind, u
     ok = __shfl_sync(0xffffffffu, ok, 0);
     if (ok) {
       for (int x = lane; x < N; x += 32) commitNode(t, x);
-      for (int p = lane; p < m.Q; p += 32) {
-        sd.coal[(size_t)l * m.Q + p] = sd.coalT[(size_t)l * m.Q + p];
-        sd.ncoal[(size_t)l * m.Q + p] = sd.ncoalT[(size_t)l * m.Q + p];
+      if (lane == 0) {
+        commitLocus(t);
+        if (kind == 0) sd.coal[(size_t)l * m.Q + pr.pop] = pr.aux;
       }
-      if (lane == 0) commitLocus(t);
     } else {
       for (int x = lane; x < N; x += 32) revertNode(t, x);
       if (lane == 0) {
