@@ -173,15 +173,66 @@ def port_sample(cfg, sample_loci, seed, reps):
     return times, w.L, 0.0, 0.0, 1
 
 
+MCMC_CONFIG, MCMC_LOCI = "hap16", 10_000     # BASELINE.json configs[1]: 10k loci x 1 kb, 16 haplotypes, 4 populations, no migration
+
+
+def reference_mcmc(threads, iterations=40):
+    """MCMC iterations/s of the reference's own OpenMP build (oracle/_ref/G-PhoCS-ref) on MCMC_CONFIG:
+    iterations / (wall - wall of a 1-iteration run), BASELINE.md 3.2.  None when the binary is absent."""
+    import tempfile
+    binary = os.path.join(ROOT, "oracle", "_ref", "G-PhoCS-ref")
+    if not os.path.exists(binary):
+        return None
+    synth = importlib.import_module("g-phocs_b200.synth")
+    model = synth.config(MCMC_CONFIG)
+    with tempfile.TemporaryDirectory() as tmp:
+        seq = os.path.join(tmp, "seqs.txt")
+        synth.generate(model, MCMC_LOCI, seed=777, seqfile=seq)
+        wall = {}
+        for iters in (1, iterations):
+            ctl = os.path.join(tmp, f"r{iters}.ctl")
+            synth.write_control_file(model, ctl, seq, os.path.join(tmp, f"r{iters}.trace"), iterations=iters, seed=4242,
+                                     iterations_per_log=iters)
+            t0 = time.perf_counter()
+            r = subprocess.run([binary, ctl, "-n", str(threads)], capture_output=True, text=True, cwd=tmp)
+            wall[iters] = time.perf_counter() - t0
+            if r.returncode != 0:
+                return None
+    return {"config": f"{MCMC_CONFIG}: {MCMC_LOCI} loci", "iterations": iterations, "threads": threads,
+            "iters_per_s": (iterations - 1) / max(wall[iterations] - wall[1], 1e-9), "wall_s": wall[iterations], "setup_s": wall[1]}
+
+
+def device_mcmc(gp, synth, device, iterations=100):
+    """MCMC iterations/s of the device-resident update steps (gphocs_b200.h group D) on MCMC_CONFIG."""
+    w = synth.generate(synth.config(MCMC_CONFIG), MCMC_LOCI, seed=777)
+    st = gp.LociStore.from_workload(w, device=device)
+    sm = gp.Sampler(st, w.pops, w.node_pop, seed=1)
+    sm.iterate(5, trace=False)
+    k0 = gp.lib().gphocsKernelLaunchCount()
+    t0 = time.perf_counter()
+    sm.iterate(iterations, trace=False)
+    dt = time.perf_counter() - t0
+    launches = gp.lib().gphocsKernelLaunchCount() - k0
+    violations, stat_err, lnl_err = sm.check()
+    s = sm.state()
+    out = {"config": f"{MCMC_CONFIG}: {MCMC_LOCI} loci", "iterations": iterations, "iters_per_s": iterations / dt,
+           "kernel_launches_per_iteration": launches / iterations,
+           "accept_rates": {m: float(s["accepted"][m]) / max(1, int(s["proposed"][m])) for m in gp.Sampler.MOVES},
+           "check": {"violations": int(violations), "max_lnl_rel_err_vs_full_recompute": lnl_err}}
+    sm.close()
+    st.close()
+    return out
+
+
 def cpu_baseline_subprocess(cfg, sample_loci, reps):
     """cpu_baseline leg: run the reference sample in a child process, parse its JSON."""
     cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", str(reps), "--warmup", "1",
-           "--config", cfg, "--sample-loci", str(sample_loci), "--gpus", "1"]
+           "--config", cfg, "--sample-loci", str(sample_loci), "--gpus", "1", "--with-mcmc"]
     env = dict(os.environ)
     for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE"):
         env.pop(k, None)
     try:
-        out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
         line = [x for x in out.stdout.splitlines() if x.startswith("{")][-1]
         return json.loads(line)["cpu_baseline"]
     except Exception as e:   # the baseline is reported, never required
@@ -209,6 +260,8 @@ def run_reference(args):
               f"computeLocusDataLikelihood(locus,0)+resetSaved and computeGenetreeStats+gtreeLnLikelihood over all loci, "
               f"OpenMP static schedule, {threads} threads; wall {time.perf_counter() - t_all0:.1f}s incl. ingest")
     cb = {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample}
+    if args.with_mcmc:
+        cb["mcmc"] = reference_mcmc(os.cpu_count() or 1)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(timed),
         "warmup": args.warmup, "ms_per_step": 1e3 * total / len(timed), "higher_is_better": True, "scaling": "weak",
@@ -371,6 +424,7 @@ def run_b200(args):
     torch.cuda.synchronize()
     inc_ms = a.elapsed_time(b)
     st.apply_ops(rej)
+    mcmc = device_mcmc(gp, synth, local_rank) if rank == 0 else None
     clocks = sampler.stop() if rank == 0 else None
 
     if rank == 0:
@@ -410,7 +464,8 @@ def run_b200(args):
                       "mcmc_cycle_proposals_per_sec_e2e": world * L * cyc / cyc_s,
                       "incremental_eval_ms_device": inc_ms,
                       "incremental_evals_per_sec_device": L / (inc_ms * 1e-3),
-                      "device_bytes_store": st.device_bytes},
+                      "device_bytes_store": st.device_bytes,
+                      "mcmc_device_resident": mcmc},
         }
         if cb is not None:
             line["cpu_baseline"] = cb
@@ -431,6 +486,7 @@ def main():
     ap.add_argument("--loci", type=int, default=100_000, help="loci per GPU")
     ap.add_argument("--sample-loci", type=int, default=2000, help="loci in the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--with-mcmc", action="store_true", help="reference arm: also time the reference's MCMC iterations/s")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
