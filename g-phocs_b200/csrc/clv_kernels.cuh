@@ -83,7 +83,7 @@ static_assert(sizeof(SchedEntry) == 48, "schedule entry layout");
 struct EvalSmem {
   size_t perScratch, offAge, offNode, offSize, offWalk, offNeed;  // per-locus scheduling scratch
   size_t perSched;                                                // per-locus schedule
-  size_t offStack, offSched, offWords, offTerm, offMeta, total;   // CTA regions
+  size_t offStack, offSched, offWords, offTerm, offMeta, offList, total;   // CTA regions
   int W32;
 };
 // Shared-memory plan for a CTA that holds up to `maxLoci` loci of `n` leaves.
@@ -108,7 +108,9 @@ __host__ __device__ inline EvalSmem evalSmemLayout(int n, int maxLoci) {
   m.offTerm = m.offWords;                                           // [kThreads] double, after the walk
   const size_t wordBytes = (size_t)m.W32 * kThreads * 4, termBytes = (size_t)kThreads * 8;
   m.offMeta = m.offWords + (wordBytes > termBytes ? wordBytes : termBytes);
-  m.total = m.offMeta + (size_t)kMaxBatchLoci * 48;
+  m.offList = m.offMeta + (size_t)kMaxBatchLoci * 48;              // [1 + maxLoci*NI] uint32: marked nodes of the batch
+  m.total = m.offList + (1 + (size_t)maxLoci * NI) * sizeof(uint32_t);
+  m.total = (m.total + 15) & ~(size_t)15;
   return m;
 }
 __host__ __device__ inline size_t evalSmemBytes(int n, int maxLoci = kMaxBatchLoci) { return evalSmemLayout(n, maxLoci).total; }
@@ -213,6 +215,8 @@ k_eval(StoreDev d, const Batch* __restrict__ batches, int batchBase, int useOld,
   int* mActive = mRoot + kMaxBatchLoci;
   double* mRate = reinterpret_cast<double*>(mActive + kMaxBatchLoci);
   double* mLnL = mRate + kMaxBatchLoci;
+  int* sListCount = reinterpret_cast<int*>(smem + lay.offList);
+  uint32_t* sList = reinterpret_cast<uint32_t*>(smem + lay.offList) + 1;
   auto sSched = [&](int s) { return reinterpret_cast<SchedEntry*>(smem + lay.offSched + lay.perSched * s); };
   auto sAge = [&](int s) { return reinterpret_cast<double*>(smem + lay.perScratch * s + lay.offAge); };
   auto sNode = [&](int s) { return reinterpret_cast<NodeRec*>(smem + lay.perScratch * s + lay.offNode); };
@@ -302,107 +306,117 @@ k_eval(StoreDev d, const Batch* __restrict__ batches, int batchBase, int useOld,
       }
     }
   }
+  if (tid == 0) *sListCount = 0;
   __syncthreads();
-  // ---- phase C: flip the buffers of the nodes to compute (copyNodeConditionals: once per proposal);
-  //      count the marked nodes of every subtree
+  // ---- phase C0: the marked nodes of the whole batch, compacted into one list so that every later phase keeps
+  //      all 128 threads busy whether 4 nodes per locus are marked (a proposal) or all of them (full evaluation);
+  //      flip the destination buffers of the marked nodes (copyNodeConditionals: once per proposal)
   for (int s = warp; s < nl; s += kWarps) {
     if (!mActive[s]) continue;
     NodeRec* nd = sNode(s);
     const uint8_t* need = sNeed(s);
+    for (int v0 = n; v0 < N; v0 += 32) {
+      const int v = v0 + lane;
+      const bool marked = v < N && need[v];
+      const unsigned ballot = __ballot_sync(0xffffffffu, marked);
+      int base = 0;
+      if (lane == 0 && ballot) base = atomicAdd(sListCount, __popc(ballot));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (marked) {
+        sList[base + __popc(ballot & ((1u << lane) - 1u))] = (uint32_t)(s << 16 | v);
+        uint8_t f = nd[v].flags;
+        if (!(f & F_RECALC)) {
+          f = (uint8_t)((f ^ F_SEL) | F_RECALC);
+          nd[v].flags = f;
+          d.node[(size_t)(b.firstLocus + s) * N + v].flags = f;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  const int listCount = *sListCount;
+  // ---- phase C: count the marked nodes of every subtree
+  for (int j = tid; j < listCount; j += kThreads) {
+    const int s = sList[j] >> 16, v = sList[j] & 0xffff;
+    const NodeRec* nd = sNode(s);
     int* size = sSize(s);
-    for (int v = n + lane; v < N; v += 32) {
-      if (!need[v]) continue;
-      uint8_t f = nd[v].flags;
-      if (!(f & F_RECALC)) {
-        f = (uint8_t)((f ^ F_SEL) | F_RECALC);
-        nd[v].flags = f;
-        d.node[(size_t)(b.firstLocus + s) * N + v].flags = f;
-      }
-      int a = v;
-      for (int it = 0; a >= 0 && it < N; it++) {
-        atomicAdd(&size[a - n], 1);
-        a = nd[a].father;
-      }
+    int a = v;
+    for (int it = 0; a >= 0 && it < N; it++) {
+      atomicAdd(&size[a - n], 1);
+      a = nd[a].father;
     }
   }
   __syncthreads();
   // ---- phase D1: what a node contributes to the post-order start of everything below it.  The heavier
   //      child of a node is visited first; a node visited second starts after its sibling's subtree.
-  for (int s = warp; s < nl; s += kWarps) {
-    if (!mActive[s]) continue;
+  for (int j = tid; j < listCount; j += kThreads) {
+    const int s = sList[j] >> 16, v = sList[j] & 0xffff;
     const NodeRec* nd = sNode(s);
     const uint8_t* need = sNeed(s);
     const int* size = sSize(s);
-    uint32_t* walk = sWalk(s);
-    for (int v = n + lane; v < N; v += 32) {
-      if (!need[v]) continue;
-      const int a = nd[v].father;
-      uint32_t contrib = 0;
-      if (a >= 0) {
-        const int l = nd[a].left, r = nd[a].right;
-        const int wl = (l >= n && need[l]) ? size[l - n] : 0;
-        const int wr = (r >= n && need[r]) ? size[r - n] : 0;
-        const int first = wl >= wr ? l : r;
-        if (v != first) contrib = (uint32_t)(v == l ? wr : wl);
-      }
-      walk[v] = (uint32_t)(a + 1) | (contrib << 16);
+    const int a = nd[v].father;
+    uint32_t contrib = 0;
+    if (a >= 0) {
+      const int l = nd[a].left, r = nd[a].right;
+      const int wl = (l >= n && need[l]) ? size[l - n] : 0;
+      const int wr = (r >= n && need[r]) ? size[r - n] : 0;
+      const int first = wl >= wr ? l : r;
+      if (v != first) contrib = (uint32_t)(v == l ? wr : wl);
     }
+    sWalk(s)[v] = (uint32_t)(a + 1) | (contrib << 16);
   }
   __syncthreads();
   // ---- phase D2: position and stack depth of every marked node, sources of its children, JC69 edge terms
-  for (int s = warp; s < nl; s += kWarps) {
-    if (!mActive[s]) continue;
+  for (int j = tid; j < listCount; j += kThreads) {
+    const int s = sList[j] >> 16, v = sList[j] & 0xffff;
     const NodeRec* nd = sNode(s);
     const uint8_t* need = sNeed(s);
     const int* size = sSize(s);
     const uint32_t* walk = sWalk(s);
     const double* age = sAge(s);
     const double rate = mRate[s];
-    for (int v = n + lane; v < N; v += 32) {
-      if (!need[v]) continue;
-      int start = 0, depth = 0;  // depth = results parked on the stack when v's subtree is entered
-      {
-        uint32_t w = walk[v];
-        for (int it = 0; it < N; it++) {
-          const uint32_t c = w >> 16;
-          start += c;
-          depth += c != 0;
-          const int a = (int)(w & 0xffffu) - 1;
-          if (a < 0) break;
-          w = walk[a];
-        }
+    int start = 0, depth = 0;  // depth = results parked on the stack when v's subtree is entered
+    {
+      uint32_t w = walk[v];
+      for (int it = 0; it < N; it++) {
+        const uint32_t c = w >> 16;
+        start += c;
+        depth += c != 0;
+        const int a = (int)(w & 0xffffu) - 1;
+        if (a < 0) break;
+        w = walk[a];
       }
-      const int l = nd[v].left, r = nd[v].right;
-      const int wl = (l >= n && need[l]) ? size[l - n] : 0;
-      const int wr = (r >= n && need[r]) ? size[r - n] : 0;
-      const bool leftFirst = wl >= wr;
-      const int A = leftFirst ? l : r, B = leftFirst ? r : l;  // visiting order
-      const int wA = leftFirst ? wl : wr, wB = leftFirst ? wr : wl;
-      const uint32_t strideBytes = (uint32_t)mP[s] * 32u;  // one (node, buffer) record of this locus
-      auto record = [&](int x) { return (uint32_t)((x - n) * 2 + (nd[x].flags & F_SEL)) * strideBytes; };
-      auto leafRef = [&](int x) { return (uint32_t)(x >> 3) * (kThreads * 4u) | ((uint32_t)(x & 7) * 4u) << 16; };
-      // a computed child sits on the stack at the depth its own subtree was entered with
-      const int slotA = depth, slotB = depth + (wA > 0);
-      uint32_t kindA, kindB, offA, offB;
-      if (A < n) { kindA = SRC_LEAF; offA = leafRef(A); }
-      else if (wA > 0 && slotA < kStack) { kindA = SRC_STACK; offA = ((uint32_t)slotA * kRow) << 16; }
-      else { kindA = SRC_GLOBAL; offA = record(A); }  // clean child, or a result the thread parked in HBM
-      if (B < n) { kindB = SRC_LEAF; offB = leafRef(B); }
-      else if (wB > 0 && slotB < kStack) { kindB = SRC_STACK; offB = ((uint32_t)slotB * kRow) << 16; }
-      else { kindB = SRC_GLOBAL; offB = record(B); }
-      SchedEntry en;
-      const double av = age[v];
-      en.e0A = edgeProb(rate * (av - age[A]));
-      en.e1A = 1.0 - 4.0 * en.e0A;
-      en.e0B = edgeProb(rate * (av - age[B]));
-      en.e1B = 1.0 - 4.0 * en.e0B;
-      en.offA = offA; en.offB = offB;
-      en.dstOff = record(v);
-      const uint32_t push = (v != mRoot[s] && depth < kStack) ? (uint32_t)depth * kRow : 0xffffu;
-      en.ctl = kindA | (kindB << 2) | (push << 16);
-      sSched(s)[start + size[v - n] - 1] = en;
-      if (v == mRoot[s]) mK[s] = size[v - n];
     }
+    const int l = nd[v].left, r = nd[v].right;
+    const int wl = (l >= n && need[l]) ? size[l - n] : 0;
+    const int wr = (r >= n && need[r]) ? size[r - n] : 0;
+    const bool leftFirst = wl >= wr;
+    const int A = leftFirst ? l : r, B = leftFirst ? r : l;  // visiting order
+    const int wA = leftFirst ? wl : wr, wB = leftFirst ? wr : wl;
+    const uint32_t strideBytes = (uint32_t)mP[s] * 32u;  // one (node, buffer) record of this locus
+    auto record = [&](int x) { return (uint32_t)((x - n) * 2 + (nd[x].flags & F_SEL)) * strideBytes; };
+    auto leafRef = [&](int x) { return (uint32_t)(x >> 3) * (kThreads * 4u) | ((uint32_t)(x & 7) * 4u) << 16; };
+    // a computed child sits on the stack at the depth its own subtree was entered with
+    const int slotA = depth, slotB = depth + (wA > 0);
+    uint32_t kindA, kindB, offA, offB;
+    if (A < n) { kindA = SRC_LEAF; offA = leafRef(A); }
+    else if (wA > 0 && slotA < kStack) { kindA = SRC_STACK; offA = ((uint32_t)slotA * kRow) << 16; }
+    else { kindA = SRC_GLOBAL; offA = record(A); }  // clean child, or a result the thread parked in HBM
+    if (B < n) { kindB = SRC_LEAF; offB = leafRef(B); }
+    else if (wB > 0 && slotB < kStack) { kindB = SRC_STACK; offB = ((uint32_t)slotB * kRow) << 16; }
+    else { kindB = SRC_GLOBAL; offB = record(B); }
+    SchedEntry en;
+    const double av = age[v];
+    en.e0A = edgeProb(rate * (av - age[A]));
+    en.e1A = 1.0 - 4.0 * en.e0A;
+    en.e0B = edgeProb(rate * (av - age[B]));
+    en.e1B = 1.0 - 4.0 * en.e0B;
+    en.offA = offA; en.offB = offB;
+    en.dstOff = record(v);
+    const uint32_t push = (v != mRoot[s] && depth < kStack) ? (uint32_t)depth * kRow : 0xffffu;
+    en.ctl = kindA | (kindB << 2) | (push << 16);
+    sSched(s)[start + size[v - n] - 1] = en;
+    if (v == mRoot[s]) mK[s] = size[v - n];
   }
   __syncthreads();
 
@@ -460,6 +474,13 @@ k_eval(StoreDev d, const Batch* __restrict__ batches, int batchBase, int useOld,
           v[0] = x.x; v[1] = x.y; v[2] = y.x; v[3] = y.y;
         }
       };
+      if (useOld) {   // clean children are the only HBM reads of a proposal: request them all before the first use
+        for (int e = 0; e < k; e++) {
+          const uint4 ix = ldsU4(entry + e * (uint32_t)sizeof(SchedEntry) + 32);
+          if ((ix.w & 3u) == SRC_GLOBAL) prefetchL2(clvCol + ix.x);
+          if (((ix.w >> 2) & 3u) == SRC_GLOBAL) prefetchL2(clvCol + ix.y);
+        }
+      }
       for (int e = 0; e < k; e++, entry += sizeof(SchedEntry)) {
         const double2 eA = ldsD2(entry), eB = ldsD2(entry + 16);   // (e0A,e1A), (e0B,e1B)
         const uint4 ix = ldsU4(entry + 32);                        // offA, offB, dstOff, ctl
