@@ -202,20 +202,41 @@ def reference_mcmc(threads, iterations=40):
             "iters_per_s": (iterations - 1) / max(wall[iterations] - wall[1], 1e-9), "wall_s": wall[iterations], "setup_s": wall[1]}
 
 
-def device_mcmc(gp, synth, device, iterations=100):
-    """MCMC iterations/s of the device-resident update steps (gphocs_b200.h group D) on MCMC_CONFIG."""
-    w = synth.generate(synth.config(MCMC_CONFIG), MCMC_LOCI, seed=777)
+def device_mcmc(gp, synth, device, total_loci, iterations, rank=0, world=1):
+    """MCMC iterations/s of the device-resident update steps (gphocs_b200.h group D) on MCMC_CONFIG with `total_loci`
+    loci sharded over `world` ranks; global decisions are taken on NCCL all-reduced sums."""
+    import torch
+    import torch.distributed as dist
+    shard = importlib.import_module("g-phocs_b200.shard")
+    lo, hi = shard.shard_range(total_loci, rank, world)
+    w = synth.generate(synth.config(MCMC_CONFIG), hi - lo, seed=777 + rank)
     st = gp.LociStore.from_workload(w, device=device)
     sm = gp.Sampler(st, w.pops, w.node_pop, seed=1)
+    if world > 1:
+        buf = torch.zeros(128, dtype=torch.float64, device=f"cuda:{device}")
+
+        def all_reduce(v):
+            buf[:len(v)] = torch.from_numpy(v)
+            dist.all_reduce(buf)
+            v[:] = buf[:len(v)].cpu().numpy()
+        sm.set_all_reduce(all_reduce, locus_offset=lo)
     sm.iterate(5, trace=False)
     k0 = gp.lib().gphocsKernelLaunchCount()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
     t0 = time.perf_counter()
     sm.iterate(iterations, trace=False)
+    torch.cuda.synchronize()
     dt = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([dt], dtype=torch.float64, device=f"cuda:{device}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
     launches = gp.lib().gphocsKernelLaunchCount() - k0
     violations, stat_err, lnl_err = sm.check()
     s = sm.state()
-    out = {"config": f"{MCMC_CONFIG}: {MCMC_LOCI} loci", "iterations": iterations, "iters_per_s": iterations / dt,
+    out = {"config": f"{MCMC_CONFIG}: {total_loci} loci over {world} GPU(s)", "iterations": iterations, "iters_per_s": iterations / dt,
            "kernel_launches_per_iteration": launches / iterations,
            "accept_rates": {m: float(s["accepted"][m]) / max(1, int(s["proposed"][m])) for m in gp.Sampler.MOVES},
            "check": {"violations": int(violations), "max_lnl_rel_err_vs_full_recompute": lnl_err}}
@@ -424,7 +445,10 @@ def run_b200(args):
     torch.cuda.synchronize()
     inc_ms = a.elapsed_time(b)
     st.apply_ops(rej)
-    mcmc = device_mcmc(gp, synth, local_rank) if rank == 0 else None
+    # MCMC iterations/s: configs[1] (10k loci) on one GPU, and 100k loci sharded over all ranks (strong scaling)
+    mcmc = {"loci_100k_sharded": device_mcmc(gp, synth, local_rank, 100_000, 30, rank, world)}
+    if world == 1:
+        mcmc["loci_10k"] = device_mcmc(gp, synth, local_rank, MCMC_LOCI, 100)
     clocks = sampler.stop() if rank == 0 else None
 
     if rank == 0:

@@ -112,6 +112,7 @@ def lib():
                                      c_dbl_p, c_dbl_p, c_int_p, C.c_ulonglong]),
         "gphocsSamplerDestroy": (ci, [vp]),
         "gphocsSamplerSetFinetunes": (ci, [vp, cd, cd, cd, cd]),
+        "gphocsSamplerSetAllReduce": (ci, [vp, vp, vp, C.c_longlong]),
         "gphocsSamplerIterate": (ci, [vp, ci, c_dbl_p]),
         "gphocsSamplerTraceWidth": (ci, [vp]),
         "gphocsSamplerGetState": (ci, [vp, c_dbl_p, c_dbl_p, c_ll_p, c_ll_p]),
@@ -461,6 +462,20 @@ class Sampler:
         self.width = self.lib.gphocsSamplerTraceWidth(self.h)
         if finetunes is not None:
             self.lib.gphocsSamplerSetFinetunes(self.h, *[float(x) for x in finetunes])
+
+    def set_all_reduce(self, fn, locus_offset=0):
+        """fn(numpy float64 vector) must sum it over all ranks in place (e.g. through an NCCL all-reduce)."""
+        proto = C.CFUNCTYPE(C.c_int, c_dbl_p, C.c_int, C.c_void_p)
+
+        def thunk(buf, count, _ctx):
+            try:
+                fn(np.ctypeslib.as_array(buf, shape=(count,)))
+                return 0
+            except Exception as e:  # noqa: BLE001 - reported through the C return code
+                print(f"all-reduce hook failed: {e}")
+                return -1
+        self._ar = proto(thunk)      # keep the callback alive
+        self.lib.gphocsSamplerSetAllReduce(self.h, C.cast(self._ar, C.c_void_p), None, int(locus_offset))
 
     def iterate(self, iterations, trace=True):
         out = np.zeros((iterations, self.width)) if trace else None

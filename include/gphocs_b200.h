@@ -214,6 +214,10 @@ GphocsSampler *gphocsSamplerCreate(GphocsStore *s, int numPops, int numCurPops, 
                                    const double *thetaAlpha, const double *thetaBeta, const double *tauAlpha,
                                    const double *tauBeta, const int *nodePop, unsigned long long seed);
 int gphocsSamplerDestroy(GphocsSampler *sm);
+/* loci sharded over ranks (one process per GPU): fn(buf, count, ctx) sums buf over all ranks in place
+ * (an NCCL all-reduce of < 1 KB); it is applied to every reduced vector before a global decision, so all ranks keep
+ * identical theta / tau.  locusOffset = global index of this rank's first locus (random streams are per global locus). */
+int gphocsSamplerSetAllReduce(GphocsSampler *sm, int (*fn)(double *, int, void *), void *ctx, long long locusOffset);
 /* finetune-coal-time, finetune-theta, finetune-tau, finetune-mixing of the control file (MCMCcontrol.c:575-787) */
 int gphocsSamplerSetFinetunes(GphocsSampler *sm, double coalTime, double theta, double tau, double mixing);
 /* `iterations` MCMC iterations; trace (may be NULL): one row per iteration of gphocsSamplerTraceWidth() doubles =

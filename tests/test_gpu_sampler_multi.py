@@ -1,0 +1,59 @@
+"""GPU, 2 ranks (skipped on a single-GPU box): loci sharded over ranks, every global decision of the device-resident
+sampler taken on all-reduced sums (NCCL), so both ranks must hold identical theta / tau after every iteration and
+each rank's shard must pass the checkAll invariants.  Run by `gpurun --gpus 2 -- python -m pytest tests -m gpu`."""
+import importlib
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")]
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, out_dir):
+    import torch.distributed as dist
+    for p in (ROOT, os.path.join(ROOT, "tests")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    gp = importlib.import_module("g-phocs_b200")
+    synth = importlib.import_module("g-phocs_b200.synth")
+    shard = importlib.import_module("g-phocs_b200.shard")
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        L = 600
+        lo, hi = shard.shard_range(L, rank, world)
+        w = synth.generate(synth.config("hap16"), hi - lo, seed=100 + rank)      # this rank's block of loci
+        st = gp.LociStore.from_workload(w, device=rank)
+        sm = gp.Sampler(st, w.pops, w.node_pop, seed=7)
+        buf = torch.zeros(64, dtype=torch.float64, device=f"cuda:{rank}")
+
+        def all_reduce(v):
+            buf[:len(v)] = torch.from_numpy(v)
+            dist.all_reduce(buf)
+            v[:] = buf[:len(v)].cpu().numpy()
+        sm.set_all_reduce(all_reduce, locus_offset=lo)
+        tr = sm.iterate(25)
+        v, es, el = sm.check()
+        np.save(os.path.join(out_dir, f"trace{rank}.npy"), tr)
+        np.save(os.path.join(out_dir, f"check{rank}.npy"), np.array([v, es, el]))
+        sm.close(); st.close()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_ranks_keep_identical_parameters(tmp_path):
+    import torch.multiprocessing as mp
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    t0, t1 = np.load(tmp_path / "trace0.npy"), np.load(tmp_path / "trace1.npy")
+    assert np.array_equal(t0, t1)                      # thetas, taus and the all-reduced log-likelihood sums
+    assert np.all(np.isfinite(t0)) and len(np.unique(t0[:, 0])) > 1
+    for r in range(2):
+        v, es, el = np.load(tmp_path / f"check{r}.npy")
+        assert v == 0 and el < 1e-9
