@@ -93,8 +93,8 @@ class Team {
 };
 
 int g_threads = 0;  // 0: hardware concurrency
-std::mutex g_poolMu;
-Team* poolTeam() { static Team* t = new Team(); return t; }      // parallelFor
+std::mutex g_poolMu[2];
+Team* poolTeam(int i) { static Team* t[2] = {new Team(), new Team()}; return t[i]; }   // parallelFor (two concurrent callers)
 Team* regionTeam() { static Team* t = new Team(); return t; }    // OpenMP regions / fiber workers
 
 int hwThreads() {
@@ -114,12 +114,20 @@ void parallelFor(long long begin, long long end, const std::function<void(long l
   const long long n = end - begin;
   if (n <= 0) return;
   int parts = (int)std::min<long long>(hostThreads(), (n + grain - 1) / grain);
-  std::unique_lock<std::mutex> lk(g_poolMu, std::try_to_lock);
-  if (parts <= 1 || !lk.owns_lock()) { f(begin, end); return; }   // small range, or the pool is busy: run inline
-  poolTeam()->run(parts, [&](int w) {
-    const long long lo = begin + n * w / parts, hi = begin + n * (w + 1) / parts;
-    if (lo < hi) f(lo, hi);
-  });
+  if (parts <= 1) { f(begin, end); return; }
+  // two teams, so that two host threads (e.g. one feeding the data-likelihood store, one the genealogy snapshot)
+  // can both run their conversions in parallel; a third concurrent caller runs inline
+  for (int i = 0; i < 2; i++) {
+    std::unique_lock<std::mutex> lk(g_poolMu[i], std::try_to_lock);
+    if (!lk.owns_lock()) continue;
+    if (i == 1) parts = std::max(1, parts / 2);
+    poolTeam(i)->run(parts, [&](int w) {
+      const long long lo = begin + n * w / parts, hi = begin + n * (w + 1) / parts;
+      if (lo < hi) f(lo, hi);
+    });
+    return;
+  }
+  f(begin, end);
 }
 
 // ------------------------------------------------------------------------------------------------ fibers
