@@ -112,12 +112,15 @@ def lib():
                                      c_dbl_p, c_dbl_p, c_int_p, C.c_ulonglong]),
         "gphocsSamplerDestroy": (ci, [vp]),
         "gphocsSamplerSetFinetunes": (ci, [vp, cd, cd, cd, cd]),
+        "gphocsSamplerSetMigration": (ci, [vp, ci, c_int_p, c_int_p, c_dbl_p, c_dbl_p, c_dbl_p, c_int_p, c_int_p, c_int_p, c_dbl_p]),
+        "gphocsSamplerSetMigFinetunes": (ci, [vp, cd, cd]),
         "gphocsSamplerSetAllReduce": (ci, [vp, vp, vp, C.c_longlong]),
         "gphocsSamplerIterate": (ci, [vp, ci, c_dbl_p]),
         "gphocsSamplerTraceWidth": (ci, [vp]),
         "gphocsSamplerGetState": (ci, [vp, c_dbl_p, c_dbl_p, c_ll_p, c_ll_p]),
         "gphocsSamplerCheck": (ci, [vp, c_dbl_p, c_dbl_p]),
         "gphocsSamplerDownload": (ci, [vp, c_int_p]),
+        "gphocsSamplerGetStats": (ci, [vp, c_dbl_p, c_int_p, c_dbl_p, c_int_p]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -437,9 +440,13 @@ class ScalarLocus:
 
 class Sampler:
     """Device-resident MCMC update steps (GphocsSampler) over the loci of a LociStore."""
-    MOVES = ("coal_time", "spr", "theta", "tau", "mixing")
+    MOVES = ("coal_time", "spr", "theta", "tau", "mixing", "mig_rate", "mig_time", "tau_conflicts")
+    MAX_MIGS = 10
 
-    def __init__(self, store, pops, node_pop, theta_prior=(1.0, 1000.0), tau_prior=None, seed=1, finetunes=None):
+    def __init__(self, store, pops, node_pop, theta_prior=(1.0, 1000.0), tau_prior=None, seed=1, finetunes=None,
+                 migration=None, mig_prior=(0.002, 0.00001), mig_finetunes=None):
+        """migration = (mig_start[L+1], mig_branch, mig_band, mig_age) CSR arrays of the genealogies' migration events
+        (synth.Workload fields); bands and their rates come from pops["band_src"/"band_tgt"/"band_rate"]."""
         self.lib = lib()
         self.store = store
         self.Q = len(pops["father"])
@@ -459,6 +466,25 @@ class Sampler:
         if not self.h:
             raise RuntimeError("gphocsSamplerCreate failed")
         self.h = C.c_void_p(self.h)
+        self.B = 0
+        if migration is not None and len(pops["band_src"]) > 0:
+            ms, mbr, mbd, mag = migration
+            L, B = store.L, len(pops["band_src"])
+            num = np.diff(np.asarray(ms)).astype(np.int32)
+            br = np.full((L, self.MAX_MIGS), -1, np.int32)
+            bd = np.zeros((L, self.MAX_MIGS), np.int32)
+            ag = np.zeros((L, self.MAX_MIGS))
+            for l in np.nonzero(num)[0]:
+                a, b = int(ms[l]), int(ms[l + 1])
+                br[l, :b - a], bd[l, :b - a], ag[l, :b - a] = mbr[a:b], mbd[a:b], mag[a:b]
+            rc = self.lib.gphocsSamplerSetMigration(self.h, B, _ip(_i32(pops["band_src"])), _ip(_i32(pops["band_tgt"])),
+                                                    _dp(_f64(pops["band_rate"])), _dp(np.full(B, float(mig_prior[0]))),
+                                                    _dp(np.full(B, float(mig_prior[1]))), _ip(num), _ip(br), _ip(bd), _dp(ag))
+            if rc != 0:
+                raise RuntimeError("gphocsSamplerSetMigration failed")
+            self.B = B
+            if mig_finetunes is not None:
+                self.lib.gphocsSamplerSetMigFinetunes(self.h, float(mig_finetunes[0]), float(mig_finetunes[1]))
         self.width = self.lib.gphocsSamplerTraceWidth(self.h)
         if finetunes is not None:
             self.lib.gphocsSamplerSetFinetunes(self.h, *[float(x) for x in finetunes])
@@ -485,7 +511,7 @@ class Sampler:
 
     def state(self):
         th, ta = np.zeros(self.Q), np.zeros(self.Q)
-        acc, prop = np.zeros(5, np.int64), np.zeros(5, np.int64)
+        acc, prop = np.zeros(8, np.int64), np.zeros(8, np.int64)
         self.lib.gphocsSamplerGetState(self.h, _dp(th), _dp(ta), _lp(acc), _lp(prop))
         return dict(theta=th, tau=ta, accepted=dict(zip(self.MOVES, acc)), proposed=dict(zip(self.MOVES, prop)))
 
@@ -493,6 +519,13 @@ class Sampler:
         a, b = C.c_double(), C.c_double()
         v = self.lib.gphocsSamplerCheck(self.h, C.byref(a), C.byref(b))
         return v, a.value, b.value
+
+    def stats(self):
+        L, Q, B = self.store.L, self.Q, max(self.B, 1)
+        coal, mig = np.zeros((L, Q)), np.zeros((L, B))
+        nc, nm = np.zeros((L, Q), np.int32), np.zeros((L, B), np.int32)
+        self.lib.gphocsSamplerGetStats(self.h, _dp(coal), _ip(nc), _dp(mig), _ip(nm))
+        return dict(coal=coal, num_coals=nc, mig=mig[:, :self.B], num_migs=nm[:, :self.B])
 
     def download(self):
         out = np.zeros((self.store.L, self.store.N), np.int32)

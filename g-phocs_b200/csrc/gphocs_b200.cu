@@ -20,6 +20,7 @@
 #include "clv_kernels.cuh"
 #include "gen_kernels.cuh"
 #include "sampler_kernels.cuh"
+#include "sampler_mig.cuh"
 #include "tree_ops.cuh"
 
 using namespace gphocs;

@@ -25,6 +25,8 @@ namespace gphocs {
 
 constexpr int kSmpMaxPops = 39;     // 2*NSPECIES-1 (patch.h:19)
 constexpr double kOldAge = 999.0;   // OLDAGE (patch.h:22): end of the root population
+constexpr int kSmpMaxBands = 32;    // migration bands the device-resident steps handle (reference: MAX_MIG_BANDS 100)
+constexpr int kSmpMaxMigs = 10;     // MAX_MIGS (patch.h:18): migration events per genealogy
 
 struct SmpModel {
   int Q, C, rootPop, n;
@@ -33,6 +35,11 @@ struct SmpModel {
   int leavesBelow[kSmpMaxPops];       // haploid samples in the current populations under each population
   unsigned long long below[kSmpMaxPops];  // bit q: population q is this population or lies below it
   double theta[kSmpMaxPops], tau[kSmpMaxPops];
+  // migration bands (MigrationBand, PopulationTree.h:60-70): backwards in time a lineage in the target population
+  // moves to the source population at rate migRate while both populations exist
+  int B;
+  int bandSrc[kSmpMaxBands], bandTgt[kSmpMaxBands];
+  double migRate[kSmpMaxBands];
 };
 
 struct SmpProposal {   // what a proposal kernel leaves for the accept kernel, per locus
@@ -52,10 +59,17 @@ struct SmpDev {
   int* ncoal;          // [L][Q] num_coals per locus
   int* ncoalT;         // [L][Q] coalescence counts of the pending proposal
   SmpProposal* prop;   // [L]
+  // migration events of every genealogy (genetree_migs, patch.h:138-148) and their saved copies
+  int *numMigs, *svNumMigs;          // [L]
+  int16_t *migBranch, *svMigBranch;  // [L][kSmpMaxMigs] genealogy branch (node below) carrying the event
+  uint8_t *migBand, *svMigBand;      // [L][kSmpMaxMigs]
+  double *migAge, *svMigAge;         // [L][kSmpMaxMigs]
+  double *mig, *migT;                // [L][B] mig_stats per locus, stored / pending
+  int *nmig, *nmigT;                 // [L][B] num_migs per locus
   unsigned long long* accepted;  // [8] acceptance counters per move kind
   double* partial;     // [blocks][kSmpPartials] block partial sums
 };
-constexpr int kSmpPartials = 4 + 2 * kSmpMaxPops;
+constexpr int kSmpPartials = 5 + 2 * kSmpMaxPops + 2 * kSmpMaxBands;
 constexpr int kSmpThreads = 128;
 
 // Counter-based random numbers: draw k of stream (seed, locus, step) is a SplitMix64-style hash of its coordinates,
@@ -525,13 +539,14 @@ __global__ void __launch_bounds__(kSmpThreads) k_smp_scale_propose(StoreDev d, S
   if (lane == 0) sd.prop[l] = pr;
 }
 
-// block partial sums: [0] data delta, [1] genealogy delta, [2] ntj0, [3] ntj1, [4..4+Q) coal totals, [4+Q..4+2Q) ncoal totals
-// mode 0: deltas of the pending global proposal; mode 1: sum of data lnL in [0] and the statistics totals
-__global__ void __launch_bounds__(kSmpThreads) k_smp_reduce(StoreDev d, SmpDev sd, int mode) {
+// block partial sums, V = 5 + 2Q + 2B values:
+//   [0] data delta (mode 0) or sum of data lnL (mode 1), [1] genealogy delta, [2] ntj0, [3] ntj1, [4] loci in conflict,
+//   [5..5+Q) coal totals, [5+Q..5+2Q) ncoal totals, [5+2Q..+B) mig totals, [..+B) nmig totals   (mode 1 only)
+__global__ void __launch_bounds__(kSmpThreads) k_smp_reduce(StoreDev d, SmpDev sd, int mode, int B) {
   __shared__ double sh[kSmpThreads];
   const int l = blockIdx.x * blockDim.x + threadIdx.x;
   const int Q = sd.Q;
-  const int V = 4 + 2 * Q;
+  const int V = mode == 0 ? 5 : 5 + 2 * Q + 2 * B;
   for (int v = 0; v < V; v++) {
     double x = 0.0;
     if (l < d.L) {
@@ -541,13 +556,15 @@ __global__ void __launch_bounds__(kSmpThreads) k_smp_reduce(StoreDev d, SmpDev s
         else if (v == 1) x = pr.genDelta;
         else if (v == 2) x = pr.ntj0;
         else if (v == 3) x = pr.ntj1;
+        else x = pr.valid && pr.node == -2 ? 1.0 : 0.0;
       } else {
         if (v == 0) x = d.lnL[l];
-        else if (v >= 4 && v < 4 + Q) x = sd.coal[(size_t)l * Q + (v - 4)];
-        else if (v >= 4 + Q) x = sd.ncoal[(size_t)l * Q + (v - 4 - Q)];
+        else if (v >= 5 && v < 5 + Q) x = sd.coal[(size_t)l * Q + (v - 5)];
+        else if (v >= 5 + Q && v < 5 + 2 * Q) x = sd.ncoal[(size_t)l * Q + (v - 5 - Q)];
+        else if (v >= 5 + 2 * Q && v < 5 + 2 * Q + B) x = sd.mig[(size_t)l * B + (v - 5 - 2 * Q)];
+        else if (v >= 5 + 2 * Q + B) x = sd.nmig[(size_t)l * B + (v - 5 - 2 * Q - B)];
       }
     }
-    if (mode == 0 && v >= 4) break;
     sh[threadIdx.x] = x;
     __syncthreads();
     for (int off = kSmpThreads / 2; off > 0; off >>= 1) {
@@ -605,7 +622,8 @@ __global__ void __launch_bounds__(kSmpThreads) k_smp_check(StoreDev d, SmpDev sd
       if (!(a >= m.tau[q] && a <= end)) v++;
       const NodeRec r = t.node[x];
       if (!(t.age[r.left] <= a && t.age[r.right] <= a)) v++;
-      if (!((m.below[q] >> np[r.left]) & 1ull) || !((m.below[q] >> np[r.right]) & 1ull)) v++;
+      // without migration a coalescence happens in its children's population or an ancestor of it
+      if (m.B == 0 && (!((m.below[q] >> np[r.left]) & 1ull) || !((m.below[q] >> np[r.right]) & 1ull))) v++;
       if (r.father >= 0 ? t.node[r.father].left != x && t.node[r.father].right != x : *t.root != x) v++;
       if (t.node[x].flags & (F_RECALC | F_SAVED)) v++;
     }

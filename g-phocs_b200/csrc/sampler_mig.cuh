@@ -1,0 +1,652 @@
+// sampler_mig.cuh — device-resident MCMC update steps for population trees WITH migration bands.
+//
+// Adds to sampler_kernels.cuh what the reference does with its per-population event chains when lineages can
+// migrate (patch.c): UpdateGB_MigrationNode (GPhoCS.c:2437-2590), the migration part of UpdateGB_MigSPR /
+// traceLineage (patch.c:886-1331), UpdateMigRates (GPhoCS.c:3110-3210) and the migration-band handling of UpdateTau
+// and mixing.  Representation: a genealogy branch is cut into SEGMENTS (population, from, to) at population
+// boundaries and at its migration events; everything the genealogy likelihood needs follows from the segment list
+// without ordering events:
+//     coal_stats[p] = sum over pairs of segments in p of 2 * overlap         ( = integral of n(n-1) )
+//     mig_stats[b]  = sum over segments in target(b) of overlap with the band's live interval  ( = integral of n )
+// One warp per locus; the locus' nodes, migration events and segments live in that warp's shared memory.
+#pragma once
+#include "sampler_kernels.cuh"
+
+namespace gphocs {
+
+struct SmgWarp {      // per-warp shared-memory view (carved by smgCarve)
+  double* age;        // [N]
+  int16_t* father;    // [N]
+  uint8_t* pop;       // [N]
+  double* migAge;     // [kSmpMaxMigs]
+  int16_t* migBranch; // [kSmpMaxMigs]
+  uint8_t* migBand;   // [kSmpMaxMigs]
+  int* numMigs;       // [1]
+  int* segCount;      // [1]
+  int* bad;           // [1] inconsistency flag raised while cutting branches into segments
+  double* segT0;      // [S]
+  double* segT1;      // [S]
+  double* segC;       // [S] partial pair sums
+  int16_t* segBranch; // [S]
+  uint8_t* segPop;    // [S]
+  double* coal;       // [Q]
+  double* mig;        // [B]
+  int* ncoal;         // [Q]
+  int* nmig;          // [B]
+  int maxSegs;
+};
+
+__host__ __device__ inline int smgMaxSegs(int N) { return 4 * N + 2 * kSmpMaxMigs + 8; }
+__host__ __device__ inline size_t smgWarpBytes(int N, int Q, int B) {
+  const size_t S = (size_t)smgMaxSegs(N);
+  size_t b = (size_t)N * 8 + kSmpMaxMigs * 8 + S * 24 + (size_t)Q * 8 + (size_t)B * 8;   // doubles first
+  b += 3 * 4 + (size_t)Q * 4 + (size_t)B * 4;                                            // ints
+  b += (size_t)N * 2 + kSmpMaxMigs * 2 + S * 2;                                          // int16
+  b += (size_t)N + kSmpMaxMigs + S;                                                      // bytes
+  return (b + 15) & ~(size_t)15;
+}
+__device__ inline SmgWarp smgCarve(unsigned char* base, int N, int Q, int B) {
+  SmgWarp w;
+  const int S = smgMaxSegs(N);
+  w.maxSegs = S;
+  double* dp = reinterpret_cast<double*>(base);
+  w.age = dp; dp += N;
+  w.migAge = dp; dp += kSmpMaxMigs;
+  w.segT0 = dp; dp += S;
+  w.segT1 = dp; dp += S;
+  w.segC = dp; dp += S;
+  w.coal = dp; dp += Q;
+  w.mig = dp; dp += B;
+  int* ip = reinterpret_cast<int*>(dp);
+  w.numMigs = ip++; w.segCount = ip++; w.bad = ip++;
+  w.ncoal = ip; ip += Q;
+  w.nmig = ip; ip += B;
+  int16_t* sp = reinterpret_cast<int16_t*>(ip);
+  w.father = sp; sp += N;
+  w.migBranch = sp; sp += kSmpMaxMigs;
+  w.segBranch = sp; sp += S;
+  uint8_t* bp = reinterpret_cast<uint8_t*>(sp);
+  w.pop = bp; bp += N;
+  w.migBand = bp; bp += kSmpMaxMigs;
+  w.segPop = bp;
+  return w;
+}
+
+__device__ inline double smgBandStart(const SmpModel& m, int b, int ovPop, double ovTau) {
+  return fmax(smpTau(m, m.bandSrc[b], ovPop, ovTau), smpTau(m, m.bandTgt[b], ovPop, ovTau));
+}
+__device__ inline double smgBandEnd(const SmpModel& m, int b, int ovPop, double ovTau) {
+  return fmin(smpPopEnd(m, m.bandSrc[b], ovPop, ovTau), smpPopEnd(m, m.bandTgt[b], ovPop, ovTau));
+}
+
+// the locus' genealogy and migration events: HBM -> this warp's shared memory
+__device__ inline void smgLoad(const SmgWarp& w, const StoreDev& d, const SmpDev& sd, int l, int lane) {
+  const int N = d.N;
+  for (int x = lane; x < N; x += 32) {
+    const size_t o = (size_t)l * N + x;
+    w.age[x] = d.age[o];
+    w.father[x] = d.node[o].father;
+    w.pop[x] = sd.nodePop[o];
+  }
+  if (lane < kSmpMaxMigs) {
+    const size_t o = (size_t)l * kSmpMaxMigs + lane;
+    w.migAge[lane] = sd.migAge[o];
+    w.migBranch[lane] = sd.migBranch[o];
+    w.migBand[lane] = sd.migBand[o];
+  }
+  if (lane == 0) { *w.numMigs = sd.numMigs[l]; *w.bad = 0; }
+  __syncwarp();
+}
+
+// migration events shared memory -> HBM (after a proposal rewired them)
+__device__ inline void smgStoreMigs(const SmgWarp& w, const SmpDev& sd, int l, int lane) {
+  __syncwarp();
+  if (lane < kSmpMaxMigs) {
+    const size_t o = (size_t)l * kSmpMaxMigs + lane;
+    sd.migAge[o] = w.migAge[lane];
+    sd.migBranch[o] = w.migBranch[lane];
+    sd.migBand[o] = w.migBand[lane];
+  }
+  if (lane == 0) sd.numMigs[l] = *w.numMigs;
+}
+// current events -> saved copy (restored if the proposal is rejected)
+__device__ inline void smgSaveMigs(const SmpDev& sd, int l, int lane) {
+  if (lane < kSmpMaxMigs) {
+    const size_t o = (size_t)l * kSmpMaxMigs + lane;
+    sd.svMigAge[o] = sd.migAge[o];
+    sd.svMigBranch[o] = sd.migBranch[o];
+    sd.svMigBand[o] = sd.migBand[o];
+  }
+  if (lane == 0) sd.svNumMigs[l] = sd.numMigs[l];
+}
+__device__ inline void smgRestoreMigs(const SmpDev& sd, int l, int lane) {
+  if (lane < kSmpMaxMigs) {
+    const size_t o = (size_t)l * kSmpMaxMigs + lane;
+    sd.migAge[o] = sd.svMigAge[o];
+    sd.migBranch[o] = sd.svMigBranch[o];
+    sd.migBand[o] = sd.svMigBand[o];
+  }
+  if (lane == 0) sd.numMigs[l] = sd.svNumMigs[l];
+}
+
+// Walks branch x (from its node up to its father, or for ever above the root) through the populations it visits:
+// up at population ends, sideways (target -> source) at its migration events.  emit(pop, from, to) per segment.
+// Returns 0 if the path is consistent: every migration event happens in its band's target population inside the
+// band's live interval, and the branch ends in the population of the father's coalescence.
+template <typename Emit>
+__device__ inline int smgWalkBranch(const SmpModel& m, const SmgWarp& w, int x, int root, int ovPop, double ovTau, Emit emit) {
+  int pop = w.pop[x];
+  double t = w.age[x];
+  const int fa = w.father[x];
+  const double tEnd = fa >= 0 ? w.age[fa] : kSmpInf;
+  const int nm = *w.numMigs;
+  int bad = (fa >= 0 && tEnd < t) || (fa < 0 && x != root);
+  unsigned used = 0;
+  for (int it = 0; it < 2 * kSmpMaxPops + kSmpMaxMigs + 2; it++) {
+    int mi = -1;   // earliest migration event of this branch not yet passed
+    double mAge = kSmpInf;
+    for (int k = 0; k < nm; k++)
+      if (w.migBranch[k] == x && !((used >> k) & 1u) && w.migAge[k] < mAge) { mi = k; mAge = w.migAge[k]; }
+    const double popEnd = m.father[pop] >= 0 ? smpTau(m, m.father[pop], ovPop, ovTau) : kSmpInf;
+    const double tNext = fmin(tEnd, fmin(popEnd, mAge));
+    emit(pop, t, tNext);
+    if (mi >= 0 && mAge <= tEnd && mAge <= popEnd) {   // sideways: target -> source of the band
+      const int b = w.migBand[mi];
+      if (pop != m.bandTgt[b] || mAge < t || mAge < smgBandStart(m, b, ovPop, ovTau) || mAge > smgBandEnd(m, b, ovPop, ovTau)) bad = 1;
+      pop = m.bandSrc[b];
+      t = mAge;
+      used |= 1u << mi;
+      continue;
+    }
+    if (mi >= 0 && tEnd <= popEnd) bad = 1;   // an event of this branch lies beyond the branch
+    if (tEnd <= popEnd) break;                // reached the father
+    if (m.father[pop] < 0) break;             // the root population never ends
+    pop = m.father[pop];
+    t = tNext;
+  }
+  if (fa >= 0 && pop != w.pop[fa]) bad = 1;
+  return bad;
+}
+
+// Segment list of the genealogy.  skipBranch: a branch left out (the pruned lineage of an SPR, -1: none);
+// relabelFrom/relabelTo: segments of branch relabelFrom are reported as belonging to relabelTo (the pruned father's
+// upper branch continues its remaining child's lineage).  Raises *w.bad on inconsistency or overflow.
+__device__ inline void smgBuildSegments(const SmpModel& m, const SmgWarp& w, int N, int root, int lane, int ovPop, double ovTau,
+                                        int skipBranch, int relabelFrom, int relabelTo) {
+  if (lane == 0) *w.segCount = 0;
+  __syncwarp();
+  for (int x0 = 0; x0 < N; x0 += 32) {
+    const int x = x0 + lane;
+    int cnt = 0, bad = 0;
+    if (x < N && x != skipBranch) bad = smgWalkBranch(m, w, x, root, ovPop, ovTau, [&](int, double, double) { cnt++; });
+    // exclusive prefix of the counts over the lanes
+    int incl = cnt;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, off);
+      if (lane >= off) incl += v;
+    }
+    const int base = *w.segCount;
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    __syncwarp();
+    if (base + total > w.maxSegs) { if (lane == 0) *w.bad = 1; __syncwarp(); return; }
+    if (x < N && x != skipBranch) {
+      int k = base + incl - cnt;
+      const int label = x == relabelFrom ? relabelTo : x;
+      smgWalkBranch(m, w, x, root, ovPop, ovTau, [&](int pop, double a, double b) {
+        w.segPop[k] = (uint8_t)pop; w.segT0[k] = a; w.segT1[k] = b; w.segBranch[k] = (int16_t)label; k++;
+      });
+    }
+    if (bad) *w.bad = 1;
+    if (lane == 0) *w.segCount = base + total;
+    __syncwarp();
+  }
+}
+
+// statistics of the locus from its segments -> w.coal / w.ncoal / w.mig / w.nmig (deterministic summation order)
+__device__ inline void smgStats(const SmpModel& m, const SmgWarp& w, int n, int N, int lane, int ovPop, double ovTau) {
+  const int S = *w.segCount, Q = m.Q, B = m.B;
+  for (int i = lane; i < S; i += 32) {   // pairs (i, j > i) in the same population
+    const int p = w.segPop[i];
+    const double a0 = w.segT0[i], a1 = w.segT1[i];
+    double c = 0.0;
+    for (int j = i + 1; j < S; j++)
+      if (w.segPop[j] == p) {
+        const double ov = fmin(a1, w.segT1[j]) - fmax(a0, w.segT0[j]);
+        if (ov > 0.0) c += ov;
+      }
+    w.segC[i] = 2.0 * c;
+  }
+  __syncwarp();
+  for (int p = lane; p < Q; p += 32) {
+    double c = 0.0;
+    for (int i = 0; i < S; i++)
+      if (w.segPop[i] == p) c += w.segC[i];
+    int k = 0;
+    for (int x = n; x < N; x++) k += w.pop[x] == p;
+    w.coal[p] = c;
+    w.ncoal[p] = k;
+  }
+  for (int b = lane; b < B; b += 32) {
+    const int tgt = m.bandTgt[b];
+    const double s0 = smgBandStart(m, b, ovPop, ovTau), s1 = smgBandEnd(m, b, ovPop, ovTau);
+    double c = 0.0;
+    for (int i = 0; i < S; i++)
+      if (w.segPop[i] == tgt) {
+        const double ov = fmin(s1, w.segT1[i]) - fmax(s0, w.segT0[i]);
+        if (ov > 0.0) c += ov;
+      }
+    int k = 0;
+    for (int e = 0; e < *w.numMigs; e++) k += w.migBand[e] == b;
+    w.mig[b] = c;
+    w.nmig[b] = k;
+  }
+  __syncwarp();
+}
+
+// genealogy log-density from statistics (gtreeLnLikelihood, patch.c:2702-2723)
+__device__ inline double smgLnL(const SmpModel& m, const double* coal, const int* ncoal, const double* mig, const int* nmig) {
+  double v = 0.0;
+  for (int p = 0; p < m.Q; p++) v += (double)ncoal[p] * log(2.0 / m.theta[p]) - coal[p] / m.theta[p];
+  for (int b = 0; b < m.B; b++)
+    if (m.migRate[b] > 0.0) v += (double)nmig[b] * log(m.migRate[b]) - mig[b] * m.migRate[b];
+  return v;
+}
+
+// w.* statistics -> the locus' stored (pending = 0) or pending (1) arrays
+__device__ inline void smgWriteStats(const SmpModel& m, const SmgWarp& w, const SmpDev& sd, int l, int lane, int pending) {
+  for (int p = lane; p < m.Q; p += 32) {
+    (pending ? sd.coalT : sd.coal)[(size_t)l * m.Q + p] = w.coal[p];
+    (pending ? sd.ncoalT : sd.ncoal)[(size_t)l * m.Q + p] = w.ncoal[p];
+  }
+  for (int b = lane; b < m.B; b += 32) {
+    (pending ? sd.migT : sd.mig)[(size_t)l * m.B + b] = w.mig[b];
+    (pending ? sd.nmigT : sd.nmig)[(size_t)l * m.B + b] = w.nmig[b];
+  }
+}
+__device__ inline double smgStoredLnL(const SmpModel& m, const SmpDev& sd, int l) {
+  return smgLnL(m, sd.coal + (size_t)l * m.Q, sd.ncoal + (size_t)l * m.Q, sd.mig + (size_t)l * m.B, sd.nmig + (size_t)l * m.B);
+}
+
+#define SMG_PROLOGUE                                                                          \
+  extern __shared__ __align__(16) unsigned char smgSmem[];                                    \
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;                                  \
+  const int l = blockIdx.x * kSmpLociPerCta + wid;                                            \
+  if (l >= d.L) return;                                                                       \
+  const SmpModel& m = *mp;                                                                    \
+  const int n = d.n, N = d.N;                                                                 \
+  const SmgWarp w = smgCarve(smgSmem + (size_t)wid * smgWarpBytes(N, m.Q, m.B), N, m.Q, m.B); \
+  const TreeView t = deviceView(d, l);                                                        \
+  (void)n; (void)lane;
+
+// ------------------------------------------------------------------------------------------ statistics from scratch
+__global__ void __launch_bounds__(kSmpThreads) k_smg_stats(StoreDev d, SmpDev sd, const SmpModel* __restrict__ mp, int pending,
+                                                           int* __restrict__ bad) {
+  SMG_PROLOGUE
+  if (*t.root < n) return;
+  smgLoad(w, d, sd, l, lane);
+  smgBuildSegments(m, w, N, *t.root, lane, -1, 0.0, -1, -1, -1);
+  smgStats(m, w, n, N, lane, -1, 0.0);
+  smgWriteStats(m, w, sd, l, lane, pending);
+  if (bad && lane == 0) bad[l] += *w.bad;
+}
+
+// ------------------------------------------------------------------------------------------ coalescence-time move
+// UpdateGB_InternalNode with migration: the node stays in its population and between the events next to it on
+// the three branches it touches (GPhoCS.c:2316-2351, findFirstMig / findLastMig patch.c:374-410).
+__global__ void __launch_bounds__(kSmpThreads)
+k_smg_age_propose(StoreDev d, SmpDev sd, const SmpModel* __restrict__ mp, int inode, double finetune, unsigned long long seed,
+                  unsigned long long step) {
+  SMG_PROLOGUE
+  SmpProposal pr = smpNoProposal();
+  pr.node = inode;
+  const int root = *t.root;
+  if (root < n) { if (lane == 0) sd.prop[l] = pr; return; }
+  smgLoad(w, d, sd, l, lane);
+  double tnew = 0.0;
+  int valid = 0;
+  if (lane == 0) {
+    const int pop = w.pop[inode];
+    const double told = w.age[inode];
+    const NodeRec rec = t.node[inode];
+    double lo = m.tau[pop];
+    double hi = m.father[pop] >= 0 ? m.tau[m.father[pop]] : kOldAge;
+    double up = inode != root ? w.age[rec.father] : kSmpInf;   // first event above on the node's own branch
+    double dl = w.age[rec.left], dr = w.age[rec.right];         // last events below on the children's branches
+    for (int k = 0; k < *w.numMigs; k++) {
+      const int br = w.migBranch[k];
+      if (br == inode) up = fmin(up, w.migAge[k]);
+      if (br == rec.left) dl = fmax(dl, w.migAge[k]);
+      if (br == rec.right) dr = fmax(dr, w.migAge[k]);
+    }
+    lo = fmax(lo, fmax(dl, dr));
+    hi = fmin(hi, up);
+    SmpRng rng(seed, (unsigned long long)l, step);
+    tnew = smpReflect(told + finetune * rng.normal2(), lo, hi);
+    valid = fabs(tnew - told) >= 1e-15;
+    if (valid) adjustAge(t, inode, tnew);
+  }
+  valid = __shfl_sync(0xffffffffu, valid, 0);
+  tnew = __shfl_sync(0xffffffffu, tnew, 0);
+  if (valid) {
+    if (lane == 0) w.age[inode] = tnew;
+    __syncwarp();
+    smgBuildSegments(m, w, N, root, lane, -1, 0.0, -1, -1, -1);
+    smgStats(m, w, n, N, lane, -1, 0.0);
+    smgWriteStats(m, w, sd, l, lane, 1);
+    if (lane == 0) {
+      pr.genDelta = smgLnL(m, w.coal, w.ncoal, w.mig, w.nmig) - smgStoredLnL(m, sd, l);
+      pr.valid = *w.bad ? 0 : 1;
+      if (*w.bad) { revertNode(t, inode); }   // cannot happen for a move inside its bounds; stay safe
+    }
+  }
+  if (lane == 0) sd.prop[l] = pr;
+}
+
+// ------------------------------------------------------------------------------------------ migration-time moves
+// UpdateGB_MigrationNode (GPhoCS.c:2437-2590): every migration event of the locus in turn moves inside its band's
+// live interval and between the events next to it on its branch; the data likelihood is not involved, so the
+// whole sweep of a locus (propose, statistics, accept / reject) is done here, one launch for all loci.
+__global__ void __launch_bounds__(kSmpThreads)
+k_smg_mignode_sweep(StoreDev d, SmpDev sd, const SmpModel* __restrict__ mp, double finetune, unsigned long long seed,
+                    unsigned long long step) {
+  SMG_PROLOGUE
+  const int root = *t.root;
+  if (root < n) return;
+  smgLoad(w, d, sd, l, lane);
+  const int nm = *w.numMigs;
+  unsigned long long acc = 0, tried = 0;
+  double cur = smgStoredLnL(m, sd, l);
+  for (int k = 0; k < nm; k++) {
+    double told = 0.0, tnew = 0.0;
+    int valid = 0;
+    if (lane == 0) {
+      const int br = w.migBranch[k], b = w.migBand[k];
+      told = w.migAge[k];
+      double lo = fmax(smgBandStart(m, b, -1, 0.0), w.age[br]);
+      double hi = fmin(smgBandEnd(m, b, -1, 0.0), w.father[br] >= 0 ? w.age[w.father[br]] : kOldAge);
+      for (int j = 0; j < nm; j++)
+        if (j != k && w.migBranch[j] == br) {
+          if (w.migAge[j] < told) lo = fmax(lo, w.migAge[j]);
+          else hi = fmin(hi, w.migAge[j]);
+        }
+      SmpRng rng(seed, (unsigned long long)l, step * 16ull + (unsigned long long)k);
+      tnew = smpReflect(told + finetune * rng.normal2(), lo, hi);
+      valid = fabs(tnew - told) >= 1e-15;
+      if (valid) w.migAge[k] = tnew;
+    }
+    valid = __shfl_sync(0xffffffffu, valid, 0);
+    tried++;
+    if (!valid) { acc++; continue; }
+    told = __shfl_sync(0xffffffffu, told, 0);
+    __syncwarp();
+    smgBuildSegments(m, w, N, root, lane, -1, 0.0, -1, -1, -1);
+    smgStats(m, w, n, N, lane, -1, 0.0);
+    int ok = 0;
+    if (lane == 0) {
+      const double next = smgLnL(m, w.coal, w.ncoal, w.mig, w.nmig);
+      const double lnacc = next - cur;
+      ok = !*w.bad && lnacc >= 0.0;
+      if (!ok && !*w.bad) {
+        SmpRng rng(seed, (unsigned long long)l, step * 16ull + (unsigned long long)k + 8ull);
+        ok = rng.uniform() < exp(lnacc);
+      }
+      if (ok) cur = next;
+      else { w.migAge[k] = told; *w.bad = 0; }
+    }
+    ok = __shfl_sync(0xffffffffu, ok, 0);
+    cur = __shfl_sync(0xffffffffu, cur, 0);
+    if (ok) { smgWriteStats(m, w, sd, l, lane, 0); acc++; }
+    __syncwarp();
+  }
+  smgStoreMigs(w, sd, l, lane);
+  if (lane == 0 && tried) { atomicAdd(sd.accepted + 5, acc); atomicAdd(sd.accepted + 6, tried); }
+}
+
+// ------------------------------------------------------------------------------------------ subtree prune and regraft
+// traceLineage with migration (patch.c:886-1331): the pruned lineage is re-simulated from the coalescent with
+// migration conditional on the rest of the genealogy.  While it sits in population p the competing clocks are a
+// coalescence with every other lineage segment in p (rate 2/theta_p while both are there) and a migration
+// through every live band into p (rate m_b); the earliest ring over the warp decides: coalescence ends the
+// walk, a migration moves the lineage to the band's source population, no ring before the population ends moves
+// it to the parent population.  Proposal = conditional prior, so acceptance is the data-likelihood ratio alone
+// (GPhoCS.c:2702-2706); more than MAX_MIGS events in the genealogy make the proposal invalid (res < 0, :2706).
+__global__ void __launch_bounds__(kSmpThreads)
+k_smg_spr_propose(StoreDev d, SmpDev sd, const SmpModel* __restrict__ mp, int node, unsigned long long seed,
+                  unsigned long long step) {
+  SMG_PROLOGUE
+  SmpProposal pr = smpNoProposal();
+  const int root = *t.root;
+  if (root < n || node == root) { if (lane == 0) sd.prop[l] = pr; return; }
+  smgLoad(w, d, sd, l, lane);
+  const int F = w.father[node];
+  const NodeRec recF = t.node[F];
+  const int S = recF.left + recF.right - node;
+  // pruned genealogy: without the branch of `node`; the father's upper branch continues the sibling's lineage
+  smgBuildSegments(m, w, N, root, lane, -1, 0.0, node, F, S);
+  const int nSeg = *w.segCount;
+  double now = w.age[node];
+  int pop = w.pop[node];
+  int newBand[kSmpMaxMigs];
+  double newAge[kSmpMaxMigs];
+  int numNew = 0, target = -1, fail = *w.bad;
+  int kept = 0;   // events of the genealogy that survive the pruning
+  for (int k = 0; k < *w.numMigs; k++) kept += w.migBranch[k] != node;
+  for (int it = 0; it < 4 * kSmpMaxPops + 2 * kSmpMaxMigs && target < 0 && !fail; it++) {
+    const double popEnd = m.father[pop] >= 0 ? m.tau[m.father[pop]] : kSmpInf;
+    double bestT = kSmpInf;
+    int bestKind = -1, bestId = -1;
+    for (int i = lane; i < nSeg; i += 32) {
+      if (w.segPop[i] != pop) continue;
+      const double a = fmax(now, w.segT0[i]), b = fmin(popEnd, w.segT1[i]);
+      if (b <= a) continue;
+      SmpRng rng(seed, (unsigned long long)l * 4096ull + (unsigned long long)i, step * 64ull + (unsigned long long)it);
+      const double T = a + rng.exponential() * m.theta[pop] * 0.5;
+      if (T < b && T < bestT) { bestT = T; bestKind = 0; bestId = i; }
+    }
+    for (int b = lane; b < m.B; b += 32) {
+      if (m.bandTgt[b] != pop || !(m.migRate[b] > 0.0)) continue;
+      const double a = fmax(now, smgBandStart(m, b, -1, 0.0)), e = fmin(popEnd, smgBandEnd(m, b, -1, 0.0));
+      if (e <= a) continue;
+      SmpRng rng(seed, (unsigned long long)l * 4096ull + 2048ull + (unsigned long long)b, step * 64ull + (unsigned long long)it);
+      const double T = a + rng.exponential() / m.migRate[b];
+      if (T < e && T < bestT) { bestT = T; bestKind = 1; bestId = b; }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const double oT = __shfl_xor_sync(0xffffffffu, bestT, off);
+      const int oK = __shfl_xor_sync(0xffffffffu, bestKind, off);
+      const int oI = __shfl_xor_sync(0xffffffffu, bestId, off);
+      if (oT < bestT || (oT == bestT && oK >= 0 && (bestKind < 0 || oK * 4096 + oI < bestKind * 4096 + bestId))) {
+        bestT = oT; bestKind = oK; bestId = oI;
+      }
+    }
+    if (bestKind == 0) {
+      target = w.segBranch[bestId];
+      now = bestT;
+    } else if (bestKind == 1) {
+      if (kept + numNew >= kSmpMaxMigs) { fail = 1; break; }
+      newBand[numNew] = bestId;
+      newAge[numNew] = bestT;
+      numNew++;
+      now = bestT;
+      pop = m.bandSrc[bestId];
+    } else {
+      if (m.father[pop] < 0) { fail = 1; break; }
+      now = popEnd;
+      pop = m.father[pop];
+    }
+  }
+  if (target >= 0 && !fail) {
+    smgSaveMigs(sd, l, lane);
+    __syncwarp();
+    if (lane == 0) {
+      // events of the genealogy after the move: the old lineage's go, the pruned father's upper branch joins the
+      // sibling, events of the target branch above the new node move to the new father's upper branch, the
+      // simulated ones sit on the regrafted branch
+      int k2 = 0;
+      const int nmOld = *w.numMigs;
+      for (int k = 0; k < nmOld; k++) {
+        int br = w.migBranch[k];
+        if (br == node) continue;
+        if (br == F) br = S;
+        if (br == target && w.migAge[k] > now) br = F;
+        w.migBranch[k2] = (int16_t)br; w.migBand[k2] = w.migBand[k]; w.migAge[k2] = w.migAge[k]; k2++;
+      }
+      for (int k = 0; k < numNew; k++) {
+        w.migBranch[k2] = (int16_t)node; w.migBand[k2] = (uint8_t)newBand[k]; w.migAge[k2] = newAge[k]; k2++;
+      }
+      *w.numMigs = k2;
+      uint8_t* np = sd.nodePop + (size_t)l * N;
+      pr.pop = np[F];
+      pr.node = F;
+      spr(t, node, target, now);
+      np[F] = (uint8_t)pop;
+      pr.valid = 1;
+      pr.ntj0 = 1;   // the migration events were rewired: restore them on rejection
+    }
+    smgStoreMigs(w, sd, l, lane);
+  }
+  if (lane == 0) sd.prop[l] = pr;
+}
+
+// ------------------------------------------------------------------------------------------ split-time move
+// Rubber band with migration: coalescences AND migration events located in the affected populations are rescaled
+// (patch.c:699-712, 727, 741-748); the move is invalid (mig_conflict, GPhoCS.c:3545-3697) if afterwards some event
+// lies outside its band's new live interval or out of order on its branch — found by re-cutting the branches.
+__global__ void __launch_bounds__(kSmpThreads)
+k_smg_tau_propose(StoreDev d, SmpDev sd, const SmpModel* __restrict__ mp, int A, double tauOld, double tauNew, double lb, double ub,
+                  double f0, double f1) {
+  SMG_PROLOGUE
+  SmpProposal pr = smpNoProposal();
+  pr.pop = A;
+  const int root = *t.root;
+  if (root < n) { if (lane == 0) sd.prop[l] = pr; return; }
+  smgLoad(w, d, sd, l, lane);
+  smgSaveMigs(sd, l, lane);
+  const bool isRoot = A == m.rootPop;
+  const int s0 = m.son0[A], s1 = m.son1[A];
+  int n0 = 0, n1 = 0;
+  for (int x0 = n; x0 < N; x0 += 32) {
+    const int x = x0 + lane;
+    int which = 0;
+    if (x < N) {
+      const int q = w.pop[x];
+      const double a = w.age[x];
+      if (q == A) { if (isRoot || (a > tauOld && a < ub)) which = 2; }
+      else if ((q == s0 || q == s1) && a > lb && a < tauOld) which = 1;
+      if (which) {
+        const double an = which == 1 || isRoot ? lb + (a - lb) * f0 : ub + (a - ub) * f1;
+        adjustAge(t, x, an);
+        w.age[x] = an;
+      }
+    }
+    n0 += __popc(__ballot_sync(0xffffffffu, which == 1));
+    n1 += __popc(__ballot_sync(0xffffffffu, which == 2));
+  }
+  {
+    int which = 0;
+    if (lane < *w.numMigs) {
+      const int b = w.migBand[lane];
+      const int ps = m.bandSrc[b], pt = m.bandTgt[b];
+      const double a = w.migAge[lane];
+      if (ps == A || pt == A) { if (isRoot || (a > tauOld && a < ub)) which = 2; }
+      else if ((ps == s0 || ps == s1 || pt == s0 || pt == s1) && a > lb && a < tauOld) which = 1;
+      if (which) w.migAge[lane] = which == 1 || isRoot ? lb + (a - lb) * f0 : ub + (a - ub) * f1;
+    }
+    n0 += __popc(__ballot_sync(0xffffffffu, which == 1));
+    n1 += __popc(__ballot_sync(0xffffffffu, which == 2));
+  }
+  __syncwarp();
+  smgBuildSegments(m, w, N, root, lane, A, tauNew, -1, -1, -1);
+  smgStats(m, w, n, N, lane, A, tauNew);
+  smgWriteStats(m, w, sd, l, lane, 1);
+  smgStoreMigs(w, sd, l, lane);
+  if (lane == 0) {
+    // log-density of the pending state under the proposed split time: theta and rates are unchanged
+    pr.genDelta = smgLnL(m, w.coal, w.ncoal, w.mig, w.nmig) - smgStoredLnL(m, sd, l);
+    pr.ntj0 = n0;
+    pr.ntj1 = n1;
+    pr.valid = 1;
+    pr.node = *w.bad ? -2 : -1;   // -2: migration conflict in this locus
+    sd.prop[l] = pr;
+  }
+}
+
+// joint rescaling of every node age and migration time by c (mixing, GPhoCS.c:4793-4801, 4822-4826)
+__global__ void __launch_bounds__(kSmpThreads) k_smg_scale_propose(StoreDev d, SmpDev sd, const SmpModel* __restrict__ mp, double c) {
+  SMG_PROLOGUE
+  (void)w;
+  SmpProposal pr = smpNoProposal();
+  if (*t.root >= n) {
+    smgSaveMigs(sd, l, lane);
+    for (int x = lane; x < N; x += 32) adjustAge(t, x, c * t.age[x]);
+    if (lane < sd.numMigs[l]) sd.migAge[(size_t)l * kSmpMaxMigs + lane] *= c;
+    pr.valid = 1;
+  }
+  if (lane == 0) sd.prop[l] = pr;
+}
+
+// per-locus accept / reject for models with migration (kind as in k_smp_accept)
+__global__ void __launch_bounds__(kSmpThreads)
+k_smg_accept(StoreDev d, SmpDev sd, const SmpModel* __restrict__ mp, int kind, unsigned long long seed, unsigned long long step) {
+  SMG_PROLOGUE
+  (void)w;
+  const SmpProposal pr = sd.prop[l];
+  int ok = 0;
+  if (pr.valid) {
+    if (lane == 0) {
+      const double lnacc = (*t.lnL - *t.savedLnL) + pr.genDelta;
+      ok = lnacc >= 0.0;
+      if (!ok) {
+        SmpRng rng(seed, (unsigned long long)l, step);
+        ok = rng.uniform() < exp(lnacc);
+      }
+    }
+    ok = __shfl_sync(0xffffffffu, ok, 0);
+    if (ok) {
+      for (int x = lane; x < N; x += 32) commitNode(t, x);
+      if (kind == 0) {   // statistics of the proposed state were left pending by the proposal kernel
+        for (int p = lane; p < m.Q; p += 32) sd.coal[(size_t)l * m.Q + p] = sd.coalT[(size_t)l * m.Q + p];
+        for (int b = lane; b < m.B; b += 32) sd.mig[(size_t)l * m.B + b] = sd.migT[(size_t)l * m.B + b];
+      }
+      if (lane == 0) commitLocus(t);
+    } else {
+      for (int x = lane; x < N; x += 32) revertNode(t, x);
+      if (kind == 1) smgRestoreMigs(sd, l, lane);
+      if (lane == 0) {
+        revertLocus(t);
+        if (kind == 1) sd.nodePop[(size_t)l * N + pr.node] = (uint8_t)pr.pop;
+      }
+    }
+  } else if (kind == 0) {
+    ok = 1;
+  }
+  if (lane == 0 && ok) atomicAdd(sd.accepted + kind, 1ull);
+}
+
+// one global accept / reject for every locus; how: 0 tau move (statistics <- pending), 1 rescaling (statistics *= c)
+__global__ void __launch_bounds__(kSmpThreads) k_smg_global_resolve(StoreDev d, SmpDev sd, const SmpModel* __restrict__ mp, int accept,
+                                                                    int how, double c) {
+  SMG_PROLOGUE
+  (void)w;
+  if (!sd.prop[l].valid) return;
+  if (accept) {
+    for (int x = lane; x < N; x += 32) commitNode(t, x);
+    for (int p = lane; p < m.Q; p += 32) {
+      double* c0 = sd.coal + (size_t)l * m.Q + p;
+      *c0 = how == 0 ? sd.coalT[(size_t)l * m.Q + p] : *c0 * c;
+    }
+    for (int b = lane; b < m.B; b += 32) {
+      double* c0 = sd.mig + (size_t)l * m.B + b;
+      *c0 = how == 0 ? sd.migT[(size_t)l * m.B + b] : *c0 * c;
+    }
+    if (lane == 0) commitLocus(t);
+  } else {
+    for (int x = lane; x < N; x += 32) revertNode(t, x);
+    smgRestoreMigs(sd, l, lane);
+    if (lane == 0) revertLocus(t);
+  }
+}
+
+}  // namespace gphocs

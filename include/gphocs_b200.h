@@ -218,17 +218,32 @@ int gphocsSamplerDestroy(GphocsSampler *sm);
  * (an NCCL all-reduce of < 1 KB); it is applied to every reduced vector before a global decision, so all ranks keep
  * identical theta / tau.  locusOffset = global index of this rank's first locus (random streams are per global locus). */
 int gphocsSamplerSetAllReduce(GphocsSampler *sm, int (*fn)(double *, int, void *), void *ctx, long long locusOffset);
+/* Migration bands (MigrationBand, PopulationTree.h:60-70; band = source -> target backwards in time) with their
+ * rates and Gamma(alpha, beta) rate priors, and the migration events of every genealogy (genetree_migs,
+ * patch.h:138-148): numMigs[numLoci]; migBranch (node below the branch), migBand, migAge are [numLoci][10]
+ * (MAX_MIGS).  Switches on UpdateGB_MigrationNode (GPhoCS.c:2437), UpdateMigRates (:3110), migration in the SPR
+ * re-simulation (traceLineage, patch.c:886) and band handling in the split-time and mixing steps.  Up to 32
+ * bands and 80 leaves.  Trace rows gain the migration rates after the taus. */
+int gphocsSamplerSetMigration(GphocsSampler *sm, int numBands, const int *bandSrc, const int *bandTgt, const double *migRate,
+                              const double *migAlpha, const double *migBeta, const int *numMigs, const int *migBranch,
+                              const int *migBand, const double *migAge);
+/* finetune-mig-time, finetune-mig-rate */
+int gphocsSamplerSetMigFinetunes(GphocsSampler *sm, double migTime, double migRate);
 /* finetune-coal-time, finetune-theta, finetune-tau, finetune-mixing of the control file (MCMCcontrol.c:575-787) */
 int gphocsSamplerSetFinetunes(GphocsSampler *sm, double coalTime, double theta, double tau, double mixing);
 /* `iterations` MCMC iterations; trace (may be NULL): one row per iteration of gphocsSamplerTraceWidth() doubles =
  * [theta (numPops), tau of ancestral populations, sum of data lnL, sum of genealogy lnL] */
 int gphocsSamplerIterate(GphocsSampler *sm, int iterations, double *trace);
 int gphocsSamplerTraceWidth(const GphocsSampler *sm);
-/* accepted[5], proposed[5] for {coalescence time, SPR, theta, tau, mixing} */
+/* accepted[8], proposed[8] for {coalescence time, SPR, theta, tau, mixing, migration rate, migration time,
+ * (proposed only) split-time moves rejected for a migration conflict} */
 int gphocsSamplerGetState(GphocsSampler *sm, double *theta, double *tau, long long *accepted, long long *proposed);
 /* checkAll (patch.c:2745) on the device: returns structural violations; largest relative deviation of the
  * incrementally maintained statistics / data log-likelihoods from a recomputation from scratch */
 int gphocsSamplerCheck(GphocsSampler *sm, double *maxStatErr, double *maxLnLErr);
+/* per-locus statistics (GENETREE_STATS, patch.h:48-51) as the sampler holds them: coal[numLoci][numPops],
+ * numCoals[numLoci][numPops], mig[numLoci][numBands], numMigs[numLoci][numBands]; any pointer may be NULL */
+int gphocsSamplerGetStats(GphocsSampler *sm, double *coal, int *numCoals, double *mig, int *numMigs);
 /* brings the store's host mirror up to date and returns nodePop[numLoci][2n-1] (may be NULL) */
 int gphocsSamplerDownload(GphocsSampler *sm, int *nodePop);
 
