@@ -199,7 +199,8 @@ FINETUNES = dict(coal_time=0.01, mig_time=0.3, theta=0.04, mig_rate=0.02, tau=0.
 
 
 def write_control_file(model: Model, path: str, seqfile: str, tracefile: str, iterations: int = 0,
-                       seed: int = 4242, iterations_per_log: int = 10, finetunes: dict = None):
+                       seed: int = 4242, iterations_per_log: int = 10, finetunes: dict = None,
+                       mig_prior=(0.002, 0.00001)):
     """Control file for the reference program, SURVEY.md Appendix C layout."""
     ft = dict(FINETUNES)
     ft.update(finetunes or {})
@@ -214,7 +215,7 @@ def write_control_file(model: Model, path: str, seqfile: str, tracefile: str, it
     if model.rate_shape > 0:
         lines.append("\tfinetune-locus-rate\t0.3")
     lines += ["\ttau-theta-print\t10000.0", "\ttau-theta-alpha\t1.0", f"\ttau-theta-beta\t{1.0 / model.theta:.1f}",
-              "\tmig-rate-print\t0.001", "\tmig-rate-alpha\t0.002", "\tmig-rate-beta\t0.00001",
+              "\tmig-rate-print\t0.001", f"\tmig-rate-alpha\t{mig_prior[0]}", f"\tmig-rate-beta\t{mig_prior[1]:.8f}",
               "GENERAL-INFO-END", "", "CURRENT-POPS-START"]
     names = iter(sample_names(model))
     for nm, k in model.cur:
