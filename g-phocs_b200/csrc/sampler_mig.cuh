@@ -244,6 +244,48 @@ __device__ inline void smgStats(const SmpModel& m, const SmgWarp& w, int n, int 
   __syncwarp();
 }
 
+// Statistics that a move inside population p can change: coal[p] and mig[b] of the bands whose target is p.  The
+// segments of p are compacted (their indices go to the front of w.segC's storage, reused as an int list) and only
+// they are paired.  Leaves the results in w.coal[p] / w.mig[b]; ncoal / nmig are unchanged by such a move.
+__device__ inline void smgPopStats(const SmpModel& m, const SmgWarp& w, int lane, int p) {
+  const int S = *w.segCount;
+  int* list = reinterpret_cast<int*>(w.segC);
+  int count = 0;
+  for (int i0 = 0; i0 < S; i0 += 32) {
+    const int i = i0 + lane;
+    const bool in = i < S && w.segPop[i] == p;
+    const unsigned ballot = __ballot_sync(0xffffffffu, in);
+    if (in) list[count + __popc(ballot & ((1u << lane) - 1u))] = i;
+    count += __popc(ballot);
+  }
+  __syncwarp();
+  double c = 0.0;
+  for (int a = lane; a < count; a += 32) {
+    const int i = list[a];
+    const double a0 = w.segT0[i], a1 = w.segT1[i];
+    for (int bq = a + 1; bq < count; bq++) {
+      const int j = list[bq];
+      const double ov = fmin(a1, w.segT1[j]) - fmax(a0, w.segT0[j]);
+      if (ov > 0.0) c += ov;
+    }
+  }
+  c = 2.0 * warpSumD(c);
+  if (lane == 0) w.coal[p] = c;
+  for (int b = 0; b < m.B; b++) {
+    if (m.bandTgt[b] != p) continue;
+    const double s0 = smgBandStart(m, b, -1, 0.0), s1 = smgBandEnd(m, b, -1, 0.0);
+    double g = 0.0;
+    for (int a = lane; a < count; a += 32) {
+      const int i = list[a];
+      const double ov = fmin(s1, w.segT1[i]) - fmax(s0, w.segT0[i]);
+      if (ov > 0.0) g += ov;
+    }
+    g = warpSumD(g);
+    if (lane == 0) w.mig[b] = g;
+  }
+  __syncwarp();
+}
+
 // genealogy log-density from statistics (gtreeLnLikelihood, patch.c:2702-2723)
 __device__ inline double smgLnL(const SmpModel& m, const double* coal, const int* ncoal, const double* mig, const int* nmig) {
   double v = 0.0;
@@ -331,11 +373,20 @@ k_smg_age_propose(StoreDev d, SmpDev sd, const SmpModel* __restrict__ mp, int in
   if (valid) {
     if (lane == 0) w.age[inode] = tnew;
     __syncwarp();
+    const int p = w.pop[inode];
     smgBuildSegments(m, w, N, root, lane, -1, 0.0, -1, -1, -1);
-    smgStats(m, w, n, N, lane, -1, 0.0);
-    smgWriteStats(m, w, sd, l, lane, 1);
+    smgPopStats(m, w, lane, p);
     if (lane == 0) {
-      pr.genDelta = smgLnL(m, w.coal, w.ncoal, w.mig, w.nmig) - smgStoredLnL(m, sd, l);
+      // only population p's coal statistic and the bands into p change (the node stays in p)
+      double delta = -(w.coal[p] - sd.coal[(size_t)l * m.Q + p]) / m.theta[p];
+      sd.coalT[(size_t)l * m.Q + p] = w.coal[p];
+      for (int b = 0; b < m.B; b++)
+        if (m.bandTgt[b] == p) {
+          sd.migT[(size_t)l * m.B + b] = w.mig[b];
+          if (m.migRate[b] > 0.0) delta -= (w.mig[b] - sd.mig[(size_t)l * m.B + b]) * m.migRate[b];
+        }
+      pr.genDelta = delta;
+      pr.pop = p;
       pr.valid = *w.bad ? 0 : 1;
       if (*w.bad) { revertNode(t, inode); }   // cannot happen for a move inside its bounds; stay safe
     }
@@ -606,9 +657,10 @@ k_smg_accept(StoreDev d, SmpDev sd, const SmpModel* __restrict__ mp, int kind, u
     ok = __shfl_sync(0xffffffffu, ok, 0);
     if (ok) {
       for (int x = lane; x < N; x += 32) commitNode(t, x);
-      if (kind == 0) {   // statistics of the proposed state were left pending by the proposal kernel
-        for (int p = lane; p < m.Q; p += 32) sd.coal[(size_t)l * m.Q + p] = sd.coalT[(size_t)l * m.Q + p];
-        for (int b = lane; b < m.B; b += 32) sd.mig[(size_t)l * m.B + b] = sd.migT[(size_t)l * m.B + b];
+      if (kind == 0) {   // the changed statistics of the proposed state were left pending by the proposal kernel
+        if (lane == 0) sd.coal[(size_t)l * m.Q + pr.pop] = sd.coalT[(size_t)l * m.Q + pr.pop];
+        for (int b = lane; b < m.B; b += 32)
+          if (m.bandTgt[b] == pr.pop) sd.mig[(size_t)l * m.B + b] = sd.migT[(size_t)l * m.B + b];
       }
       if (lane == 0) commitLocus(t);
     } else {

@@ -14,7 +14,8 @@ ap.add_argument("--iterations", type=int, default=50)
 args = ap.parse_args()
 w = synth.generate(synth.config(args.config), args.loci, seed=777)
 st = gp.LociStore.from_workload(w)
-sm = gp.Sampler(st, w.pops, w.node_pop, seed=1)
+mig = (w.mig_start, w.mig_branch, w.mig_band, w.mig_age) if len(w.pops["band_src"]) else None
+sm = gp.Sampler(st, w.pops, w.node_pop, seed=1, migration=mig)
 sm.iterate(3, trace=False)
 k0 = gp.lib().gphocsKernelLaunchCount()
 t0 = time.perf_counter()
