@@ -202,16 +202,17 @@ def reference_mcmc(threads, iterations=40):
             "iters_per_s": (iterations - 1) / max(wall[iterations] - wall[1], 1e-9), "wall_s": wall[iterations], "setup_s": wall[1]}
 
 
-def device_mcmc(gp, synth, device, total_loci, iterations, rank=0, world=1):
-    """MCMC iterations/s of the device-resident update steps (gphocs_b200.h group D) on MCMC_CONFIG with `total_loci`
+def device_mcmc(gp, synth, device, total_loci, iterations, rank=0, world=1, cfg=MCMC_CONFIG):
+    """MCMC iterations/s of the device-resident update steps (gphocs_b200.h group D) on workload `cfg` with `total_loci`
     loci sharded over `world` ranks; global decisions are taken on NCCL all-reduced sums."""
     import torch
     import torch.distributed as dist
     shard = importlib.import_module("g-phocs_b200.shard")
     lo, hi = shard.shard_range(total_loci, rank, world)
-    w = synth.generate(synth.config(MCMC_CONFIG), hi - lo, seed=777 + rank)
+    w = synth.generate(synth.config(cfg), hi - lo, seed=777 + rank)
     st = gp.LociStore.from_workload(w, device=device)
-    sm = gp.Sampler(st, w.pops, w.node_pop, seed=1)
+    mig = (w.mig_start, w.mig_branch, w.mig_band, w.mig_age) if len(w.pops["band_src"]) else None
+    sm = gp.Sampler(st, w.pops, w.node_pop, seed=1, migration=mig)
     if world > 1:
         buf = torch.zeros(128, dtype=torch.float64, device=f"cuda:{device}")
 
@@ -236,10 +237,11 @@ def device_mcmc(gp, synth, device, total_loci, iterations, rank=0, world=1):
     launches = gp.lib().gphocsKernelLaunchCount() - k0
     violations, stat_err, lnl_err = sm.check()
     s = sm.state()
-    out = {"config": f"{MCMC_CONFIG}: {total_loci} loci over {world} GPU(s)", "iterations": iterations, "iters_per_s": iterations / dt,
+    out = {"config": f"{cfg}: {total_loci} loci over {world} GPU(s)", "iterations": iterations, "iters_per_s": iterations / dt,
            "kernel_launches_per_iteration": launches / iterations,
-           "accept_rates": {m: float(s["accepted"][m]) / max(1, int(s["proposed"][m])) for m in gp.Sampler.MOVES},
-           "check": {"violations": int(violations), "max_lnl_rel_err_vs_full_recompute": lnl_err}}
+           "accept_rates": {m: float(s["accepted"][m]) / max(1, int(s["proposed"][m])) for m in gp.Sampler.MOVES[:7]},
+           "check": {"violations": int(violations), "max_stat_rel_err_vs_recompute": stat_err,
+                     "max_lnl_rel_err_vs_full_recompute": lnl_err}}
     sm.close()
     st.close()
     return out
@@ -445,10 +447,13 @@ def run_b200(args):
     torch.cuda.synchronize()
     inc_ms = a.elapsed_time(b)
     st.apply_ops(rej)
-    # MCMC iterations/s: configs[1] (10k loci) on one GPU, and 100k loci sharded over all ranks (strong scaling)
-    mcmc = {"loci_100k_sharded": device_mcmc(gp, synth, local_rank, 100_000, 30, rank, world)}
+    # MCMC iterations/s of the device-resident steps: BASELINE.json configs[3] (100k loci, 6 populations + 4 bands) and
+    # the migration-free 100k-locus shape sharded over all ranks (strong scaling); configs[1] and [2] (10k loci) at N=1
+    mcmc = {"configs3_pop6mig4_100k_sharded": device_mcmc(gp, synth, local_rank, 100_000, 10, rank, world, cfg="pop6mig4"),
+            "hap16_100k_sharded": device_mcmc(gp, synth, local_rank, 100_000, 30, rank, world)}
     if world == 1:
-        mcmc["loci_10k"] = device_mcmc(gp, synth, local_rank, MCMC_LOCI, 100)
+        mcmc["configs1_hap16_10k"] = device_mcmc(gp, synth, local_rank, MCMC_LOCI, 100)
+        mcmc["configs2_dip8mig_10k"] = device_mcmc(gp, synth, local_rank, 10_000, 50, cfg="dip8mig")
     clocks = sampler.stop() if rank == 0 else None
 
     if rank == 0:
