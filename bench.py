@@ -212,7 +212,13 @@ def device_mcmc(gp, synth, device, total_loci, iterations, rank=0, world=1, cfg=
     w = synth.generate(synth.config(cfg), hi - lo, seed=777 + rank)
     st = gp.LociStore.from_workload(w, device=device)
     mig = (w.mig_start, w.mig_branch, w.mig_band, w.mig_age) if len(w.pops["band_src"]) else None
-    sm = gp.Sampler(st, w.pops, w.node_pop, seed=1, migration=mig)
+    model = synth.config(cfg)
+    extra = {}
+    if model.sample_age or model.rate_shape > 0:        # configs[4]: estimated sample ages, locus-mut-rate VAR
+        st.set_rates([1.0] * w.L)
+        extra = dict(estimate_sample_age=[1 if nm in model.sample_age else 0 for nm, _ in model.cur],
+                     locus_rate_finetune=0.3 if model.rate_shape > 0 else 0.0)
+    sm = gp.Sampler(st, w.pops, w.node_pop, seed=1, migration=mig, **extra)
     if world > 1:
         buf = torch.zeros(128, dtype=torch.float64, device=f"cuda:{device}")
 
@@ -239,7 +245,7 @@ def device_mcmc(gp, synth, device, total_loci, iterations, rank=0, world=1, cfg=
     s = sm.state()
     out = {"config": f"{cfg}: {total_loci} loci over {world} GPU(s)", "iterations": iterations, "iters_per_s": iterations / dt,
            "kernel_launches_per_iteration": launches / iterations,
-           "accept_rates": {m: float(s["accepted"][m]) / max(1, int(s["proposed"][m])) for m in gp.Sampler.MOVES[:7]},
+           "accept_rates": {m: float(s["accepted"][m]) / max(1, int(s["proposed"][m])) for m in gp.Sampler.MOVES if m != "tau_conflicts"},
            "check": {"violations": int(violations), "max_stat_rel_err_vs_recompute": stat_err,
                      "max_lnl_rel_err_vs_full_recompute": lnl_err}}
     sm.close()
@@ -451,6 +457,7 @@ def run_b200(args):
     # MCMC iterations/s of the device-resident steps: BASELINE.json configs[3] (100k loci, 6 populations + 4 bands) and
     # the migration-free 100k-locus shape sharded over all ranks (strong scaling); configs[1] and [2] (10k loci) at N=1
     mcmc = {"configs3_pop6mig4_100k_sharded": device_mcmc(gp, synth, local_rank, 100_000, 10, rank, world, cfg="pop6mig4"),
+            "configs4_ancient_50k_sharded": device_mcmc(gp, synth, local_rank, 50_000, 20, rank, world, cfg="ancient"),
             "hap16_100k_sharded": device_mcmc(gp, synth, local_rank, 100_000, 30, rank, world)}
     if world == 1:
         mcmc["configs1_hap16_10k"] = device_mcmc(gp, synth, local_rank, MCMC_LOCI, 100)

@@ -87,6 +87,7 @@ def lib():
         "gphocsStoreEvaluate": (ci, [vp, ci, c_int_p, ci, c_dbl_p, c_dbl_p]),
         "gphocsStoreEvaluateDevice": (ci, [vp, ci, C.POINTER(vp), C.POINTER(vp)]),
         "gphocsStoreGetLnL": (ci, [vp, ci, c_int_p, c_dbl_p]),
+        "gphocsStoreGetRates": (ci, [vp, ci, c_int_p, c_dbl_p]),
         "gphocsStoreGetClv": (ci, [vp, ci, ci, ci, c_dbl_p]),
         "gphocsStoreSync": (ci, [vp]),
         "gphocsStoreSetDebug": (ci, [vp, ci]),
@@ -114,6 +115,7 @@ def lib():
         "gphocsSamplerSetFinetunes": (ci, [vp, cd, cd, cd, cd]),
         "gphocsSamplerSetMigration": (ci, [vp, ci, c_int_p, c_int_p, c_dbl_p, c_dbl_p, c_dbl_p, c_int_p, c_int_p, c_int_p, c_dbl_p]),
         "gphocsSamplerSetMigFinetunes": (ci, [vp, cd, cd]),
+        "gphocsSamplerSetAncient": (ci, [vp, c_int_p, c_dbl_p, cd, cd]),
         "gphocsSamplerSetAllReduce": (ci, [vp, vp, vp, C.c_longlong]),
         "gphocsSamplerIterate": (ci, [vp, ci, c_dbl_p]),
         "gphocsSamplerTraceWidth": (ci, [vp]),
@@ -210,6 +212,12 @@ class LociStore:
         r = _f64(rates)
         self._check(self.lib.gphocsStoreSetRates(self.h, len(r), _ip(None if ids is None else _i32(ids)), _dp(r)),
                     "gphocsStoreSetRates")
+
+    def get_rates(self, ids=None):
+        out = np.zeros(self.L if ids is None else len(ids))
+        self._check(self.lib.gphocsStoreGetRates(self.h, len(out), _ip(None if ids is None else _i32(ids)), _dp(out)),
+                    "gphocsStoreGetRates")
+        return out
 
     def apply_ops(self, ops, want_status=False):
         ops = np.ascontiguousarray(ops, OP_DTYPE)
@@ -440,12 +448,16 @@ class ScalarLocus:
 
 class Sampler:
     """Device-resident MCMC update steps (GphocsSampler) over the loci of a LociStore."""
-    MOVES = ("coal_time", "spr", "theta", "tau", "mixing", "mig_rate", "mig_time", "tau_conflicts")
+    MOVES = ("coal_time", "spr", "theta", "tau", "mixing", "mig_rate", "mig_time", "tau_conflicts", "locus_rate",
+             "sample_age")
     MAX_MIGS = 10
 
     def __init__(self, store, pops, node_pop, theta_prior=(1.0, 1000.0), tau_prior=None, seed=1, finetunes=None,
-                 migration=None, mig_prior=(0.002, 0.00001), mig_finetunes=None):
-        """migration = (mig_start[L+1], mig_branch, mig_band, mig_age) CSR arrays of the genealogies' migration events
+                 migration=None, mig_prior=(0.002, 0.00001), mig_finetunes=None, estimate_sample_age=None,
+                 locus_rate_finetune=0.0, rate_alpha=1.0):
+        """pops["sample_age"] (ages of the current populations' samples) must agree with the leaf ages in the store;
+        estimate_sample_age[C] marks the ones that are parameters; locus_rate_finetune > 0 turns on locus-rate moves.
+        migration = (mig_start[L+1], mig_branch, mig_band, mig_age) CSR arrays of the genealogies' migration events
         (synth.Workload fields); bands and their rates come from pops["band_src"/"band_tgt"/"band_rate"]."""
         self.lib = lib()
         self.store = store
@@ -457,11 +469,15 @@ class Sampler:
         if tau_prior is None:        # the control files written by synth.write_control_file: alpha 1, beta 1/tau-initial
             aa = np.full(Q, 1.0)
             ab = np.array([1.0 / t if t > 0 else 1.0 for t in pops["age"]])
+            aa[:self.C] = ab[:self.C] = 0.0      # sample ages: no prior density (PopulationTree.c:121)
         else:
             aa, ab = (np.ascontiguousarray(x, np.float64) for x in tau_prior)
+        tau0 = _f64(pops["age"]).copy()
+        if "sample_age" in pops:
+            tau0[:self.C] = pops["sample_age"]
         self.h = self.lib.gphocsSamplerCreate(store.h, Q, self.C, _ip(_i32(pops["father"])), _ip(_i32(pops["son0"])),
                                               _ip(_i32(pops["son1"])), _ip(_i32(pops["samples_per_pop"])),
-                                              _dp(_f64(pops["theta"])), _dp(_f64(pops["age"])), _dp(ta), _dp(tb), _dp(aa), _dp(ab),
+                                              _dp(_f64(pops["theta"])), _dp(tau0), _dp(ta), _dp(tb), _dp(aa), _dp(ab),
                                               _ip(_i32(node_pop)), int(seed))
         if not self.h:
             raise RuntimeError("gphocsSamplerCreate failed")
@@ -485,6 +501,9 @@ class Sampler:
             self.B = B
             if mig_finetunes is not None:
                 self.lib.gphocsSamplerSetMigFinetunes(self.h, float(mig_finetunes[0]), float(mig_finetunes[1]))
+        if estimate_sample_age is not None or locus_rate_finetune > 0.0:
+            est = _i32(estimate_sample_age if estimate_sample_age is not None else np.zeros(self.C))
+            self.lib.gphocsSamplerSetAncient(self.h, _ip(est), None, float(locus_rate_finetune), float(rate_alpha))
         self.width = self.lib.gphocsSamplerTraceWidth(self.h)
         if finetunes is not None:
             self.lib.gphocsSamplerSetFinetunes(self.h, *[float(x) for x in finetunes])
@@ -511,7 +530,7 @@ class Sampler:
 
     def state(self):
         th, ta = np.zeros(self.Q), np.zeros(self.Q)
-        acc, prop = np.zeros(8, np.int64), np.zeros(8, np.int64)
+        acc, prop = np.zeros(10, np.int64), np.zeros(10, np.int64)
         self.lib.gphocsSamplerGetState(self.h, _dp(th), _dp(ta), _lp(acc), _lp(prop))
         return dict(theta=th, tau=ta, accepted=dict(zip(self.MOVES, acc)), proposed=dict(zip(self.MOVES, prop)))
 

@@ -454,6 +454,17 @@ extern "C" int gphocsStoreGetTrees(GphocsStore* s, int nLoci, const int* locusId
   return 0;
 }
 
+// rates of the host mirror (getLocusMutationRate, LocusDataLikelihood.c:382, for many loci)
+extern "C" int gphocsStoreGetRates(GphocsStore* s, int nLoci, const int* locusIds, double* rates) {
+  std::lock_guard<std::mutex> lk(s->mu);
+  for (int k = 0; k < nLoci; k++) {
+    const int l = locusIds ? locusIds[k] : k;
+    if (l < 0 || l >= s->L) return -1;
+    rates[k] = s->hRate[l];
+  }
+  return 0;
+}
+
 // ---- edits
 // Ships edit records to the device (grouped by locus, call order kept within a locus) and, while the copy and
 // the kernel run, applies the same records to the host mirror with all host threads (loci are independent).

@@ -495,21 +495,25 @@ k_smp_tau_propose(StoreDev d, SmpDev sd, const SmpModel* __restrict__ mp, int A,
   WarpLocus<R> w;
   wlLoad(w, d, sd, l, lane);
   const bool isRoot = A == m.rootPop;
-  const int s0 = m.son0[A], s1 = m.son1[A];
+  // A current population: its SAMPLE AGE moves (UpdateSampleAge, GPhoCS.c:4006-4590) — the leaves of A take the new
+  // age, the coalescences of A above it are rubber-banded towards the population's end; there are no sons.
+  const int s0 = A >= m.C ? m.son0[A] : -1, s1 = A >= m.C ? m.son1[A] : -1;
   int n0 = 0, n1 = 0;
 #pragma unroll
   for (int r = 0; r < R; r++) {
     const int x = lane + 32 * r;
-    int which = 0;   // 1: lower band, 2: upper band
+    int which = 0;   // 1: lower band, 2: upper band, 3: sample of A
     if (x >= n && x < N) {
       const int q = w.pop[r];
       const double a = w.age[r];
       if (q == A) { if (isRoot || (a > tauOld && a < ub)) which = 2; }
       else if ((q == s0 || q == s1) && a > lb && a < tauOld) which = 1;
+    } else if (x < n && A < m.C && w.pop[r] == A) {
+      which = 3;
     }
     if (which) {
       const double a = w.age[r];
-      const double an = which == 1 || isRoot ? lb + (a - lb) * f0 : ub + (a - ub) * f1;
+      const double an = which == 3 ? tauNew : (which == 1 || isRoot ? lb + (a - lb) * f0 : ub + (a - ub) * f1);
       adjustAge(t, x, an);
       w.age[r] = an;
     }
@@ -559,6 +563,8 @@ __global__ void __launch_bounds__(kSmpThreads) k_smp_reduce(StoreDev d, SmpDev s
         else x = pr.valid && pr.node == -2 ? 1.0 : 0.0;
       } else {
         if (v == 0) x = d.lnL[l];
+        else if (v == 1) x = (d.rate[l] - 1.0) * (d.rate[l] - 1.0);
+        else if (v == 2) x = 1.0;   // loci (of all ranks after the all-reduce)
         else if (v >= 5 && v < 5 + Q) x = sd.coal[(size_t)l * Q + (v - 5)];
         else if (v >= 5 + Q && v < 5 + 2 * Q) x = sd.ncoal[(size_t)l * Q + (v - 5 - Q)];
         else if (v >= 5 + 2 * Q && v < 5 + 2 * Q + B) x = sd.mig[(size_t)l * B + (v - 5 - 2 * Q)];
@@ -603,6 +609,87 @@ __global__ void __launch_bounds__(kSmpThreads) k_smp_init_stats(StoreDev d, SmpD
   wlLoad(w, d, sd, l, lane);
   wlStats<R>(m, w, n, N, lane, -1, 0.0, scratch, (toTentative ? sd.coalT : sd.coal) + (size_t)l * m.Q,
              (toTentative ? sd.ncoalT : sd.ncoal) + (size_t)l * m.Q);
+}
+
+// ------------------------------------------------------------------------------------------ locus-rate moves
+// UpdateLocusRate (GPhoCS.c:4598-4675) keeps the mean rate at 1 by moving rate between a locus and a reference locus,
+// one locus after the other.  Here the same move — rate shifted between TWO loci, their sum kept, Dirichlet(alpha)
+// prior ratio, both data likelihoods recomputed from scratch — is made on disjoint pairs (l, l + offset) for all
+// pairs at once; the offset changes every iteration so rate can travel between any two loci.
+// Loci are first rotated by `shift` (so that every pair of loci can meet), then (l', l' + offset) pair up inside
+// blocks of 2 * offset.  Returns the partner (-1: unpaired this round); *proposer = this locus is the lower of its pair.
+__device__ inline int smpRatePartner(int l, int L, int offset, int shift, bool* proposer) {
+  const int lp = (l + shift) % L;
+  const bool lower = ((lp / offset) & 1) == 0;
+  *proposer = lower;
+  const int pp = lower ? lp + offset : lp - offset;
+  if (pp >= L) return -1;
+  return (pp - shift + L) % L;
+}
+__global__ void __launch_bounds__(kSmpThreads)
+k_smp_rate_propose(StoreDev d, SmpDev sd, int offset, int shift, double finetune, unsigned long long seed, unsigned long long step) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= d.L) return;
+  SmpProposal pr = smpNoProposal();
+  bool proposer;
+  const int partner = smpRatePartner(l, d.L, offset, shift, &proposer);
+  if (partner >= 0 && proposer && d.root[l] >= d.n && d.root[partner] >= d.n) {
+    const double r0 = d.rate[l], r1 = d.rate[partner];
+    SmpRng rng(seed, (unsigned long long)l, step);
+    const double rn = smpReflect(r0 + finetune * rng.normal2(), 0.0, r0 + r1);
+    pr.genDelta = r0;        // old rates, for the prior ratio and for a rejection
+    pr.aux = r1;
+    pr.node = partner;
+    pr.valid = 1;
+    d.rate[l] = rn;
+    d.rate[partner] = r0 + r1 - rn;
+  }
+  sd.prop[l] = pr;
+}
+// after a full evaluation (useOld = 0) of every locus: both loci of a pair reach the same decision from the same
+// numbers; the decision is left in prop[l].ntj1 for k_smp_rate_restore (rates are restored in a second launch so
+// that no thread reads a rate its partner has already put back)
+__global__ void __launch_bounds__(kSmpThreads)
+k_smp_rate_accept(StoreDev d, SmpDev sd, int offset, int shift, double alpha, unsigned long long seed, unsigned long long step) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= d.L) return;
+  bool proposer;
+  const int partner = smpRatePartner(l, d.L, offset, shift, &proposer);
+  int ok = 0;
+  if (partner >= 0) {
+    const int lo = proposer ? l : partner;
+    const SmpProposal pr = sd.prop[lo];
+    if (pr.valid) {
+      const int hi = pr.node;
+      const double r0 = pr.genDelta, r1 = pr.aux;
+      double lnacc = (d.lnL[lo] - d.savedLnL[lo]) + (d.lnL[hi] - d.savedLnL[hi]);
+      lnacc += (alpha - 1.0) * log((d.rate[lo] * d.rate[hi]) / (r0 * r1));
+      ok = lnacc >= 0.0;
+      if (!ok) {
+        SmpRng rng(seed, (unsigned long long)lo, step);
+        ok = rng.uniform() < exp(lnacc);
+      }
+    }
+  }
+  sd.prop[l].ntj1 = ok;
+}
+__global__ void __launch_bounds__(kSmpThreads) k_smp_rate_restore(StoreDev d, SmpDev sd, int offset, int shift) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= d.L) return;
+  bool proposer;
+  const int partner = smpRatePartner(l, d.L, offset, shift, &proposer);
+  const int ok = sd.prop[l].ntj1;
+  const TreeView t = deviceView(d, l);
+  if (ok) {
+    commit(t);
+    if (proposer) atomicAdd(sd.accepted + 2, 1ull);
+  } else {
+    revert(t);   // also for unpaired loci: the full evaluation flipped their buffers
+    if (partner >= 0) {
+      const SmpProposal pr = sd.prop[proposer ? l : partner];
+      if (pr.valid) d.rate[l] = proposer ? pr.genDelta : pr.aux;
+    }
+  }
 }
 
 // consistency of the population assignment: every coalescence lies inside its population's time span and above

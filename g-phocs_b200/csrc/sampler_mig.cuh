@@ -72,8 +72,11 @@ __device__ inline SmgWarp smgCarve(unsigned char* base, int N, int Q, int B) {
   return w;
 }
 
+// a band is live while both populations exist; a current population exists from time 0 whatever the age of its
+// samples (updateMigrationBandTimes uses pops[]->age, PopulationTree.c:448)
+__device__ inline double smgPopBirth(const SmpModel& m, int p, int ovPop, double ovTau) { return p < m.C ? 0.0 : smpTau(m, p, ovPop, ovTau); }
 __device__ inline double smgBandStart(const SmpModel& m, int b, int ovPop, double ovTau) {
-  return fmax(smpTau(m, m.bandSrc[b], ovPop, ovTau), smpTau(m, m.bandTgt[b], ovPop, ovTau));
+  return fmax(smgPopBirth(m, m.bandSrc[b], ovPop, ovTau), smgPopBirth(m, m.bandTgt[b], ovPop, ovTau));
 }
 __device__ inline double smgBandEnd(const SmpModel& m, int b, int ovPop, double ovTau) {
   return fmin(smpPopEnd(m, m.bandSrc[b], ovPop, ovTau), smpPopEnd(m, m.bandTgt[b], ovPop, ovTau));
@@ -576,18 +579,25 @@ k_smg_tau_propose(StoreDev d, SmpDev sd, const SmpModel* __restrict__ mp, int A,
   smgLoad(w, d, sd, l, lane);
   smgSaveMigs(sd, l, lane);
   const bool isRoot = A == m.rootPop;
-  const int s0 = m.son0[A], s1 = m.son1[A];
+  // A current population: its SAMPLE AGE moves (UpdateSampleAge, GPhoCS.c:4006-4590): the leaves of A take the new age
+  const int s0 = A >= m.C ? m.son0[A] : -1, s1 = A >= m.C ? m.son1[A] : -1;
   int n0 = 0, n1 = 0;
-  for (int x0 = n; x0 < N; x0 += 32) {
+  for (int x0 = 0; x0 < N; x0 += 32) {
     const int x = x0 + lane;
     int which = 0;
     if (x < N) {
       const int q = w.pop[x];
       const double a = w.age[x];
-      if (q == A) { if (isRoot || (a > tauOld && a < ub)) which = 2; }
-      else if ((q == s0 || q == s1) && a > lb && a < tauOld) which = 1;
+      if (x >= n) {
+        if (q == A) {
+          if (isRoot || (a > tauOld && a < ub)) which = 2;
+          else if (A < m.C && a < tauOld) which = 1;   // migrants that entered A before its samples: scaled towards 0
+        } else if ((q == s0 || q == s1) && a > lb && a < tauOld) which = 1;
+      } else if (A < m.C && q == A) {
+        which = 3;
+      }
       if (which) {
-        const double an = which == 1 || isRoot ? lb + (a - lb) * f0 : ub + (a - ub) * f1;
+        const double an = which == 3 ? tauNew : (which == 1 || isRoot ? lb + (a - lb) * f0 : ub + (a - ub) * f1);
         adjustAge(t, x, an);
         w.age[x] = an;
       }
@@ -601,8 +611,10 @@ k_smg_tau_propose(StoreDev d, SmpDev sd, const SmpModel* __restrict__ mp, int A,
       const int b = w.migBand[lane];
       const int ps = m.bandSrc[b], pt = m.bandTgt[b];
       const double a = w.migAge[lane];
-      if (ps == A || pt == A) { if (isRoot || (a > tauOld && a < ub)) which = 2; }
-      else if ((ps == s0 || ps == s1 || pt == s0 || pt == s1) && a > lb && a < tauOld) which = 1;
+      if (ps == A || pt == A) {
+        if (isRoot || (a > tauOld && a < ub)) which = 2;
+        else if (A < m.C && a < tauOld) which = 1;
+      } else if ((ps == s0 || ps == s1 || pt == s0 || pt == s1) && a > lb && a < tauOld) which = 1;
       if (which) w.migAge[lane] = which == 1 || isRoot ? lb + (a - lb) * f0 : ub + (a - ub) * f1;
     }
     n0 += __popc(__ballot_sync(0xffffffffu, which == 1));

@@ -127,6 +127,7 @@ int gphocsStoreSetTrees(GphocsStore *s, int nLoci, const int *locusIds, const in
 int gphocsStoreGetTrees(GphocsStore *s, int nLoci, const int *locusIds, int *father, int *left, int *right,
                         double *age, int *root);
 int gphocsStoreSetRates(GphocsStore *s, int nLoci, const int *locusIds, const double *rates);
+int gphocsStoreGetRates(GphocsStore *s, int nLoci, const int *locusIds, double *rates);
 
 /* proposals / accept / reject: applied to the host mirror at once and to the device copy in order.
  * Several records may target one locus (they apply in array order).  outStatus[nOps] may be NULL. */
@@ -229,14 +230,24 @@ int gphocsSamplerSetMigration(GphocsSampler *sm, int numBands, const int *bandSr
                               const int *migBand, const double *migAge);
 /* finetune-mig-time, finetune-mig-rate */
 int gphocsSamplerSetMigFinetunes(GphocsSampler *sm, double migTime, double migRate);
+/* Ancient samples and rate variation (BASELINE.json configs[4]).  tau[p < numCurPops] given at creation is the age of
+ * population p's samples (pops[p]->sampleAge, PopulationTree.h:97; the leaves' ages in the store must agree).
+ * estimate[numCurPops] marks the sample ages that are parameters (`age <x> e`, MCMCcontrol.c:893-910; UpdateSampleAge,
+ * GPhoCS.c:4006); finetune[numCurPops] their step sizes (NULL or <= 0: finetune-tau, as MCMCcontrol.c:960).  Their
+ * Gamma prior is tauAlpha/tauBeta[p] given at creation (the reference has 0, 0: PopulationTree.c:121).
+ * locusRateFinetune > 0 turns on the locus-rate move (UpdateLocusRate, GPhoCS.c:4598) under a Dirichlet(rateAlpha)
+ * prior (`locus-mut-rate VAR <alpha>`, finetune-locus-rate).  Trace rows gain the estimated sample ages and the
+ * standard deviation of the locus rates before the two likelihood columns. */
+int gphocsSamplerSetAncient(GphocsSampler *sm, const int *estimate, const double *finetune, double locusRateFinetune,
+                            double rateAlpha);
 /* finetune-coal-time, finetune-theta, finetune-tau, finetune-mixing of the control file (MCMCcontrol.c:575-787) */
 int gphocsSamplerSetFinetunes(GphocsSampler *sm, double coalTime, double theta, double tau, double mixing);
 /* `iterations` MCMC iterations; trace (may be NULL): one row per iteration of gphocsSamplerTraceWidth() doubles =
  * [theta (numPops), tau of ancestral populations, sum of data lnL, sum of genealogy lnL] */
 int gphocsSamplerIterate(GphocsSampler *sm, int iterations, double *trace);
 int gphocsSamplerTraceWidth(const GphocsSampler *sm);
-/* accepted[8], proposed[8] for {coalescence time, SPR, theta, tau, mixing, migration rate, migration time,
- * (proposed only) split-time moves rejected for a migration conflict} */
+/* accepted[10], proposed[10] for {coalescence time, SPR, theta, tau, mixing, migration rate, migration time,
+ * (proposed only) split-time moves rejected for a migration conflict, locus rate (pairs of loci), sample age} */
 int gphocsSamplerGetState(GphocsSampler *sm, double *theta, double *tau, long long *accepted, long long *proposed);
 /* checkAll (patch.c:2745) on the device: returns structural violations; largest relative deviation of the
  * incrementally maintained statistics / data log-likelihoods from a recomputation from scratch */

@@ -1,0 +1,118 @@
+"""GPU: device-resident update steps for BASELINE.json configs[4] — ancient samples (UpdateSampleAge, GPhoCS.c:4006)
+and per-locus rate variation (UpdateLocusRate, GPhoCS.c:4598).  Evidence as in tests/test_gpu_sampler.py: invariants
+after iterating, prior recovery with uninformative data, posterior means against the reference's own chain."""
+import importlib
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not torch.cuda.is_available(), reason="needs a CUDA device")]
+
+gp = importlib.import_module("g-phocs_b200")
+synth = importlib.import_module("g-phocs_b200.synth")
+from test_gpu_dropin import REF, read_trace  # noqa: E402
+from test_gpu_sampler import batch_se  # noqa: E402
+
+
+def estimated(model):
+    return np.array([1 if nm in model.sample_age else 0 for nm, _ in model.cur], np.int32)
+
+
+def test_state_stays_consistent_with_ancient_samples_and_rates():
+    model = synth.config("ancient")
+    w = synth.generate(model, 401, seed=17)          # odd number of loci: one locus sits out every rate round
+    st = gp.LociStore.from_workload(w)
+    st.set_rates(np.ones(w.L))
+    sm = gp.Sampler(st, w.pops, w.node_pop, seed=5, estimate_sample_age=estimated(model), locus_rate_finetune=0.3,
+                    finetunes=(0.01, 0.04, 0.00002, 0.003))
+    assert sm.width == 2 * sm.Q - sm.C + 2 + 2
+    tr = sm.iterate(40)
+    assert np.all(np.isfinite(tr))
+    v, es, el = sm.check()
+    assert v == 0, v
+    assert es < 1e-9 and el < 1e-9, (es, el)
+    s = sm.state()
+    for move in ("coal_time", "spr", "theta", "tau", "sample_age", "locus_rate"):
+        assert 0 < s["accepted"][move] <= s["proposed"][move], (move, s)
+    b = [nm for nm, _ in model.cur].index("B")
+    assert s["tau"][b] != model.sample_age["B"] and np.all(s["tau"][:sm.C][estimated(model) == 0] == 0.0)
+    sm.download()                                    # device state -> host mirror
+    leaves_b = np.asarray(w.node_pop).reshape(w.L, -1)[:, :w.n] == b
+    ages = st.get_trees()[3][:, :w.n]
+    assert np.all(ages[leaves_b] == s["tau"][b]) and np.all(ages[~leaves_b] == 0.0)
+    rates = st.get_rates()
+    assert abs(rates.sum() - w.L) < 1e-9 * w.L and rates.min() > 0 and rates.std() > 0
+    assert abs(tr[-1, -3] - np.sqrt(np.mean((rates - 1) ** 2))) < 1e-12
+    sm.close(); st.close()
+
+
+def test_uninformative_data_recovers_the_prior_of_sample_age_and_rates():
+    """Every base missing => posterior = prior.  The sample age s of A and the root split time tau have independent
+    Gamma priors restricted to s < tau (moments by rejection sampling); the locus rates / L are Dirichlet(alpha):
+    Var(rate) = (L - 1) / (alpha L + 1)."""
+    m = synth.Model("prior_anc", [("A", 3), ("B", 3)], [("root", "A", "B", 1e-3)], sample_age={"A": 1e-4})
+    L = 3
+    w = synth.generate(m, L, seed=3)
+    n = w.n
+    chars = np.full((L, n), ord("N"), np.uint8)
+    st = gp.LociStore(n, np.arange(L + 1), np.arange(L + 1), chars, np.ones(L, np.int32), np.ones(L, np.int32))
+    st.set_trees(w.father, w.left, w.right, w.age, w.root)
+    alpha, beta, sbeta, ralpha = 3.0, 3000.0, 12000.0, 2.0
+    Q = 3
+    ta, tb = np.full(Q, alpha), np.array([sbeta, 1.0, beta])
+    sm = gp.Sampler(st, w.pops, w.node_pop, theta_prior=(alpha, beta), tau_prior=(ta, tb), seed=11,
+                    finetunes=(0.01, 0.6, 0.0008, 0.3), estimate_sample_age=[1, 0], locus_rate_finetune=0.8, rate_alpha=ralpha)
+    sm.iterate(3000, trace=False)
+    tr = sm.iterate(60000)
+    assert sm.check()[0] == 0
+    rng = np.random.default_rng(1)
+    s0, t0 = rng.gamma(alpha, 1 / sbeta, 4_000_000), rng.gamma(alpha, 1 / beta, 4_000_000)
+    keep = s0 < t0
+    expect = {"theta_A": (alpha / beta, np.sqrt(alpha) / beta), "theta_root": (alpha / beta, np.sqrt(alpha) / beta),
+              "tau_root": (t0[keep].mean(), t0[keep].std()), "sample_age_A": (s0[keep].mean(), s0[keep].std())}
+    for col, name in [(0, "theta_A"), (2, "theta_root"), (3, "tau_root"), (4, "sample_age_A")]:
+        x = tr[:, col]
+        mean, sd = expect[name]
+        se = batch_se(x)
+        assert abs(x.mean() - mean) < 4.5 * se + 0.01 * mean, (name, x.mean(), mean, se)
+        assert abs(x.std() - sd) < 0.12 * sd, (name, x.std(), sd)
+    var = tr[:, 5] ** 2                                  # trace column = sqrt(mean (rate - 1)^2)
+    want = (L - 1) / (ralpha * L + 1)
+    assert abs(var.mean() - want) < 4.5 * batch_se(var) + 0.01 * want, (var.mean(), want)
+    assert np.all(tr[:, -2] == 0.0)
+    sm.close(); st.close()
+
+
+@pytest.mark.skipif(not os.path.exists(REF), reason="oracle/_ref/G-PhoCS-ref not built")
+def test_posterior_means_match_the_reference_chain_with_ancient_samples(tmp_path):
+    """BASELINE.json configs[4] shape (ancient samples in B, `locus-mut-rate VAR 1.0`) at 60 loci: posterior means of
+    the thetas, taus, the sample age and the rate spread against the reference's own chain on the same alignment."""
+    import subprocess
+    model = synth.config("ancient")
+    L, iters, burn = 60, 12000, 2000
+    seq = str(tmp_path / "seqs.txt")
+    w = synth.generate(model, L, seed=77, seqfile=seq)
+    ft = dict(coal_time=0.01, theta=0.3, tau=0.0002, mixing=0.05)
+    ctl, trace = str(tmp_path / "ref.ctl"), str(tmp_path / "ref.trace")
+    synth.write_control_file(model, ctl, seq, trace, iterations=iters, seed=4242, iterations_per_log=iters, finetunes=ft)
+    r = subprocess.run([REF, ctl, "-n", "4"], capture_output=True, text=True, timeout=1500, cwd=str(tmp_path))
+    assert r.returncode == 0, r.stdout[-2000:]
+    names, ref = read_trace(trace)
+    Q, C = model.numPops, model.numCurPops
+    K = 2 * Q - C
+    assert names[1 + K].startswith("tau_") and names[2 + K] == "Variance-Mut", names
+    ref = ref[burn:, 1:3 + K]
+    ref[:, :K + 1] /= 10000.0                            # tau-theta-print factor of the control file
+    st = gp.LociStore.from_workload(w)
+    st.set_rates(np.ones(w.L))
+    sm = gp.Sampler(st, w.pops, w.node_pop, seed=2024, finetunes=(ft["coal_time"], ft["theta"], ft["tau"], ft["mixing"]),
+                    estimate_sample_age=estimated(model), locus_rate_finetune=0.3)
+    tr = sm.iterate(iters)[burn:, :K + 2]
+    assert sm.check()[0] == 0
+    for k in range(K + 2):
+        a, b = ref[:, k], tr[:, k]
+        se = np.hypot(batch_se(a), batch_se(b))
+        assert abs(a.mean() - b.mean()) < 4.5 * se + 0.02 * abs(a.mean()), (names[1 + k], a.mean(), b.mean(), se)
+    sm.close(); st.close()
