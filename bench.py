@@ -253,6 +253,43 @@ def device_mcmc(gp, synth, device, total_loci, iterations, rank=0, world=1, cfg=
     return out
 
 
+def ingest_bench(gp, synth, device, cfg="dip8mig", loci=10_000, ref_loci=1500):
+    """Alignment ingest (header group E): sequence file -> initializeLocusData's arguments.
+    Product: text parse on the host threads + k_ingest (two passes) on the device, timed separately.  Reference:
+    readSeqFile + processHetPatterns per locus of the compiled reference on the first `ref_loci` loci of the same
+    file (its pattern pool makes it slower per locus the more loci it reads, so this flatters it)."""
+    import tempfile
+    model = synth.config(cfg)
+    names = synth.sample_slots(model)
+    with tempfile.TemporaryDirectory() as tmp:
+        path = os.path.join(tmp, "seqs.txt")
+        synth.generate(model, loci, seed=4242, seqfile=path)
+        size = os.path.getsize(path)
+        gp.Alignment.read(path, names, device=device).close()        # warm-up (page cache, module load)
+        t0 = time.perf_counter()
+        a = gp.Alignment.read(path, names, device=device)
+        wall = time.perf_counter() - t0
+        t = a.timings()
+        out = {"config": f"{cfg}: {loci} loci x 1 kb, {sum(1 for x in names if x)} samples", "file_bytes": size,
+               "loci_per_s_e2e": loci / wall, "file_GBps_e2e": size / wall / 1e9, "seconds": {k: t[k] for k in ("parse_s", "h2d_s", "kernel_s", "d2h_s")},
+               "kernel_loci_per_s": loci / t["kernel_s"],
+               "kernel_GBps": 2 * t["raw_bytes"] / t["kernel_s"] / 1e9,   # both passes read every symbol row once
+               "patterns": int(a.U), "phased_patterns": int(a.P)}
+        a.close()
+        try:
+            from oracle import bindings as ob
+            from oracle import ingest as oi
+            if ob.have_ref():
+                t0 = time.perf_counter()
+                r = oi.reference_ingest(path, names, ref_loci)
+                dt = time.perf_counter() - t0
+                out["reference"] = {"loci": len(r), "loci_per_s": len(r) / dt, "cores": 1,
+                                    "sample": f"first {ref_loci} loci of the same file, single thread (the reference ingest is serial)"}
+        except Exception as e:   # reported, never required
+            out["reference"] = {"unavailable": str(e)[:200]}
+    return out
+
+
 def cpu_baseline_subprocess(cfg, sample_loci, reps):
     """cpu_baseline leg: run the reference sample in a child process, parse its JSON."""
     cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", str(reps), "--warmup", "1",
@@ -463,6 +500,7 @@ def run_b200(args):
         mcmc["configs1_hap16_10k"] = device_mcmc(gp, synth, local_rank, MCMC_LOCI, 100)
         mcmc["configs2_dip8mig_10k"] = device_mcmc(gp, synth, local_rank, 10_000, 50, cfg="dip8mig")
     clocks = sampler.stop() if rank == 0 else None
+    ingest = ingest_bench(gp, synth, local_rank) if (rank == 0 and not args.no_cpu_baseline) else None
 
     if rank == 0:
         peak, peak_src = measured_peak()
@@ -502,7 +540,7 @@ def run_b200(args):
                       "incremental_eval_ms_device": inc_ms,
                       "incremental_evals_per_sec_device": L / (inc_ms * 1e-3),
                       "device_bytes_store": st.device_bytes,
-                      "mcmc_device_resident": mcmc},
+                      "mcmc_device_resident": mcmc, "ingest": ingest},
         }
         if cb is not None:
             line["cpu_baseline"] = cb

@@ -123,6 +123,19 @@ def lib():
         "gphocsSamplerCheck": (ci, [vp, c_dbl_p, c_dbl_p]),
         "gphocsSamplerDownload": (ci, [vp, c_int_p]),
         "gphocsSamplerGetStats": (ci, [vp, c_dbl_p, c_int_p, c_dbl_p, c_int_p]),
+        # E. alignment ingest
+        "gphocsReadSeqFile": (vp, [C.c_char_p, ci, C.POINTER(C.c_char_p), ci, ci]),
+        "gphocsPhasePatterns": (vp, [ci, ci, C.c_char_p, c_int_p, C.c_char_p, c_int_p, ci, ci]),
+        "gphocsAlignmentDims": (ci, [vp, c_int_p, c_int_p, c_int_p, c_int_p]),
+        "gphocsAlignmentGet": (ci, [vp, c_ll_p, c_ll_p, C.c_char_p, c_int_p, c_int_p, C.c_char_p]),
+        "gphocsAlignmentLocusName": (C.c_char_p, [vp, ci]),
+        "gphocsAlignmentTimings": (ci, [vp, c_dbl_p, c_dbl_p, c_dbl_p, c_dbl_p, c_ll_p, c_ll_p]),
+        "gphocsAlignmentFree": (None, [vp]),
+        "gphocsStoreFromAlignment": (vp, [vp, ci]),
+        "readSeqFile": (ci, [C.c_char_p, ci, C.POINTER(C.c_char_p), ci]),
+        "processHetPatterns": (ci, [C.POINTER(C.c_char_p), c_int_p, ci, cus, vp, vp, c_int_p]),
+        "freeAlignmentData": (ci, []),
+        "printAlignmentError": (None, []),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -170,6 +183,12 @@ class LociStore:
         self.h = C.c_void_p(self.h)
         if stream is not None:
             self.lib.gphocsStoreSetStream(self.h, C.c_void_p(stream))
+
+    @classmethod
+    def _adopt(cls, handle, L, n):
+        s = cls.__new__(cls)
+        s.lib, s.n, s.N, s.L, s.h = lib(), int(n), 2 * int(n) - 1, int(L), C.c_void_p(handle)
+        return s
 
     @classmethod
     def from_workload(cls, w, device=0, stream=None):
@@ -444,6 +463,73 @@ class ScalarLocus:
         if self.h:
             self.lib.freeLocusData(self.h)
             self.h = None
+
+
+class Alignment:
+    """Sequence file -> initializeLocusData's arguments for every locus (GphocsAlignment, header group E)."""
+
+    def __init__(self, handle):
+        if not handle:
+            raise ValueError("the sequence file was rejected (message on stderr)")
+        self.lib = lib()
+        self.h = C.c_void_p(handle)
+        d = [C.c_int() for _ in range(4)]
+        self.lib.gphocsAlignmentDims(self.h, *[C.byref(x) for x in d])
+        self.L, self.n, self.P, self.U = (x.value for x in d)
+        self.patt_start, self.unph_start = np.zeros(self.L + 1, np.int64), np.zeros(self.L + 1, np.int64)
+        self.chars = np.zeros((max(self.P, 1), self.n), np.uint8)
+        self.canon = np.zeros((max(self.U, 1), self.n), np.uint8)
+        self.num_phases, self.counts = np.zeros(max(self.P, 1), np.int32), np.zeros(max(self.U, 1), np.int32)
+        self.lib.gphocsAlignmentGet(self.h, _lp(self.patt_start), _lp(self.unph_start), self.chars.ctypes.data_as(C.c_char_p),
+                                    _ip(self.num_phases), _ip(self.counts), self.canon.ctypes.data_as(C.c_char_p))
+        self.chars, self.canon = self.chars[:self.P], self.canon[:self.U]
+        self.num_phases, self.counts = self.num_phases[:self.P], self.counts[:self.U]
+
+    @classmethod
+    def read(cls, path, sample_names, num_loci_to_read=0, device=0):
+        """sample_names: one entry per haploid slot, "" for the second slot of a diploid sample."""
+        arr = (C.c_char_p * len(sample_names))(*[nm.encode() for nm in sample_names])
+        return cls(lib().gphocsReadSeqFile(str(path).encode(), len(sample_names), arr, int(num_loci_to_read), int(device)))
+
+    @classmethod
+    def phase(cls, start, patterns, counts, is_diploid, break_symmetries=1, device=0):
+        """processHetPatterns alone: canonical patterns uint8 [sum U][n] of several loci (CSR offsets `start`)."""
+        patterns = np.ascontiguousarray(patterns, np.uint8)
+        dip = bytes(1 if d else 0 for d in is_diploid)
+        return cls(lib().gphocsPhasePatterns(len(start) - 1, len(dip), dip, _ip(_i32(start)), patterns.ctypes.data_as(C.c_char_p),
+                                             _ip(_i32(counts)), int(break_symmetries), int(device)))
+
+    def locus(self, l):
+        """(chars [P][n], num_phases [P], counts [U]) of one locus"""
+        a, b, c, d = self.patt_start[l], self.patt_start[l + 1], self.unph_start[l], self.unph_start[l + 1]
+        return self.chars[a:b], self.num_phases[a:b], self.counts[c:d]
+
+    def locus_name(self, l):
+        return self.lib.gphocsAlignmentLocusName(self.h, int(l)).decode()
+
+    def timings(self):
+        t = [C.c_double() for _ in range(4)]
+        b = [C.c_longlong() for _ in range(2)]
+        self.lib.gphocsAlignmentTimings(self.h, *[C.byref(x) for x in t], *[C.byref(x) for x in b])
+        return dict(parse_s=t[0].value, h2d_s=t[1].value, kernel_s=t[2].value, d2h_s=t[3].value, raw_bytes=b[0].value,
+                    out_bytes=b[1].value)
+
+    def store(self, device=0):
+        h = self.lib.gphocsStoreFromAlignment(self.h, int(device))
+        if not h:
+            raise RuntimeError("gphocsStoreFromAlignment failed")
+        return LociStore._adopt(h, self.L, self.n)
+
+    def close(self):
+        if self.h:
+            self.lib.gphocsAlignmentFree(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class Sampler:

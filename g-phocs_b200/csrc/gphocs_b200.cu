@@ -19,6 +19,7 @@
 
 #include "clv_kernels.cuh"
 #include "gen_kernels.cuh"
+#include "ingest_kernels.cuh"
 #include "sampler_kernels.cuh"
 #include "sampler_mig.cuh"
 #include "tree_ops.cuh"
@@ -1022,3 +1023,4 @@ extern "C" int gphocsGenSync(GphocsGenealogy* g) {
 
 #include "locus_api.inc"
 #include "sampler.inc"
+#include "ingest.inc"

@@ -195,6 +195,14 @@ def sample_names(model: Model):
     return out
 
 
+def sample_slots(model: Model):
+    """dataSetup.sampleNames: one entry per leaf, "" for the second leaf of a diploid sample."""
+    out = []
+    for nm in sample_names(model):
+        out += [nm, ""] if model.diploid else [nm]
+    return out
+
+
 FINETUNES = dict(coal_time=0.01, mig_time=0.3, theta=0.04, mig_rate=0.02, tau=0.0000008, mixing=0.003)
 
 

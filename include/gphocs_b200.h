@@ -258,6 +258,49 @@ int gphocsSamplerGetStats(GphocsSampler *sm, double *coal, int *numCoals, double
 /* brings the store's host mirror up to date and returns nodePop[numLoci][2n-1] (may be NULL) */
 int gphocsSamplerDownload(GphocsSampler *sm, int *nodePop);
 
+/* ===================================================================================== E. alignment ingest
+ * The step that produces initializeLocusData's arguments: readSeqFile + processLocusAlignment +
+ * cannonizeJCpattern (AlignmentProcessor.c:468-990, 1595-1655) and, per locus, processHetPatterns with
+ * computeHetSymmetryBreaks and getAllPhases (:998-1158, 1706-1895, 2242-2290), as called by processAlignments
+ * (GPhoCS.c:258-440).  The host parses the text; canonisation, pattern counting in order of first appearance, the
+ * greedy choice of arbitrarily phased het genotypes and the phase expansion run on the device for all loci at once.
+ * Limits: 64 haploid sample slots, 1024 distinct site patterns per locus, 2^20 phasings per pattern. */
+typedef struct GphocsAlignment GphocsAlignment;
+/* sampleNames[numSamples] as dataSetup.sampleNames: one entry per haploid slot, "" (or NULL) for the second slot
+ * of a diploid sample (MCMCcontrol.c:850-880).  numLociToRead <= 0: all loci of the file.  NULL and a message on
+ * stderr where the reference returns -1 (missing file, short/long sequence, illegal base, ambiguity code in a haploid
+ * sample, a sample of the control file that never occurs, ...). */
+GphocsAlignment *gphocsReadSeqFile(const char *seqFileName, int numSamples, const char *const *sampleNames,
+                                   int numLociToRead, int device);
+/* processHetPatterns alone, for numLoci loci at once: canonical patterns [start[numLoci]][numSamples] (characters of
+ * "TCAGYWKMSRVDBHN"), their counts, isDiploid[numSamples] (AlignmentData.isDiploid) */
+GphocsAlignment *gphocsPhasePatterns(int numLoci, int numSamples, const unsigned char *isDiploid, const int *start,
+                                     const char *patterns, const int *counts, int breakSymmetries, int device);
+int gphocsAlignmentDims(const GphocsAlignment *a, int *numLoci, int *numSamples, int *numPhasedPatterns, int *numPatterns);
+/* CSR offsets pattStart/unphStart [numLoci+1]; chars [numPhasedPatterns][numSamples], numPhases [numPhasedPatterns],
+ * counts [numPatterns]: initializeLocusData's arguments for every locus, gphocsStoreCreate's layout; canon
+ * [numPatterns][numSamples]: the canonical patterns before phasing (AlignmentData.patternArray rows).  Any may be NULL. */
+int gphocsAlignmentGet(const GphocsAlignment *a, long long *pattStart, long long *unphStart, char *chars, int *numPhases,
+                       int *counts, char *canon);
+const char *gphocsAlignmentLocusName(const GphocsAlignment *a, int locus);
+/* seconds parsing text / host-to-device / inside the kernels / device-to-host; bytes of symbol rows and of output */
+int gphocsAlignmentTimings(const GphocsAlignment *a, double *parse, double *h2d, double *kernel, double *d2h,
+                           long long *rawBytes, long long *outBytes);
+void gphocsAlignmentFree(GphocsAlignment *a);
+/* createLocusData + initializeLocusData for every locus of the alignment (GPhoCS.c:354-403) */
+GphocsStore *gphocsStoreFromAlignment(const GphocsAlignment *a, int device);
+
+/* The reference's own entry points for this step (src/AlignmentProcessor.h:137,182,100,124), exported with the
+ * same names and meaning so that G-PhoCS links without AlignmentProcessor.o.  They fill and free
+ * the host program's `AlignmentData` (struct ALIGNMENT_DATA_STRUCT in AlignmentProcessor.h). */
+#ifndef ALIGNMENT_PROCESSOR_H
+int readSeqFile(const char *seqFileName, int numSamples, char **sampleNames, int numLociToRead);
+int processHetPatterns(char **patternArray, int *patternCounts, int numPatterns, unsigned short breakSymmetries,
+                       char ***phasedPatternArray_ptr, int **numPhasesArray_ptr, int *maxNumPhasedPatterns);
+int freeAlignmentData(void);
+void printAlignmentError(void);
+#endif
+
 #ifdef __cplusplus
 }
 #endif

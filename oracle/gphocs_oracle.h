@@ -72,6 +72,14 @@ int orc_gen_stats(const OrcPopTree *pt, const int *popStart, const int *type, co
 double orc_gen_lnl(const OrcPopTree *pt, const double *coal_stats, const int *num_coals,
                    const double *mig_stats, const int *num_migs);
 
+/* ---- pattern / phase producer: follows src/AlignmentProcessor.c, see ingest_oracle.c ---- */
+int orc_base_type(char c);
+int orc_canonize_column(const char *column, char *pattern, int n);
+int orc_locus_patterns(const char *const *rows, int n, int seqLength, char *patterns, int *counts);
+int orc_symmetry_breaks(const char *patterns, const int *counts, int U, int n, unsigned char *breaks);
+int orc_expand_phases(const char *patterns, const int *counts, int U, int n, const unsigned char *isDiploid,
+                      int breakSymmetries, char *phased, int *numPhases, int capacity);
+
 #ifdef __cplusplus
 }
 #endif

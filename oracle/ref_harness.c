@@ -100,6 +100,52 @@ int refh_recorded_get(int i, char *chars, int *numPhases, int *counts) {
   return 0;
 }
 
+/* ------------------------------------------------------------------ ingest alone
+ * The reference's readSeqFile + processHetPatterns(breakSymmetries = 1) per locus, exactly the sequence of
+ * processAlignments (GPhoCS.c:258-440) without creating LocusData; what would be handed to initializeLocusData is
+ * appended to the recorder.  sampleNames: one entry per slot, "" for the second slot of a diploid.  May be called
+ * repeatedly.  Returns the number of loci or -1 (the reference's error text goes to stderr). */
+static void clearRecorded(void) {
+  for (int i = 0; i < numRecorded; i++) { free(recorded[i].chars); free(recorded[i].numPhases); free(recorded[i].counts); }
+  numRecorded = 0;
+}
+int refh_ingest(const char *seqFile, int numSamples, char **sampleNames, int numLociToRead) {
+  clearRecorded();
+  if (readSeqFile(seqFile, numSamples, sampleNames, numLociToRead) < 0) return -1;
+  int maxPhased = 4 * AlignmentData.numPatterns + 4;
+  char **patt = (char **)malloc(sizeof(char *) * (AlignmentData.numPatterns + 1));
+  char **phased = (char **)malloc(sizeof(char *) * maxPhased);
+  phased[0] = (char *)malloc((size_t)numSamples * maxPhased);
+  int *numPhases = (int *)malloc(sizeof(int) * maxPhased);
+  int saveLeaves = recordLeaves;
+  recordLeaves = numSamples;
+  int rc = AlignmentData.numLoci;
+  for (int gen = 0; gen < AlignmentData.numLoci && rc >= 0; gen++) {
+    LocusProfile *lp = &AlignmentData.locusProfiles[gen];
+    for (int p = 0; p < lp->numPatterns; p++) patt[p] = AlignmentData.patternArray[lp->patternIds[p]];
+    int P = processHetPatterns(patt, lp->patternCounts, lp->numPatterns, 1, &phased, &numPhases, &maxPhased);
+    if (P < 0) { printAlignmentError(); rc = -1; break; }
+    if (numRecorded == capRecorded) {
+      capRecorded = capRecorded ? 2 * capRecorded : 1024;
+      recorded = (RecordedLocus *)realloc(recorded, capRecorded * sizeof(RecordedLocus));
+    }
+    RecordedLocus *r = &recorded[numRecorded++];
+    r->locus = NULL;
+    r->numLeaves = numSamples;
+    r->numPatterns = P;
+    r->numUnphased = lp->numPatterns;
+    r->chars = (char *)malloc((size_t)(P > 0 ? P : 1) * numSamples);
+    r->numPhases = (int *)malloc(sizeof(int) * (P > 0 ? P : 1));
+    r->counts = (int *)malloc(sizeof(int) * (lp->numPatterns > 0 ? lp->numPatterns : 1));
+    for (int p = 0; p < P; p++) { memcpy(r->chars + (size_t)p * numSamples, phased[p], numSamples); r->numPhases[p] = numPhases[p]; }
+    for (int p = 0; p < lp->numPatterns; p++) r->counts[p] = lp->patternCounts[p];
+  }
+  recordLeaves = saveLeaves;
+  free(patt); free(phased[0]); free(phased); free(numPhases);
+  freeAlignmentData();
+  return rc;
+}
+
 /* ------------------------------------------------------------------ set-up, as main() does it */
 int refh_setup(const char *ctl, int nthreads, int verboseFlag) {
   int res;
