@@ -119,6 +119,8 @@ def lib():
         "gphocsSamplerSetAllReduce": (ci, [vp, vp, vp, C.c_longlong]),
         "gphocsSamplerIterate": (ci, [vp, ci, c_dbl_p]),
         "gphocsSamplerTraceWidth": (ci, [vp]),
+        "gphocsSamplerOpenTrace": (ci, [vp, C.c_char_p, C.POINTER(C.c_char_p), cd, cd, ci]),
+        "gphocsSamplerCloseTrace": (ci, [vp]),
         "gphocsSamplerGetState": (ci, [vp, c_dbl_p, c_dbl_p, c_ll_p, c_ll_p]),
         "gphocsSamplerCheck": (ci, [vp, c_dbl_p, c_dbl_p]),
         "gphocsSamplerDownload": (ci, [vp, c_int_p]),
@@ -607,6 +609,16 @@ class Sampler:
                 return -1
         self._ar = proto(thunk)      # keep the callback alive
         self.lib.gphocsSamplerSetAllReduce(self.h, C.cast(self._ar, C.c_void_p), None, int(locus_offset))
+
+    def open_trace(self, path, pop_names, theta_tau_print=10000.0, mig_rate_print=0.001, sample_skip=0):
+        """Trace file in the reference's format; rows are appended by iterate()."""
+        arr = (C.c_char_p * len(pop_names))(*[x.encode() for x in pop_names])
+        if self.lib.gphocsSamplerOpenTrace(self.h, str(path).encode(), arr, float(theta_tau_print), float(mig_rate_print),
+                                           int(sample_skip)) != 0:
+            raise RuntimeError("gphocsSamplerOpenTrace failed")
+
+    def close_trace(self):
+        self.lib.gphocsSamplerCloseTrace(self.h)
 
     def iterate(self, iterations, trace=True):
         out = np.zeros((iterations, self.width)) if trace else None

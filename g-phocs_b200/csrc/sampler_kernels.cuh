@@ -297,12 +297,21 @@ __device__ inline double smpGenDelta(const SmpModel& m, const double* coalOld, c
   return delta;
 }
 
+// the model is read with lane-dependent indices inside dependent loops (population walks): a shared-memory copy per
+// CTA instead of global loads
+#define SMP_STAGE_MODEL                                                                          \
+  __shared__ SmpModel smpModelShared;                                                            \
+  for (int i_ = threadIdx.x; i_ < (int)(sizeof(SmpModel) / sizeof(int)); i_ += blockDim.x)       \
+    ((int*)&smpModelShared)[i_] = ((const int*)mp)[i_];                                          \
+  __syncthreads();
+
 #define SMP_WARP_PROLOGUE                                                       \
   extern __shared__ int smpScratch[];                                           \
+  SMP_STAGE_MODEL                                                               \
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;                    \
   const int l = blockIdx.x * kSmpLociPerCta + wid;                              \
   if (l >= d.L) return;                                                         \
-  const SmpModel& m = *mp;                                                      \
+  const SmpModel& m = smpModelShared;                                           \
   int* scratch = smpScratch + wid * 2 * kSmpMaxPops;                            \
   const TreeView t = deviceView(d, l);                                          \
   const int n = d.n, N = d.N;                                                   \
@@ -314,12 +323,16 @@ __device__ inline SmpProposal smpNoProposal() {
   return pr;
 }
 
+__device__ inline void smpResolve(const StoreDev& d, const SmpDev& sd, const SmpModel& m, const TreeView& t, int l, int lane, int N,
+                                  int kind, unsigned long long seed, unsigned long long step);
+
 // ------------------------------------------------------------------------------------------ coalescence-time move
 template <int R>
 __global__ void __launch_bounds__(kSmpThreads)
 k_smp_age_propose(StoreDev d, SmpDev sd, const SmpModel* __restrict__ mp, int inode, double finetune, unsigned long long seed,
-                  unsigned long long step) {
+                  unsigned long long step, int pendKind, unsigned long long pendStep) {
   SMP_WARP_PROLOGUE
+  if (pendKind >= 0) smpResolve(d, sd, m, t, l, lane, N, pendKind, seed, pendStep);   // the previous proposal of this locus
   SmpProposal pr = smpNoProposal();
   pr.node = inode;
   const int root = *t.root;
@@ -379,8 +392,9 @@ k_smp_age_propose(StoreDev d, SmpDev sd, const SmpModel* __restrict__ mp, int in
 template <int R>
 __global__ void __launch_bounds__(kSmpThreads)
 k_smp_spr_propose(StoreDev d, SmpDev sd, const SmpModel* __restrict__ mp, int node, unsigned long long seed,
-                  unsigned long long step) {
+                  unsigned long long step, int pendKind, unsigned long long pendStep) {
   SMP_WARP_PROLOGUE
+  if (pendKind >= 0) smpResolve(d, sd, m, t, l, lane, N, pendKind, seed, pendStep);
   SmpProposal pr = smpNoProposal();
   const int root = *t.root;
   if (root < n || node == root) { if (lane == 0) sd.prop[l] = pr; return; }
@@ -446,9 +460,8 @@ k_smp_spr_propose(StoreDev d, SmpDev sd, const SmpModel* __restrict__ mp, int no
 // kind 0: coalescence-time move (likelihood ratio of data and genealogy); kind 1: SPR (data likelihood ratio).
 // A coalescence-time move changes one population's statistic (carried in the proposal record); after an SPR
 // sweep the statistics of all loci are recomputed in one launch.
-__global__ void __launch_bounds__(kSmpThreads)
-k_smp_accept(StoreDev d, SmpDev sd, const SmpModel* __restrict__ mp, int kind, unsigned long long seed, unsigned long long step) {
-  SMP_WARP_PROLOGUE
+__device__ inline void smpResolve(const StoreDev& d, const SmpDev& sd, const SmpModel& m, const TreeView& t, int l, int lane, int N,
+                                  int kind, unsigned long long seed, unsigned long long step) {
   const SmpProposal pr = sd.prop[l];
   int ok = 0;
   if (pr.valid) {
@@ -478,6 +491,12 @@ k_smp_accept(StoreDev d, SmpDev sd, const SmpModel* __restrict__ mp, int kind, u
     ok = 1;   // an unchanged age counts as accepted (GPhoCS.c:2354-2358)
   }
   if (lane == 0 && ok) atomicAdd(sd.accepted + kind, 1ull);
+  __syncwarp();   // the lanes that follow read what other lanes have just committed or reverted
+}
+__global__ void __launch_bounds__(kSmpThreads)
+k_smp_accept(StoreDev d, SmpDev sd, const SmpModel* __restrict__ mp, int kind, unsigned long long seed, unsigned long long step) {
+  SMP_WARP_PROLOGUE
+  smpResolve(d, sd, m, t, l, lane, N, kind, seed, step);
 }
 
 // ------------------------------------------------------------------------------------------ split-time move

@@ -315,10 +315,11 @@ __device__ inline double smgStoredLnL(const SmpModel& m, const SmpDev& sd, int l
 
 #define SMG_PROLOGUE                                                                          \
   extern __shared__ __align__(16) unsigned char smgSmem[];                                    \
+  SMP_STAGE_MODEL                                                                             \
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;                                  \
   const int l = blockIdx.x * kSmpLociPerCta + wid;                                            \
   if (l >= d.L) return;                                                                       \
-  const SmpModel& m = *mp;                                                                    \
+  const SmpModel& m = smpModelShared;                                                         \
   const int n = d.n, N = d.N;                                                                 \
   const SmgWarp w = smgCarve(smgSmem + (size_t)wid * smgWarpBytes(N, m.Q, m.B), N, m.Q, m.B); \
   const TreeView t = deviceView(d, l);                                                        \
@@ -336,13 +337,17 @@ __global__ void __launch_bounds__(kSmpThreads) k_smg_stats(StoreDev d, SmpDev sd
   if (bad && lane == 0) bad[l] += *w.bad;
 }
 
+__device__ inline void smgResolve(const StoreDev& d, const SmpDev& sd, const SmpModel& m, const TreeView& t, int l, int lane, int N,
+                                  int kind, unsigned long long seed, unsigned long long step);
+
 // ------------------------------------------------------------------------------------------ coalescence-time move
 // UpdateGB_InternalNode with migration: the node stays in its population and between the events next to it on
 // the three branches it touches (GPhoCS.c:2316-2351, findFirstMig / findLastMig patch.c:374-410).
 __global__ void __launch_bounds__(kSmpThreads)
 k_smg_age_propose(StoreDev d, SmpDev sd, const SmpModel* __restrict__ mp, int inode, double finetune, unsigned long long seed,
-                  unsigned long long step) {
+                  unsigned long long step, int pendKind, unsigned long long pendStep) {
   SMG_PROLOGUE
+  if (pendKind >= 0) smgResolve(d, sd, m, t, l, lane, N, pendKind, seed, pendStep);   // the previous proposal of this locus
   SmpProposal pr = smpNoProposal();
   pr.node = inode;
   const int root = *t.root;
@@ -467,8 +472,9 @@ k_smg_mignode_sweep(StoreDev d, SmpDev sd, const SmpModel* __restrict__ mp, doub
 // (GPhoCS.c:2702-2706); more than MAX_MIGS events in the genealogy make the proposal invalid (res < 0, :2706).
 __global__ void __launch_bounds__(kSmpThreads)
 k_smg_spr_propose(StoreDev d, SmpDev sd, const SmpModel* __restrict__ mp, int node, unsigned long long seed,
-                  unsigned long long step) {
+                  unsigned long long step, int pendKind, unsigned long long pendStep) {
   SMG_PROLOGUE
+  if (pendKind >= 0) smgResolve(d, sd, m, t, l, lane, N, pendKind, seed, pendStep);
   SmpProposal pr = smpNoProposal();
   const int root = *t.root;
   if (root < n || node == root) { if (lane == 0) sd.prop[l] = pr; return; }
@@ -651,10 +657,8 @@ __global__ void __launch_bounds__(kSmpThreads) k_smg_scale_propose(StoreDev d, S
 }
 
 // per-locus accept / reject for models with migration (kind as in k_smp_accept)
-__global__ void __launch_bounds__(kSmpThreads)
-k_smg_accept(StoreDev d, SmpDev sd, const SmpModel* __restrict__ mp, int kind, unsigned long long seed, unsigned long long step) {
-  SMG_PROLOGUE
-  (void)w;
+__device__ inline void smgResolve(const StoreDev& d, const SmpDev& sd, const SmpModel& m, const TreeView& t, int l, int lane, int N,
+                                  int kind, unsigned long long seed, unsigned long long step) {
   const SmpProposal pr = sd.prop[l];
   int ok = 0;
   if (pr.valid) {
@@ -687,6 +691,13 @@ k_smg_accept(StoreDev d, SmpDev sd, const SmpModel* __restrict__ mp, int kind, u
     ok = 1;
   }
   if (lane == 0 && ok) atomicAdd(sd.accepted + kind, 1ull);
+  __syncwarp();
+}
+__global__ void __launch_bounds__(kSmpThreads)
+k_smg_accept(StoreDev d, SmpDev sd, const SmpModel* __restrict__ mp, int kind, unsigned long long seed, unsigned long long step) {
+  SMG_PROLOGUE
+  (void)w;
+  smgResolve(d, sd, m, t, l, lane, N, kind, seed, step);
 }
 
 // one global accept / reject for every locus; how: 0 tau move (statistics <- pending), 1 rescaling (statistics *= c)

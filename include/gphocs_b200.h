@@ -246,6 +246,13 @@ int gphocsSamplerSetFinetunes(GphocsSampler *sm, double coalTime, double theta, 
  * [theta (numPops), tau of ancestral populations, sum of data lnL, sum of genealogy lnL] */
 int gphocsSamplerIterate(GphocsSampler *sm, int iterations, double *trace);
 int gphocsSamplerTraceWidth(const GphocsSampler *sm);
+/* The trace file performMCMC writes (GPhoCS.c:1255-1313 header, 1762-1769 rows; printParamVals :746): once opened,
+ * gphocsSamplerIterate appends a row every (sampleSkip+1)-th iteration — iteration, parameters times their print
+ * factor (thetaTauPrint = tau-theta-print, migRatePrint = mig-rate-print), mean full log-likelihood per locus, data
+ * log-likelihood.  popNames[numPops].  With several GPUs one rank opens the trace. */
+int gphocsSamplerOpenTrace(GphocsSampler *sm, const char *path, const char *const *popNames, double thetaTauPrint,
+                           double migRatePrint, int sampleSkip);
+int gphocsSamplerCloseTrace(GphocsSampler *sm);
 /* accepted[10], proposed[10] for {coalescence time, SPR, theta, tau, mixing, migration rate, migration time,
  * (proposed only) split-time moves rejected for a migration conflict, locus rate (pairs of loci), sample age} */
 int gphocsSamplerGetState(GphocsSampler *sm, double *theta, double *tau, long long *accepted, long long *proposed);

@@ -116,3 +116,41 @@ def test_posterior_means_match_the_reference_chain_with_ancient_samples(tmp_path
         se = np.hypot(batch_se(a), batch_se(b))
         assert abs(a.mean() - b.mean()) < 4.5 * se + 0.02 * abs(a.mean()), (names[1 + k], a.mean(), b.mean(), se)
     sm.close(); st.close()
+
+
+@pytest.mark.parametrize("cfg", ["ancient", "dip8mig"])
+def test_trace_file_has_the_reference_format(cfg, tmp_path):
+    """gphocsSamplerOpenTrace: header and row layout of performMCMC's trace file (GPhoCS.c:1255-1313, 1762-1769); where
+    the reference binary is present its header for the same model is compared literally."""
+    import subprocess
+    model = synth.config(cfg)
+    seq = str(tmp_path / "seqs.txt")
+    w = synth.generate(model, 30, seed=7, seqfile=seq)
+    st = gp.LociStore.from_workload(w)
+    mig = (w.mig_start, w.mig_branch, w.mig_band, w.mig_age) if len(w.pops["band_src"]) else None
+    extra = dict(estimate_sample_age=estimated(model), locus_rate_finetune=0.3) if cfg == "ancient" else {}
+    sm = gp.Sampler(st, w.pops, w.node_pop, seed=3, migration=mig, **extra)
+    path = str(tmp_path / "dev.trace")
+    sm.open_trace(path, model.names, theta_tau_print=10000.0, mig_rate_print=0.001, sample_skip=1)
+    rows = sm.iterate(6)
+    sm.iterate(2, trace=False)
+    sm.close_trace()
+    names, tr = read_trace(path)
+    assert list(tr[:, 0]) == [0, 2, 4, 6]
+    K, B = 2 * sm.Q - sm.C, sm.B
+    params = sm.width - 2
+    factor = np.full(params, 10000.0)
+    factor[K:K + B] = 0.001
+    if cfg == "ancient":
+        factor[-1] = 1.0
+    for i, it in enumerate((0, 2, 4)):
+        assert np.allclose(tr[i, 1:1 + params], rows[it, :params] * factor, rtol=0, atol=6e-6)
+        assert abs(tr[i, 1 + params] - (rows[it, -2] + rows[it, -1]) / w.L) < 1e-6 and abs(tr[i, 2 + params] - rows[it, -2]) < 1e-6
+    assert names[0] == "Sample" and names[-2:] == ["Data-ld-ln", "Full-ld-ln"] and len(names) == params + 3
+    if os.path.exists(REF):
+        ctl, rtrace = str(tmp_path / "ref.ctl"), str(tmp_path / "ref.trace")
+        synth.write_control_file(model, ctl, seq, rtrace, iterations=2, seed=1)
+        r = subprocess.run([REF, ctl], capture_output=True, text=True, timeout=600, cwd=str(tmp_path))
+        assert r.returncode == 0, r.stdout[-1500:]
+        assert open(rtrace).readline() == open(path).readline()
+    sm.close(); st.close()
