@@ -121,6 +121,7 @@ def lib():
         "gphocsSamplerTraceWidth": (ci, [vp]),
         "gphocsSamplerOpenTrace": (ci, [vp, C.c_char_p, C.POINTER(C.c_char_p), cd, cd, ci]),
         "gphocsSamplerCloseTrace": (ci, [vp]),
+        "gphocsSamplerSetFusedSweep": (ci, [vp, ci]),
         "gphocsSamplerGetState": (ci, [vp, c_dbl_p, c_dbl_p, c_ll_p, c_ll_p]),
         "gphocsSamplerCheck": (ci, [vp, c_dbl_p, c_dbl_p]),
         "gphocsSamplerDownload": (ci, [vp, c_int_p]),
@@ -616,6 +617,9 @@ class Sampler:
         if self.lib.gphocsSamplerOpenTrace(self.h, str(path).encode(), arr, float(theta_tau_print), float(mig_rate_print),
                                            int(sample_skip)) != 0:
             raise RuntimeError("gphocsSamplerOpenTrace failed")
+
+    def set_fused_sweep(self, on):
+        self.lib.gphocsSamplerSetFusedSweep(self.h, int(bool(on)))
 
     def close_trace(self):
         self.lib.gphocsSamplerCloseTrace(self.h)

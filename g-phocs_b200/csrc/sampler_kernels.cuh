@@ -20,6 +20,7 @@
 #include <stdint.h>
 
 #include "clv_kernels.cuh"
+#include "warp_eval.cuh"
 
 namespace gphocs {
 
@@ -328,11 +329,8 @@ __device__ inline void smpResolve(const StoreDev& d, const SmpDev& sd, const Smp
 
 // ------------------------------------------------------------------------------------------ coalescence-time move
 template <int R>
-__global__ void __launch_bounds__(kSmpThreads)
-k_smp_age_propose(StoreDev d, SmpDev sd, const SmpModel* __restrict__ mp, int inode, double finetune, unsigned long long seed,
-                  unsigned long long step, int pendKind, unsigned long long pendStep) {
-  SMP_WARP_PROLOGUE
-  if (pendKind >= 0) smpResolve(d, sd, m, t, l, lane, N, pendKind, seed, pendStep);   // the previous proposal of this locus
+__device__ inline void smpAgeProposeBody(const StoreDev& d, const SmpDev& sd, const SmpModel& m, const TreeView& t, int l, int lane,
+                                         int n, int N, int inode, double finetune, unsigned long long seed, unsigned long long step) {
   SmpProposal pr = smpNoProposal();
   pr.node = inode;
   const int root = *t.root;
@@ -380,6 +378,14 @@ k_smp_age_propose(StoreDev d, SmpDev sd, const SmpModel* __restrict__ mp, int in
   }
   if (lane == 0) sd.prop[l] = pr;
 }
+template <int R>
+__global__ void __launch_bounds__(kSmpThreads)
+k_smp_age_propose(StoreDev d, SmpDev sd, const SmpModel* __restrict__ mp, int inode, double finetune, unsigned long long seed,
+                  unsigned long long step, int pendKind, unsigned long long pendStep) {
+  SMP_WARP_PROLOGUE
+  if (pendKind >= 0) smpResolve(d, sd, m, t, l, lane, N, pendKind, seed, pendStep);   // the previous proposal of this locus
+  smpAgeProposeBody<R>(d, sd, m, t, l, lane, n, N, inode, finetune, seed, step);
+}
 
 // ------------------------------------------------------------------------------------------ subtree prune and regraft
 // The pruned lineage is re-attached by the coalescent conditional on the rest of the genealogy: while it shares
@@ -390,11 +396,8 @@ k_smp_age_propose(StoreDev d, SmpDev sd, const SmpModel* __restrict__ mp, int in
 // intervals of the event chain (traceLineage, patch.c:886-1331, without migration).  The proposal is the
 // conditional prior, so the acceptance ratio is the data-likelihood ratio alone (GPhoCS.c:2702-2706).
 template <int R>
-__global__ void __launch_bounds__(kSmpThreads)
-k_smp_spr_propose(StoreDev d, SmpDev sd, const SmpModel* __restrict__ mp, int node, unsigned long long seed,
-                  unsigned long long step, int pendKind, unsigned long long pendStep) {
-  SMP_WARP_PROLOGUE
-  if (pendKind >= 0) smpResolve(d, sd, m, t, l, lane, N, pendKind, seed, pendStep);
+__device__ inline void smpSprProposeBody(const StoreDev& d, const SmpDev& sd, const SmpModel& m, const TreeView& t, int l, int lane,
+                                         int n, int N, int node, unsigned long long seed, unsigned long long step) {
   SmpProposal pr = smpNoProposal();
   const int root = *t.root;
   if (root < n || node == root) { if (lane == 0) sd.prop[l] = pr; return; }
@@ -455,6 +458,14 @@ k_smp_spr_propose(StoreDev d, SmpDev sd, const SmpModel* __restrict__ mp, int no
   }
   if (lane == 0) sd.prop[l] = pr;
 }
+template <int R>
+__global__ void __launch_bounds__(kSmpThreads)
+k_smp_spr_propose(StoreDev d, SmpDev sd, const SmpModel* __restrict__ mp, int node, unsigned long long seed,
+                  unsigned long long step, int pendKind, unsigned long long pendStep) {
+  SMP_WARP_PROLOGUE
+  if (pendKind >= 0) smpResolve(d, sd, m, t, l, lane, N, pendKind, seed, pendStep);
+  smpSprProposeBody<R>(d, sd, m, t, l, lane, n, N, node, seed, step);
+}
 
 // ------------------------------------------------------------------------------------------ per-locus accept / reject
 // kind 0: coalescence-time move (likelihood ratio of data and genealogy); kind 1: SPR (data likelihood ratio).
@@ -497,6 +508,31 @@ __global__ void __launch_bounds__(kSmpThreads)
 k_smp_accept(StoreDev d, SmpDev sd, const SmpModel* __restrict__ mp, int kind, unsigned long long seed, unsigned long long step) {
   SMP_WARP_PROLOGUE
   smpResolve(d, sd, m, t, l, lane, N, kind, seed, step);
+}
+
+// ------------------------------------------------------------------------------------------ whole sweeps in one launch
+// UpdateGB_InternalNode and UpdateGB_MigSPR for a model without migration bands: a warp keeps its locus for the whole
+// coalescence-time sweep and the whole SPR sweep — propose, incremental data likelihood (warp_eval.cuh) and accept /
+// reject for one node after the other — instead of two launches per node.  The random-number streams are keyed by
+// (locus, step), the step numbering is that of the launch-per-node path, and warpEvalIncremental reproduces k_eval
+// bit for bit, so both paths produce the same chain.
+template <int R>
+__global__ void __launch_bounds__(kSmpThreads)
+k_smp_sweep(StoreDev d, SmpDev sd, const SmpModel* __restrict__ mp, double ftCoal, unsigned long long seed, unsigned long long step) {
+  SMP_WARP_PROLOGUE
+  if (ftCoal > 0.0)
+    for (int inode = n; inode < N; inode++, step += 2) {
+      smpAgeProposeBody<R>(d, sd, m, t, l, lane, n, N, inode, ftCoal, seed, step);
+      __syncwarp();
+      warpEvalIncremental(d, t, l, lane);
+      smpResolve(d, sd, m, t, l, lane, N, 0, seed, step + 1);
+    }
+  for (int node = 0; node < N; node++, step += 2) {
+    smpSprProposeBody<R>(d, sd, m, t, l, lane, n, N, node, seed, step);
+    __syncwarp();
+    warpEvalIncremental(d, t, l, lane);
+    smpResolve(d, sd, m, t, l, lane, N, 1, seed, step + 1);
+  }
 }
 
 // ------------------------------------------------------------------------------------------ split-time move

@@ -253,6 +253,11 @@ int gphocsSamplerTraceWidth(const GphocsSampler *sm);
 int gphocsSamplerOpenTrace(GphocsSampler *sm, const char *path, const char *const *popNames, double thetaTauPrint,
                            double migRatePrint, int sampleSkip);
 int gphocsSamplerCloseTrace(GphocsSampler *sm);
+/* 1: the coalescence-time and SPR sweeps of a model without migration bands (<= 64 nodes) run as one launch that keeps
+ * every locus on a warp (propose, incremental likelihood, accept per node); 0 (default): one proposal and one
+ * evaluation launch per node.  Same random streams and arithmetic: both give the same chain bit for bit.  Measured
+ * slower on B200, hence opt-in. */
+int gphocsSamplerSetFusedSweep(GphocsSampler *sm, int on);
 /* accepted[10], proposed[10] for {coalescence time, SPR, theta, tau, mixing, migration rate, migration time,
  * (proposed only) split-time moves rejected for a migration conflict, locus rate (pairs of loci), sample age} */
 int gphocsSamplerGetState(GphocsSampler *sm, double *theta, double *tau, long long *accepted, long long *proposed);
