@@ -220,13 +220,7 @@ def device_mcmc(gp, synth, device, total_loci, iterations, rank=0, world=1, cfg=
                      locus_rate_finetune=0.3 if model.rate_shape > 0 else 0.0)
     sm = gp.Sampler(st, w.pops, w.node_pop, seed=1, migration=mig, **extra)
     if world > 1:
-        buf = torch.zeros(128, dtype=torch.float64, device=f"cuda:{device}")
-
-        def all_reduce(v):
-            buf[:len(v)] = torch.from_numpy(v)
-            dist.all_reduce(buf)
-            v[:] = buf[:len(v)].cpu().numpy()
-        sm.set_all_reduce(all_reduce, locus_offset=lo)
+        sm.init_nccl(rank, world, locus_offset=lo)      # the library's own communicator: sums stay on the device
     sm.iterate(5, trace=False)
     k0 = gp.lib().gphocsKernelLaunchCount()
     if world > 1:

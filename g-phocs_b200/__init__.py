@@ -117,6 +117,8 @@ def lib():
         "gphocsSamplerSetMigFinetunes": (ci, [vp, cd, cd]),
         "gphocsSamplerSetAncient": (ci, [vp, c_int_p, c_dbl_p, cd, cd]),
         "gphocsSamplerSetAllReduce": (ci, [vp, vp, vp, C.c_longlong]),
+        "gphocsNcclUniqueId": (ci, [C.c_char_p]),
+        "gphocsSamplerInitNccl": (ci, [vp, C.c_char_p, ci, ci, C.c_longlong]),
         "gphocsSamplerIterate": (ci, [vp, ci, c_dbl_p]),
         "gphocsSamplerTraceWidth": (ci, [vp]),
         "gphocsSamplerOpenTrace": (ci, [vp, C.c_char_p, C.POINTER(C.c_char_p), cd, cd, ci]),
@@ -623,6 +625,22 @@ class Sampler:
 
     def close_trace(self):
         self.lib.gphocsSamplerCloseTrace(self.h)
+
+    def init_nccl(self, rank, world, locus_offset=0, broadcast=None):
+        """Own NCCL communicator of the library over `world` ranks.  broadcast(bytes_or_None) -> bytes must hand rank 0's
+        128-byte id to every rank; default: torch.distributed.broadcast_object_list."""
+        uid = C.create_string_buffer(128)
+        if rank == 0 and self.lib.gphocsNcclUniqueId(uid) != 0:
+            raise RuntimeError("gphocsNcclUniqueId failed")
+        if broadcast is None:
+            import torch.distributed as dist
+            box = [uid.raw if rank == 0 else None]
+            dist.broadcast_object_list(box, src=0)
+            raw = box[0]
+        else:
+            raw = broadcast(uid.raw if rank == 0 else None)
+        if self.lib.gphocsSamplerInitNccl(self.h, raw, int(rank), int(world), int(locus_offset)) != 0:
+            raise RuntimeError("gphocsSamplerInitNccl failed")
 
     def iterate(self, iterations, trace=True):
         out = np.zeros((iterations, self.width)) if trace else None

@@ -2,6 +2,7 @@
 // and the reference-compatible LocusData C ABI (include/gphocs_b200.h).  sm_100a only, no CPU fallback:
 // every entry point that evaluates a likelihood launches a CUDA kernel or fails loudly.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>

@@ -637,6 +637,17 @@ __global__ void __launch_bounds__(kSmpThreads) k_smp_reduce(StoreDev d, SmpDev s
   }
 }
 
+// total[v] = sum over blocks of partial[block][v] in block order (v < nv; the rest 0): one thread per value
+__global__ void __launch_bounds__(128) k_smp_reduce_final(const double* __restrict__ partial, int blocks, int nv, int V,
+                                                          double* __restrict__ total) {
+  for (int v = threadIdx.x; v < V; v += blockDim.x) {
+    double acc = 0.0;
+    if (v < nv)
+      for (int b = 0; b < blocks; b++) acc += partial[(size_t)b * kSmpPartials + v];
+    total[v] = acc;
+  }
+}
+
 // one global accept / reject for every locus; how: 0 tau move (statistics <- tentative), 1 rescaling (statistics *= c)
 __global__ void __launch_bounds__(kSmpThreads) k_smp_global_resolve(StoreDev d, SmpDev sd, const SmpModel* __restrict__ mp, int accept,
                                                                     int how, double c) {

@@ -228,6 +228,13 @@ int gphocsSamplerSetAllReduce(GphocsSampler *sm, int (*fn)(double *, int, void *
 int gphocsSamplerSetMigration(GphocsSampler *sm, int numBands, const int *bandSrc, const int *bandTgt, const double *migRate,
                               const double *migAlpha, const double *migBeta, const int *numMigs, const int *migBranch,
                               const int *migBand, const double *migAge);
+/* Multi-GPU without a host hook: the library opens its own NCCL communicator (libnccl.so.2, bound at run time) over
+ * the ranks that share the model.  One rank obtains a unique id and distributes the 128 bytes; every rank then calls
+ * gphocsSamplerInitNccl(sm, id, rank, worldSize, global index of its first locus).  The per-proposal sums
+ * (GPhoCS.c:3807-3836, 4796-4803) and the totals (patch.c:2134-2164) are then summed on the device and all-reduced on
+ * the sampler's stream; only the reduced vector crosses PCIe. */
+int gphocsNcclUniqueId(char *out128);
+int gphocsSamplerInitNccl(GphocsSampler *sm, const char *uniqueId128, int rank, int worldSize, long long locusOffset);
 /* finetune-mig-time, finetune-mig-rate */
 int gphocsSamplerSetMigFinetunes(GphocsSampler *sm, double migTime, double migRate);
 /* Ancient samples and rate variation (BASELINE.json configs[4]).  tau[p < numCurPops] given at creation is the age of

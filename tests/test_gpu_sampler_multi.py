@@ -14,7 +14,7 @@ pytestmark = [pytest.mark.gpu, pytest.mark.skipif(torch.cuda.device_count() < 2,
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, out_dir):
+def _worker(rank, world, port, out_dir, mode):
     import torch.distributed as dist
     for p in (ROOT, os.path.join(ROOT, "tests")):
         if p not in sys.path:
@@ -37,7 +37,10 @@ def _worker(rank, world, port, out_dir):
             buf[:len(v)] = torch.from_numpy(v)
             dist.all_reduce(buf)
             v[:] = buf[:len(v)].cpu().numpy()
-        sm.set_all_reduce(all_reduce, locus_offset=lo)
+        if mode == "hook":
+            sm.set_all_reduce(all_reduce, locus_offset=lo)
+        else:                                             # the library's own NCCL communicator (gphocsSamplerInitNccl)
+            sm.init_nccl(rank, world, locus_offset=lo)
         tr = sm.iterate(25)
         v, es, el = sm.check()
         np.save(os.path.join(out_dir, f"trace{rank}.npy"), tr)
@@ -47,11 +50,17 @@ def _worker(rank, world, port, out_dir):
         dist.destroy_process_group()
 
 
-def test_two_ranks_keep_identical_parameters(tmp_path):
+@pytest.mark.parametrize("mode", ["hook", "nccl"])
+def test_two_ranks_keep_identical_parameters(tmp_path, mode):
     import torch.multiprocessing as mp
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
-    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, port, str(tmp_path), mode), nprocs=2, join=True)
     t0, t1 = np.load(tmp_path / "trace0.npy"), np.load(tmp_path / "trace1.npy")
+    keep = os.path.join(os.path.dirname(str(tmp_path)), "multi_trace_hook.npy")
+    if mode == "hook":
+        np.save(keep, t0)
+    elif os.path.exists(keep):                            # summing two ranks is order-free: both routes give the same bits
+        assert np.array_equal(np.load(keep), t0)
     assert np.array_equal(t0, t1)                      # thetas, taus and the all-reduced log-likelihood sums
     assert np.all(np.isfinite(t0)) and len(np.unique(t0[:, 0])) > 1
     for r in range(2):
