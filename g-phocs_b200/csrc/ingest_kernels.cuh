@@ -4,9 +4,11 @@
 // arbitrarily (computeHetSymmetryBreaks, :1706-1895) and all phasings of the others (processHetPatterns +
 // getAllPhases, :998-1158, 2242-2290).
 //
-// One CTA per locus.  Columns are canonised by the threads (one column each, rows read coalesced), packed 4 bits per
-// slot and de-duplicated in a shared-memory hash table that remembers first site and multiplicity; the table is
-// then ordered by first site.  The kernel runs twice: a counting pass (patterns U, phased columns P per locus), a
+// One CTA per locus.  The kernel reads the TEXT of the sequence file (uploaded as it is; the host only locates the
+// rows): characters are mapped to the canonical alphabet and validated here.  Columns are canonised by the threads
+// (one column each, rows read coalesced), packed 4 bits per slot and de-duplicated in a shared-memory hash table that
+// remembers first site and multiplicity (one atomic per distinct pattern per warp); the table is then ordered by
+// first site.  The kernel runs twice: a counting pass (patterns U, phased columns P per locus), a
 // host prefix sum, and an emitting pass that writes the final arrays — no per-locus scratch in HBM.
 #pragma once
 #include <cuda_runtime.h>
@@ -22,18 +24,21 @@ constexpr int kIngMaxHets = 32;                                     // diploid s
 constexpr int kIngMaxFree = 20;                                     // un-phased genotypes per pattern: 2^20 columns
 
 // status bits per locus
-enum { ING_OVERFLOW = 1, ING_COLLISION = 2, ING_TOO_MANY_PHASES = 4 };
+enum { ING_OVERFLOW = 1, ING_COLLISION = 2, ING_TOO_MANY_PHASES = 4, ING_BAD_CHAR = 8 };
 
 struct IngestTables {
   uint32_t permMask[15][15];   // permMask[symbol][image] = base permutations (24 bits) mapping symbol to image
-  int8_t slotRow[kIngMaxSlots];    // row of the slot's sequence inside a locus block, -1: no sequence (all N)
+  int8_t slotRow[kIngMaxSlots];    // row (named sample) of the slot, -1: second slot of a diploid (all N)
   uint8_t isDiploid[kIngMaxSlots];
+  int8_t symbolOf[256];            // character -> index in "TCAGYWKMSRVDBHN" (either case), -1: not a base symbol
 };
 
 struct IngestDev {
-  int L, n, R;                       // loci, slots, rows (named samples) per locus block
-  const uint8_t* raw;                // symbol indices 0..14; locus l: rows [R][S_l] at raw + rawStart[l]
-  const long long* rawStart;         // [L+1]
+  int L, n, R;                       // loci, slots, rows (named samples)
+  const char* text;                  // the sequence file
+  const long long* rowOff;           // [L][R] offset of the first base of the row in `text`, -1: sample absent (all N)
+  const int* seqLen;                 // [L]
+  unsigned long long* firstBad;      // out: smallest (locus << 40 | row << 32 | site) holding an illegal character
   const int* locusIds;               // NULL: all loci; else the loci this launch handles (grid = count)
   // pattern mode (processHetPatterns called on its own): canonical patterns + counts instead of raw columns
   const uint8_t* givenPatterns;      // [sum U][n] symbol indices, locus l at givenStart[l]
@@ -100,6 +105,7 @@ __global__ void __launch_bounds__(kIngThreads)
 k_ingest(IngestDev d, const IngestTables* __restrict__ tabs, int H, int emit, uint64_t salt) {
   extern __shared__ __align__(16) unsigned char ingSmem[];
   __shared__ uint32_t sPerm[15][15];
+  __shared__ int8_t sSym[256];
   __shared__ int sNumUnique, sFlags, sTotal;
   const int tid = threadIdx.x;
   const int l = d.locusIds ? d.locusIds[blockIdx.x] : blockIdx.x;
@@ -122,6 +128,7 @@ k_ingest(IngestDev d, const IngestTables* __restrict__ tabs, int H, int emit, ui
   const int Umax = H / 2;
 
   for (int i = tid; i < 225; i += kIngThreads) sPerm[i / 15][i % 15] = tabs->permMask[i / 15][i % 15];
+  for (int i = tid; i < 256; i += kIngThreads) sSym[i] = tabs->symbolOf[i];
   for (int h = tid; h < H; h += kIngThreads) { tag[h] = 0ull; first[h] = 0x7fffffff; cnt[h] = 0; }
   if (tid == 0) { sNumUnique = 0; sFlags = 0; sTotal = 0; }
   __syncthreads();
@@ -129,9 +136,8 @@ k_ingest(IngestDev d, const IngestTables* __restrict__ tabs, int H, int emit, ui
   int U = 0;
   if (d.givenPatterns == nullptr) {
     // ---------------------------------------------------------------- columns -> distinct canonical patterns
-    const long long base = d.rawStart[l];
-    const int S = (int)((d.rawStart[l + 1] - base) / (d.R > 0 ? d.R : 1));
-    const uint8_t* rows = d.raw + base;
+    const int S = d.seqLen[l];
+    const long long* rowOff = d.rowOff + (size_t)l * d.R;
     for (int c0 = 0; c0 < S; c0 += kIngChunk) {
       uint64_t key[kIngColsPerThread][W];
       int slotOf[kIngColsPerThread];
@@ -139,45 +145,62 @@ k_ingest(IngestDev d, const IngestTables* __restrict__ tabs, int H, int emit, ui
       for (int i = 0; i < kIngColsPerThread; i++) {
         const int site = c0 + i * kIngThreads + tid;
         slotOf[i] = -1;
-        if (site >= S) continue;
+        bool informative = false;
 #pragma unroll
         for (int w = 0; w < W; w++) key[i][w] = 0ull;
-        uint32_t alive = 0xFFFFFFu;
-        bool informative = false;
-        for (int s = 0; s < n; s++) {
-          const int row = tabs->slotRow[s];
-          const int sym = row >= 0 ? rows[(size_t)row * S + site] : 14;
-          int image = 14;
-          if (sym != 14) {
-            informative = true;
-            const int lo = sym < 4 ? 0 : (sym < 10 ? 4 : 10), hi = sym < 4 ? 3 : (sym < 10 ? 9 : 13);
-            for (image = lo; image < hi; image++)
-              if (alive & sPerm[sym][image]) break;
-            alive &= sPerm[sym][image];
+        if (site < S) {
+          uint32_t alive = 0xFFFFFFu;
+          for (int s = 0; s < n; s++) {
+            const int row = tabs->slotRow[s];
+            const long long off = row >= 0 ? rowOff[row] : -1;
+            int sym = 14;
+            if (off >= 0) {
+              sym = sSym[(unsigned char)d.text[off + site]];
+              // readSeqs (:806-826): not a base symbol, or an ambiguity code in a haploid sample
+              if (sym < 0 || (sym >= 4 && sym < 14 && !tabs->isDiploid[s])) {
+                atomicMin(d.firstBad, (unsigned long long)l << 40 | (unsigned long long)row << 32 | (unsigned)site);
+                atomicOr(&sFlags, ING_BAD_CHAR);
+                sym = 14;
+              }
+            }
+            int image = 14;
+            if (sym != 14) {
+              informative = true;
+              const int lo = sym < 4 ? 0 : (sym < 10 ? 4 : 10), hi = sym < 4 ? 3 : (sym < 10 ? 9 : 13);
+              for (image = lo; image < hi; image++)
+                if (alive & sPerm[sym][image]) break;
+              alive &= sPerm[sym][image];
+            }
+            key[i][s >> 4] |= (uint64_t)image << ((s & 15) * 4);
           }
-          key[i][s >> 4] |= (uint64_t)image << ((s & 15) * 4);
         }
-        if (!informative) continue;           // columns of N only are dropped (:910-912)
+        // columns of N only are dropped (:910-912).  One lane per distinct pattern of the warp does the insertion.
         uint64_t hsh = salt;
 #pragma unroll
         for (int w = 0; w < W; w++) hsh = ingMix(hsh ^ key[i][w]);
-        const unsigned long long t = hsh | 1ull;
-        int h = (int)(hsh >> 20) & (H - 1);
-        int probes = 0;
-        for (;; h = (h + 1) & (H - 1)) {
-          const unsigned long long old = atomicCAS(&tag[h], 0ull, t);
-          if (old == 0ull) {
-            if (atomicAdd(&sNumUnique, 1) >= Umax) atomicOr(&sFlags, ING_OVERFLOW);
-            break;
+        const unsigned long long t = informative ? (hsh | 1ull) : 0ull;
+        const unsigned peers = __match_any_sync(0xffffffffu, t);
+        const int leader = __ffs(peers) - 1;
+        int h = -1;
+        if (informative && (tid & 31) == leader) {
+          h = (int)(hsh >> 20) & (H - 1);
+          int probes = 0;
+          for (;; h = (h + 1) & (H - 1)) {
+            const unsigned long long old = atomicCAS(&tag[h], 0ull, t);
+            if (old == 0ull) {
+              if (atomicAdd(&sNumUnique, 1) >= Umax) atomicOr(&sFlags, ING_OVERFLOW);
+              break;
+            }
+            if (old == t) break;
+            if (++probes >= H) { atomicOr(&sFlags, ING_OVERFLOW); h = -1; break; }
           }
-          if (old == t) break;
-          if (++probes >= H) { atomicOr(&sFlags, ING_OVERFLOW); h = -1; break; }
+          if (h >= 0) {
+            atomicMin(&first[h], site);              // the leader is the lowest lane = the lowest site of its peers
+            atomicAdd(&cnt[h], __popc(peers));
+          }
         }
-        slotOf[i] = h;
-        if (h >= 0) {
-          atomicMin(&first[h], site);
-          atomicAdd(&cnt[h], 1);
-        }
+        h = __shfl_sync(0xffffffffu, h, leader);
+        slotOf[i] = informative ? h : -1;
       }
       __syncthreads();
 #pragma unroll

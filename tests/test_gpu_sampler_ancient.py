@@ -149,7 +149,7 @@ def test_trace_file_has_the_reference_format(cfg, tmp_path):
     assert names[0] == "Sample" and names[-2:] == ["Data-ld-ln", "Full-ld-ln"] and len(names) == params + 3
     if os.path.exists(REF):
         ctl, rtrace = str(tmp_path / "ref.ctl"), str(tmp_path / "ref.trace")
-        synth.write_control_file(model, ctl, seq, rtrace, iterations=2, seed=1)
+        synth.write_control_file(model, ctl, seq, rtrace, iterations=20, seed=1, iterations_per_log=10)
         r = subprocess.run([REF, ctl], capture_output=True, text=True, timeout=600, cwd=str(tmp_path))
         assert r.returncode == 0, r.stdout[-1500:]
         assert open(rtrace).readline() == open(path).readline()
