@@ -124,6 +124,7 @@ def lib():
         "gphocsSamplerOpenTrace": (ci, [vp, C.c_char_p, C.POINTER(C.c_char_p), cd, cd, ci]),
         "gphocsSamplerCloseTrace": (ci, [vp]),
         "gphocsSamplerSetFusedSweep": (ci, [vp, ci]),
+        "gphocsSamplerSetScheduledEval": (ci, [vp, ci]),
         "gphocsSamplerGetState": (ci, [vp, c_dbl_p, c_dbl_p, c_ll_p, c_ll_p]),
         "gphocsSamplerCheck": (ci, [vp, c_dbl_p, c_dbl_p]),
         "gphocsSamplerDownload": (ci, [vp, c_int_p]),
@@ -622,6 +623,9 @@ class Sampler:
 
     def set_fused_sweep(self, on):
         self.lib.gphocsSamplerSetFusedSweep(self.h, int(bool(on)))
+
+    def set_scheduled_eval(self, on):
+        self.lib.gphocsSamplerSetScheduledEval(self.h, int(bool(on)))
 
     def close_trace(self):
         self.lib.gphocsSamplerCloseTrace(self.h)

@@ -103,6 +103,7 @@ struct GphocsStore {
   StoreDev d{};
   uint8_t* dMask = nullptr;
   Batch* dBatches = nullptr;
+  bool anyOversized = false;   // some locus has more than kThreads columns (a CTA batch of its own)
   double* dSum = nullptr;
   int numBatches = 0;
   int maxBatchLoci = 1;  // most loci any CTA batch holds (sizes the kernel's shared memory)
@@ -252,6 +253,7 @@ extern "C" GphocsStore* gphocsStoreCreate(int device, int numLoci, int numLeaves
     flush();
   }
   s->numBatches = (int)s->batches.size();
+  s->anyOversized = scratchCols > 0;
   for (const Batch& bt : s->batches) s->maxBatchLoci = std::max(s->maxBatchLoci, bt.numLoci);
 
   // ---- device allocations

@@ -381,10 +381,15 @@ __device__ inline void smpAgeProposeBody(const StoreDev& d, const SmpDev& sd, co
 template <int R>
 __global__ void __launch_bounds__(kSmpThreads)
 k_smp_age_propose(StoreDev d, SmpDev sd, const SmpModel* __restrict__ mp, int inode, double finetune, unsigned long long seed,
-                  unsigned long long step, int pendKind, unsigned long long pendStep) {
+                  unsigned long long step, int pendKind, unsigned long long pendStep, IncEntry* sched, int* schedCount) {
   SMP_WARP_PROLOGUE
   if (pendKind >= 0) smpResolve(d, sd, m, t, l, lane, N, pendKind, seed, pendStep);   // the previous proposal of this locus
   smpAgeProposeBody<R>(d, sd, m, t, l, lane, n, N, inode, finetune, seed, step);
+  if (sched) {   // tree-side half of the incremental evaluation, for k_eval_sched (warp_eval.cuh)
+    __syncwarp();
+    const int k = warpBuildSchedule(d, t, l, lane, sched + (size_t)l * d.NI);
+    if (lane == 0) schedCount[l] = k;
+  }
 }
 
 // ------------------------------------------------------------------------------------------ subtree prune and regraft
@@ -461,10 +466,15 @@ __device__ inline void smpSprProposeBody(const StoreDev& d, const SmpDev& sd, co
 template <int R>
 __global__ void __launch_bounds__(kSmpThreads)
 k_smp_spr_propose(StoreDev d, SmpDev sd, const SmpModel* __restrict__ mp, int node, unsigned long long seed,
-                  unsigned long long step, int pendKind, unsigned long long pendStep) {
+                  unsigned long long step, int pendKind, unsigned long long pendStep, IncEntry* sched, int* schedCount) {
   SMP_WARP_PROLOGUE
   if (pendKind >= 0) smpResolve(d, sd, m, t, l, lane, N, pendKind, seed, pendStep);
   smpSprProposeBody<R>(d, sd, m, t, l, lane, n, N, node, seed, step);
+  if (sched) {
+    __syncwarp();
+    const int k = warpBuildSchedule(d, t, l, lane, sched + (size_t)l * d.NI);
+    if (lane == 0) schedCount[l] = k;
+  }
 }
 
 // ------------------------------------------------------------------------------------------ per-locus accept / reject

@@ -343,11 +343,9 @@ __device__ inline void smgResolve(const StoreDev& d, const SmpDev& sd, const Smp
 // ------------------------------------------------------------------------------------------ coalescence-time move
 // UpdateGB_InternalNode with migration: the node stays in its population and between the events next to it on
 // the three branches it touches (GPhoCS.c:2316-2351, findFirstMig / findLastMig patch.c:374-410).
-__global__ void __launch_bounds__(kSmpThreads)
-k_smg_age_propose(StoreDev d, SmpDev sd, const SmpModel* __restrict__ mp, int inode, double finetune, unsigned long long seed,
-                  unsigned long long step, int pendKind, unsigned long long pendStep) {
-  SMG_PROLOGUE
-  if (pendKind >= 0) smgResolve(d, sd, m, t, l, lane, N, pendKind, seed, pendStep);   // the previous proposal of this locus
+__device__ inline void smgAgeProposeBody(const StoreDev& d, const SmpDev& sd, const SmpModel& m, const SmgWarp& w, const TreeView& t,
+                                         int l, int lane, int n, int N, int inode, double finetune, unsigned long long seed,
+                                         unsigned long long step) {
   SmpProposal pr = smpNoProposal();
   pr.node = inode;
   const int root = *t.root;
@@ -400,6 +398,18 @@ k_smg_age_propose(StoreDev d, SmpDev sd, const SmpModel* __restrict__ mp, int in
     }
   }
   if (lane == 0) sd.prop[l] = pr;
+}
+__global__ void __launch_bounds__(kSmpThreads)
+k_smg_age_propose(StoreDev d, SmpDev sd, const SmpModel* __restrict__ mp, int inode, double finetune, unsigned long long seed,
+                  unsigned long long step, int pendKind, unsigned long long pendStep, IncEntry* sched, int* schedCount) {
+  SMG_PROLOGUE
+  if (pendKind >= 0) smgResolve(d, sd, m, t, l, lane, N, pendKind, seed, pendStep);   // the previous proposal of this locus
+  smgAgeProposeBody(d, sd, m, w, t, l, lane, n, N, inode, finetune, seed, step);
+  if (sched) {   // tree-side half of the incremental evaluation, for k_eval_sched
+    __syncwarp();
+    const int k = warpBuildSchedule(d, t, l, lane, sched + (size_t)l * d.NI);
+    if (lane == 0) schedCount[l] = k;
+  }
 }
 
 // ------------------------------------------------------------------------------------------ migration-time moves
@@ -470,11 +480,8 @@ k_smg_mignode_sweep(StoreDev d, SmpDev sd, const SmpModel* __restrict__ mp, doub
 // walk, a migration moves the lineage to the band's source population, no ring before the population ends moves
 // it to the parent population.  Proposal = conditional prior, so acceptance is the data-likelihood ratio alone
 // (GPhoCS.c:2702-2706); more than MAX_MIGS events in the genealogy make the proposal invalid (res < 0, :2706).
-__global__ void __launch_bounds__(kSmpThreads)
-k_smg_spr_propose(StoreDev d, SmpDev sd, const SmpModel* __restrict__ mp, int node, unsigned long long seed,
-                  unsigned long long step, int pendKind, unsigned long long pendStep) {
-  SMG_PROLOGUE
-  if (pendKind >= 0) smgResolve(d, sd, m, t, l, lane, N, pendKind, seed, pendStep);
+__device__ inline void smgSprProposeBody(const StoreDev& d, const SmpDev& sd, const SmpModel& m, const SmgWarp& w, const TreeView& t,
+                                         int l, int lane, int n, int N, int node, unsigned long long seed, unsigned long long step) {
   SmpProposal pr = smpNoProposal();
   const int root = *t.root;
   if (root < n || node == root) { if (lane == 0) sd.prop[l] = pr; return; }
@@ -568,6 +575,18 @@ k_smg_spr_propose(StoreDev d, SmpDev sd, const SmpModel* __restrict__ mp, int no
     smgStoreMigs(w, sd, l, lane);
   }
   if (lane == 0) sd.prop[l] = pr;
+}
+__global__ void __launch_bounds__(kSmpThreads)
+k_smg_spr_propose(StoreDev d, SmpDev sd, const SmpModel* __restrict__ mp, int node, unsigned long long seed,
+                  unsigned long long step, int pendKind, unsigned long long pendStep, IncEntry* sched, int* schedCount) {
+  SMG_PROLOGUE
+  if (pendKind >= 0) smgResolve(d, sd, m, t, l, lane, N, pendKind, seed, pendStep);
+  smgSprProposeBody(d, sd, m, w, t, l, lane, n, N, node, seed, step);
+  if (sched) {
+    __syncwarp();
+    const int k = warpBuildSchedule(d, t, l, lane, sched + (size_t)l * d.NI);
+    if (lane == 0) schedCount[l] = k;
+  }
 }
 
 // ------------------------------------------------------------------------------------------ split-time move

@@ -265,6 +265,11 @@ int gphocsSamplerCloseTrace(GphocsSampler *sm);
  * evaluation launch per node.  Same random streams and arithmetic: both give the same chain bit for bit.  Measured
  * slower on B200, hence opt-in. */
 int gphocsSamplerSetFusedSweep(GphocsSampler *sm, int on);
+/* 1: the per-locus proposal kernels finish the tree-side half of the incremental evaluation (dirty nodes, buffer
+ * flips, children-first order, JC69 edge terms) and a column-walk kernel does the rest; 0 (default): k_eval builds the
+ * schedule from the flags.  Same arithmetic: the chain does not depend on the choice.  Measured slower on B200
+ * (DESIGN.md 4b), hence opt-in. */
+int gphocsSamplerSetScheduledEval(GphocsSampler *sm, int on);
 /* accepted[10], proposed[10] for {coalescence time, SPR, theta, tau, mixing, migration rate, migration time,
  * (proposed only) split-time moves rejected for a migration conflict, locus rate (pairs of loci), sample age} */
 int gphocsSamplerGetState(GphocsSampler *sm, double *theta, double *tau, long long *accepted, long long *proposed);

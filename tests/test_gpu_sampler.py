@@ -70,25 +70,29 @@ def test_two_nodes_per_lane_path_stays_consistent():
     st.close()
 
 
-@pytest.mark.parametrize("cfg,L", [("hap16", 300), ("ancient", 200), ("pop6nomig", 150)])
-def test_fused_sweep_gives_the_same_chain(cfg, L):
-    """k_smp_sweep (whole sweeps in one launch, warp-level incremental likelihood) against the launch-per-node path:
-    same random streams, same arithmetic -> identical traces, statistics, genealogies and conditional vectors."""
+@pytest.mark.parametrize("cfg,L", [("hap16", 300), ("ancient", 200), ("pop6nomig", 150), ("dip8mig", 200), ("pop6mig4", 120)])
+def test_evaluation_routes_give_the_same_chain(cfg, L):
+    """Three routes to the likelihood of a proposal — k_eval rebuilding its schedule from the flags ("plain"), the
+    proposal kernel handing a schedule to k_eval_sched ("sched", default), whole sweeps on a warp with the warp-level
+    evaluation ("sweep", models without migration) — use the same random streams and the same arithmetic: identical
+    traces, statistics, genealogies, log-likelihoods and conditional vectors."""
     if cfg == "pop6nomig":      # 24 leaves, 47 nodes: two nodes per lane
         base = synth.config("pop6mig4")
         model = synth.Model("pop6nomig", base.cur, base.anc, diploid=base.diploid)
     else:
         model = synth.config(cfg)
     w = synth.generate(model, L, seed=41)
-    out = []
-    for fused in (1, 0):
+    mig = (w.mig_start, w.mig_branch, w.mig_band, w.mig_age) if len(w.pops["band_src"]) else None
+    out = {}
+    for route in ("plain", "sched") + (() if mig else ("sweep",)):
         st = gp.LociStore.from_workload(w)
         extra = {}
         if model.sample_age:
             st.set_rates(np.ones(w.L))
             extra = dict(estimate_sample_age=[1 if nm in model.sample_age else 0 for nm, _ in model.cur], locus_rate_finetune=0.3)
-        sm = gp.Sampler(st, w.pops, w.node_pop, seed=77, **extra)
-        sm.set_fused_sweep(fused)
+        sm = gp.Sampler(st, w.pops, w.node_pop, seed=77, migration=mig, **extra)
+        sm.set_scheduled_eval(route == "sched")
+        sm.set_fused_sweep(route == "sweep")
         k0 = gp.lib().gphocsKernelLaunchCount()
         tr = sm.iterate(12)
         launches = gp.lib().gphocsKernelLaunchCount() - k0
@@ -97,16 +101,19 @@ def test_fused_sweep_gives_the_same_chain(cfg, L):
         node_pop = sm.download()
         trees = st.get_trees()
         clv = st.clv(0, st.n + 1, P=int(w.patt_start[1] - w.patt_start[0]))
-        out.append((tr, stats, node_pop, trees, st.lnl(), launches, clv))
+        out[route] = (tr, stats, node_pop, trees, st.lnl(), launches, clv)
         sm.close(); st.close()
-    a, b = out
-    assert np.array_equal(a[0], b[0])
-    assert np.array_equal(a[1]["coal"], b[1]["coal"]) and np.array_equal(a[1]["num_coals"], b[1]["num_coals"])
-    assert np.array_equal(a[2], b[2])
-    for x, y in zip(a[3], b[3]):
-        assert np.array_equal(x, y)
-    assert np.array_equal(a[4], b[4]) and np.array_equal(a[6], b[6])
-    assert a[5] < b[5] / 3, (a[5], b[5])
+    a = out["plain"]
+    for route, b in out.items():
+        assert np.array_equal(a[0], b[0]), route
+        assert np.array_equal(a[1]["coal"], b[1]["coal"]) and np.array_equal(a[1]["num_coals"], b[1]["num_coals"]), route
+        assert np.array_equal(a[1]["mig"], b[1]["mig"]) and np.array_equal(a[1]["num_migs"], b[1]["num_migs"]), route
+        assert np.array_equal(a[2], b[2]), route
+        for x, y in zip(a[3], b[3]):
+            assert np.array_equal(x, y), route
+        assert np.array_equal(a[4], b[4]) and np.array_equal(a[6], b[6]), route
+    if "sweep" in out:
+        assert out["sweep"][5] < a[5] / 3, (out["sweep"][5], a[5])
 
 
 def test_uninformative_data_recovers_the_prior():
