@@ -64,8 +64,25 @@ def test_two_nodes_per_lane_path_stays_consistent():
     assert v == 0 and es < 1e-9 and el < 1e-9, (v, es, el)
     s = sm.state()
     assert 0 < s["accepted"]["spr"] < s["proposed"]["spr"] and 0 < s["accepted"]["coal_time"]
-    # statistics against the oracle's event-chain statistics for the final state
-    from oracle import bindings as ob
+    sm.close()
+    st.close()
+
+
+@pytest.mark.parametrize("leaves", [40, 72])
+def test_many_leaves_per_locus_stay_consistent(leaves):
+    """79 and 143 nodes per genealogy: four and thirteen nodes per lane in the migration-free kernels, several leaf
+    words per column in k_eval."""
+    k = leaves // 2
+    m = synth.Model("wide", [("A", k), ("B", leaves - k)], [("root", "A", "B", 1e-3)])
+    w = synth.generate(m, 60, seed=8)
+    st = gp.LociStore.from_workload(w)
+    sm = gp.Sampler(st, w.pops, w.node_pop, seed=9)
+    tr = sm.iterate(6)
+    assert np.all(np.isfinite(tr))
+    v, es, el = sm.check()
+    assert v == 0 and es < 1e-9 and el < 1e-9, (v, es, el)
+    s = sm.state()
+    assert 0 < s["accepted"]["spr"] < s["proposed"]["spr"] and 0 < s["accepted"]["coal_time"]
     sm.close()
     st.close()
 
