@@ -23,7 +23,7 @@
 namespace gphocs {
 
 constexpr int kGenTile = 32;      // loci per CTA
-constexpr int kGenThreads = 384;   // upper bound; launched with one thread per (locus, population) chain of the tile, rounded to warps
+constexpr int kGenThreads = 128;
 constexpr int kMaxPops = 39;      // 2*NSPECIES-1 (patch.h:19,49)
 constexpr int kMaxBands = 100;    // MAX_MIG_BANDS  (patch.h:17)
 
@@ -59,7 +59,6 @@ struct GenDev {
 __host__ __device__ inline int genTotalsLen(int Q, int B) { return 1 + 2 * Q + 2 * B; }
 
 __global__ void __launch_bounds__(kGenThreads) k_gen_eval(GenDev d, int maxTileEvents) {
-  const int nThreads = blockDim.x;
   extern __shared__ __align__(16) unsigned char smem[];
   const int tid = threadIdx.x;
   const int Q = d.Q, B = d.B, V = genTotalsLen(Q, B);
@@ -79,22 +78,22 @@ __global__ void __launch_bounds__(kGenThreads) k_gen_eval(GenDev d, int maxTileE
   uint16_t* sPopStart = sCode + maxTileEvents;                         // [tile][Q+1]
   __shared__ GenParams prm;
 
-  for (int i = tid; i < (int)(sizeof(GenParams) / sizeof(int)); i += nThreads)
+  for (int i = tid; i < (int)(sizeof(GenParams) / sizeof(int)); i += kGenThreads)
     reinterpret_cast<int*>(&prm)[i] = reinterpret_cast<const int*>(d.params)[i];
   const int e0 = d.evStart[l0];
   const int tileEvents = d.evStart[l0 + nl] - e0;
   if (tid <= nl) sEvBase[tid] = d.evStart[l0 + tid] - e0;
-  for (int i = tid; i < tileEvents; i += nThreads) {
+  for (int i = tid; i < tileEvents; i += kGenThreads) {
     sTime[i] = d.evTime[e0 + i];
     sCode[i] = d.evCode[e0 + i];
   }
-  for (int i = tid; i < nl * (Q + 1); i += nThreads) sPopStart[i] = d.popStart[(size_t)l0 * (Q + 1) + i];
-  for (int i = tid; i < kGenTile * B; i += nThreads) { sMig[i] = 0.0; sNumMigs[i] = 0; }
-  for (int i = tid; i < V; i += nThreads) sTot[i] = 0.0;
+  for (int i = tid; i < nl * (Q + 1); i += kGenThreads) sPopStart[i] = d.popStart[(size_t)l0 * (Q + 1) + i];
+  for (int i = tid; i < kGenTile * B; i += kGenThreads) { sMig[i] = 0.0; sNumMigs[i] = 0; }
+  for (int i = tid; i < V; i += kGenThreads) sTot[i] = 0.0;
   __syncthreads();
 
   // pass A: net lineage change of each chain (SAMPLES_START +samples, COAL -1, IN_MIG -1, OUT_MIG +1)
-  for (int it = tid; it < nl * Q; it += nThreads) {
+  for (int it = tid; it < nl * Q; it += kGenThreads) {
     const int j = it / Q, p = it - j * Q;
     const int a = sEvBase[j] + sPopStart[j * (Q + 1) + p], b = sEvBase[j] + sPopStart[j * (Q + 1) + p + 1];
     int delta = 0;
@@ -118,7 +117,7 @@ __global__ void __launch_bounds__(kGenThreads) k_gen_eval(GenDev d, int maxTileE
   }
   __syncthreads();
   // pass B: statistics per chain, in the reference's order of operations (patch.c:2403-2486)
-  for (int it = tid; it < nl * Q; it += nThreads) {
+  for (int it = tid; it < nl * Q; it += kGenThreads) {
     const int j = it / Q, p = it - j * Q;
     const int a = sEvBase[j] + sPopStart[j * (Q + 1) + p], b = sEvBase[j] + sPopStart[j * (Q + 1) + p + 1];
     int n = sDelta[it], ncoal = 0;
@@ -170,17 +169,17 @@ __global__ void __launch_bounds__(kGenThreads) k_gen_eval(GenDev d, int maxTileE
     sLnL[j] = lnLd;
     d.lnL[l0 + j] = lnLd;
   }
-  for (int i = tid; i < nl * Q; i += nThreads) {
+  for (int i = tid; i < nl * Q; i += kGenThreads) {
     d.coal[(size_t)l0 * Q + i] = sCoal[i];
     d.numCoals[(size_t)l0 * Q + i] = sNumCoals[i];
   }
-  for (int i = tid; i < nl * B; i += nThreads) {
+  for (int i = tid; i < nl * B; i += kGenThreads) {
     d.mig[(size_t)l0 * B + i] = sMig[i];
     d.numMigs[(size_t)l0 * B + i] = sNumMigs[i];
   }
   __syncthreads();
   // per-CTA totals, fixed order over the tile's loci
-  for (int v = tid; v < V; v += nThreads) {
+  for (int v = tid; v < V; v += kGenThreads) {
     double acc = 0.0;
     for (int j = 0; j < nl; j++) {
       double x;
