@@ -106,6 +106,8 @@ k_ingest(IngestDev d, const IngestTables* __restrict__ tabs, int H, int emit, ui
   extern __shared__ __align__(16) unsigned char ingSmem[];
   __shared__ uint32_t sPerm[15][15];
   __shared__ int8_t sSym[256];
+  __shared__ long long sRowOff[kIngMaxSlots];   // per slot: offset of the row in the text, -1 = all N
+  __shared__ uint8_t sHaploid[kIngMaxSlots];
   __shared__ int sNumUnique, sFlags, sTotal;
   const int tid = threadIdx.x;
   const int l = d.locusIds ? d.locusIds[blockIdx.x] : blockIdx.x;
@@ -129,6 +131,11 @@ k_ingest(IngestDev d, const IngestTables* __restrict__ tabs, int H, int emit, ui
 
   for (int i = tid; i < 225; i += kIngThreads) sPerm[i / 15][i % 15] = tabs->permMask[i / 15][i % 15];
   for (int i = tid; i < 256; i += kIngThreads) sSym[i] = tabs->symbolOf[i];
+  if (tid < n) {
+    const int row = tabs->slotRow[tid];
+    sRowOff[tid] = (row >= 0 && d.givenPatterns == nullptr) ? d.rowOff[(size_t)l * d.R + row] : -1;
+    sHaploid[tid] = tabs->isDiploid[tid] ? 0 : 1;
+  }
   for (int h = tid; h < H; h += kIngThreads) { tag[h] = 0ull; first[h] = 0x7fffffff; cnt[h] = 0; }
   if (tid == 0) { sNumUnique = 0; sFlags = 0; sTotal = 0; }
   __syncthreads();
@@ -137,7 +144,6 @@ k_ingest(IngestDev d, const IngestTables* __restrict__ tabs, int H, int emit, ui
   if (d.givenPatterns == nullptr) {
     // ---------------------------------------------------------------- columns -> distinct canonical patterns
     const int S = d.seqLen[l];
-    const long long* rowOff = d.rowOff + (size_t)l * d.R;
     for (int c0 = 0; c0 < S; c0 += kIngChunk) {
       uint64_t key[kIngColsPerThread][W];
       int slotOf[kIngColsPerThread];
@@ -151,14 +157,13 @@ k_ingest(IngestDev d, const IngestTables* __restrict__ tabs, int H, int emit, ui
         if (site < S) {
           uint32_t alive = 0xFFFFFFu;
           for (int s = 0; s < n; s++) {
-            const int row = tabs->slotRow[s];
-            const long long off = row >= 0 ? rowOff[row] : -1;
+            const long long off = sRowOff[s];
             int sym = 14;
             if (off >= 0) {
               sym = sSym[(unsigned char)d.text[off + site]];
               // readSeqs (:806-826): not a base symbol, or an ambiguity code in a haploid sample
-              if (sym < 0 || (sym >= 4 && sym < 14 && !tabs->isDiploid[s])) {
-                atomicMin(d.firstBad, (unsigned long long)l << 40 | (unsigned long long)row << 32 | (unsigned)site);
+              if (sym < 0 || (sym >= 4 && sym < 14 && sHaploid[s])) {
+                atomicMin(d.firstBad, (unsigned long long)l << 40 | (unsigned long long)tabs->slotRow[s] << 32 | (unsigned)site);
                 atomicOr(&sFlags, ING_BAD_CHAR);
                 sym = 14;
               }
