@@ -125,6 +125,7 @@ def lib():
         "gphocsSamplerCloseTrace": (ci, [vp]),
         "gphocsSamplerSetFusedSweep": (ci, [vp, ci]),
         "gphocsSamplerSetScheduledEval": (ci, [vp, ci]),
+        "gphocsSamplerSetSweepStreams": (ci, [vp, ci]),
         "gphocsSamplerGetState": (ci, [vp, c_dbl_p, c_dbl_p, c_ll_p, c_ll_p]),
         "gphocsSamplerCheck": (ci, [vp, c_dbl_p, c_dbl_p]),
         "gphocsSamplerDownload": (ci, [vp, c_int_p]),
@@ -626,6 +627,9 @@ class Sampler:
 
     def set_scheduled_eval(self, on):
         self.lib.gphocsSamplerSetScheduledEval(self.h, int(bool(on)))
+
+    def set_sweep_streams(self, streams):
+        self.lib.gphocsSamplerSetSweepStreams(self.h, int(streams))
 
     def close_trace(self):
         self.lib.gphocsSamplerCloseTrace(self.h)

@@ -565,12 +565,12 @@ extern "C" int gphocsStoreSetRates(GphocsStore* s, int nLoci, const int* locusId
 
 // ---- evaluation
 // masked: evaluate only loci whose mask byte is set; [bLo, bHi] restricts the launch to that range of CTA batches
-static int launchEval(GphocsStore* s, int useOld, int onlyLocus, bool masked, int bLo = 0, int bHi = -1) {
+static int launchEval(GphocsStore* s, int useOld, int onlyLocus, bool masked, int bLo = 0, int bHi = -1, cudaStream_t onStream = nullptr) {
   cudaSetDevice(s->device);
   StoreDev d = s->d;
   d.active = masked ? s->dMask : nullptr;
   if (bHi >= bLo && onlyLocus < 0) {
-    k_eval<<<bHi - bLo + 1, kThreads, s->smemBytes, s->stream>>>(d, s->dBatches, bLo, useOld, -1, s->maxBatchLoci, s->prefetchAhead);
+    k_eval<<<bHi - bLo + 1, kThreads, s->smemBytes, onStream ? onStream : s->stream>>>(d, s->dBatches, bLo, useOld, -1, s->maxBatchLoci, s->prefetchAhead);
     g_launches++;
   } else if (onlyLocus >= 0) {
     const int b = s->locusBatch[onlyLocus];

@@ -54,6 +54,7 @@ struct SmpProposal {   // what a proposal kernel leaves for the accept kernel, p
 
 struct SmpDev {
   int L, Q;
+  int l0, l1;          // loci [l0, l1) a warp-per-locus launch works on (a sweep may be split over streams)
   uint8_t* nodePop;    // [L][N] population of every genealogy node (nodePops, patch.h:123)
   double* coal;        // [L][Q] coal_stats per locus
   double* coalT;       // [L][Q] statistics of the pending proposal
@@ -310,8 +311,8 @@ __device__ inline double smpGenDelta(const SmpModel& m, const double* coalOld, c
   extern __shared__ int smpScratch[];                                           \
   SMP_STAGE_MODEL                                                               \
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;                    \
-  const int l = blockIdx.x * kSmpLociPerCta + wid;                              \
-  if (l >= d.L) return;                                                         \
+  const int l = sd.l0 + blockIdx.x * kSmpLociPerCta + wid;                      \
+  if (l >= sd.l1) return;                                                       \
   const SmpModel& m = smpModelShared;                                           \
   int* scratch = smpScratch + wid * 2 * kSmpMaxPops;                            \
   const TreeView t = deviceView(d, l);                                          \

@@ -317,8 +317,8 @@ __device__ inline double smgStoredLnL(const SmpModel& m, const SmpDev& sd, int l
   extern __shared__ __align__(16) unsigned char smgSmem[];                                    \
   SMP_STAGE_MODEL                                                                             \
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;                                  \
-  const int l = blockIdx.x * kSmpLociPerCta + wid;                                            \
-  if (l >= d.L) return;                                                                       \
+  const int l = sd.l0 + blockIdx.x * kSmpLociPerCta + wid;                                    \
+  if (l >= sd.l1) return;                                                                     \
   const SmpModel& m = smpModelShared;                                                         \
   const int n = d.n, N = d.N;                                                                 \
   const SmgWarp w = smgCarve(smgSmem + (size_t)wid * smgWarpBytes(N, m.Q, m.B), N, m.Q, m.B); \

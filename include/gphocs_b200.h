@@ -270,6 +270,9 @@ int gphocsSamplerSetFusedSweep(GphocsSampler *sm, int on);
  * schedule from the flags.  Same arithmetic: the chain does not depend on the choice.  Measured slower on B200
  * (DESIGN.md 4b), hence opt-in. */
 int gphocsSamplerSetScheduledEval(GphocsSampler *sm, int on);
+/* CUDA streams the per-locus sweeps are spread over: loci are independent there, so the sweeps can be cut in two halves
+ * that run side by side.  1 (default) or 2; the chain does not depend on it.  Measured: no gain on B200. */
+int gphocsSamplerSetSweepStreams(GphocsSampler *sm, int streams);
 /* accepted[10], proposed[10] for {coalescence time, SPR, theta, tau, mixing, migration rate, migration time,
  * (proposed only) split-time moves rejected for a migration conflict, locus rate (pairs of loci), sample age} */
 int gphocsSamplerGetState(GphocsSampler *sm, double *theta, double *tau, long long *accepted, long long *proposed);

@@ -89,7 +89,8 @@ def test_many_leaves_per_locus_stay_consistent(leaves):
 
 @pytest.mark.parametrize("cfg,L", [("hap16", 300), ("ancient", 200), ("pop6nomig", 150), ("dip8mig", 200), ("pop6mig4", 120)])
 def test_evaluation_routes_give_the_same_chain(cfg, L):
-    """Three routes to the likelihood of a proposal — k_eval rebuilding its schedule from the flags ("plain"), the
+    """Routes to the likelihood of a proposal — k_eval rebuilding its schedule from the flags ("plain"; the same with
+    the loci cut in two halves on two streams, "two_streams"), the
     proposal kernel handing a schedule to k_eval_sched ("sched", default), whole sweeps on a warp with the warp-level
     evaluation ("sweep", models without migration) — use the same random streams and the same arithmetic: identical
     traces, statistics, genealogies, log-likelihoods and conditional vectors."""
@@ -101,7 +102,7 @@ def test_evaluation_routes_give_the_same_chain(cfg, L):
     w = synth.generate(model, L, seed=41)
     mig = (w.mig_start, w.mig_branch, w.mig_band, w.mig_age) if len(w.pops["band_src"]) else None
     out = {}
-    for route in ("plain", "sched") + (() if mig else ("sweep",)):
+    for route in ("plain", "sched", "two_streams") + (() if mig else ("sweep",)):
         st = gp.LociStore.from_workload(w)
         extra = {}
         if model.sample_age:
@@ -110,6 +111,7 @@ def test_evaluation_routes_give_the_same_chain(cfg, L):
         sm = gp.Sampler(st, w.pops, w.node_pop, seed=77, migration=mig, **extra)
         sm.set_scheduled_eval(route == "sched")
         sm.set_fused_sweep(route == "sweep")
+        sm.set_sweep_streams(2 if route == "two_streams" else 1)
         k0 = gp.lib().gphocsKernelLaunchCount()
         tr = sm.iterate(12)
         launches = gp.lib().gphocsKernelLaunchCount() - k0
