@@ -444,12 +444,22 @@ def run_b200(args):
     h2d = L * w.father.shape[1] * (3 * 2 + 8) + 8 * L + int(E.sum()) * 10 + L * (Q + 1) * 2 + 4 * (L + 1)
     d2h = 8 * L + 8 + 8 * L + 8 * V
 
+    # The host calls are the asynchronous ones of the C ABI (gphocsStoreEvaluateDevice, gphocsGenEvaluateDevice,
+    # gphocsCopyDeviceAsync): the data-likelihood kernel and its read-back run while the host converts the event
+    # snapshot; everything is back in host memory before the step ends.
+    lib.gphocsGenSetStream(gen.h, None)        # the genealogy object on a stream of its own for this section
+    host_sums = gp.pinned_like(np.zeros(2 + V))
+
     def e2e_step():
         st.set_trees(hw["father"], hw["left"], hw["right"], hw["age"], hw["root"])
-        _, sdata = st.evaluate(0, want_sum=True, out=lnl_host)
+        dlnl, dsum = st.evaluate_device(0)
+        sp = C.c_void_p(stream.cuda_stream)
+        lib.gphocsCopyDeviceAsync(C.c_void_p(lnl_host.ctypes.data), C.c_void_p(dlnl), 8 * L, sp)
+        lib.gphocsCopyDeviceAsync(C.c_void_p(host_sums.ctypes.data), C.c_void_p(dsum), 8, sp)
         gen.set_events(hw["ev_start"], hw["pop_start"], hw["ev_type"], hw["ev_id"], hw["ev_time"])
-        r = gen.evaluate(per_locus_stats=False)
-        return sdata, r["sum_lnl"]
+        r = gen.evaluate(per_locus_stats=False)      # per-locus genealogy lnL + totals, back on the host
+        stream.synchronize()
+        return float(host_sums[0]), r["sum_lnl"]
 
     e2e_step()
     barrier()
@@ -463,6 +473,10 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
     e2e_value = world * L * e2e_steps / e2e_s
+    # the end-to-end pass computes the same numbers as the resident one (this rank's sums before the all-reduce)
+    if world == 1:
+        assert abs(sdata - total_data_lnl) <= 1e-9 * abs(total_data_lnl), (sdata, total_data_lnl)
+        assert abs(sgen - total_gen_lnl) <= 1e-9 * abs(total_gen_lnl), (sgen, total_gen_lnl)
 
     # ---- MCMC-style cycle (extra): one node-age proposal per locus -> incremental evaluation -> accept/reject
     node = n + 2

@@ -350,10 +350,10 @@ extern "C" int gphocsStoreNumLeaves(const GphocsStore* s) { return s->n; }
 extern "C" long long gphocsStoreNumColumns(const GphocsStore* s) { return s->Ct; }
 extern "C" long long gphocsStoreDeviceBytes(const GphocsStore* s) { return s->deviceBytes; }
 extern "C" long long gphocsKernelLaunchCount(void) { return g_launches.load(); }
-// stream-ordered device-to-device copy, so callers can gather results into their own buffers (e.g. the
-// all-reduce payload of SURVEY.md §8e) without a host round trip
+// stream-ordered copy out of the library's device results, so callers can gather them into their own buffers — on
+// the device (e.g. the all-reduce payload of SURVEY.md §8e) or in page-locked host memory — without blocking
 extern "C" int gphocsCopyDeviceAsync(void* dst, const void* src, long long bytes, void* cudaStream) {
-  CUDA_TRY(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)cudaStream));
+  CUDA_TRY(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDefault, (cudaStream_t)cudaStream));
   return 0;
 }
 // host threads used for staging conversions and the host mirror (defaults to OpenMP's choice, which launchers

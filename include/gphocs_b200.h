@@ -161,7 +161,8 @@ long long gphocsFiberSelfTest(int numFibers, int parks, int threads, int useFibe
  * batched calls run at full PCIe speed; plain malloc'd arrays work too, slower */
 void *gphocsHostAlloc(long long bytes);
 int gphocsHostFree(void *p);
-/* stream-ordered device-to-device copy (gathers device-resident results into a caller's buffer) */
+/* stream-ordered copy of device-resident results into a caller's buffer: device memory, or page-locked host memory
+ * (gphocsHostAlloc) for a read-back that does not block the host */
 int gphocsCopyDeviceAsync(void *dst, const void *src, long long bytes, void *cudaStream);
 
 /* ===================================================================================== C. genealogy likelihood */
