@@ -407,15 +407,20 @@ static int setTreesLocked(GphocsStore* s, int nLoci, const int* locusIds, const 
     for (int k = (int)lo_; k < (int)hi_; k++) {
       const int l = locusIds ? locusIds[k] : k;
       const size_t o = (size_t)l * N, in = (size_t)k * N;
-      int16_t* o3 = s->i16.host + in * 3;
-      double* oa = s->f64.host + in;
-      for (int i = 0; i < N; i++) {
-        NodeRec& r = s->hNode[o + i];
-        r.father = o3[3 * i] = (int16_t)father[in + i];
-        r.left = o3[3 * i + 1] = (int16_t)left[in + i];
-        r.right = o3[3 * i + 2] = (int16_t)right[in + i];
-        s->hAge[o + i] = oa[i] = age[in + i];
+      int16_t* __restrict__ o3 = s->i16.host + in * 3;
+      NodeRec* __restrict__ hn = s->hNode.data() + o;
+      const int* __restrict__ fa = father + in;
+      const int* __restrict__ le = left + in;
+      const int* __restrict__ ri = right + in;
+      for (int i = 0; i < N; i++) {     // one 8-byte store per mirror record (flag byte kept), three shorts to staging
+        NodeRec rec = hn[i];
+        rec.father = o3[3 * i] = (int16_t)fa[i];
+        rec.left = o3[3 * i + 1] = (int16_t)le[i];
+        rec.right = o3[3 * i + 2] = (int16_t)ri[i];
+        hn[i] = rec;
       }
+      memcpy(s->f64.host + in, age + in, sizeof(double) * (size_t)N);
+      memcpy(s->hAge.data() + o, age + in, sizeof(double) * (size_t)N);
       s->hRoot[l] = s->seg.host[k] = root[k];
       s->ids.host[k] = l;
     }
