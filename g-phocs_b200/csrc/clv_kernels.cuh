@@ -154,6 +154,17 @@ __global__ void k_set_trees(StoreDev d, const int* __restrict__ ids, const int16
   if (v == 0) d.root[l] = root[k];
 }
 
+// the same for loci 0..nLoci-1 whose int32 topology arrays were copied to the device as they are (ages and roots
+// went straight to their final arrays)
+__global__ void k_set_topology32(StoreDev d, const int* __restrict__ father, const int* __restrict__ left,
+                                 const int* __restrict__ right, size_t count) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  NodeRec r = d.node[i];
+  r.father = (int16_t)father[i]; r.left = (int16_t)left[i]; r.right = (int16_t)right[i];
+  d.node[i] = r;
+}
+
 // computeEdgeConditionalJC (.c:1831-1848): off-diagonal JC69 transition probability
 __device__ __forceinline__ double edgeProb(double edgeLength) {
   if (edgeLength < 1e-100) return 0.0;

@@ -121,6 +121,8 @@ struct GphocsStore {
   Staging<int> seg, status, ids;
   Staging<double> f64;
   Staging<int16_t> i16;
+  int* dTopo32 = nullptr;      // device scratch for int32 topology copied straight from page-locked caller arrays
+  size_t topo32Cap = 0;
   std::vector<Op> pending;  // edits queued by the scalar API, flushed before the next evaluation
   bool debugMirror = false;  // also mirror SEL/RECALC bits on the host (tests)
   bool opsInFlight = false;  // an edit batch was enqueued without a stream synchronisation
@@ -331,6 +333,7 @@ extern "C" int gphocsStoreDestroy(GphocsStore* s) {
                   d.age, d.svAge, d.root, d.savedRoot, d.rate, d.lnL,
                   d.savedLnL, d.rootScratch, d.ctaSum, s->dMask, s->dBatches, s->dSum};
   for (void* p : ptrs) if (p) cudaFree(p);
+  if (s->dTopo32) cudaFree(s->dTopo32);
   s->ops.release(); s->seg.release(); s->status.release(); s->ids.release(); s->f64.release(); s->i16.release();
   if (s->ownStream && s->stream) cudaStreamDestroy(s->stream);
   delete s;
@@ -395,8 +398,51 @@ static int setTreesLocked(GphocsStore* s, int nLoci, const int* locusIds, const 
     CUDA_TRY(cudaStreamSynchronize(s->stream));
     s->opsInFlight = false;
   }
-  if (s->i16.reserve(cnt * 3) || s->f64.reserve(cnt) || s->ids.reserve(nLoci) || s->seg.reserve(nLoci)) return -1;
   StoreDev& d = s->d;
+  // Page-locked caller arrays covering loci 0..nLoci-1: the DMA engine reads them where they are — ages and roots go
+  // straight to their final device arrays, the int32 topology to a scratch that k_set_topology32 packs — while the
+  // host threads bring the mirror up to date; nothing is staged.
+  auto pageLocked = [](const void* p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+  };
+  if (!locusIds && nLoci >= 1024 && pageLocked(father) && pageLocked(left) && pageLocked(right) && pageLocked(age) && pageLocked(root)) {
+    if (cnt * 3 > s->topo32Cap) {
+      if (s->dTopo32) cudaFree(s->dTopo32);
+      s->dTopo32 = nullptr;
+      s->topo32Cap = 0;
+      if (devAlloc(&s->dTopo32, cnt * 3)) return -1;
+      s->topo32Cap = cnt * 3;
+    }
+    CUDA_TRY(cudaMemcpyAsync(s->dTopo32, father, sizeof(int) * cnt, cudaMemcpyHostToDevice, s->stream));
+    CUDA_TRY(cudaMemcpyAsync(s->dTopo32 + cnt, left, sizeof(int) * cnt, cudaMemcpyHostToDevice, s->stream));
+    CUDA_TRY(cudaMemcpyAsync(s->dTopo32 + 2 * cnt, right, sizeof(int) * cnt, cudaMemcpyHostToDevice, s->stream));
+    CUDA_TRY(cudaMemcpyAsync(d.age, age, sizeof(double) * cnt, cudaMemcpyHostToDevice, s->stream));
+    CUDA_TRY(cudaMemcpyAsync(d.root, root, sizeof(int) * (size_t)nLoci, cudaMemcpyHostToDevice, s->stream));
+    k_set_topology32<<<(unsigned)((cnt + 255) / 256), 256, 0, s->stream>>>(d, s->dTopo32, s->dTopo32 + cnt, s->dTopo32 + 2 * cnt, cnt);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    parallelFor(0, nLoci, [&](long long lo_, long long hi_) {   // the mirror, while the copies are in flight
+      for (int k = (int)lo_; k < (int)hi_; k++) {
+        const size_t o = (size_t)k * N;
+        NodeRec* __restrict__ hn = s->hNode.data() + o;
+        const int* __restrict__ fa = father + o;
+        const int* __restrict__ le = left + o;
+        const int* __restrict__ ri = right + o;
+        for (int i = 0; i < N; i++) {
+          NodeRec rec = hn[i];
+          rec.father = (int16_t)fa[i]; rec.left = (int16_t)le[i]; rec.right = (int16_t)ri[i];
+          hn[i] = rec;
+        }
+        memcpy(s->hAge.data() + o, age + o, sizeof(double) * (size_t)N);
+        s->hRoot[k] = root[k];
+      }
+    }, 256);
+    CUDA_TRY(cudaStreamSynchronize(s->stream));   // the caller's arrays are free again when the call returns
+    return 0;
+  }
+  if (s->i16.reserve(cnt * 3) || s->f64.reserve(cnt) || s->ids.reserve(nLoci) || s->seg.reserve(nLoci)) return -1;
   // Loci are converted in chunks by all host threads straight into page-locked staging (int16 topology, fp64 ages,
   // roots, ids) and each chunk's copies are enqueued at once, so PCIe transfers overlap the conversion of the next
   // chunk.  The host mirror is updated in the same pass; flag bytes (buffer selectors) are kept on both sides.

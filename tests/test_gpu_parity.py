@@ -320,3 +320,30 @@ def test_full_size_genealogy_properties():
     delta = -(lnc * r["total_num_coals"][3] + (1 / theta2[3] - 1 / w.pops["theta"][3]) * r["total_coal"][3])
     assert abs((r2["sum_lnl"] - r["sum_lnl"]) - delta) <= 1e-9 * abs(delta)
     gen.close()
+
+
+def test_page_locked_genealogies_take_the_direct_route():
+    """gphocsStoreSetTrees with page-locked arrays covering all loci copies them as they are (no staging); mirror,
+    device state and likelihoods must equal those of the staged route."""
+    w = synth.generate(synth.config("dip8mig"), 3000, seed=21)
+    a = gp.LociStore.from_workload(w)
+    b = gp.LociStore(w.n, w.patt_start, w.unph_start, w.chars, w.num_phases, w.counts)
+    hw = {k: gp.pinned_like(getattr(w, k)) for k in ("father", "left", "right", "age", "root")}
+    k0 = gp.lib().gphocsKernelLaunchCount()
+    b.set_trees(hw["father"], hw["left"], hw["right"], hw["age"], hw["root"])
+    assert gp.lib().gphocsKernelLaunchCount() == k0 + 1
+    b.set_rates(w.rate)
+    for x, y in zip(a.get_trees(), b.get_trees()):
+        assert np.array_equal(x, y)
+    assert a.check_mirror() == 0 and b.check_mirror() == 0
+    assert np.array_equal(a.evaluate(0), b.evaluate(0))
+    # a second full set after proposals were made and rejected: buffer selectors stay consistent on both sides
+    ops = gp.make_ops(np.arange(w.L), gp.OP_ADJUST_AGE, a=w.n + 1, x=w.age[:, w.n + 1] * 1.001)
+    for st in (a, b):
+        st.apply_ops(gp.make_ops(np.arange(w.L), gp.OP_COMMIT)); st.apply_ops(ops); st.evaluate(1)
+        st.apply_ops(gp.make_ops(np.arange(w.L), gp.OP_REVERT))
+    a.set_trees(w.father, w.left, w.right, w.age, w.root)
+    b.set_trees(hw["father"], hw["left"], hw["right"], hw["age"], hw["root"])
+    assert b.check_mirror() == 0
+    assert np.array_equal(a.evaluate(0), b.evaluate(0))
+    a.close(); b.close()
