@@ -440,9 +440,9 @@ def run_b200(args):
                                                        "ev_type", "ev_id", "ev_time")}   # inputs in page-locked host memory
     e2e_steps = max(3, min(args.steps, 20))
     # bytes that cross PCIe per step, counted from the buffers the library copies: the page-locked genealogy arrays as
-    # they are (int32 topology, fp64 ages, roots); 10 bytes per event + chain offsets; back: per-locus data lnL + its
-    # sum, genealogy lnL + totals
-    h2d = L * w.father.shape[1] * (3 * 4 + 8) + 4 * L + int(E.sum()) * 10 + L * (Q + 1) * 2 + 4 * (L + 1)
+    # they are (int32 topology, fp64 ages, roots; int32 event types and ids, fp64 elapsed times, int32 chain offsets,
+    # int64 event offsets); back: per-locus data lnL + its sum, genealogy lnL + totals
+    h2d = L * w.father.shape[1] * (3 * 4 + 8) + 4 * L + int(E.sum()) * 16 + L * (Q + 1) * 4 + 8 * (L + 1)
     d2h = 8 * L + 8 + 8 * L + 8 * V
 
     # The host calls are the asynchronous ones of the C ABI (gphocsStoreEvaluateDevice, gphocsGenEvaluateDevice,

@@ -194,6 +194,34 @@ __global__ void __launch_bounds__(kGenThreads) k_gen_eval(GenDev d, int maxTileE
   }
 }
 
+// event snapshot copied from page-locked caller arrays as it is: int32 type / id -> 16-bit code, int32 chain offsets
+// -> 16-bit, int64 event offsets -> int32 relative to the first event; *bad counts malformed entries
+__global__ void __launch_bounds__(256) k_gen_pack(const int* __restrict__ evType, const int* __restrict__ evId, long long numEvents,
+                                                  const int* __restrict__ popStart, long long numPopStart,
+                                                  const long long* __restrict__ evStart, int L, int B,
+                                                  uint16_t* __restrict__ code, uint16_t* __restrict__ ps, int* __restrict__ es,
+                                                  int* __restrict__ bad) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long first = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  int wrong = 0;
+  for (long long e = first; e < numEvents; e += stride) {
+    const int t = evType[e], id = evId[e];
+    const bool needsBand = (t == EV_IN_MIG || t == EV_BAND_START || t == EV_BAND_END);
+    if (t < 0 || t > EV_DUMMY || (needsBand && (id < 0 || id >= B))) wrong = 1;
+    code[e] = (uint16_t)(t | ((needsBand ? id : 0) << 3));
+  }
+  for (long long i = first; i < numPopStart; i += stride) ps[i] = (uint16_t)popStart[i];
+  const long long e0 = evStart[0];
+  for (long long l = first; l <= L; l += stride) {
+    es[l] = (int)(evStart[l] - e0);
+    if (l < L) {
+      const long long nEv = evStart[l + 1] - evStart[l];
+      if (nEv > 65535 || nEv < 0) wrong = 1;
+    }
+  }
+  if (wrong) atomicAdd(bad, 1);
+}
+
 // out[v] = sum over CTAs of ctaTotals[cta][v], fixed order (one block per v)
 __global__ void __launch_bounds__(256) k_gen_reduce(const double* __restrict__ ctaTotals, int numCtas, int V,
                                                     double* __restrict__ out) {

@@ -859,6 +859,10 @@ struct GphocsGenealogy {
   Staging<double> out;
   Staging<int> sEs;
   Staging<uint16_t> sPs, sCode;
+  int* dRaw32 = nullptr;          // device scratch for int32 event types / ids / chain offsets copied as they are
+  long long* dRawStart = nullptr;
+  int* dBadEvents = nullptr;
+  size_t raw32Cap = 0;
   std::vector<int> postOrder;
 };
 
@@ -920,6 +924,9 @@ extern "C" int gphocsGenDestroy(GphocsGenealogy* g) {
   void* ptrs[] = {g->dParams, g->dEvStart, g->dPopStart, g->dEvTime, g->dEvCode, g->dLineages, g->dTotals, g->d.lnL,
                   g->d.coal, g->d.numCoals, g->d.mig, g->d.numMigs, g->d.ctaTotals};
   for (void* p : ptrs) if (p) cudaFree(p);
+  if (g->dRaw32) cudaFree(g->dRaw32);
+  if (g->dRawStart) cudaFree(g->dRawStart);
+  if (g->dBadEvents) cudaFree(g->dBadEvents);
   g->out.release(); g->sEs.release(); g->sPs.release(); g->sCode.release();
   if (g->ownStream && g->stream) cudaStreamDestroy(g->stream);
   delete g;
@@ -965,6 +972,49 @@ extern "C" int gphocsGenSetEvents(GphocsGenealogy* g, const long long* evStart, 
     if (devAlloc(&g->dEvTime, g->evCap) || devAlloc(&g->dEvCode, g->evCap) || devAlloc(&g->dLineages, g->evCap)) return -1;
   }
   g->totalEvents = E;
+  // Page-locked caller arrays: the DMA engine reads them where they are and k_gen_pack narrows them on the device;
+  // the host only finds the largest tile (for the shared-memory size) while the copies are in flight.
+  auto pageLocked = [](const void* p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+  };
+  if (L >= 1024 && pageLocked(evStart) && pageLocked(popStart) && pageLocked(evType) && pageLocked(evId) && pageLocked(evTime)) {
+    const size_t nPs = (size_t)L * (Q + 1), need = 2 * (size_t)E + nPs;
+    if (need > g->raw32Cap) {
+      if (g->dRaw32) cudaFree(g->dRaw32);
+      g->dRaw32 = nullptr;
+      g->raw32Cap = 0;
+      if (devAlloc(&g->dRaw32, need + need / 8)) return -1;
+      g->raw32Cap = need + need / 8;
+    }
+    if (!g->dRawStart && (devAlloc(&g->dRawStart, (size_t)L + 1) || devAlloc(&g->dBadEvents, 1))) return -1;
+    const long long first = evStart[0];
+    int* dType = g->dRaw32;
+    int* dId = g->dRaw32 + E;
+    int* dPs32 = g->dRaw32 + 2 * E;
+    CUDA_TRY(cudaMemsetAsync(g->dBadEvents, 0, sizeof(int), g->stream));
+    CUDA_TRY(cudaMemcpyAsync(dType, evType + first, sizeof(int) * (size_t)E, cudaMemcpyHostToDevice, g->stream));
+    CUDA_TRY(cudaMemcpyAsync(dId, evId + first, sizeof(int) * (size_t)E, cudaMemcpyHostToDevice, g->stream));
+    CUDA_TRY(cudaMemcpyAsync(dPs32, popStart, sizeof(int) * nPs, cudaMemcpyHostToDevice, g->stream));
+    CUDA_TRY(cudaMemcpyAsync(g->dRawStart, evStart, sizeof(long long) * ((size_t)L + 1), cudaMemcpyHostToDevice, g->stream));
+    CUDA_TRY(cudaMemcpyAsync(g->dEvTime, evTime + first, sizeof(double) * (size_t)E, cudaMemcpyHostToDevice, g->stream));
+    k_gen_pack<<<1184, 256, 0, g->stream>>>(dType, dId, E, dPs32, (long long)nPs, g->dRawStart, L, g->B, g->dEvCode, g->dPopStart,
+                                            g->dEvStart, g->dBadEvents);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    int maxTile = 0;
+    for (int l0 = 0; l0 < L; l0 += kGenTile) maxTile = std::max(maxTile, (int)(evStart[std::min(L, l0 + kGenTile)] - evStart[l0]));
+    g->maxTileEvents = maxTile;
+    int badCount = 0;
+    CUDA_TRY(cudaMemcpyAsync(&badCount, g->dBadEvents, sizeof(int), cudaMemcpyDeviceToHost, g->stream));
+    CUDA_TRY(cudaStreamSynchronize(g->stream));
+    if (badCount) { fprintf(stderr, "gphocs_b200: malformed event snapshot\n"); return -1; }
+    const size_t smemDirect = genSmemBytes(g->Q, g->B, g->maxTileEvents);
+    if (smemDirect > 200 * 1024) { fprintf(stderr, "gphocs_b200: event tile too large for shared memory (%zu bytes)\n", smemDirect); return -1; }
+    CUDA_TRY(cudaFuncSetAttribute(k_gen_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemDirect));
+    return 0;
+  }
   if (g->sEs.reserve(L + 1) || g->sPs.reserve((size_t)L * (Q + 1)) || g->sCode.reserve((size_t)E)) return -1;
   int* es = g->sEs.host;            // pinned staging: conversions land where the DMA engine reads them
   uint16_t* ps = g->sPs.host;

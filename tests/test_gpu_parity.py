@@ -347,3 +347,28 @@ def test_page_locked_genealogies_take_the_direct_route():
     assert b.check_mirror() == 0
     assert np.array_equal(a.evaluate(0), b.evaluate(0))
     a.close(); b.close()
+
+
+def test_page_locked_event_snapshot_takes_the_direct_route():
+    """gphocsGenSetEvents with page-locked arrays: copied as they are and narrowed on the device; same statistics and
+    log-densities as the staged route, and a malformed snapshot is still refused."""
+    w = synth.generate(synth.config("pop6mig4"), 2500, seed=22)
+    res = []
+    for pinned in (False, True):
+        gen = gp.Genealogy(w.L, w.pops)
+        arrs = [getattr(w, k) for k in ("ev_start", "pop_start", "ev_type", "ev_id", "ev_time")]
+        if pinned:
+            arrs = [gp.pinned_like(a) for a in arrs]
+        gen.set_events(*arrs)
+        res.append(gen.evaluate())
+        if pinned:
+            bad = [a.copy() for a in arrs]
+            bad = [gp.pinned_like(a) for a in bad]
+            bad[2][5] = 99                                   # not an event type
+            with pytest.raises(RuntimeError):
+                gen.set_events(*bad)
+        gen.close()
+    a, b = res
+    for key in ("lnl", "coal", "num_coals", "mig", "num_migs", "total_coal", "total_num_coals", "total_mig", "total_num_migs"):
+        assert np.array_equal(a[key], b[key]), key
+    assert a["sum_lnl"] == b["sum_lnl"]
