@@ -502,10 +502,10 @@ def run_b200(args):
     st.apply_ops(rej)
     # MCMC iterations/s of the device-resident steps: BASELINE.json configs[3] (100k loci, 6 populations + 4 bands) and
     # the migration-free 100k-locus shape sharded over all ranks (strong scaling); configs[1] and [2] (10k loci) at N=1
-    mcmc = {"configs3_pop6mig4_100k_sharded": device_mcmc(gp, synth, local_rank, 100_000, 10, rank, world, cfg="pop6mig4"),
+    mcmc = {} if args.no_mcmc else {"configs3_pop6mig4_100k_sharded": device_mcmc(gp, synth, local_rank, 100_000, 10, rank, world, cfg="pop6mig4"),
             "configs4_ancient_50k_sharded": device_mcmc(gp, synth, local_rank, 50_000, 20, rank, world, cfg="ancient"),
             "hap16_100k_sharded": device_mcmc(gp, synth, local_rank, 100_000, 30, rank, world)}
-    if world == 1:
+    if world == 1 and not args.no_mcmc:
         mcmc["configs1_hap16_10k"] = device_mcmc(gp, synth, local_rank, MCMC_LOCI, 100)
         mcmc["configs2_dip8mig_10k"] = device_mcmc(gp, synth, local_rank, 10_000, 50, cfg="dip8mig")
     clocks = sampler.stop() if rank == 0 else None
@@ -570,6 +570,7 @@ def main():
     ap.add_argument("--loci", type=int, default=100_000, help="loci per GPU")
     ap.add_argument("--sample-loci", type=int, default=2000, help="loci in the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-mcmc", action="store_true", help="skip the device-resident MCMC extras (development runs)")
     ap.add_argument("--with-mcmc", action="store_true", help="reference arm: also time the reference's MCMC iterations/s")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -21,11 +21,13 @@
 //   D  every marked node finds its own position in a post-order that visits the heavier child first by
 //      walking up its ancestors (no serial traversal), and writes its schedule entry: destination,
 //      where each child's vector comes from, JC69 edge terms
-//   E  every thread walks its locus' schedule for its own column.  Results are pushed on a per-column
-//      stack in shared memory (depth <= log2(n)+1 because the heavier child goes first), so in a full
-//      evaluation a child is never re-read from HBM: leaves come from a 16-entry table, computed
-//      children from the stack, clean children (incremental evaluation) from HBM.  The new vector is
-//      written to the node's *other* buffer, so accept/reject never copies.
+//   E  every thread walks its locus' schedule for its own column.  The vector computed last stays in
+//      registers: in a post-order it is a child of the next entry unless that entry starts a new subtree.
+//      Only a result whose sibling subtree is computed after it is parked on a per-column stack in shared
+//      memory (depth <= log2(n) because the heavier child goes first), leaves are expanded from their
+//      4-bit masks, clean children (incremental evaluation) come from HBM: in a full evaluation a child is
+//      never re-read from HBM and about a third of the nodes touch shared memory at all.  The new vector
+//      is written with one 32-byte store to the node's *other* buffer, so accept/reject never copies.
 //   F  root: sum 4*phases conditionals per phase group, count*log, per-locus sum in shared memory.
 #pragma once
 #include <cuda_runtime.h>
@@ -38,7 +40,18 @@ namespace gphocs {
 constexpr int kThreads = 128;      // threads (= columns) per CTA
 constexpr int kWarps = kThreads / 32;
 constexpr int kMaxBatchLoci = 16;  // loci per CTA batch
-constexpr int kStack = 3;          // on-chip result slots per column; deeper results are re-read from HBM
+#ifndef GPHOCS_KSTACK
+#define GPHOCS_KSTACK 3
+#endif
+#ifndef GPHOCS_EVAL_MINBLOCKS
+#define GPHOCS_EVAL_MINBLOCKS 0
+#endif
+#if GPHOCS_EVAL_MINBLOCKS > 0
+#define GPHOCS_EVAL_BOUNDS __launch_bounds__(kThreads, GPHOCS_EVAL_MINBLOCKS)
+#else
+#define GPHOCS_EVAL_BOUNDS __launch_bounds__(kThreads)
+#endif
+constexpr int kStack = GPHOCS_KSTACK;  // parked results per column in shared memory; deeper ones are re-read from HBM
 
 struct Batch {
   int firstLocus, numLoci;
@@ -65,18 +78,19 @@ struct StoreDev {
 };
 
 // One schedule entry = one node to (re)compute; entries are ordered so that children precede parents.
-enum : uint32_t { SRC_LEAF = 0, SRC_STACK = 1, SRC_GLOBAL = 2 };
+enum : uint32_t { SRC_LEAF = 0, SRC_STACK = 1, SRC_GLOBAL = 2, SRC_TOP = 3 };
 constexpr uint32_t kRow = kThreads * 16;       // bytes per stack row (one double2 per column)
-constexpr uint32_t kHi = kStack * kRow + 256;  // distance from the lo half of a vector to its hi half
+constexpr uint32_t kHi = kStack * kRow;        // distance from the lo half of a vector to its hi half
 struct __align__(16) SchedEntry {
   double e0A, e1A, e0B, e1B;  // JC69 edge terms of the two children: p and 1-4p (.c:1596-1602)
   // where a child's vector comes from, ready to use by the column threads:
   //   leaf    byte offset of its 32-bit code word row | bit shift << 16
   //   stack   (slot * row bytes) << 16
   //   global  byte offset of the source record from the column's base
+  //   top     the vector of the previous entry, still in registers
   uint32_t offA, offB;
   uint32_t dstOff;            // byte offset of the destination record from the column's base
-  uint32_t ctl;               // bits 0-1 kind of A, 2-3 kind of B, bits 16-31 stack byte offset to push to (0xffff: none)
+  uint32_t ctl;               // bits 0-1 kind of A, 2-3 kind of B, bits 16-31 stack byte offset to park the result at (0xffff: none)
 };
 static_assert(sizeof(SchedEntry) == 48, "schedule entry layout");
 
@@ -99,7 +113,7 @@ __host__ __device__ inline EvalSmem evalSmemLayout(int n, int maxLoci) {
   m.perScratch = (m.offNeed + (size_t)N + 15) & ~(size_t)15;
   m.perSched = (size_t)NI * sizeof(SchedEntry);
   // Region 0 is used twice: first as the scheduling scratch of the batch's loci, then (phase E) as the
-  // per-column stack: lo halves [kStack][kThreads] double2 + 16-entry leaf table, then the hi halves.
+  // per-column stack: lo halves [kStack][kThreads] double2, then the hi halves.
   // The root vectors reuse its first rows after the walk.
   const size_t stackBytes = 2 * (size_t)kHi, scratchBytes = m.perScratch * (size_t)maxLoci;
   m.offStack = 0;
@@ -195,6 +209,13 @@ __device__ __forceinline__ uint4 ldsU4(uint32_t a) {
   asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
   return v;
 }
+// one (node, column) record = 4 doubles = one 32-byte sector: a single 256-bit access per thread (sm_100)
+__device__ __forceinline__ void ldgD4(const void* p, double (&v)[4]) {
+  asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
+}
+__device__ __forceinline__ void stgD4(void* p, const double (&v)[4]) {
+  asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(v[0]), "d"(v[1]), "d"(v[2]), "d"(v[3]) : "memory");
+}
 // rare path of the column walk
 __device__ __forceinline__ void missingSubtree(const double (&a)[4], const double (&b)[4], double sA, double sB, double qA,
                                             double qB, double e1A, double e1B, double (&v)[4]) {
@@ -206,7 +227,7 @@ __device__ __forceinline__ void missingSubtree(const double (&a)[4], const doubl
   }
 }
 
-__global__ void __launch_bounds__(kThreads)
+__global__ void GPHOCS_EVAL_BOUNDS
 k_eval(StoreDev d, const Batch* __restrict__ batches, int batchBase, int useOld, int onlyLocus, int maxLoci,
        int prefetchAhead) {
   extern __shared__ __align__(16) unsigned char smem[];
@@ -407,14 +428,16 @@ k_eval(StoreDev d, const Batch* __restrict__ batches, int batchBase, int useOld,
     const uint32_t strideBytes = (uint32_t)mP[s] * 32u;  // one (node, buffer) record of this locus
     auto record = [&](int x) { return (uint32_t)((x - n) * 2 + (nd[x].flags & F_SEL)) * strideBytes; };
     auto leafRef = [&](int x) { return (uint32_t)(x >> 3) * (kThreads * 4u) | ((uint32_t)(x & 7) * 4u) << 16; };
-    // a computed child sits on the stack at the depth its own subtree was entered with
-    const int slotA = depth, slotB = depth + (wA > 0);
-    uint32_t kindA, kindB, offA, offB;
+    // The entry right before v's is the root of the subtree visited last, so that child's vector is still in the
+    // walking thread's registers.  When both subtrees are computed, A's result was parked on the stack at the depth
+    // v's subtree was entered with (or, beyond kStack, is re-read from the record the thread has just written).
+    uint32_t kindA, kindB, offA = 0, offB = 0;
     if (A < n) { kindA = SRC_LEAF; offA = leafRef(A); }
-    else if (wA > 0 && slotA < kStack) { kindA = SRC_STACK; offA = ((uint32_t)slotA * kRow) << 16; }
+    else if (wA > 0 && wB == 0) { kindA = SRC_TOP; }
+    else if (wA > 0 && depth < kStack) { kindA = SRC_STACK; offA = ((uint32_t)depth * kRow) << 16; }
     else { kindA = SRC_GLOBAL; offA = record(A); }  // clean child, or a result the thread parked in HBM
     if (B < n) { kindB = SRC_LEAF; offB = leafRef(B); }
-    else if (wB > 0 && slotB < kStack) { kindB = SRC_STACK; offB = ((uint32_t)slotB * kRow) << 16; }
+    else if (wB > 0) { kindB = SRC_TOP; }
     else { kindB = SRC_GLOBAL; offB = record(B); }
     SchedEntry en;
     const double av = age[v];
@@ -424,7 +447,19 @@ k_eval(StoreDev d, const Batch* __restrict__ batches, int batchBase, int useOld,
     en.e1B = 1.0 - 4.0 * en.e0B;
     en.offA = offA; en.offB = offB;
     en.dstOff = record(v);
-    const uint32_t push = (v != mRoot[s] && depth < kStack) ? (uint32_t)depth * kRow : 0xffffu;
+    // v's own result is parked iff v is visited first and its sibling's subtree is computed too
+    uint32_t push = 0xffffu;
+    {
+      const int f = nd[v].father;
+      if (f >= 0 && v != mRoot[s] && depth < kStack) {
+        const int fl = nd[f].left, fr = nd[f].right;
+        const int wfl = (fl >= n && need[fl]) ? size[fl - n] : 0;
+        const int wfr = (fr >= n && need[fr]) ? size[fr - n] : 0;
+        const int first = wfl >= wfr ? fl : fr;
+        const int wSibling = v == fl ? wfr : wfl;
+        if (v == first && wSibling > 0) push = (uint32_t)depth * kRow;
+      }
+    }
     en.ctl = kindA | (kindB << 2) | (push << 16);
     sSched(s)[start + size[v - n] - 1] = en;
     if (v == mRoot[s]) mK[s] = size[v - n];
@@ -432,15 +467,9 @@ k_eval(StoreDev d, const Batch* __restrict__ batches, int batchBase, int useOld,
   __syncthreads();
 
   // ---- phase E: every thread walks its locus' schedule for its own column.  The scheduling scratch is dead;
-  //      its space becomes the per-column stack and the leaf table.
-  if (tid < 16) {  // conditional vectors of a leaf by base mask (computeLeafConditionals, .c:1336-1386)
-    stsD2(stackBase + kStack * kRow + tid * 16, (tid & 1) ? 1.0 : 0.0, (tid & 2) ? 1.0 : 0.0);
-    stsD2(stackBase + kStack * kRow + kHi + tid * 16, (tid & 4) ? 1.0 : 0.0, (tid & 8) ? 1.0 : 0.0);
-  }
-  __syncthreads();
+  //      its space becomes the per-column stack.
   const int numChunks = (b.numCols + kThreads - 1) / kThreads;
   const uint32_t myStack = stackBase + tid * 16;
-  const uint32_t leafRel = kStack * kRow - tid * 16;  // leaf table relative to this column's stack
   const uint32_t myWords = smemAddr(smem + lay.offWords) + tid * 4;
   int s = 0, k = 0;
   for (int chunk = 0; chunk < numChunks; chunk++) {
@@ -471,18 +500,23 @@ k_eval(StoreDev d, const Batch* __restrict__ batches, int batchBase, int useOld,
       }
       char* clvCol = reinterpret_cast<char*>(d.clv + (size_t)mColStart[s] * NI * 8 + (size_t)p * 4);
       uint32_t entry = smemAddr(sSched(s));
+      // pv = the vector computed by the previous entry (the register-resident top of the stack)
       auto childValue = [&](uint32_t kind, uint32_t off, double (&v)[4]) {
-        if (kind == SRC_GLOBAL) {
-          const double2* g = reinterpret_cast<const double2*>(clvCol + off);
-          const double2 x = g[0], y = g[1];
-          v[0] = x.x; v[1] = x.y; v[2] = y.x; v[3] = y.y;
-        } else {
-          // leaf: table row picked by the 4-bit mask of this column; stack: this column's slot
-          const uint32_t word = ldsU32(myWords + (off & 0xffffu));
-          const uint32_t hi = off >> 16;
-          const uint32_t a = myStack + (kind == SRC_LEAF ? leafRel + (((word >> hi) & 15u) << 4) : hi);
+        if (kind == SRC_TOP) {
+#pragma unroll
+          for (int q = 0; q < 4; q++) v[q] = pv[q];
+        } else if (kind == SRC_LEAF) {
+          // conditional vector of a leaf from its 4-bit base mask (computeLeafConditionals, .c:1336-1386):
+          // 1.0 = 0x3ff00000'00000000 where the bit is set, 0.0 elsewhere
+          const uint32_t m = ldsU32(myWords + (off & 0xffffu)) >> (off >> 16);
+#pragma unroll
+          for (int q = 0; q < 4; q++) v[q] = __hiloint2double((int)(((m >> q) & 1u) * 0x3ff00000u), 0);
+        } else if (kind == SRC_STACK) {
+          const uint32_t a = myStack + (off >> 16);
           const double2 x = ldsD2(a), y = ldsD2(a + kHi);
           v[0] = x.x; v[1] = x.y; v[2] = y.x; v[3] = y.y;
+        } else {
+          ldgD4(clvCol + off, v);
         }
       };
       if (useOld) {   // clean children are the only HBM reads of a proposal: request them all before the first use
@@ -509,9 +543,7 @@ k_eval(StoreDev d, const Batch* __restrict__ batches, int batchBase, int useOld,
           // a child whose conditionals sum to 4 is an all-missing subtree and contributes exactly 1 (.c:1660-1663)
           missingSubtree(a, bb, sA, sB, qA, qB, eA.y, eB.y, v);
         }
-        double2* dst = reinterpret_cast<double2*>(clvCol + ix.z);
-        dst[0] = make_double2(v[0], v[1]);
-        dst[1] = make_double2(v[2], v[3]);
+        stgD4(clvCol + ix.z, v);
         const uint32_t push = ix.w >> 16;
         if (push != 0xffffu) {
           stsD2(myStack + push, v[0], v[1]);

@@ -9,12 +9,11 @@
 //   evTime[e]  fp64 elapsed_time,  evCode[e] = type | id << 3  (id = migration band where relevant)
 // i.e. 10 bytes per event instead of the reference's 32-byte linked-list node.
 //
-// A CTA stages the events of a tile of 32 loci in shared memory with coalesced loads, then works
-// per (locus, population): pass A sums the lineage deltas of each chain, a per-locus post-order sweep
-// over the population tree turns them into lineages entering each population, pass B re-walks each
-// chain in the reference's event order accumulating n(n-1)t and n*t per live band.  Per-population sums
-// are sequential in chain order and products are not fused, so the statistics and the log-density are
-// bit-identical to the reference on the same elapsed times.  Totals are reduced per CTA and then by a
+// A CTA stages the events of a tile of 32 loci in shared memory with coalesced loads; then one thread per
+// locus walks the populations in post-order (lineages entering an ancestral population = lineages its sons
+// end with) and every chain in the reference's event order, accumulating n(n-1)t and n*t per live band.
+// Per-population sums are sequential in chain order and products are not fused, so the statistics and the
+// log-density are bit-identical to the reference on the same elapsed times.  Totals are reduced per CTA and then by a
 // fixed-order second kernel (deterministic run to run).
 #pragma once
 #include <cuda_runtime.h>
@@ -70,7 +69,7 @@ __global__ void __launch_bounds__(kGenThreads) k_gen_eval(GenDev d, int maxTileE
   double* sCoal = sMig + kGenTile * B;                                 // [tile][Q]
   double* sTot = sCoal + kGenTile * Q;                                 // [V]
   double* sLnL = sTot + V;                                             // [tile]
-  int* sDelta = reinterpret_cast<int*>(sLnL + kGenTile);               // [tile][Q] lineage delta, then n at chain start
+  int* sDelta = reinterpret_cast<int*>(sLnL + kGenTile);               // [tile][Q] lineages at the end of each chain
   int* sNumCoals = sDelta + kGenTile * Q;                              // [tile][Q]
   int* sNumMigs = sNumCoals + kGenTile * Q;                            // [tile][B]
   int* sEvBase = sNumMigs + kGenTile * B;                              // [tile+1] event offsets relative to tile
@@ -92,66 +91,60 @@ __global__ void __launch_bounds__(kGenThreads) k_gen_eval(GenDev d, int maxTileE
   for (int i = tid; i < V; i += kGenThreads) sTot[i] = 0.0;
   __syncthreads();
 
-  // pass A: net lineage change of each chain (SAMPLES_START +samples, COAL -1, IN_MIG -1, OUT_MIG +1)
-  for (int it = tid; it < nl * Q; it += kGenThreads) {
-    const int j = it / Q, p = it - j * Q;
-    const int a = sEvBase[j] + sPopStart[j * (Q + 1) + p], b = sEvBase[j] + sPopStart[j * (Q + 1) + p + 1];
-    int delta = 0;
-    for (int e = a; e < b; e++) {
-      const int type = sCode[e] & 7;
-      delta += type == EV_SAMPLES_START ? prm.samplesPerPop[p] : (type == EV_COAL || type == EV_IN_MIG) ? -1 : (type == EV_OUT_MIG) ? 1 : 0;
-    }
-    sDelta[it] = delta;
-  }
-  __syncthreads();
-  // lineages entering each population: post-order over the population tree (patch.c:2336-2347)
-  if (tid < nl) {
-    int nEnd[kMaxPops];
-    int* dl = sDelta + tid * Q;
-    for (int i = 0; i < Q; i++) {
-      const int p = prm.postOrder[i];
-      const int n0 = p >= prm.C ? nEnd[prm.son0[p]] + nEnd[prm.son1[p]] : 0;
-      nEnd[p] = n0 + dl[p];
-      dl[p] = n0;
-    }
-  }
-  __syncthreads();
-  // pass B: statistics per chain, in the reference's order of operations (patch.c:2403-2486)
-  for (int it = tid; it < nl * Q; it += kGenThreads) {
-    const int j = it / Q, p = it - j * Q;
-    const int a = sEvBase[j] + sPopStart[j * (Q + 1) + p], b = sEvBase[j] + sPopStart[j * (Q + 1) + p + 1];
-    int n = sDelta[it], ncoal = 0;
-    double coal = 0.0;
-    unsigned long long live0 = 0ull, live1 = 0ull;  // live migration bands (ids 0..127)
-    double* mg = sMig + j * B;
-    int* nm = sNumMigs + j * B;
-    for (int e = a; e < b; e++) {
-      const double t = sTime[e];
-      const int code = sCode[e], type = code & 7, id = code >> 3;
-      if (d.evLineages) d.evLineages[e0 + e] = (uint8_t)n;
-      coal = __dadd_rn(coal, __dmul_rn((double)(n * (n - 1)), t));
-      if (live0 | live1) {
-        const double nt = __dmul_rn((double)n, t);
-        for (unsigned long long m = live0; m; m &= m - 1) { const int bnd = __ffsll((long long)m) - 1; mg[bnd] = __dadd_rn(mg[bnd], nt); }
-        for (unsigned long long m = live1; m; m &= m - 1) { const int bnd = 64 + __ffsll((long long)m) - 1; mg[bnd] = __dadd_rn(mg[bnd], nt); }
-      }
-      switch (type) {
-        case EV_SAMPLES_START: n += prm.samplesPerPop[p]; break;
-        case EV_COAL: ncoal++; n--; break;
-        case EV_IN_MIG: nm[id]++; n--; break;
-        case EV_OUT_MIG: n++; break;
-        case EV_BAND_START: if (id < 64) live0 |= 1ull << id; else live1 |= 1ull << (id - 64); mg[id] = 0.0; nm[id] = 0; break;
-        case EV_BAND_END: if (id < 64) live0 &= ~(1ull << id); else live1 &= ~(1ull << (id - 64)); break;
-        default: break;
-      }
-    }
-    sCoal[it] = coal;
-    sNumCoals[it] = ncoal;
-  }
-  __syncthreads();
-  // per-locus log-density (patch.c:2709-2723) and per-locus outputs
+  // One thread per locus walks the whole genealogy: populations in post-order (patch.c:2336-2347: an ancestral
+  // population starts with the lineages its two sons end with, a leaf population with none), every chain in the
+  // reference's event order accumulating n(n-1)t and n*t per live band (patch.c:2403-2486), then the log-density
+  // (patch.c:2709-2723).  The 32 loci of the tile are the lanes of one warp: chains of a population are about
+  // equally long in every locus, so the lanes stay together, and the whole tile costs one chain walk instead of
+  // one per (locus, population).
   if (tid < nl) {
     const int j = tid;
+    const int eb = sEvBase[j];
+    const uint16_t* ps = sPopStart + j * (Q + 1);
+    int* nEnd = sDelta + j * Q;        // lineages at the end of each chain
+    double* mg = sMig + j * B;
+    int* nm = sNumMigs + j * B;
+    const bool wantLineages = d.evLineages != nullptr;
+    for (int i = 0; i < Q; i++) {
+      const int p = prm.postOrder[i];
+      int n = p >= prm.C ? nEnd[prm.son0[p]] + nEnd[prm.son1[p]] : 0;
+      const int a = eb + ps[p], b = eb + ps[p + 1];
+      int ncoal = 0;
+      double coal = 0.0;
+      unsigned long long live0 = 0ull, live1 = 0ull;  // live migration bands (ids 0..127)
+      const int smp = prm.samplesPerPop[p];
+      // the next event is requested while the current one is processed (the walk is a chain of dependent
+      // operations; its loads need not be part of it)
+      double tNext = 0.0;
+      int codeNext = 0;
+      if (a < b) { tNext = sTime[a]; codeNext = sCode[a]; }
+      for (int e = a; e < b; e++) {
+        const double t = tNext;
+        const int code = codeNext, type = code & 7;
+        const int en = min(e + 1, b - 1);
+        tNext = sTime[en]; codeNext = sCode[en];
+        if (wantLineages) d.evLineages[e0 + e] = (uint8_t)n;
+        coal = __dadd_rn(coal, __dmul_rn((double)(n * (n - 1)), t));
+        // everything that touches a migration band: statistics of the live bands, band start / end, migrations
+        if ((live0 | live1) != 0ull || (type >= EV_IN_MIG && type <= EV_BAND_END)) {
+          const int id = code >> 3;
+          if (live0 | live1) {
+            const double nt = __dmul_rn((double)n, t);
+            for (unsigned long long m = live0; m; m &= m - 1) { const int bnd = __ffsll((long long)m) - 1; mg[bnd] = __dadd_rn(mg[bnd], nt); }
+            for (unsigned long long m = live1; m; m &= m - 1) { const int bnd = 64 + __ffsll((long long)m) - 1; mg[bnd] = __dadd_rn(mg[bnd], nt); }
+          }
+          if (type == EV_IN_MIG) nm[id]++;
+          else if (type == EV_BAND_START) { if (id < 64) live0 |= 1ull << id; else live1 |= 1ull << (id - 64); mg[id] = 0.0; nm[id] = 0; }
+          else if (type == EV_BAND_END) { if (id < 64) live0 &= ~(1ull << id); else live1 &= ~(1ull << (id - 64)); }
+        }
+        ncoal += type == EV_COAL;
+        n += type == EV_SAMPLES_START ? smp : (type == EV_COAL || type == EV_IN_MIG) ? -1 : type == EV_OUT_MIG ? 1 : 0;
+      }
+      nEnd[p] = n;
+      sCoal[j * Q + p] = coal;
+      sNumCoals[j * Q + p] = ncoal;
+    }
+    // per-locus log-density (patch.c:2709-2723)
     double lnLd = 0.0;
     for (int p = 0; p < Q; p++) {
       const double term = __dsub_rn(__dmul_rn((double)sNumCoals[j * Q + p], prm.log2OverTheta[p]),
@@ -169,6 +162,7 @@ __global__ void __launch_bounds__(kGenThreads) k_gen_eval(GenDev d, int maxTileE
     sLnL[j] = lnLd;
     d.lnL[l0 + j] = lnLd;
   }
+  __syncthreads();
   for (int i = tid; i < nl * Q; i += kGenThreads) {
     d.coal[(size_t)l0 * Q + i] = sCoal[i];
     d.numCoals[(size_t)l0 * Q + i] = sNumCoals[i];

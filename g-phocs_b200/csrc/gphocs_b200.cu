@@ -231,7 +231,9 @@ extern "C" GphocsStore* gphocsStoreCreate(int device, int numLoci, int numLeaves
   // loci per batch are also capped so that the per-locus staging area fits a 64 KB shared-memory budget
   // (keeps several CTAs resident per SM whatever the number of leaves)
   int lociCap = kMaxBatchLoci;
-  while (lociCap > 1 && evalSmemBytes(n, lociCap) > 64 * 1024) lociCap--;
+  size_t smemBudget = 64 * 1024;
+  if (const char* e = getenv("GPHOCS_EVAL_SMEM_BUDGET")) smemBudget = (size_t)atol(e);
+  while (lociCap > 1 && evalSmemBytes(n, lociCap) > smemBudget) lociCap--;
   {
     Batch cur{0, 0, 0, 0, -1, 0};
     auto flush = [&]() { if (cur.numLoci > 0) s->batches.push_back(cur); cur = Batch{0, 0, 0, 0, -1, 0}; };
