@@ -126,6 +126,7 @@ struct GphocsStore {
   std::vector<Op> pending;  // edits queued by the scalar API, flushed before the next evaluation
   bool debugMirror = false;  // also mirror SEL/RECALC bits on the host (tests)
   bool opsInFlight = false;  // an edit batch was enqueued without a stream synchronisation
+  std::atomic<bool> mirrorStale{false};  // topology / ages / roots of the mirror are behind the device copy (refreshMirrorLocked)
   std::mutex mu;
 
   TreeView hostView(int l) {
@@ -233,6 +234,7 @@ extern "C" GphocsStore* gphocsStoreCreate(int device, int numLoci, int numLeaves
   int lociCap = kMaxBatchLoci;
   size_t smemBudget = 64 * 1024;
   if (const char* e = getenv("GPHOCS_EVAL_SMEM_BUDGET")) smemBudget = (size_t)atol(e);
+  if (const char* e = getenv("GPHOCS_EVAL_MAX_LOCI")) lociCap = std::max(1, std::min(kMaxBatchLoci, atoi(e)));
   while (lociCap > 1 && evalSmemBytes(n, lociCap) > smemBudget) lociCap--;
   {
     Batch cur{0, 0, 0, 0, -1, 0};
@@ -386,6 +388,39 @@ extern "C" int gphocsStoreSync(GphocsStore* s) {
 }
 
 // ---- genealogies
+// The page-locked route of gphocsStoreSetTrees does not touch the host mirror (updating 100k genealogies costs the
+// host as long as the PCIe transfer itself): it marks the mirror's topology, ages and roots stale, and whoever
+// reads the mirror next — an edit batch, a getter of the scalar API, gphocsStoreGetTrees, the mirror check — brings
+// it up to date from the device copy first.  Flag bytes of the mirror are its own and are kept.
+static int refreshMirrorLocked(GphocsStore* s) {
+  if (!s->mirrorStale.load(std::memory_order_acquire)) return 0;
+  cudaSetDevice(s->device);
+  CUDA_TRY(cudaStreamSynchronize(s->stream));
+  const size_t LN = (size_t)s->L * s->N;
+  std::vector<NodeRec> nd(LN);
+  CUDA_TRY(cudaMemcpy(nd.data(), s->d.node, LN * sizeof(NodeRec), cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(s->hAge.data(), s->d.age, LN * sizeof(double), cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(s->hRoot.data(), s->d.root, (size_t)s->L * sizeof(int), cudaMemcpyDeviceToHost));
+  NodeRec* hn = s->hNode.data();
+  const NodeRec* dn = nd.data();
+  parallelFor(0, (long long)LN, [&](long long lo_, long long hi_) {
+    for (long long i = lo_; i < hi_; i++) {
+      NodeRec rec = hn[i];
+      rec.father = dn[i].father; rec.left = dn[i].left; rec.right = dn[i].right;
+      hn[i] = rec;
+    }
+  }, 65536);
+  s->mirrorStale.store(false, std::memory_order_release);
+  return 0;
+}
+// for readers that do not hold the store's mutex (the scalar API's getters: one relaxed load on the fast path)
+void ensureMirror(GphocsStore* s) {
+  if (__builtin_expect(s->mirrorStale.load(std::memory_order_acquire), 0)) {
+    std::lock_guard<std::mutex> lk(s->mu);
+    refreshMirrorLocked(s);
+  }
+}
+
 static int setTreesLocked(GphocsStore* s, int nLoci, const int* locusIds, const int* father, const int* left,
                           const int* right, const double* age, const int* root) {
   const int N = s->N;
@@ -402,8 +437,8 @@ static int setTreesLocked(GphocsStore* s, int nLoci, const int* locusIds, const 
   }
   StoreDev& d = s->d;
   // Page-locked caller arrays covering loci 0..nLoci-1: the DMA engine reads them where they are — ages and roots go
-  // straight to their final device arrays, the int32 topology to a scratch that k_set_topology32 packs — while the
-  // host threads bring the mirror up to date; nothing is staged.
+  // straight to their final device arrays, the int32 topology to a scratch that k_set_topology32 packs; nothing is
+  // staged and the host mirror is brought up to date only when somebody reads it.
   auto pageLocked = [](const void* p) {
     cudaPointerAttributes at;
     if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
@@ -425,22 +460,7 @@ static int setTreesLocked(GphocsStore* s, int nLoci, const int* locusIds, const 
     k_set_topology32<<<(unsigned)((cnt + 255) / 256), 256, 0, s->stream>>>(d, s->dTopo32, s->dTopo32 + cnt, s->dTopo32 + 2 * cnt, cnt);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
-    parallelFor(0, nLoci, [&](long long lo_, long long hi_) {   // the mirror, while the copies are in flight
-      for (int k = (int)lo_; k < (int)hi_; k++) {
-        const size_t o = (size_t)k * N;
-        NodeRec* __restrict__ hn = s->hNode.data() + o;
-        const int* __restrict__ fa = father + o;
-        const int* __restrict__ le = left + o;
-        const int* __restrict__ ri = right + o;
-        for (int i = 0; i < N; i++) {
-          NodeRec rec = hn[i];
-          rec.father = (int16_t)fa[i]; rec.left = (int16_t)le[i]; rec.right = (int16_t)ri[i];
-          hn[i] = rec;
-        }
-        memcpy(s->hAge.data() + o, age + o, sizeof(double) * (size_t)N);
-        s->hRoot[k] = root[k];
-      }
-    }, 256);
+    s->mirrorStale.store(true, std::memory_order_release);   // the mirror follows on demand (refreshMirrorLocked)
     CUDA_TRY(cudaStreamSynchronize(s->stream));   // the caller's arrays are free again when the call returns
     return 0;
   }
@@ -495,6 +515,7 @@ extern "C" int gphocsStoreSetTrees(GphocsStore* s, int nLoci, const int* locusId
 extern "C" int gphocsStoreGetTrees(GphocsStore* s, int nLoci, const int* locusIds, int* father, int* left, int* right,
                                    double* age, int* root) {
   std::lock_guard<std::mutex> lk(s->mu);
+  if (refreshMirrorLocked(s)) return -1;
   const int N = s->N;
   for (int k = 0; k < nLoci; k++) {
     const int l = locusIds ? locusIds[k] : k;
@@ -529,6 +550,7 @@ extern "C" int gphocsStoreGetRates(GphocsStore* s, int nLoci, const int* locusId
 static int launchOps(GphocsStore* s, const Op* ops, int nOps, int* outStatus, bool mirror) {
   if (nOps <= 0) return 0;
   cudaSetDevice(s->device);
+  if (mirror && refreshMirrorLocked(s)) return -1;   // before anything of this batch reaches the device
   if (s->opsInFlight) {   // the previous batch may still be reading the staging buffers
     CUDA_TRY(cudaStreamSynchronize(s->stream));
     s->opsInFlight = false;
@@ -749,6 +771,7 @@ static int evaluateLocked(GphocsStore* s, int nLoci, const int* locusIds, int us
     g_launches++;
     CUDA_TRY(cudaMemcpyAsync(s->f64.host + s->L, s->dSum, sizeof(double), cudaMemcpyDeviceToHost, s->stream));
   }
+  if (s->debugMirror && refreshMirrorLocked(s)) return -1;
   if (s->debugMirror)
     for (int k = 0; k < nLoci; k++) replayFlipsOnMirror(s, all ? k : locusIds[k], useOld);
   if (readLnL(s, nLoci, locusIds, outLnL, true)) return -1;  // synchronises the stream
@@ -769,6 +792,7 @@ static int evaluateLocked(GphocsStore* s, int nLoci, const int* locusIds, int us
 extern "C" int gphocsStoreCheckMirror(GphocsStore* s) {
   std::lock_guard<std::mutex> lk(s->mu);
   if (flushPending(s)) return -1;
+  if (refreshMirrorLocked(s)) return -1;
   cudaSetDevice(s->device);
   CUDA_TRY(cudaStreamSynchronize(s->stream));
   const size_t LN = (size_t)s->L * s->N;

@@ -346,6 +346,15 @@ def test_page_locked_genealogies_take_the_direct_route():
     b.set_trees(hw["father"], hw["left"], hw["right"], hw["age"], hw["root"])
     assert b.check_mirror() == 0
     assert np.array_equal(a.evaluate(0), b.evaluate(0))
+    # the direct route leaves the host mirror to whoever reads it next: an edit batch right after it must land on
+    # the new genealogies on both sides
+    b.set_trees(hw["father"], hw["left"], hw["right"], hw["age"], hw["root"])
+    for st in (a, b):
+        st.apply_ops(ops)
+    for x, y in zip(a.get_trees(), b.get_trees()):
+        assert np.array_equal(x, y)
+    assert a.check_mirror() == 0 and b.check_mirror() == 0
+    assert np.array_equal(a.evaluate(1), b.evaluate(1))
     a.close(); b.close()
 
 
