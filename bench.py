@@ -438,43 +438,64 @@ def run_b200(args):
     lnl_host = gp.pinned_like(np.zeros(L))
     hw = {k: gp.pinned_like(getattr(w, k)) for k in ("father", "left", "right", "age", "root", "ev_start", "pop_start",
                                                        "ev_type", "ev_id", "ev_time")}   # inputs in page-locked host memory
+    # the same inputs in the library's wire formats (16-bit topology triples, 16-bit event codes and chain offsets,
+    # 32-bit event offsets): what a host that flattens its genealogies for the GPU writes instead of int32 arrays
+    es32, ps16, code16 = gp.pack_events(w.ev_start, w.pop_start, w.ev_type, w.ev_id)
+    hp = {"topo": gp.pinned_like(gp.pack_trees(w.father, w.left, w.right)), "es": gp.pinned_like(es32),
+          "ps": gp.pinned_like(ps16), "code": gp.pinned_like(code16)}
     e2e_steps = max(3, min(args.steps, 20))
-    # bytes that cross PCIe per step, counted from the buffers the library copies: the page-locked genealogy arrays as
-    # they are (int32 topology, fp64 ages, roots; int32 event types and ids, fp64 elapsed times, int32 chain offsets,
-    # int64 event offsets); back: per-locus data lnL + its sum, genealogy lnL + totals
-    h2d = L * w.father.shape[1] * (3 * 4 + 8) + 4 * L + int(E.sum()) * 16 + L * (Q + 1) * 4 + 8 * (L + 1)
+    # bytes that cross PCIe per step, counted from the buffers the library copies.  Packed route: int16 topology
+    # triples, fp64 ages, roots; uint16 event codes, fp64 elapsed times, uint16 chain offsets, int32 event offsets.
+    # int32 route: the page-locked arrays as they are (int32 topology / event types / ids / chain offsets, int64
+    # event offsets).  Back: per-locus data lnL + its sum, genealogy lnL + totals.
+    nN = w.father.shape[1]
+    h2d = L * nN * (3 * 2 + 8) + 4 * L + int(E.sum()) * 10 + L * (Q + 1) * 2 + 4 * (L + 1)
+    h2d_int32 = L * nN * (3 * 4 + 8) + 4 * L + int(E.sum()) * 16 + L * (Q + 1) * 4 + 8 * (L + 1)
     d2h = 8 * L + 8 + 8 * L + 8 * V
 
     # The host calls are the asynchronous ones of the C ABI (gphocsStoreEvaluateDevice, gphocsGenEvaluateDevice,
-    # gphocsCopyDeviceAsync): the data-likelihood kernel and its read-back run while the host converts the event
-    # snapshot; everything is back in host memory before the step ends.
+    # gphocsCopyDeviceAsync): the data-likelihood kernel and its read-back run while the event snapshot crosses
+    # PCIe; everything is back in host memory before the step ends.
     lib.gphocsGenSetStream(gen.h, None)        # the genealogy object on a stream of its own for this section
     host_sums = gp.pinned_like(np.zeros(2 + V))
 
-    def e2e_step():
-        st.set_trees(hw["father"], hw["left"], hw["right"], hw["age"], hw["root"])
+    def e2e_step(packed=True):
+        if packed:
+            st.set_trees_packed(hp["topo"], hw["age"], hw["root"])
+        else:
+            st.set_trees(hw["father"], hw["left"], hw["right"], hw["age"], hw["root"])
         dlnl, dsum = st.evaluate_device(0)
         sp = C.c_void_p(stream.cuda_stream)
         lib.gphocsCopyDeviceAsync(C.c_void_p(lnl_host.ctypes.data), C.c_void_p(dlnl), 8 * L, sp)
         lib.gphocsCopyDeviceAsync(C.c_void_p(host_sums.ctypes.data), C.c_void_p(dsum), 8, sp)
-        gen.set_events(hw["ev_start"], hw["pop_start"], hw["ev_type"], hw["ev_id"], hw["ev_time"])
+        if packed:
+            gen.set_events_packed(hp["es"], hp["ps"], hp["code"], hw["ev_time"])
+        else:
+            gen.set_events(hw["ev_start"], hw["pop_start"], hw["ev_type"], hw["ev_id"], hw["ev_time"])
         r = gen.evaluate(per_locus_stats=False)      # per-locus genealogy lnL + totals, back on the host
         stream.synchronize()
         return float(host_sums[0]), r["sum_lnl"]
 
-    e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        sdata, sgen = e2e_step()
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    e2e_value = world * L * e2e_steps / e2e_s
+    def e2e_run(packed):
+        e2e_step(packed)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            sd_, sg_ = e2e_step(packed)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        return world * L * e2e_steps / dt, sd_, sg_
+
+    e2e_int32_value, sdata, sgen = e2e_run(False)
     # the end-to-end pass computes the same numbers as the resident one (this rank's sums before the all-reduce)
+    if world == 1:
+        assert abs(sdata - total_data_lnl) <= 1e-9 * abs(total_data_lnl), (sdata, total_data_lnl)
+        assert abs(sgen - total_gen_lnl) <= 1e-9 * abs(total_gen_lnl), (sgen, total_gen_lnl)
+    e2e_value, sdata, sgen = e2e_run(True)
     if world == 1:
         assert abs(sdata - total_data_lnl) <= 1e-9 * abs(total_data_lnl), (sdata, total_data_lnl)
         assert abs(sgen - total_gen_lnl) <= 1e-9 * abs(total_gen_lnl), (sgen, total_gen_lnl)
@@ -541,7 +562,10 @@ def run_b200(args):
                          "ms_per_launch": ms_data, "genealogy_kernel_ms": ms_gen,
                          "genealogy_achieved_gbs": bytes_gen / (ms_gen * 1e-3) / 1e9},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "steps": e2e_steps, "host_threads_per_rank": host_threads},
+                    "steps": e2e_steps, "host_threads_per_rank": host_threads,
+                    "route": "gphocsStoreSetTreesPacked + gphocsGenSetEventsPacked (16-bit topology and event codes on the wire)",
+                    "int32_route": {"value": e2e_int32_value, "h2d_bytes_per_step": int(h2d_int32),
+                                    "route": "gphocsStoreSetTrees + gphocsGenSetEvents (int32 arrays copied as they are)"}},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "extra": {"sum_data_lnl": total_data_lnl, "sum_gen_lnl": total_gen_lnl,

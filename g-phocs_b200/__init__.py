@@ -81,6 +81,7 @@ def lib():
         "gphocsStoreNumColumns": (C.c_longlong, [vp]),
         "gphocsStoreDeviceBytes": (C.c_longlong, [vp]),
         "gphocsStoreSetTrees": (ci, [vp, ci, c_int_p, c_int_p, c_int_p, c_int_p, c_dbl_p, c_int_p]),
+        "gphocsStoreSetTreesPacked": (ci, [vp, ci, C.POINTER(C.c_short), c_dbl_p, c_int_p]),
         "gphocsStoreGetTrees": (ci, [vp, ci, c_int_p, c_int_p, c_int_p, c_int_p, c_dbl_p, c_int_p]),
         "gphocsStoreSetRates": (ci, [vp, ci, c_int_p, c_dbl_p]),
         "gphocsStoreApplyOps": (ci, [vp, ci, vp, c_int_p]),
@@ -104,6 +105,7 @@ def lib():
         "gphocsGenSetStream": (ci, [vp, vp]),
         "gphocsGenSetParams": (ci, [vp, c_dbl_p, c_dbl_p]),
         "gphocsGenSetEvents": (ci, [vp, c_ll_p, c_int_p, c_int_p, c_int_p, c_dbl_p]),
+        "gphocsGenSetEventsPacked": (ci, [vp, c_int_p, C.POINTER(C.c_ushort), C.POINTER(C.c_ushort), c_dbl_p]),
         "gphocsGenEvaluate": (ci, [vp, c_dbl_p, c_dbl_p, c_int_p, c_dbl_p, c_int_p, c_dbl_p, c_ll_p, c_dbl_p, c_ll_p, c_dbl_p]),
         "gphocsGenEvaluateDevice": (ci, [vp, C.POINTER(vp), C.POINTER(vp)]),
         "gphocsGenGetLineages": (ci, [vp, c_int_p]),
@@ -225,6 +227,13 @@ class LociStore:
         self._check(self.lib.gphocsStoreSetTrees(self.h, k, _ip(None if ids is None else _i32(ids)), _ip(f), _ip(l),
                                                  _ip(r), _dp(a), _ip(ro)), "gphocsStoreSetTrees")
 
+    def set_trees_packed(self, topo16, age, root):
+        """Loci 0..k-1 in the device's wire format: topo16[k][N][3] int16 (father, left, right), see pack_trees."""
+        t = np.ascontiguousarray(topo16, np.int16)
+        a, ro = _f64(age), _i32(root)
+        self._check(self.lib.gphocsStoreSetTreesPacked(self.h, len(ro), t.ctypes.data_as(C.POINTER(C.c_short)), _dp(a),
+                                                       _ip(ro)), "gphocsStoreSetTreesPacked")
+
     def get_trees(self, ids=None):
         k = self.L if ids is None else len(ids)
         f, l, r = (np.zeros((k, self.N), np.int32) for _ in range(3))
@@ -322,6 +331,21 @@ def free_pinned():
         L.gphocsHostFree(C.c_void_p(p))
 
 
+def pack_trees(father, left, right):
+    """int32 [L][N] topology arrays -> the wire format of gphocsStoreSetTreesPacked: int16 [L][N][3]."""
+    return np.ascontiguousarray(np.stack([np.asarray(father), np.asarray(left), np.asarray(right)], axis=-1).astype(np.int16))
+
+
+def pack_events(ev_start, pop_start, ev_type, ev_id):
+    """The arrays of gphocsGenSetEvents -> (evStart32, popStart16, evCode16) of gphocsGenSetEventsPacked."""
+    es = np.asarray(ev_start, np.int64)
+    t = np.asarray(ev_type, np.int64)[es[0]:es[-1]]
+    i = np.asarray(ev_id, np.int64)[es[0]:es[-1]]
+    band = (t == 1) | (t == 3) | (t == 4)          # IN_MIG, MIG_BAND_START, MIG_BAND_END carry a band id
+    code = (t | (np.where(band, i, 0) << 3)).astype(np.uint16)
+    return (es - es[0]).astype(np.int32), np.asarray(pop_start).astype(np.uint16), code
+
+
 def make_ops(locus, type_, a=0, b=0, x=0.0):
     """Edit-record array from broadcastable columns."""
     locus = np.atleast_1d(np.asarray(locus))
@@ -371,6 +395,16 @@ class Genealogy:
         if self.lib.gphocsGenSetEvents(self.h, _lp(es), _ip(_i32(pop_start)), _ip(_i32(ev_type)), _ip(_i32(ev_id)),
                                        _dp(_f64(ev_time))) != 0:
             raise RuntimeError("gphocsGenSetEvents failed")
+
+    def set_events_packed(self, ev_start32, pop_start16, ev_code16, ev_time):
+        """The snapshot in the device's own format, see pack_events."""
+        es = np.ascontiguousarray(ev_start32, np.int32)
+        ps = np.ascontiguousarray(pop_start16, np.uint16)
+        code = np.ascontiguousarray(ev_code16, np.uint16)
+        self.E = int(es[-1])
+        if self.lib.gphocsGenSetEventsPacked(self.h, _ip(es), ps.ctypes.data_as(C.POINTER(C.c_ushort)),
+                                             code.ctypes.data_as(C.POINTER(C.c_ushort)), _dp(_f64(ev_time))) != 0:
+            raise RuntimeError("gphocsGenSetEventsPacked failed")
 
     def evaluate(self, per_locus_stats=True):
         L, Q, B = self.L, self.Q, self.B

@@ -179,6 +179,17 @@ __global__ void k_set_topology32(StoreDev d, const int* __restrict__ father, con
   d.node[i] = r;
 }
 
+// the same for 16-bit (father, left, right) triples; *bad counts ids outside [-1, N-1]
+__global__ void k_set_topology16(StoreDev d, const int16_t* __restrict__ topo, size_t count, int* __restrict__ bad) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const int16_t f = topo[3 * i], l = topo[3 * i + 1], r = topo[3 * i + 2];
+  if (f < -1 || f >= d.N || l < -1 || l >= d.N || r < -1 || r >= d.N) { atomicAdd(bad, 1); return; }
+  NodeRec rec = d.node[i];
+  rec.father = f; rec.left = l; rec.right = r;
+  d.node[i] = rec;
+}
+
 // computeEdgeConditionalJC (.c:1831-1848): off-diagonal JC69 transition probability
 __device__ __forceinline__ double edgeProb(double edgeLength) {
   if (edgeLength < 1e-100) return 0.0;

@@ -216,6 +216,30 @@ __global__ void __launch_bounds__(256) k_gen_pack(const int* __restrict__ evType
   if (wrong) atomicAdd(bad, 1);
 }
 
+// a snapshot that arrived in the device's own format: the same checks k_gen_pack makes while it converts
+__global__ void __launch_bounds__(256) k_gen_check_packed(const uint16_t* __restrict__ code, long long numEvents,
+                                                          const uint16_t* __restrict__ ps, const int* __restrict__ es, int L,
+                                                          int Q, int B, int* __restrict__ bad) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long first = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  int wrong = 0;
+  for (long long e = first; e < numEvents; e += stride) {
+    const int t = code[e] & 7, id = code[e] >> 3;
+    const bool needsBand = (t == EV_IN_MIG || t == EV_BAND_START || t == EV_BAND_END);
+    if (needsBand ? id >= B : id != 0) wrong = 1;
+  }
+  for (long long l = first; l < L; l += stride) {
+    const long long nEv = (long long)es[l + 1] - es[l];
+    if (nEv > 65535 || nEv < 0) wrong = 1;
+    const uint16_t* p = ps + l * (Q + 1);
+    if (p[0] != 0 || (long long)p[Q] != nEv) wrong = 1;
+    for (int q = 0; q < Q; q++)
+      if (p[q + 1] < p[q]) wrong = 1;
+  }
+  if (first == 0 && es[0] != 0) wrong = 1;
+  if (wrong) atomicAdd(bad, 1);
+}
+
 // out[v] = sum over CTAs of ctaTotals[cta][v], fixed order (one block per v)
 __global__ void __launch_bounds__(256) k_gen_reduce(const double* __restrict__ ctaTotals, int numCtas, int V,
                                                     double* __restrict__ out) {

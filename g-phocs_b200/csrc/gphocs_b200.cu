@@ -123,6 +123,7 @@ struct GphocsStore {
   Staging<int16_t> i16;
   int* dTopo32 = nullptr;      // device scratch for int32 topology copied straight from page-locked caller arrays
   size_t topo32Cap = 0;
+  int* dBadTopo = nullptr;
   std::vector<Op> pending;  // edits queued by the scalar API, flushed before the next evaluation
   bool debugMirror = false;  // also mirror SEL/RECALC bits on the host (tests)
   bool opsInFlight = false;  // an edit batch was enqueued without a stream synchronisation
@@ -338,6 +339,7 @@ extern "C" int gphocsStoreDestroy(GphocsStore* s) {
                   d.savedLnL, d.rootScratch, d.ctaSum, s->dMask, s->dBatches, s->dSum};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (s->dTopo32) cudaFree(s->dTopo32);
+  if (s->dBadTopo) cudaFree(s->dBadTopo);
   s->ops.release(); s->seg.release(); s->status.release(); s->ids.release(); s->f64.release(); s->i16.release();
   if (s->ownStream && s->stream) cudaStreamDestroy(s->stream);
   delete s;
@@ -510,6 +512,45 @@ extern "C" int gphocsStoreSetTrees(GphocsStore* s, int nLoci, const int* locusId
                                    const int* right, const double* age, const int* root) {
   std::lock_guard<std::mutex> lk(s->mu);
   return setTreesLocked(s, nLoci, locusIds, father, left, right, age, root);
+}
+
+// genealogies of loci 0..nLoci-1 in the wire format of the device (16-bit topology triples): three copies and one
+// pack kernel; the mirror follows on demand like on the page-locked route above
+extern "C" int gphocsStoreSetTreesPacked(GphocsStore* s, int nLoci, const short* topo, const double* age, const int* root) {
+  std::lock_guard<std::mutex> lk(s->mu);
+  const int N = s->N;
+  cudaSetDevice(s->device);
+  if (nLoci <= 0) return 0;
+  if (nLoci > s->L) { fprintf(stderr, "gphocs_b200: %d genealogies for %d loci\n", nLoci, s->L); return -1; }
+  const size_t cnt = (size_t)nLoci * N;
+  if (s->opsInFlight) {
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    s->opsInFlight = false;
+  }
+  // scratch: the int32 scratch of the page-locked route holds the 16-bit triples as well (3 shorts < 3 ints per node)
+  if (cnt * 3 > s->topo32Cap) {
+    if (s->dTopo32) cudaFree(s->dTopo32);
+    s->dTopo32 = nullptr;
+    s->topo32Cap = 0;
+    if (devAlloc(&s->dTopo32, cnt * 3)) return -1;
+    s->topo32Cap = cnt * 3;
+  }
+  if (!s->dBadTopo && devAlloc(&s->dBadTopo, 1)) return -1;
+  int16_t* dTopo = reinterpret_cast<int16_t*>(s->dTopo32);
+  StoreDev& d = s->d;
+  CUDA_TRY(cudaMemsetAsync(s->dBadTopo, 0, sizeof(int), s->stream));
+  CUDA_TRY(cudaMemcpyAsync(dTopo, topo, sizeof(int16_t) * 3 * cnt, cudaMemcpyHostToDevice, s->stream));
+  CUDA_TRY(cudaMemcpyAsync(d.age, age, sizeof(double) * cnt, cudaMemcpyHostToDevice, s->stream));
+  CUDA_TRY(cudaMemcpyAsync(d.root, root, sizeof(int) * (size_t)nLoci, cudaMemcpyHostToDevice, s->stream));
+  k_set_topology16<<<(unsigned)((cnt + 255) / 256), 256, 0, s->stream>>>(d, dTopo, cnt, s->dBadTopo);
+  g_launches++;
+  CUDA_TRY(cudaGetLastError());
+  int bad = 0;
+  CUDA_TRY(cudaMemcpyAsync(&bad, s->dBadTopo, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+  s->mirrorStale.store(true, std::memory_order_release);
+  CUDA_TRY(cudaStreamSynchronize(s->stream));   // the caller's arrays are free again when the call returns
+  if (bad) { fprintf(stderr, "gphocs_b200: %d node records with ids outside the tree\n", bad); return -1; }
+  return 0;
 }
 
 extern "C" int gphocsStoreGetTrees(GphocsStore* s, int nLoci, const int* locusIds, int* father, int* left, int* right,
@@ -1080,6 +1121,49 @@ extern "C" int gphocsGenSetEvents(GphocsGenealogy* g, const long long* evStart, 
   g->maxTileEvents = maxTile;
   CUDA_TRY(cudaMemcpyAsync(g->dEvStart, es, sizeof(int) * (L + 1), cudaMemcpyHostToDevice, g->stream));
   CUDA_TRY(cudaStreamSynchronize(g->stream));
+  const size_t smem = genSmemBytes(g->Q, g->B, g->maxTileEvents);
+  if (smem > 200 * 1024) { fprintf(stderr, "gphocs_b200: event tile too large for shared memory (%zu bytes)\n", smem); return -1; }
+  CUDA_TRY(cudaFuncSetAttribute(k_gen_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  return 0;
+}
+
+// the snapshot in the device's own format: four copies straight into the final arrays and one checking kernel
+extern "C" int gphocsGenSetEventsPacked(GphocsGenealogy* g, const int* evStart, const unsigned short* popStart,
+                                        const unsigned short* evCode, const double* evTime) {
+  cudaSetDevice(g->device);
+  const int L = g->L, Q = g->Q;
+  const long long E = evStart[L];
+  if (evStart[0] != 0 || E <= 0 || E >= (1ll << 31)) { fprintf(stderr, "gphocs_b200: bad event count %lld\n", E); return -1; }
+  if ((size_t)E > g->evCap) {
+    if (g->dEvTime) cudaFree(g->dEvTime);
+    if (g->dEvCode) cudaFree(g->dEvCode);
+    if (g->dLineages) cudaFree(g->dLineages);
+    g->evCap = (size_t)E + (size_t)E / 8;
+    if (devAlloc(&g->dEvTime, g->evCap) || devAlloc(&g->dEvCode, g->evCap) || devAlloc(&g->dLineages, g->evCap)) return -1;
+  }
+  g->totalEvents = E;
+  if (!g->dBadEvents && devAlloc(&g->dBadEvents, 1)) return -1;
+  const size_t nPs = (size_t)L * (Q + 1);
+  CUDA_TRY(cudaMemsetAsync(g->dBadEvents, 0, sizeof(int), g->stream));
+  CUDA_TRY(cudaMemcpyAsync(g->dEvStart, evStart, sizeof(int) * ((size_t)L + 1), cudaMemcpyHostToDevice, g->stream));
+  CUDA_TRY(cudaMemcpyAsync(g->dPopStart, popStart, sizeof(uint16_t) * nPs, cudaMemcpyHostToDevice, g->stream));
+  CUDA_TRY(cudaMemcpyAsync(g->dEvCode, evCode, sizeof(uint16_t) * (size_t)E, cudaMemcpyHostToDevice, g->stream));
+  CUDA_TRY(cudaMemcpyAsync(g->dEvTime, evTime, sizeof(double) * (size_t)E, cudaMemcpyHostToDevice, g->stream));
+  k_gen_check_packed<<<1184, 256, 0, g->stream>>>(g->dEvCode, E, g->dPopStart, g->dEvStart, L, Q, g->B, g->dBadEvents);
+  g_launches++;
+  CUDA_TRY(cudaGetLastError());
+  int maxTile = 0;   // while the copies are in flight
+  bool bad = false;
+  for (int l0 = 0; l0 < L; l0 += kGenTile) {
+    const int n = evStart[std::min(L, l0 + kGenTile)] - evStart[l0];
+    if (n < 0) bad = true;
+    maxTile = std::max(maxTile, n);
+  }
+  g->maxTileEvents = maxTile;
+  int badCount = 0;
+  CUDA_TRY(cudaMemcpyAsync(&badCount, g->dBadEvents, sizeof(int), cudaMemcpyDeviceToHost, g->stream));
+  CUDA_TRY(cudaStreamSynchronize(g->stream));
+  if (badCount || bad) { g->totalEvents = 0; fprintf(stderr, "gphocs_b200: malformed event snapshot\n"); return -1; }
   const size_t smem = genSmemBytes(g->Q, g->B, g->maxTileEvents);
   if (smem > 200 * 1024) { fprintf(stderr, "gphocs_b200: event tile too large for shared memory (%zu bytes)\n", smem); return -1; }
   CUDA_TRY(cudaFuncSetAttribute(k_gen_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

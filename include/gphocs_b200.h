@@ -126,6 +126,11 @@ int gphocsStoreSetTrees(GphocsStore *s, int nLoci, const int *locusIds, const in
                         const int *right, const double *age, const int *root);
 int gphocsStoreGetTrees(GphocsStore *s, int nLoci, const int *locusIds, int *father, int *left, int *right,
                         double *age, int *root);
+/* The same for loci 0..nLoci-1 in the store's own wire format: topo[nLoci][2*numLeaves-1][3] = father, left,
+ * right as 16-bit ids (the nodeArray fields of LocusDataLikelihood.c:60-66; -1 where absent).  PCIe is what an
+ * end-to-end evaluation waits for, and a host that flattens its genealogies anyway can write 14 instead of 20
+ * bytes per node.  Every id must lie in [-1, 2*numLeaves-2] (checked on the device, -1 returned). */
+int gphocsStoreSetTreesPacked(GphocsStore *s, int nLoci, const short *topo, const double *age, const int *root);
 int gphocsStoreSetRates(GphocsStore *s, int nLoci, const int *locusIds, const double *rates);
 int gphocsStoreGetRates(GphocsStore *s, int nLoci, const int *locusIds, double *rates);
 
@@ -186,6 +191,11 @@ int gphocsGenSetParams(GphocsGenealogy *g, const double *theta, const double *mi
  * recalcStats resolves it at patch.c:2425) and elapsed_time. */
 int gphocsGenSetEvents(GphocsGenealogy *g, const long long *evStart, const int *popStart, const int *evType,
                        const int *evId, const double *evTime);
+/* The same snapshot in the device's own format (10 instead of 16 bytes per event on the wire): evStart[numLoci+1]
+ * 32-bit with evStart[0] == 0, popStart 16-bit, evCode = type | band << 3 (band = 0 unless the event is
+ * IN_MIG / MIG_BAND_START / MIG_BAND_END), elapsed times as above.  Malformed codes or offsets: -1. */
+int gphocsGenSetEventsPacked(GphocsGenealogy *g, const int *evStart, const unsigned short *popStart,
+                             const unsigned short *evCode, const double *evTime);
 /* computeGenetreeStats + gtreeLnLikelihood for every locus, computeTotalStats over them.
  * Host outputs (any may be NULL): lnL[numLoci]; per-locus stats coal[numLoci][numPops],
  * numCoals[numLoci][numPops], mig[numLoci][numBands], numMigs[numLoci][numBands];

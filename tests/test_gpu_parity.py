@@ -381,3 +381,56 @@ def test_page_locked_event_snapshot_takes_the_direct_route():
     for key in ("lnl", "coal", "num_coals", "mig", "num_migs", "total_coal", "total_num_coals", "total_mig", "total_num_migs"):
         assert np.array_equal(a[key], b[key]), key
     assert a["sum_lnl"] == b["sum_lnl"]
+
+
+def test_packed_wire_formats_equal_the_plain_ones():
+    """gphocsStoreSetTreesPacked / gphocsGenSetEventsPacked (16-bit topology and event codes on the wire) leave the
+    device in the state gphocsStoreSetTrees / gphocsGenSetEvents leave it in: genealogies, mirror, every
+    log-likelihood and statistic bit for bit; malformed packed input is refused."""
+    w = synth.generate(synth.config("pop6mig4"), 2000, seed=23)
+    a = gp.LociStore.from_workload(w)
+    b = gp.LociStore(w.n, w.patt_start, w.unph_start, w.chars, w.num_phases, w.counts)
+    topo = gp.pack_trees(w.father, w.left, w.right)
+    assert topo.dtype == np.int16 and topo.shape == (w.L, 2 * w.n - 1, 3)
+    for pinned in (False, True):
+        t, ag, ro = (gp.pinned_like(x) for x in (topo, w.age, w.root)) if pinned else (topo, w.age, w.root)
+        b.set_trees_packed(t, ag, ro)
+        if not pinned:
+            b.set_rates(w.rate)
+        for x, y in zip(a.get_trees(), b.get_trees()):
+            assert np.array_equal(x, y)
+        assert b.check_mirror() == 0
+        assert np.array_equal(a.evaluate(0), b.evaluate(0))
+    bad = topo.copy()
+    bad[7, 3, 1] = 2 * w.n - 1                                # a son outside the tree
+    with pytest.raises(RuntimeError):
+        b.set_trees_packed(bad, w.age, w.root)
+    a.close(); b.close()
+
+    es, ps, code = gp.pack_events(w.ev_start, w.pop_start, w.ev_type, w.ev_id)
+    assert es.dtype == np.int32 and ps.dtype == np.uint16 and code.dtype == np.uint16
+    ga = gp.Genealogy(w.L, w.pops)
+    ga.set_events(w.ev_start, w.pop_start, w.ev_type, w.ev_id, w.ev_time)
+    ra = ga.evaluate()
+    gb = gp.Genealogy(w.L, w.pops)
+    for pinned in (False, True):
+        arrs = (es, ps, code, w.ev_time)
+        if pinned:
+            arrs = tuple(gp.pinned_like(x) for x in arrs)
+        gb.set_events_packed(*arrs)
+        rb = gb.evaluate()
+        for key in ("lnl", "coal", "num_coals", "mig", "num_migs", "total_coal", "total_num_coals", "total_mig", "total_num_migs"):
+            assert np.array_equal(ra[key], rb[key]), key
+        assert ra["sum_lnl"] == rb["sum_lnl"]
+    nb = len(w.pops["band_src"])
+    for k, v in ((5, 7 | (1 << 3)),                           # a band id on an event that carries none
+                 (int(np.flatnonzero((code & 7) == 3)[0]), 3 | (nb << 3))):   # a band that does not exist
+        wrong = code.copy()
+        wrong[k] = v
+        with pytest.raises(RuntimeError):
+            gb.set_events_packed(es, ps, wrong, w.ev_time)
+    wrong = ps.copy()
+    wrong[11, 2] = wrong[11, 3] + 1                           # chains out of order
+    with pytest.raises(RuntimeError):
+        gb.set_events_packed(es, wrong, code, w.ev_time)
+    ga.close(); gb.close()
