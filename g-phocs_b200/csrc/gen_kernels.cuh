@@ -9,11 +9,13 @@
 //   evTime[e]  fp64 elapsed_time,  evCode[e] = type | id << 3  (id = migration band where relevant)
 // i.e. 10 bytes per event instead of the reference's 32-byte linked-list node.
 //
-// A CTA stages the events of a tile of 32 loci in shared memory with coalesced loads; then one thread per
-// locus walks the populations in post-order (lineages entering an ancestral population = lineages its sons
-// end with) and every chain in the reference's event order, accumulating n(n-1)t and n*t per live band.
-// Per-population sums are sequential in chain order and products are not fused, so the statistics and the
-// log-density are bit-identical to the reference on the same elapsed times.  Totals are reduced per CTA and then by a
+// A CTA stages the events of a tile of 32 loci in shared memory with coalesced loads, then works per
+// (population, locus) chain with the loci of the tile as the lanes of a warp: pass A sums the lineage deltas of
+// each chain, a per-locus post-order sweep over the population tree turns them into lineages entering each
+// population, pass B re-walks each chain in the reference's event order accumulating n(n-1)t and n*t per live
+// band and leaves the chain's term of the log-density.  Per-population sums are sequential in chain order and
+// products are not fused, so the statistics and the log-density are bit-identical to the reference on the same
+// elapsed times.  Totals are reduced per CTA and then by a
 // fixed-order second kernel (deterministic run to run).
 #pragma once
 #include <cuda_runtime.h>
@@ -57,7 +59,7 @@ struct GenDev {
 
 __host__ __device__ inline int genTotalsLen(int Q, int B) { return 1 + 2 * Q + 2 * B; }
 
-__global__ void __launch_bounds__(kGenThreads) k_gen_eval(GenDev d, int maxTileEvents) {
+__global__ void __launch_bounds__(kGenThreads) k_gen_eval(GenDev d, int maxTileEvents, const __grid_constant__ GenParams prm) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int tid = threadIdx.x;
   const int Q = d.Q, B = d.B, V = genTotalsLen(Q, B);
@@ -67,47 +69,98 @@ __global__ void __launch_bounds__(kGenThreads) k_gen_eval(GenDev d, int maxTileE
   double* sTime = reinterpret_cast<double*>(smem);                     // [maxTileEvents]
   double* sMig = sTime + maxTileEvents;                                // [tile][B]
   double* sCoal = sMig + kGenTile * B;                                 // [tile][Q]
-  double* sTot = sCoal + kGenTile * Q;                                 // [V]
+  double* sTermP = sCoal + kGenTile * Q;                               // [tile][Q] chain terms of the log-density
+  double* sTot = sTermP + kGenTile * Q;                                // [V]
   double* sLnL = sTot + V;                                             // [tile]
-  int* sDelta = reinterpret_cast<int*>(sLnL + kGenTile);               // [tile][Q] lineages at the end of each chain
-  int* sNumCoals = sDelta + kGenTile * Q;                              // [tile][Q]
+  int* sNumCoals = reinterpret_cast<int*>(sLnL + kGenTile);            // [tile][Q]
   int* sNumMigs = sNumCoals + kGenTile * Q;                            // [tile][B]
   int* sEvBase = sNumMigs + kGenTile * B;                              // [tile+1] event offsets relative to tile
   uint16_t* sCode = reinterpret_cast<uint16_t*>(sEvBase + kGenTile + 1);  // [maxTileEvents]
   uint16_t* sPopStart = sCode + maxTileEvents;                         // [tile][Q+1]
-  __shared__ GenParams prm;
+  int16_t* sDelta = reinterpret_cast<int16_t*>(sPopStart + kGenTile * (Q + 1));  // [tile][Q] lineage delta, then n at chain start
+  uint8_t* sEnd = reinterpret_cast<uint8_t*>(sDelta + kGenTile * Q);   // [tile][Q] lineages at the end of each chain
+  // the model (populations, bands, parameters: 2.9 KB) arrives in the kernel's parameter space: every index into it
+  // is uniform over a warp, so reads are constant-cache broadcasts and no CTA spends a round trip staging it
 
-  for (int i = tid; i < (int)(sizeof(GenParams) / sizeof(int)); i += kGenThreads)
-    reinterpret_cast<int*>(&prm)[i] = reinterpret_cast<const int*>(d.params)[i];
   const int e0 = d.evStart[l0];
   const int tileEvents = d.evStart[l0 + nl] - e0;
   if (tid <= nl) sEvBase[tid] = d.evStart[l0 + tid] - e0;
-  for (int i = tid; i < tileEvents; i += kGenThreads) {
-    sTime[i] = d.evTime[e0 + i];
-    sCode[i] = d.evCode[e0 + i];
+  // staging: four loads in flight per thread and array before the first store (the trip count is not known to the
+  // compiler, which would otherwise wait for every load in turn)
+  {
+    const double* __restrict__ gt = d.evTime + e0;
+    const uint16_t* __restrict__ gc = d.evCode + e0;
+    int i = tid;
+    for (; i + 3 * kGenThreads < tileEvents; i += 4 * kGenThreads) {
+      const double t0 = gt[i], t1 = gt[i + kGenThreads], t2 = gt[i + 2 * kGenThreads], t3 = gt[i + 3 * kGenThreads];
+      const uint16_t c0 = gc[i], c1 = gc[i + kGenThreads], c2 = gc[i + 2 * kGenThreads], c3 = gc[i + 3 * kGenThreads];
+      sTime[i] = t0; sTime[i + kGenThreads] = t1; sTime[i + 2 * kGenThreads] = t2; sTime[i + 3 * kGenThreads] = t3;
+      sCode[i] = c0; sCode[i + kGenThreads] = c1; sCode[i + 2 * kGenThreads] = c2; sCode[i + 3 * kGenThreads] = c3;
+    }
+    for (; i < tileEvents; i += kGenThreads) {
+      sTime[i] = gt[i];
+      sCode[i] = gc[i];
+    }
+    const uint16_t* __restrict__ gp = d.popStart + (size_t)l0 * (Q + 1);
+    const int np = nl * (Q + 1);
+    i = tid;
+    for (; i + 2 * kGenThreads < np; i += 3 * kGenThreads) {
+      const uint16_t p0 = gp[i], p1 = gp[i + kGenThreads], p2 = gp[i + 2 * kGenThreads];
+      sPopStart[i] = p0; sPopStart[i + kGenThreads] = p1; sPopStart[i + 2 * kGenThreads] = p2;
+    }
+    for (; i < np; i += kGenThreads) sPopStart[i] = gp[i];
   }
-  for (int i = tid; i < nl * (Q + 1); i += kGenThreads) sPopStart[i] = d.popStart[(size_t)l0 * (Q + 1) + i];
   for (int i = tid; i < kGenTile * B; i += kGenThreads) { sMig[i] = 0.0; sNumMigs[i] = 0; }
   for (int i = tid; i < V; i += kGenThreads) sTot[i] = 0.0;
   __syncthreads();
 
-  // One thread per locus walks the whole genealogy: populations in post-order (patch.c:2336-2347: an ancestral
-  // population starts with the lineages its two sons end with, a leaf population with none), every chain in the
-  // reference's event order accumulating n(n-1)t and n*t per live band (patch.c:2403-2486), then the log-density
-  // (patch.c:2709-2723).  The 32 loci of the tile are the lanes of one warp: chains of a population are about
-  // equally long in every locus, so the lanes stay together, and the whole tile costs one chain walk instead of
-  // one per (locus, population).
-  if (tid < nl) {
-    const int j = tid;
-    const int eb = sEvBase[j];
+  // Work items are (population, locus) chains with the 32 loci of the tile as the lanes of a warp: chains of one
+  // population are about equally long in every locus, so the lanes stay together; the warps take the populations
+  // in turn.
+  const int lane = tid & 31, warp = tid >> 5;
+  constexpr int kGenWarps = kGenThreads / 32;
+  // pass A: net lineage change of each chain (SAMPLES_START +samples, COAL -1, IN_MIG -1, OUT_MIG +1); event types only
+  if (lane < nl) {
+    const int j = lane, eb = sEvBase[j];
     const uint16_t* ps = sPopStart + j * (Q + 1);
-    int* nEnd = sDelta + j * Q;        // lineages at the end of each chain
+    for (int p = warp; p < Q; p += kGenWarps) {
+      const int a = eb + ps[p], b = eb + ps[p + 1];
+      const int smp = prm.samplesPerPop[p];
+      int delta = 0;
+      for (int e = a; e < b; e++) {
+        const int type = sCode[e] & 7;
+        delta += type == EV_SAMPLES_START ? smp : (type == EV_COAL || type == EV_IN_MIG) ? -1 : type == EV_OUT_MIG ? 1 : 0;
+      }
+      sDelta[j * Q + p] = (int16_t)delta;
+    }
+  }
+  __syncthreads();
+  // lineages entering each population: post-order over the population tree (patch.c:2336-2347); the deltas are
+  // replaced by the number of lineages at the start of the chain
+  if (tid < nl) {
+    int16_t* dl = sDelta + tid * Q;
+    for (int i = 0; i < Q; i++) {
+      const int p = prm.postOrder[i];
+      int n0 = 0;
+      if (p >= prm.C) {
+        const int s0 = prm.son0[p], s1 = prm.son1[p];
+        n0 = sEnd[tid * Q + s0] + sEnd[tid * Q + s1];
+      }
+      sEnd[tid * Q + p] = (uint8_t)(n0 + dl[p]);
+      dl[p] = (int16_t)n0;
+    }
+  }
+  __syncthreads();
+  // pass B: statistics per chain in the reference's order of operations (patch.c:2403-2486), and the chain's term of
+  // the log-density (patch.c:2709-2712) — the division is the expensive part of it and is off the per-locus sum
+  if (lane < nl) {
+    const int j = lane, eb = sEvBase[j];
+    const uint16_t* ps = sPopStart + j * (Q + 1);
     double* mg = sMig + j * B;
     int* nm = sNumMigs + j * B;
     const bool wantLineages = d.evLineages != nullptr;
-    for (int i = 0; i < Q; i++) {
-      const int p = prm.postOrder[i];
-      int n = p >= prm.C ? nEnd[prm.son0[p]] + nEnd[prm.son1[p]] : 0;
+    for (int p = warp; p < Q; p += kGenWarps) {
+      int n = sDelta[j * Q + p];
       const int a = eb + ps[p], b = eb + ps[p + 1];
       int ncoal = 0;
       double coal = 0.0;
@@ -125,7 +178,8 @@ __global__ void __launch_bounds__(kGenThreads) k_gen_eval(GenDev d, int maxTileE
         tNext = sTime[en]; codeNext = sCode[en];
         if (wantLineages) d.evLineages[e0 + e] = (uint8_t)n;
         coal = __dadd_rn(coal, __dmul_rn((double)(n * (n - 1)), t));
-        // everything that touches a migration band: statistics of the live bands, band start / end, migrations
+        // everything that touches a migration band: statistics of the live bands, band start / end, migrations.
+        // A band's events lie in its target population's chain, so no two threads of a locus share a band.
         if ((live0 | live1) != 0ull || (type >= EV_IN_MIG && type <= EV_BAND_END)) {
           const int id = code >> 3;
           if (live0 | live1) {
@@ -140,17 +194,17 @@ __global__ void __launch_bounds__(kGenThreads) k_gen_eval(GenDev d, int maxTileE
         ncoal += type == EV_COAL;
         n += type == EV_SAMPLES_START ? smp : (type == EV_COAL || type == EV_IN_MIG) ? -1 : type == EV_OUT_MIG ? 1 : 0;
       }
-      nEnd[p] = n;
       sCoal[j * Q + p] = coal;
       sNumCoals[j * Q + p] = ncoal;
+      sTermP[j * Q + p] = __dsub_rn(__dmul_rn((double)ncoal, prm.log2OverTheta[p]), __ddiv_rn(coal, prm.theta[p]));
     }
-    // per-locus log-density (patch.c:2709-2723)
+  }
+  __syncthreads();
+  // per-locus log-density (patch.c:2709-2723): the chains' terms in population order, then the bands'
+  if (tid < nl) {
+    const int j = tid;
     double lnLd = 0.0;
-    for (int p = 0; p < Q; p++) {
-      const double term = __dsub_rn(__dmul_rn((double)sNumCoals[j * Q + p], prm.log2OverTheta[p]),
-                                    __ddiv_rn(sCoal[j * Q + p], prm.theta[p]));
-      lnLd = __dadd_rn(lnLd, term);
-    }
+    for (int p = 0; p < Q; p++) lnLd = __dadd_rn(lnLd, sTermP[j * Q + p]);
     for (int bnd = 0; bnd < B; bnd++) {
       const double m = prm.migRate[bnd];
       if (m > 0.0) {
@@ -175,14 +229,20 @@ __global__ void __launch_bounds__(kGenThreads) k_gen_eval(GenDev d, int maxTileE
   // per-CTA totals, fixed order over the tile's loci
   for (int v = tid; v < V; v += kGenThreads) {
     double acc = 0.0;
-    for (int j = 0; j < nl; j++) {
-      double x;
-      if (v == 0) x = sLnL[j];
-      else if (v < 1 + Q) x = sCoal[j * Q + (v - 1)];
-      else if (v < 1 + 2 * Q) x = (double)sNumCoals[j * Q + (v - 1 - Q)];
-      else if (v < 1 + 2 * Q + B) x = sMig[j * B + (v - 1 - 2 * Q)];
-      else x = (double)sNumMigs[j * B + (v - 1 - 2 * Q - B)];
-      acc += x;
+    if (v == 0) {
+      for (int j = 0; j < nl; j++) acc += sLnL[j];
+    } else if (v < 1 + Q) {
+      const double* x = sCoal + (v - 1);
+      for (int j = 0; j < nl; j++) acc += x[j * Q];
+    } else if (v < 1 + 2 * Q) {
+      const int* x = sNumCoals + (v - 1 - Q);
+      for (int j = 0; j < nl; j++) acc += (double)x[j * Q];
+    } else if (v < 1 + 2 * Q + B) {
+      const double* x = sMig + (v - 1 - 2 * Q);
+      for (int j = 0; j < nl; j++) acc += x[j * B];
+    } else {
+      const int* x = sNumMigs + (v - 1 - 2 * Q - B);
+      for (int j = 0; j < nl; j++) acc += (double)x[j * B];
     }
     d.ctaTotals[(size_t)blockIdx.x * V + v] = acc;
   }
@@ -258,10 +318,10 @@ __global__ void __launch_bounds__(256) k_gen_reduce(const double* __restrict__ c
 
 __host__ __device__ inline size_t genSmemBytes(int Q, int B, int maxTileEvents) {
   const int V = genTotalsLen(Q, B);
-  size_t bytes = (size_t)maxTileEvents * 8 + (size_t)kGenTile * B * 8 + (size_t)kGenTile * Q * 8 + (size_t)V * 8 +
+  size_t bytes = (size_t)maxTileEvents * 8 + (size_t)kGenTile * B * 8 + (size_t)kGenTile * Q * 8 * 2 + (size_t)V * 8 +
                  (size_t)kGenTile * 8;
-  bytes += (size_t)kGenTile * Q * 4 * 2 + (size_t)kGenTile * B * 4 + (size_t)(kGenTile + 1) * 4;
-  bytes += (size_t)maxTileEvents * 2 + (size_t)kGenTile * (Q + 1) * 2;
+  bytes += (size_t)kGenTile * Q * 4 + (size_t)kGenTile * B * 4 + (size_t)(kGenTile + 1) * 4;
+  bytes += (size_t)maxTileEvents * 2 + (size_t)kGenTile * (Q + 1) * 2 + (size_t)kGenTile * Q * 3;
   return bytes + 32;
 }
 

@@ -1179,7 +1179,7 @@ static int genLaunch(GphocsGenealogy* g, bool wantLineages) {
   d.evLineages = wantLineages ? g->dLineages : nullptr;
   d.params = g->dParams;
   const size_t smem = genSmemBytes(g->Q, g->B, g->maxTileEvents);
-  k_gen_eval<<<g->numCtas, kGenThreads, smem, g->stream>>>(d, g->maxTileEvents);
+  k_gen_eval<<<g->numCtas, kGenThreads, smem, g->stream>>>(d, g->maxTileEvents, g->hp);
   k_gen_reduce<<<g->V, 256, 0, g->stream>>>(g->d.ctaTotals, g->numCtas, g->V, g->dTotals);
   g_launches += 2;
   CUDA_TRY(cudaGetLastError());
