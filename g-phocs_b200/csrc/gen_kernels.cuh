@@ -59,6 +59,10 @@ struct GenDev {
 
 __host__ __device__ inline int genTotalsLen(int Q, int B) { return 1 + 2 * Q + 2 * B; }
 
+// lineages gained by an event of the given type, SAMPLES_START aside: COAL -1, IN_MIG -1, OUT_MIG +1, others 0
+// (recalcStats' switch, patch.c:2415-2484) — 4-bit two's complement entries of a table in a register
+__device__ __forceinline__ int lineageStep(int type) { return ((int)(0x000001ffu << (28 - 4 * type))) >> 28; }
+
 __global__ void __launch_bounds__(kGenThreads) k_gen_eval(GenDev d, int maxTileEvents, const __grid_constant__ GenParams prm) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int tid = threadIdx.x;
@@ -129,7 +133,7 @@ __global__ void __launch_bounds__(kGenThreads) k_gen_eval(GenDev d, int maxTileE
       int delta = 0;
       for (int e = a; e < b; e++) {
         const int type = sCode[e] & 7;
-        delta += type == EV_SAMPLES_START ? smp : (type == EV_COAL || type == EV_IN_MIG) ? -1 : type == EV_OUT_MIG ? 1 : 0;
+        delta += type == EV_SAMPLES_START ? smp : lineageStep(type);
       }
       sDelta[j * Q + p] = (int16_t)delta;
     }
@@ -192,7 +196,7 @@ __global__ void __launch_bounds__(kGenThreads) k_gen_eval(GenDev d, int maxTileE
           else if (type == EV_BAND_END) { if (id < 64) live0 &= ~(1ull << id); else live1 &= ~(1ull << (id - 64)); }
         }
         ncoal += type == EV_COAL;
-        n += type == EV_SAMPLES_START ? smp : (type == EV_COAL || type == EV_IN_MIG) ? -1 : type == EV_OUT_MIG ? 1 : 0;
+        n += type == EV_SAMPLES_START ? smp : lineageStep(type);
       }
       sCoal[j * Q + p] = coal;
       sNumCoals[j * Q + p] = ncoal;

@@ -318,6 +318,7 @@ extern "C" GphocsStore* gphocsStoreCreate(int device, int numLoci, int numLeaves
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_eval, kThreads, s->smemBytes);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     s->prefetchAhead = std::max(1, perSm) * std::max(1, sms);
+    if (const char* e = getenv("GPHOCS_EVAL_PREFETCH")) if (atoi(e) == 0) s->prefetchAhead = 0;
   }
   // ---- host mirror
   s->hNode.assign(LN, NodeRec{-1, -1, -1, 0, 0}); s->hsNode.assign(LN, NodeRec{-1, -1, -1, 0, 0});

@@ -2,12 +2,10 @@
 mkdir -p gpurun_out
 OUT=gpurun_out/variants.log
 : > $OUT
-run() { GPHOCS_EVAL_SMEM_BUDGET=$2 timeout 120 python scripts/keval_variants.py $1 ${3:-pop6mig4} ${4:-100000} 2>&1 | tail -1 >> $OUT; }
-run g-phocs_b200/csrc/libgphocs_b200.so 65536
-run gpurun_variants/lib_k3b0.so 65536
-run gpurun_variants/lib_k3b9.so 65536
-run gpurun_variants/lib_k2b0.so 18400
-run gpurun_variants/lib_k2b10.so 22300
-run gpurun_variants/lib_k2b10.so 20200
-nvidia-smi --query-gpu=clocks.sm,clocks.mem,power.draw,clocks_throttle_reasons.active --format=csv >> $OUT
+run() { timeout 120 python scripts/keval_variants.py $1 ${2:-pop6mig4} ${3:-100000} 2>&1 | tail -1 >> $OUT; }
+run g-phocs_b200/csrc/libgphocs_b200.so
+GPHOCS_EVAL_PREFETCH=0 run g-phocs_b200/csrc/libgphocs_b200.so
+for v in sel lf sellf; do run gpurun_variants/lib_$v.so; done
+run g-phocs_b200/csrc/libgphocs_b200.so hap16
+run gpurun_variants/lib_sellf.so hap16
 cat $OUT
