@@ -121,7 +121,11 @@ int gphocsStoreNumLeaves(const GphocsStore *s);
 long long gphocsStoreNumColumns(const GphocsStore *s);
 long long gphocsStoreDeviceBytes(const GphocsStore *s);
 
-/* genealogies host -> device.  locusIds NULL = loci 0..nLoci-1.  Arrays are [nLoci][2*numLeaves-1]. */
+/* genealogies host -> device.  locusIds NULL = loci 0..nLoci-1.  Arrays are [nLoci][2*numLeaves-1].
+ * Page-locked arrays (gphocsHostAlloc) covering all loci are read by the DMA engine where they are.  On that route,
+ * and with gphocsStoreSetTreesPacked, the host mirror behind getNodeAge / getNodeFather / getNodeSon / getLocusRoot
+ * is not updated by the call: its next reader (those getters, an edit batch, gphocsStoreGetTrees) refreshes it from
+ * the device copy, so a loop that only sets genealogies and evaluates never pays for it. */
 int gphocsStoreSetTrees(GphocsStore *s, int nLoci, const int *locusIds, const int *father, const int *left,
                         const int *right, const double *age, const int *root);
 int gphocsStoreGetTrees(GphocsStore *s, int nLoci, const int *locusIds, int *father, int *left, int *right,
