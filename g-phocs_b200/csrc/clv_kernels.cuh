@@ -342,6 +342,8 @@ k_eval(StoreDev d, const Batch* __restrict__ batches, int batchBase, int useOld,
         if (v >= n) need[v] = 1;
       } else if (nd[v].flags & F_RECALC) {
         int u = v < n ? nd[v].father : v;  // a moved leaf dirties its father (.c:1569-1575)
+        // lanes may walk the same ancestors at once: every writer stores the same 1 and a reader that misses it only
+        // walks a little further (racecheck reports these read/write pairs as warnings; they are the only ones)
         for (int it = 0; u >= 0 && !need[u] && it < N; it++) {
           need[u] = 1;
           u = nd[u].father;
