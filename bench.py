@@ -247,6 +247,27 @@ def device_mcmc(gp, synth, device, total_loci, iterations, rank=0, world=1, cfg=
     return out
 
 
+class quiet_stdout:
+    """Sends file descriptor 1 to /dev/null for the duration (C code called through ctypes writes there directly)."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        self.null = os.open(os.devnull, os.O_WRONLY)
+        os.dup2(self.null, 1)
+
+    def __exit__(self, *exc):
+        try:
+            import ctypes
+            ctypes.CDLL(None).fflush(None)     # what the C side still buffers goes to /dev/null too
+        except Exception:
+            pass
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+        os.close(self.null)
+        return False
+
+
 def ingest_bench(gp, synth, device, cfg="dip8mig", loci=10_000, ref_loci=1500):
     """Alignment ingest (header group E): sequence file -> initializeLocusData's arguments.
     Product: text parse on the host threads + k_ingest (two passes) on the device, timed separately.  Reference:
@@ -275,7 +296,8 @@ def ingest_bench(gp, synth, device, cfg="dip8mig", loci=10_000, ref_loci=1500):
             from oracle import ingest as oi
             if ob.have_ref():
                 t0 = time.perf_counter()
-                r = oi.reference_ingest(path, names, ref_loci)
+                with quiet_stdout():      # the reference reports its progress on stdout; this script prints one JSON line
+                    r = oi.reference_ingest(path, names, ref_loci)
                 dt = time.perf_counter() - t0
                 out["reference"] = {"loci": len(r), "loci_per_s": len(r) / dt, "cores": 1,
                                     "sample": f"first {ref_loci} loci of the same file, single thread (the reference ingest is serial)"}
