@@ -514,32 +514,16 @@ k_eval(StoreDev d, const Batch* __restrict__ batches, int batchBase, int useOld,
       char* clvCol = reinterpret_cast<char*>(d.clv + (size_t)mColStart[s] * NI * 8 + (size_t)p * 4);
       uint32_t entry = smemAddr(sSched(s));
       // pv = the vector computed by the previous entry (the register-resident top of the stack)
-      auto leafValue = [&](uint32_t off, double (&v)[4]) {
-        // conditional vector of a leaf from its 4-bit base mask (computeLeafConditionals, .c:1336-1386):
-        // 1.0 = 0x3ff00000'00000000 where the bit is set, 0.0 elsewhere
-        const uint32_t m = ldsU32(myWords + (off & 0xffffu)) >> (off >> 16);
-#if defined(GPHOCS_LEAF_SELECT)
-#pragma unroll
-        for (int q = 0; q < 4; q++) v[q] = (m >> q) & 1u ? 1.0 : 0.0;
-#else
-#pragma unroll
-        for (int q = 0; q < 4; q++) v[q] = __hiloint2double((int)(((m >> q) & 1u) * 0x3ff00000u), 0);
-#endif
-      };
       auto childValue = [&](uint32_t kind, uint32_t off, double (&v)[4]) {
-#if defined(GPHOCS_LEAF_FIRST)
-        if (kind == SRC_LEAF) {
-          leafValue(off, v);
-        } else if (kind == SRC_TOP) {
-#pragma unroll
-          for (int q = 0; q < 4; q++) v[q] = pv[q];
-#else
         if (kind == SRC_TOP) {
 #pragma unroll
           for (int q = 0; q < 4; q++) v[q] = pv[q];
         } else if (kind == SRC_LEAF) {
-          leafValue(off, v);
-#endif
+          // conditional vector of a leaf from its 4-bit base mask (computeLeafConditionals, .c:1336-1386):
+          // 1.0 = 0x3ff00000'00000000 where the bit is set, 0.0 elsewhere
+          const uint32_t m = ldsU32(myWords + (off & 0xffffu)) >> (off >> 16);
+#pragma unroll
+          for (int q = 0; q < 4; q++) v[q] = __hiloint2double((int)(((m >> q) & 1u) * 0x3ff00000u), 0);
         } else if (kind == SRC_STACK) {
           const uint32_t a = myStack + (off >> 16);
           const double2 x = ldsD2(a), y = ldsD2(a + kHi);
