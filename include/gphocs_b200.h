@@ -133,7 +133,8 @@ int gphocsStoreGetTrees(GphocsStore *s, int nLoci, const int *locusIds, int *fat
 /* The same for loci 0..nLoci-1 in the store's own wire format: topo[nLoci][2*numLeaves-1][3] = father, left,
  * right as 16-bit ids (the nodeArray fields of LocusDataLikelihood.c:60-66; -1 where absent).  PCIe is what an
  * end-to-end evaluation waits for, and a host that flattens its genealogies anyway can write 14 instead of 20
- * bytes per node.  Every id must lie in [-1, 2*numLeaves-2] (checked on the device, -1 returned). */
+ * bytes per node.  Every id must lie in [-1, 2*numLeaves-2] (checked on the device; on -1 the genealogies of the
+ * store are undefined until the next successful upload). */
 int gphocsStoreSetTreesPacked(GphocsStore *s, int nLoci, const short *topo, const double *age, const int *root);
 int gphocsStoreSetRates(GphocsStore *s, int nLoci, const int *locusIds, const double *rates);
 int gphocsStoreGetRates(GphocsStore *s, int nLoci, const int *locusIds, double *rates);
@@ -197,7 +198,8 @@ int gphocsGenSetEvents(GphocsGenealogy *g, const long long *evStart, const int *
                        const int *evId, const double *evTime);
 /* The same snapshot in the device's own format (10 instead of 16 bytes per event on the wire): evStart[numLoci+1]
  * 32-bit with evStart[0] == 0, popStart 16-bit, evCode = type | band << 3 (band = 0 unless the event is
- * IN_MIG / MIG_BAND_START / MIG_BAND_END), elapsed times as above.  Malformed codes or offsets: -1. */
+ * IN_MIG / MIG_BAND_START / MIG_BAND_END), elapsed times as above.  Malformed codes or offsets: -1, and the object
+ * holds no snapshot until the next successful call. */
 int gphocsGenSetEventsPacked(GphocsGenealogy *g, const int *evStart, const unsigned short *popStart,
                              const unsigned short *evCode, const double *evTime);
 /* computeGenetreeStats + gtreeLnLikelihood for every locus, computeTotalStats over them.
