@@ -418,7 +418,7 @@ static int refreshMirrorLocked(GphocsStore* s) {
   return 0;
 }
 // for readers that do not hold the store's mutex (the scalar API's getters: one relaxed load on the fast path)
-void ensureMirror(GphocsStore* s) {
+static void ensureMirror(GphocsStore* s) {
   if (__builtin_expect(s->mirrorStale.load(std::memory_order_acquire), 0)) {
     std::lock_guard<std::mutex> lk(s->mu);
     refreshMirrorLocked(s);
