@@ -171,9 +171,11 @@ __global__ void k_set_trees(StoreDev d, const int* __restrict__ ids, const int16
 // the same for loci 0..nLoci-1 whose int32 topology arrays were copied to the device as they are (ages and roots
 // went straight to their final arrays)
 __global__ void k_set_topology32(StoreDev d, const int* __restrict__ father, const int* __restrict__ left,
-                                 const int* __restrict__ right, size_t count) {
+                                 const int* __restrict__ right, size_t count, int* __restrict__ bad) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= count) return;
+  const int f = father[i], l = left[i], rr = right[i];
+  if (f < -1 || f >= d.N || l < -1 || l >= d.N || rr < -1 || rr >= d.N) { atomicAdd(bad, 1); return; }
   NodeRec r = d.node[i];
   r.father = (int16_t)father[i]; r.left = (int16_t)left[i]; r.right = (int16_t)right[i];
   d.node[i] = r;

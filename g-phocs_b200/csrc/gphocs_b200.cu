@@ -49,6 +49,22 @@ static int devAlloc(T** p, size_t count) {
   return 0;
 }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is one setting per function and device, shared by every store /
+// genealogy / sampler of the process: only ever raise it (per function: the largest request seen so far), so that a
+// second object with a smaller need cannot lower the limit under the first one's next launch.
+static int raiseDynamicSmem(const void* func, size_t bytes) {
+  static std::mutex mu;
+  static std::vector<std::pair<const void*, size_t>> seen;
+  std::lock_guard<std::mutex> lk(mu);
+  size_t want = bytes;
+  bool found = false;
+  for (auto& e : seen)
+    if (e.first == func) { found = true; e.second = want = std::max(e.second, bytes); }
+  if (!found) seen.emplace_back(func, bytes);
+  CUDA_TRY(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)want));
+  return 0;
+}
+
 // growable pinned host + device buffer pair
 template <typename T>
 struct Staging {
@@ -129,6 +145,7 @@ struct GphocsStore {
   bool debugMirror = false;  // also mirror SEL/RECALC bits on the host (tests)
   bool opsInFlight = false;  // an edit batch was enqueued without a stream synchronisation
   std::atomic<bool> mirrorStale{false};  // topology / ages / roots of the mirror are behind the device copy (refreshMirrorLocked)
+  std::atomic<bool> lnlStale{false};     // lnL / savedLnL of the mirror are behind it (gphocsStoreEvaluateDevice, the sampler)
   std::mutex mu;
 
   TreeView hostView(int l) {
@@ -308,8 +325,7 @@ extern "C" GphocsStore* gphocsStoreCreate(int device, int numLoci, int numLeaves
     delete s;
     return nullptr;
   }
-  if (cudaFuncSetAttribute(k_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smemBytes) != cudaSuccess ||
-      cudaDeviceSynchronize() != cudaSuccess) {
+  if (raiseDynamicSmem((const void*)k_eval, s->smemBytes) != 0 || cudaDeviceSynchronize() != cudaSuccess) {
     fprintf(stderr, "gphocs_b200: device initialisation failed: %s\n", cudaGetErrorString(cudaGetLastError()));
     delete s;
     return nullptr;
@@ -397,6 +413,13 @@ extern "C" int gphocsStoreSync(GphocsStore* s) {
 // reads the mirror next — an edit batch, a getter of the scalar API, gphocsStoreGetTrees, the mirror check — brings
 // it up to date from the device copy first.  Flag bytes of the mirror are its own and are kept.
 static int refreshMirrorLocked(GphocsStore* s) {
+  if (s->lnlStale.load(std::memory_order_acquire)) {
+    cudaSetDevice(s->device);
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    CUDA_TRY(cudaMemcpy(s->hLnL.data(), s->d.lnL, (size_t)s->L * sizeof(double), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(s->hSavedLnL.data(), s->d.savedLnL, (size_t)s->L * sizeof(double), cudaMemcpyDeviceToHost));
+    s->lnlStale.store(false, std::memory_order_release);
+  }
   if (!s->mirrorStale.load(std::memory_order_acquire)) return 0;
   cudaSetDevice(s->device);
   CUDA_TRY(cudaStreamSynchronize(s->stream));
@@ -405,6 +428,7 @@ static int refreshMirrorLocked(GphocsStore* s) {
   CUDA_TRY(cudaMemcpy(nd.data(), s->d.node, LN * sizeof(NodeRec), cudaMemcpyDeviceToHost));
   CUDA_TRY(cudaMemcpy(s->hAge.data(), s->d.age, LN * sizeof(double), cudaMemcpyDeviceToHost));
   CUDA_TRY(cudaMemcpy(s->hRoot.data(), s->d.root, (size_t)s->L * sizeof(int), cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(s->hRate.data(), s->d.rate, (size_t)s->L * sizeof(double), cudaMemcpyDeviceToHost));
   NodeRec* hn = s->hNode.data();
   const NodeRec* dn = nd.data();
   parallelFor(0, (long long)LN, [&](long long lo_, long long hi_) {
@@ -419,12 +443,13 @@ static int refreshMirrorLocked(GphocsStore* s) {
 }
 // for readers that do not hold the store's mutex (the scalar API's getters: one relaxed load on the fast path)
 static void ensureMirror(GphocsStore* s) {
-  if (__builtin_expect(s->mirrorStale.load(std::memory_order_acquire), 0)) {
+  if (__builtin_expect(s->mirrorStale.load(std::memory_order_acquire) || s->lnlStale.load(std::memory_order_acquire), 0)) {
     std::lock_guard<std::mutex> lk(s->mu);
     refreshMirrorLocked(s);
   }
 }
 
+static int flushPending(GphocsStore* s);
 static int setTreesLocked(GphocsStore* s, int nLoci, const int* locusIds, const int* father, const int* left,
                           const int* right, const double* age, const int* root) {
   const int N = s->N;
@@ -461,14 +486,31 @@ static int setTreesLocked(GphocsStore* s, int nLoci, const int* locusIds, const 
     CUDA_TRY(cudaMemcpyAsync(s->dTopo32 + 2 * cnt, right, sizeof(int) * cnt, cudaMemcpyHostToDevice, s->stream));
     CUDA_TRY(cudaMemcpyAsync(d.age, age, sizeof(double) * cnt, cudaMemcpyHostToDevice, s->stream));
     CUDA_TRY(cudaMemcpyAsync(d.root, root, sizeof(int) * (size_t)nLoci, cudaMemcpyHostToDevice, s->stream));
-    k_set_topology32<<<(unsigned)((cnt + 255) / 256), 256, 0, s->stream>>>(d, s->dTopo32, s->dTopo32 + cnt, s->dTopo32 + 2 * cnt, cnt);
+    if (!s->dBadTopo && devAlloc(&s->dBadTopo, 1)) return -1;
+    CUDA_TRY(cudaMemsetAsync(s->dBadTopo, 0, sizeof(int), s->stream));
+    k_set_topology32<<<(unsigned)((cnt + 255) / 256), 256, 0, s->stream>>>(d, s->dTopo32, s->dTopo32 + cnt, s->dTopo32 + 2 * cnt, cnt,
+                                                                           s->dBadTopo);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
+    int bad = 0;
+    CUDA_TRY(cudaMemcpyAsync(&bad, s->dBadTopo, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
     s->mirrorStale.store(true, std::memory_order_release);   // the mirror follows on demand (refreshMirrorLocked)
     CUDA_TRY(cudaStreamSynchronize(s->stream));   // the caller's arrays are free again when the call returns
+    if (bad) { fprintf(stderr, "gphocs_b200: %d node records with ids outside the tree\n", bad); return -1; }
     return 0;
   }
   if (s->i16.reserve(cnt * 3) || s->f64.reserve(cnt) || s->ids.reserve(nLoci) || s->seg.reserve(nLoci)) return -1;
+  {   // ids are narrowed to 16 bits below: refuse anything outside the tree before the mirror or the device is touched
+    std::atomic<int> badIds{0};
+    parallelFor(0, (long long)cnt, [&](long long lo_, long long hi_) {
+      int b = 0;
+      for (long long i = lo_; i < hi_; i++)
+        b += father[i] < -1 || father[i] >= N || left[i] < -1 || left[i] >= N || right[i] < -1 || right[i] >= N;
+      if (b) badIds.fetch_add(b);
+    }, 65536);
+    for (int k = 0; k < nLoci; k++) badIds.fetch_add(root[k] < -1 || root[k] >= N);
+    if (badIds.load()) { fprintf(stderr, "gphocs_b200: %d node records with ids outside the tree\n", badIds.load()); return -1; }
+  }
   // Loci are converted in chunks by all host threads straight into page-locked staging (int16 topology, fp64 ages,
   // roots, ids) and each chunk's copies are enqueued at once, so PCIe transfers overlap the conversion of the next
   // chunk.  The host mirror is updated in the same pass; flag bytes (buffer selectors) are kept on both sides.
@@ -513,6 +555,7 @@ static int setTreesLocked(GphocsStore* s, int nLoci, const int* locusIds, const 
 extern "C" int gphocsStoreSetTrees(GphocsStore* s, int nLoci, const int* locusIds, const int* father, const int* left,
                                    const int* right, const double* age, const int* root) {
   std::lock_guard<std::mutex> lk(s->mu);
+  if (flushPending(s)) return -1;   // edits queued by the scalar API belong to the genealogies they were made on
   return setTreesLocked(s, nLoci, locusIds, father, left, right, age, root);
 }
 
@@ -520,6 +563,7 @@ extern "C" int gphocsStoreSetTrees(GphocsStore* s, int nLoci, const int* locusId
 // pack kernel; the mirror follows on demand like on the page-locked route above
 extern "C" int gphocsStoreSetTreesPacked(GphocsStore* s, int nLoci, const short* topo, const double* age, const int* root) {
   std::lock_guard<std::mutex> lk(s->mu);
+  if (flushPending(s)) return -1;
   const int N = s->N;
   cudaSetDevice(s->device);
   if (nLoci <= 0) return 0;
@@ -670,8 +714,14 @@ extern "C" int gphocsStoreApplyOps(GphocsStore* s, int nOps, const GphocsOp* ops
   std::lock_guard<std::mutex> lk(s->mu);
   const Op* ops = reinterpret_cast<const Op*>(ops_);
   if (flushPending(s)) return -1;
-  for (int i = 0; i < nOps; i++)
-    if (ops[i].locus < 0 || ops[i].locus >= s->L) { fprintf(stderr, "gphocs_b200: locus %d out of range\n", ops[i].locus); return -1; }
+  for (int i = 0; i < nOps; i++) {
+    const Op& o = ops[i];
+    if (o.locus < 0 || o.locus >= s->L) { fprintf(stderr, "gphocs_b200: locus %d out of range\n", o.locus); return -1; }
+    bool ok = o.type >= OP_ADJUST_AGE && o.type <= OP_SET_RATE;
+    if (o.type == OP_ADJUST_AGE) ok = o.a >= 0 && o.a < s->N;
+    if (o.type == OP_SPR) ok = o.a >= 0 && o.a < s->N && o.b >= 0 && o.b < s->N && o.a != o.b;
+    if (!ok) { fprintf(stderr, "gphocs_b200: edit %d (type %d, nodes %d, %d) is outside the tree of locus %d\n", i, o.type, o.a, o.b, o.locus); return -1; }
+  }
   return launchOps(s, ops, nOps, outStatus, true);
 }
 
@@ -707,6 +757,7 @@ extern "C" int gphocsStoreEvaluateDevice(GphocsStore* s, int useOld, void** devL
   std::lock_guard<std::mutex> lk(s->mu);
   if (flushPending(s)) return -1;
   if (launchEval(s, useOld, -1, false)) return -1;
+  s->lnlStale.store(true, std::memory_order_release);   // the mirror's lnL / savedLnL follow on demand
   k_reduce_sum<<<1, 1024, 0, s->stream>>>(s->d.ctaSum, s->numBatches, s->dSum);
   g_launches++;
   CUDA_TRY(cudaGetLastError());
@@ -776,6 +827,7 @@ static int evaluateLocked(GphocsStore* s, int nLoci, const int* locusIds, int us
   const bool all = (locusIds == nullptr);
   if (all && nLoci != s->L) { fprintf(stderr, "gphocs_b200: locusIds == NULL requires nLoci == numLoci\n"); return -1; }
   if (s->f64.reserve((size_t)s->L + 1)) return -1;
+  if (s->lnlStale.load(std::memory_order_acquire) && refreshMirrorLocked(s)) return -1;
   // mirror: savedLnL <- lnL for every evaluated locus (.c:440; loci without patterns or tree hold 0 in both)
   if (all) {
     memcpy(s->hSavedLnL.data(), s->hLnL.data(), sizeof(double) * s->L);
@@ -1027,20 +1079,34 @@ extern "C" int gphocsGenSetParams(GphocsGenealogy* g, const double* theta, const
   return 0;
 }
 
+// device arrays for E events; the capacity is recorded only once all three allocations have succeeded
+static int genReserveEvents(GphocsGenealogy* g, size_t E) {
+  if (E <= g->evCap) return 0;
+  if (g->dEvTime) cudaFree(g->dEvTime);
+  if (g->dEvCode) cudaFree(g->dEvCode);
+  if (g->dLineages) cudaFree(g->dLineages);
+  g->dEvTime = nullptr; g->dEvCode = nullptr; g->dLineages = nullptr;
+  g->evCap = 0;
+  const size_t cap = E + E / 8;
+  if (devAlloc(&g->dEvTime, cap) || devAlloc(&g->dEvCode, cap) || devAlloc(&g->dLineages, cap)) {
+    if (g->dEvTime) cudaFree(g->dEvTime);
+    if (g->dEvCode) cudaFree(g->dEvCode);
+    if (g->dLineages) cudaFree(g->dLineages);
+    g->dEvTime = nullptr; g->dEvCode = nullptr; g->dLineages = nullptr;
+    return -1;
+  }
+  g->evCap = cap;
+  return 0;
+}
+
 extern "C" int gphocsGenSetEvents(GphocsGenealogy* g, const long long* evStart, const int* popStart, const int* evType,
                                   const int* evId, const double* evTime) {
   cudaSetDevice(g->device);
   const int L = g->L, Q = g->Q;
   const long long E = evStart[L] - evStart[0];
   if (E <= 0 || E >= (1ll << 31)) { fprintf(stderr, "gphocs_b200: bad event count %lld\n", E); return -1; }
-  if ((size_t)E > g->evCap) {
-    if (g->dEvTime) cudaFree(g->dEvTime);
-    if (g->dEvCode) cudaFree(g->dEvCode);
-    if (g->dLineages) cudaFree(g->dLineages);
-    g->evCap = (size_t)E + (size_t)E / 8;
-    if (devAlloc(&g->dEvTime, g->evCap) || devAlloc(&g->dEvCode, g->evCap) || devAlloc(&g->dLineages, g->evCap)) return -1;
-  }
-  g->totalEvents = E;
+  g->totalEvents = 0;   // the object holds no snapshot until this call has succeeded
+  if (genReserveEvents(g, (size_t)E)) return -1;
   // Page-locked caller arrays: the DMA engine reads them where they are and k_gen_pack narrows them on the device;
   // the host only finds the largest tile (for the shared-memory size) while the copies are in flight.
   auto pageLocked = [](const void* p) {
@@ -1081,7 +1147,8 @@ extern "C" int gphocsGenSetEvents(GphocsGenealogy* g, const long long* evStart, 
     if (badCount) { fprintf(stderr, "gphocs_b200: malformed event snapshot\n"); return -1; }
     const size_t smemDirect = genSmemBytes(g->Q, g->B, g->maxTileEvents);
     if (smemDirect > 200 * 1024) { fprintf(stderr, "gphocs_b200: event tile too large for shared memory (%zu bytes)\n", smemDirect); return -1; }
-    CUDA_TRY(cudaFuncSetAttribute(k_gen_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemDirect));
+    if (raiseDynamicSmem((const void*)k_gen_eval, smemDirect)) return -1;
+    g->totalEvents = E;
     return 0;
   }
   if (g->sEs.reserve(L + 1) || g->sPs.reserve((size_t)L * (Q + 1)) || g->sCode.reserve((size_t)E)) return -1;
@@ -1125,7 +1192,8 @@ extern "C" int gphocsGenSetEvents(GphocsGenealogy* g, const long long* evStart, 
   CUDA_TRY(cudaStreamSynchronize(g->stream));
   const size_t smem = genSmemBytes(g->Q, g->B, g->maxTileEvents);
   if (smem > 200 * 1024) { fprintf(stderr, "gphocs_b200: event tile too large for shared memory (%zu bytes)\n", smem); return -1; }
-  CUDA_TRY(cudaFuncSetAttribute(k_gen_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (raiseDynamicSmem((const void*)k_gen_eval, smem)) return -1;
+  g->totalEvents = E;
   return 0;
 }
 
@@ -1136,14 +1204,8 @@ extern "C" int gphocsGenSetEventsPacked(GphocsGenealogy* g, const int* evStart, 
   const int L = g->L, Q = g->Q;
   const long long E = evStart[L];
   if (evStart[0] != 0 || E <= 0 || E >= (1ll << 31)) { fprintf(stderr, "gphocs_b200: bad event count %lld\n", E); return -1; }
-  if ((size_t)E > g->evCap) {
-    if (g->dEvTime) cudaFree(g->dEvTime);
-    if (g->dEvCode) cudaFree(g->dEvCode);
-    if (g->dLineages) cudaFree(g->dLineages);
-    g->evCap = (size_t)E + (size_t)E / 8;
-    if (devAlloc(&g->dEvTime, g->evCap) || devAlloc(&g->dEvCode, g->evCap) || devAlloc(&g->dLineages, g->evCap)) return -1;
-  }
-  g->totalEvents = E;
+  g->totalEvents = 0;   // the object holds no snapshot until this call has succeeded
+  if (genReserveEvents(g, (size_t)E)) return -1;
   if (!g->dBadEvents && devAlloc(&g->dBadEvents, 1)) return -1;
   const size_t nPs = (size_t)L * (Q + 1);
   CUDA_TRY(cudaMemsetAsync(g->dBadEvents, 0, sizeof(int), g->stream));
@@ -1165,10 +1227,11 @@ extern "C" int gphocsGenSetEventsPacked(GphocsGenealogy* g, const int* evStart, 
   int badCount = 0;
   CUDA_TRY(cudaMemcpyAsync(&badCount, g->dBadEvents, sizeof(int), cudaMemcpyDeviceToHost, g->stream));
   CUDA_TRY(cudaStreamSynchronize(g->stream));
-  if (badCount || bad) { g->totalEvents = 0; fprintf(stderr, "gphocs_b200: malformed event snapshot\n"); return -1; }
+  if (badCount || bad) { fprintf(stderr, "gphocs_b200: malformed event snapshot\n"); return -1; }
   const size_t smem = genSmemBytes(g->Q, g->B, g->maxTileEvents);
   if (smem > 200 * 1024) { fprintf(stderr, "gphocs_b200: event tile too large for shared memory (%zu bytes)\n", smem); return -1; }
-  CUDA_TRY(cudaFuncSetAttribute(k_gen_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (raiseDynamicSmem((const void*)k_gen_eval, smem)) return -1;
+  g->totalEvents = E;
   return 0;
 }
 

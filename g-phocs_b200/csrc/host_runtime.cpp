@@ -30,15 +30,21 @@ inline void cpuRelax() { __builtin_ia32_pause(); }
 class Team {
  public:
   ~Team() { shutdown(); }
+  // The generation counter and the number of active workers are published in ONE atomic word (generation << 20 |
+  // active): a worker decides from a single load whether a generation concerns it, so a worker that sat out generation
+  // G and is preempted can neither run G+1's job under G's number nor run it twice.  job_ is read only by workers that
+  // are active in the generation they have just observed, and the caller cannot leave that generation (and overwrite
+  // job_) before every one of them has decremented pending_.
   void run(int n, const std::function<void(int)>& job) {
     if (n <= 1) { job(0); return; }
+    if (n - 1 > kMaxActive) { fprintf(stderr, "gphocs_b200: a team of %d host threads is not supported\n", n); abort(); }
     grow(n - 1);
     job_ = &job;
-    active_ = n - 1;
     pending_.store(n - 1, std::memory_order_relaxed);
     {
       std::lock_guard<std::mutex> lk(mu_);
-      gen_.fetch_add(1, std::memory_order_release);
+      const uint64_t g = (gen_.load(std::memory_order_relaxed) >> kActiveBits) + 1;
+      gen_.store(g << kActiveBits | (uint64_t)(n - 1), std::memory_order_release);
     }
     cv_.notify_all();
     job(0);
@@ -57,17 +63,18 @@ class Team {
     }
   }
   void loop(int w) {
-    uint64_t seen = 0;
+    uint64_t seen = 0;   // generation number last observed
     for (;;) {
       int spins = 0;
-      while (gen_.load(std::memory_order_acquire) == seen && !stop_.load(std::memory_order_relaxed)) {
+      uint64_t g;
+      while (((g = gen_.load(std::memory_order_acquire)) >> kActiveBits) == seen && !stop_.load(std::memory_order_relaxed)) {
         if (++spins < 20000) { cpuRelax(); continue; }
         std::unique_lock<std::mutex> lk(mu_);
-        cv_.wait(lk, [&] { return gen_.load(std::memory_order_acquire) != seen || stop_.load(); });
+        cv_.wait(lk, [&] { return (gen_.load(std::memory_order_acquire) >> kActiveBits) != seen || stop_.load(); });
       }
       if (stop_.load()) return;
-      seen = gen_.load(std::memory_order_acquire);
-      if (w <= active_) {
+      seen = g >> kActiveBits;
+      if ((uint64_t)w <= (g & kActiveMask)) {
         (*job_)(w);
         pending_.fetch_sub(1, std::memory_order_release);
       }
@@ -89,7 +96,9 @@ class Team {
   std::atomic<int> pending_{0};
   std::atomic<bool> stop_{false};
   const std::function<void(int)>* job_ = nullptr;
-  int active_ = 0;
+  static constexpr int kActiveBits = 20;
+  static constexpr uint64_t kActiveMask = (1ull << kActiveBits) - 1;
+  static constexpr int kMaxActive = 4096;
 };
 
 int g_threads = 0;  // 0: hardware concurrency

@@ -220,7 +220,8 @@ int gphocsGenSync(GphocsGenealogy *g);
 /* ===================================================================================== D. device-resident MCMC steps
  * the update steps of GPhoCS.c run for all loci per launch with no host round trip inside a sweep —
  * UpdateGB_InternalNode (:2287), UpdateGB_MigSPR (:2598), UpdateTheta (:3035), UpdateTau (:3224), mixing (:4688).
- * This version covers population trees without migration bands, samples of age 0 and constant locus rates.
+ * Migration bands (gphocsSamplerSetMigration: UpdateGB_MigrationNode :2437, UpdateMigRates :3110), estimated sample
+ * ages and locus-rate variation (gphocsSamplerSetAncient: UpdateSampleAge :4006, UpdateLocusRate :4598) are covered.
  * The sampler edits the device copy of the store's genealogies; call gphocsSamplerDownload before reading them
  * through the store or the LocusData getters. */
 typedef struct GphocsSampler GphocsSampler;
