@@ -125,9 +125,7 @@ def lib():
         "gphocsSamplerTraceWidth": (ci, [vp]),
         "gphocsSamplerOpenTrace": (ci, [vp, C.c_char_p, C.POINTER(C.c_char_p), cd, cd, ci]),
         "gphocsSamplerCloseTrace": (ci, [vp]),
-        "gphocsSamplerSetFusedSweep": (ci, [vp, ci]),
-        "gphocsSamplerSetScheduledEval": (ci, [vp, ci]),
-        "gphocsSamplerSetSweepStreams": (ci, [vp, ci]),
+        "gphocsSamplerSetStepwise": (ci, [vp, ci]),
         "gphocsSamplerGetState": (ci, [vp, c_dbl_p, c_dbl_p, c_ll_p, c_ll_p]),
         "gphocsSamplerCheck": (ci, [vp, c_dbl_p, c_dbl_p]),
         "gphocsSamplerDownload": (ci, [vp, c_int_p]),
@@ -656,14 +654,9 @@ class Sampler:
                                            int(sample_skip)) != 0:
             raise RuntimeError("gphocsSamplerOpenTrace failed")
 
-    def set_fused_sweep(self, on):
-        self.lib.gphocsSamplerSetFusedSweep(self.h, int(bool(on)))
-
-    def set_scheduled_eval(self, on):
-        self.lib.gphocsSamplerSetScheduledEval(self.h, int(bool(on)))
-
-    def set_sweep_streams(self, streams):
-        self.lib.gphocsSamplerSetSweepStreams(self.h, int(streams))
+    def set_stepwise(self, on):
+        """1: per-node launches even where the one-launch sweep applies (same chain either way)."""
+        self.lib.gphocsSamplerSetStepwise(self.h, int(bool(on)))
 
     def close_trace(self):
         self.lib.gphocsSamplerCloseTrace(self.h)

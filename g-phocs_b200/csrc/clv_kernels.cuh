@@ -93,6 +93,13 @@ struct __align__(16) SchedEntry {
   uint32_t ctl;               // bits 0-1 kind of A, 2-3 kind of B, bits 16-31 stack byte offset to park the result at (0xffff: none)
 };
 static_assert(sizeof(SchedEntry) == 48, "schedule entry layout");
+// the same without the two 1-4p terms, which the walking thread then derives from p (same expression, same bits): the
+// fused sweep kernel keeps more CTAs per SM with 32-byte entries
+struct __align__(16) SchedEntryCompact {
+  double e0A, e0B;
+  uint32_t offA, offB, dstOff, ctl;
+};
+static_assert(sizeof(SchedEntryCompact) == 32, "compact schedule entry layout");
 
 struct EvalSmem {
   size_t perScratch, offAge, offNode, offSize, offWalk, offNeed;  // per-locus scheduling scratch
@@ -237,6 +244,76 @@ __device__ __forceinline__ void missingSubtree(const double (&a)[4], const doubl
     const double fa = sA >= 4.0 ? 1.0 : (qA + a[q] * e1A);
     const double fb = sB >= 4.0 ? 1.0 : (qB + b[q] * e1B);
     v[q] = fa * fb;
+  }
+}
+
+// Phase E of k_eval, shared with the fused sweep kernel (sweep_kernels.cuh): one thread walks the k schedule entries at
+// shared-memory address `entry` for its own column.  clvCol = the column's base in the conditional-vector store,
+// myStack / myWords = this thread's column of the parking stack and of the leaf-code rows.  pv returns the vector
+// computed last (the root's, when the schedule ends at the root).  HI = bytes from the lo half of a parked vector to
+// its hi half (= rows of the stack * kRow).
+template <uint32_t HI = kHi, bool COMPACT = false>
+__device__ __forceinline__ void columnWalk(uint32_t entry, int k, char* clvCol, uint32_t myStack, uint32_t myWords, bool useOld,
+                                           double (&pv)[4]) {
+  constexpr uint32_t kEntryBytes = COMPACT ? sizeof(SchedEntryCompact) : sizeof(SchedEntry);
+  // pv = the vector computed by the previous entry (the register-resident top of the stack)
+  auto childValue = [&](uint32_t kind, uint32_t off, double (&v)[4]) {
+    if (kind == SRC_TOP) {
+#pragma unroll
+      for (int q = 0; q < 4; q++) v[q] = pv[q];
+    } else if (kind == SRC_LEAF) {
+      // conditional vector of a leaf from its 4-bit base mask (computeLeafConditionals, .c:1336-1386):
+      // 1.0 = 0x3ff00000'00000000 where the bit is set, 0.0 elsewhere
+      const uint32_t m = ldsU32(myWords + (off & 0xffffu)) >> (off >> 16);
+#pragma unroll
+      for (int q = 0; q < 4; q++) v[q] = __hiloint2double((int)(((m >> q) & 1u) * 0x3ff00000u), 0);
+    } else if (kind == SRC_STACK) {
+      const uint32_t a = myStack + (off >> 16);
+      const double2 x = ldsD2(a), y = ldsD2(a + HI);
+      v[0] = x.x; v[1] = x.y; v[2] = y.x; v[3] = y.y;
+    } else {
+      ldgD4(clvCol + off, v);
+    }
+  };
+  if (useOld) {   // clean children are the only HBM reads of a proposal: request them all before the first use
+    for (int e = 0; e < k; e++) {
+      const uint4 ix = ldsU4(entry + e * kEntryBytes + kEntryBytes - 16);
+      if ((ix.w & 3u) == SRC_GLOBAL) prefetchL2(clvCol + ix.x);
+      if (((ix.w >> 2) & 3u) == SRC_GLOBAL) prefetchL2(clvCol + ix.y);
+    }
+  }
+  for (int e = 0; e < k; e++, entry += kEntryBytes) {
+    double2 eA, eB;                                            // (e0A,e1A), (e0B,e1B)
+    if (COMPACT) {
+      const double2 e0 = ldsD2(entry);
+      eA.x = e0.x; eA.y = 1.0 - 4.0 * e0.x;
+      eB.x = e0.y; eB.y = 1.0 - 4.0 * e0.y;
+    } else {
+      eA = ldsD2(entry); eB = ldsD2(entry + 16);
+    }
+    const uint4 ix = ldsU4(entry + kEntryBytes - 16);          // offA, offB, dstOff, ctl
+    double a[4], bb[4], v[4];
+    childValue(ix.w & 3u, ix.x, a);
+    childValue((ix.w >> 2) & 3u, ix.y, bb);
+    // computeSubtreeConditionals_new (.c:1650-1673) for both children
+    const double sA = ((a[0] + a[1]) + a[2]) + a[3];
+    const double sB = ((bb[0] + bb[1]) + bb[2]) + bb[3];
+    const double qA = sA * eA.x, qB = sB * eB.x;
+#pragma unroll
+    for (int q = 0; q < 4; q++) v[q] = (qA + a[q] * eA.y) * (qB + bb[q] * eB.y);
+    // sums are positive, so s >= 4.0 can be read off the high word (4.0 = 0x40100000'00000000)
+    if (__builtin_expect((__double2hiint(sA) >= 0x40100000) | (__double2hiint(sB) >= 0x40100000), 0)) {
+      // a child whose conditionals sum to 4 is an all-missing subtree and contributes exactly 1 (.c:1660-1663)
+      missingSubtree(a, bb, sA, sB, qA, qB, eA.y, eB.y, v);
+    }
+    stgD4(clvCol + ix.z, v);
+    const uint32_t push = ix.w >> 16;
+    if (push != 0xffffu) {
+      stsD2(myStack + push, v[0], v[1]);
+      stsD2(myStack + push + HI, v[2], v[3]);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; q++) pv[q] = v[q];
   }
 }
 
@@ -514,59 +591,7 @@ k_eval(StoreDev d, const Batch* __restrict__ batches, int batchBase, int useOld,
         if (2 * w + 1 < lay.W32) stsU32(myWords + (2 * w + 1) * kThreads * 4, (uint32_t)(word >> 32));
       }
       char* clvCol = reinterpret_cast<char*>(d.clv + (size_t)mColStart[s] * NI * 8 + (size_t)p * 4);
-      uint32_t entry = smemAddr(sSched(s));
-      // pv = the vector computed by the previous entry (the register-resident top of the stack)
-      auto childValue = [&](uint32_t kind, uint32_t off, double (&v)[4]) {
-        if (kind == SRC_TOP) {
-#pragma unroll
-          for (int q = 0; q < 4; q++) v[q] = pv[q];
-        } else if (kind == SRC_LEAF) {
-          // conditional vector of a leaf from its 4-bit base mask (computeLeafConditionals, .c:1336-1386):
-          // 1.0 = 0x3ff00000'00000000 where the bit is set, 0.0 elsewhere
-          const uint32_t m = ldsU32(myWords + (off & 0xffffu)) >> (off >> 16);
-#pragma unroll
-          for (int q = 0; q < 4; q++) v[q] = __hiloint2double((int)(((m >> q) & 1u) * 0x3ff00000u), 0);
-        } else if (kind == SRC_STACK) {
-          const uint32_t a = myStack + (off >> 16);
-          const double2 x = ldsD2(a), y = ldsD2(a + kHi);
-          v[0] = x.x; v[1] = x.y; v[2] = y.x; v[3] = y.y;
-        } else {
-          ldgD4(clvCol + off, v);
-        }
-      };
-      if (useOld) {   // clean children are the only HBM reads of a proposal: request them all before the first use
-        for (int e = 0; e < k; e++) {
-          const uint4 ix = ldsU4(entry + e * (uint32_t)sizeof(SchedEntry) + 32);
-          if ((ix.w & 3u) == SRC_GLOBAL) prefetchL2(clvCol + ix.x);
-          if (((ix.w >> 2) & 3u) == SRC_GLOBAL) prefetchL2(clvCol + ix.y);
-        }
-      }
-      for (int e = 0; e < k; e++, entry += sizeof(SchedEntry)) {
-        const double2 eA = ldsD2(entry), eB = ldsD2(entry + 16);   // (e0A,e1A), (e0B,e1B)
-        const uint4 ix = ldsU4(entry + 32);                        // offA, offB, dstOff, ctl
-        double a[4], bb[4], v[4];
-        childValue(ix.w & 3u, ix.x, a);
-        childValue((ix.w >> 2) & 3u, ix.y, bb);
-        // computeSubtreeConditionals_new (.c:1650-1673) for both children
-        const double sA = ((a[0] + a[1]) + a[2]) + a[3];
-        const double sB = ((bb[0] + bb[1]) + bb[2]) + bb[3];
-        const double qA = sA * eA.x, qB = sB * eB.x;
-#pragma unroll
-        for (int q = 0; q < 4; q++) v[q] = (qA + a[q] * eA.y) * (qB + bb[q] * eB.y);
-        // sums are positive, so s >= 4.0 can be read off the high word (4.0 = 0x40100000'00000000)
-        if (__builtin_expect((__double2hiint(sA) >= 0x40100000) | (__double2hiint(sB) >= 0x40100000), 0)) {
-          // a child whose conditionals sum to 4 is an all-missing subtree and contributes exactly 1 (.c:1660-1663)
-          missingSubtree(a, bb, sA, sB, qA, qB, eA.y, eB.y, v);
-        }
-        stgD4(clvCol + ix.z, v);
-        const uint32_t push = ix.w >> 16;
-        if (push != 0xffffu) {
-          stsD2(myStack + push, v[0], v[1]);
-          stsD2(myStack + push + kHi, v[2], v[3]);
-        }
-#pragma unroll
-        for (int q = 0; q < 4; q++) pv[q] = v[q];
-      }
+      columnWalk(smemAddr(sSched(s)), k, clvCol, myStack, myWords, useOld != 0, pv);
     }
     // ---- root conditionals -> shared (or scratch for an oversized locus)
     if (!oversized) {

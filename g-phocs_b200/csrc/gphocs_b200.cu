@@ -23,6 +23,7 @@
 #include "ingest_kernels.cuh"
 #include "sampler_kernels.cuh"
 #include "sampler_mig.cuh"
+#include "sweep_kernels.cuh"
 #include "tree_ops.cuh"
 
 using namespace gphocs;

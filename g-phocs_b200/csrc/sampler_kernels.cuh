@@ -20,7 +20,6 @@
 #include <stdint.h>
 
 #include "clv_kernels.cuh"
-#include "warp_eval.cuh"
 
 namespace gphocs {
 
@@ -36,6 +35,7 @@ struct SmpModel {
   int leavesBelow[kSmpMaxPops];       // haploid samples in the current populations under each population
   unsigned long long below[kSmpMaxPops];  // bit q: population q is this population or lies below it
   double theta[kSmpMaxPops], tau[kSmpMaxPops];
+  double coalRate[kSmpMaxPops];       // 2 / theta, refreshed with every upload of the model (smpUploadModel)
   // migration bands (MigrationBand, PopulationTree.h:60-70): backwards in time a lineage in the target population
   // moves to the source population at rate migRate while both populations exist
   int B;
@@ -102,6 +102,12 @@ struct SmpRng {
     return uniform() < 0.5 ? z : -z;
   }
   __device__ double exponential() { return -log(uniform()); }
+  // draw `idx` of a family of independent streams under this (seed, stream, step): one hash per draw, for loops that
+  // need one exponential per branch or segment (the competing clocks of the SPR proposal)
+  __device__ double exponentialAt(unsigned long long idx) const {
+    const unsigned long long r = mix(key + (idx + 0x1000ull) * 0x9E3779B97F4A7C15ull);
+    return -log(((double)(r >> 11) + 0.5) * (1.0 / 9007199254740992.0));
+  }
 };
 
 // reflect (utils.c:333-398): folds x into (a, b)
@@ -382,15 +388,10 @@ __device__ inline void smpAgeProposeBody(const StoreDev& d, const SmpDev& sd, co
 template <int R>
 __global__ void __launch_bounds__(kSmpThreads)
 k_smp_age_propose(StoreDev d, SmpDev sd, const SmpModel* __restrict__ mp, int inode, double finetune, unsigned long long seed,
-                  unsigned long long step, int pendKind, unsigned long long pendStep, IncEntry* sched, int* schedCount) {
+                  unsigned long long step, int pendKind, unsigned long long pendStep) {
   SMP_WARP_PROLOGUE
   if (pendKind >= 0) smpResolve(d, sd, m, t, l, lane, N, pendKind, seed, pendStep);   // the previous proposal of this locus
   smpAgeProposeBody<R>(d, sd, m, t, l, lane, n, N, inode, finetune, seed, step);
-  if (sched) {   // tree-side half of the incremental evaluation, for k_eval_sched (warp_eval.cuh)
-    __syncwarp();
-    const int k = warpBuildSchedule(d, t, l, lane, sched + (size_t)l * d.NI);
-    if (lane == 0) schedCount[l] = k;
-  }
 }
 
 // ------------------------------------------------------------------------------------------ subtree prune and regraft
@@ -418,6 +419,7 @@ __device__ inline void smpSprProposeBody(const StoreDev& d, const SmpDev& sd, co
   const double ageG = G >= 0 ? t.age[G] : kSmpInf;
   double bestT = kSmpInf;
   int bestX = -1, bestPop = -1;
+  const SmpRng rng(seed, (unsigned long long)l, step);
 #pragma unroll
   for (int r = 0; r < R; r++) {
     const int x = lane + 32 * r;
@@ -428,12 +430,11 @@ __device__ inline void smpSprProposeBody(const StoreDev& d, const SmpDev& sd, co
     double sNow = fmax(fmax(t0, w.age[r]), m.tau[q]);
     if (sNow >= endx) continue;
     while (m.father[q] >= 0 && m.tau[m.father[q]] <= sNow) q = m.father[q];
-    SmpRng rng(seed, (unsigned long long)l * 512ull + (unsigned long long)x, step);
-    double need = rng.exponential();
+    double need = rng.exponentialAt((unsigned long long)x);
     for (int it = 0; it < kSmpMaxPops; it++) {
       const double popEnd = m.father[q] >= 0 ? m.tau[m.father[q]] : kSmpInf;
       const double segEnd = fmin(endx, popEnd);
-      const double rate = 2.0 / m.theta[q];
+      const double rate = m.coalRate[q];
       if (rate * (segEnd - sNow) >= need) {
         const double T = sNow + need / rate;
         if (T < bestT) { bestT = T; bestX = x; bestPop = q; }
@@ -467,15 +468,10 @@ __device__ inline void smpSprProposeBody(const StoreDev& d, const SmpDev& sd, co
 template <int R>
 __global__ void __launch_bounds__(kSmpThreads)
 k_smp_spr_propose(StoreDev d, SmpDev sd, const SmpModel* __restrict__ mp, int node, unsigned long long seed,
-                  unsigned long long step, int pendKind, unsigned long long pendStep, IncEntry* sched, int* schedCount) {
+                  unsigned long long step, int pendKind, unsigned long long pendStep) {
   SMP_WARP_PROLOGUE
   if (pendKind >= 0) smpResolve(d, sd, m, t, l, lane, N, pendKind, seed, pendStep);
   smpSprProposeBody<R>(d, sd, m, t, l, lane, n, N, node, seed, step);
-  if (sched) {
-    __syncwarp();
-    const int k = warpBuildSchedule(d, t, l, lane, sched + (size_t)l * d.NI);
-    if (lane == 0) schedCount[l] = k;
-  }
 }
 
 // ------------------------------------------------------------------------------------------ per-locus accept / reject
@@ -519,31 +515,6 @@ __global__ void __launch_bounds__(kSmpThreads)
 k_smp_accept(StoreDev d, SmpDev sd, const SmpModel* __restrict__ mp, int kind, unsigned long long seed, unsigned long long step) {
   SMP_WARP_PROLOGUE
   smpResolve(d, sd, m, t, l, lane, N, kind, seed, step);
-}
-
-// ------------------------------------------------------------------------------------------ whole sweeps in one launch
-// UpdateGB_InternalNode and UpdateGB_MigSPR for a model without migration bands: a warp keeps its locus for the whole
-// coalescence-time sweep and the whole SPR sweep — propose, incremental data likelihood (warp_eval.cuh) and accept /
-// reject for one node after the other — instead of two launches per node.  The random-number streams are keyed by
-// (locus, step), the step numbering is that of the launch-per-node path, and warpEvalIncremental reproduces k_eval
-// bit for bit, so both paths produce the same chain.
-template <int R>
-__global__ void __launch_bounds__(kSmpThreads)
-k_smp_sweep(StoreDev d, SmpDev sd, const SmpModel* __restrict__ mp, double ftCoal, unsigned long long seed, unsigned long long step) {
-  SMP_WARP_PROLOGUE
-  if (ftCoal > 0.0)
-    for (int inode = n; inode < N; inode++, step += 2) {
-      smpAgeProposeBody<R>(d, sd, m, t, l, lane, n, N, inode, ftCoal, seed, step);
-      __syncwarp();
-      warpEvalIncremental(d, t, l, lane);
-      smpResolve(d, sd, m, t, l, lane, N, 0, seed, step + 1);
-    }
-  for (int node = 0; node < N; node++, step += 2) {
-    smpSprProposeBody<R>(d, sd, m, t, l, lane, n, N, node, seed, step);
-    __syncwarp();
-    warpEvalIncremental(d, t, l, lane);
-    smpResolve(d, sd, m, t, l, lane, N, 1, seed, step + 1);
-  }
 }
 
 // ------------------------------------------------------------------------------------------ split-time move

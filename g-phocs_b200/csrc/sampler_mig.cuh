@@ -401,15 +401,10 @@ __device__ inline void smgAgeProposeBody(const StoreDev& d, const SmpDev& sd, co
 }
 __global__ void __launch_bounds__(kSmpThreads)
 k_smg_age_propose(StoreDev d, SmpDev sd, const SmpModel* __restrict__ mp, int inode, double finetune, unsigned long long seed,
-                  unsigned long long step, int pendKind, unsigned long long pendStep, IncEntry* sched, int* schedCount) {
+                  unsigned long long step, int pendKind, unsigned long long pendStep) {
   SMG_PROLOGUE
   if (pendKind >= 0) smgResolve(d, sd, m, t, l, lane, N, pendKind, seed, pendStep);   // the previous proposal of this locus
   smgAgeProposeBody(d, sd, m, w, t, l, lane, n, N, inode, finetune, seed, step);
-  if (sched) {   // tree-side half of the incremental evaluation, for k_eval_sched
-    __syncwarp();
-    const int k = warpBuildSchedule(d, t, l, lane, sched + (size_t)l * d.NI);
-    if (lane == 0) schedCount[l] = k;
-  }
 }
 
 // ------------------------------------------------------------------------------------------ migration-time moves
@@ -578,15 +573,10 @@ __device__ inline void smgSprProposeBody(const StoreDev& d, const SmpDev& sd, co
 }
 __global__ void __launch_bounds__(kSmpThreads)
 k_smg_spr_propose(StoreDev d, SmpDev sd, const SmpModel* __restrict__ mp, int node, unsigned long long seed,
-                  unsigned long long step, int pendKind, unsigned long long pendStep, IncEntry* sched, int* schedCount) {
+                  unsigned long long step, int pendKind, unsigned long long pendStep) {
   SMG_PROLOGUE
   if (pendKind >= 0) smgResolve(d, sd, m, t, l, lane, N, pendKind, seed, pendStep);
   smgSprProposeBody(d, sd, m, w, t, l, lane, n, N, node, seed, step);
-  if (sched) {
-    __syncwarp();
-    const int k = warpBuildSchedule(d, t, l, lane, sched + (size_t)l * d.NI);
-    if (lane == 0) schedCount[l] = k;
-  }
 }
 
 // ------------------------------------------------------------------------------------------ split-time move

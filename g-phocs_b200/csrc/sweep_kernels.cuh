@@ -1,0 +1,650 @@
+// sweep_kernels.cuh — the two per-locus sweeps of an MCMC iteration in ONE launch, loci batched across a CTA.
+//
+//   UpdateGB_InternalNode  GPhoCS.c:2287-2424   one coalescence-time proposal per internal node
+//   UpdateGB_MigSPR        GPhoCS.c:2598-2760   one prune-and-regraft proposal per node (models without migration bands)
+//
+// Loci are independent inside these sweeps (GPhoCS.c:2297, 2608: `omp parallel for` over loci), so a CTA keeps its
+// batch of loci — the same batches k_eval works on: whole loci whose pattern columns fit the CTA's 128 threads — for
+// the WHOLE of both sweeps.  Genealogies, population assignments, coal statistics and the leaf codes of the batch are
+// staged once in shared memory; per step the CTA runs
+//   team phase   8 threads per locus: accept / reject of the previous proposal (smpResolve), the next proposal
+//                (smpAgeProposeBody / smpSprProposeBody) edited through tree_ops.cuh on the shared-memory genealogy,
+//                dirty marking and compaction of the nodes to recompute (k_eval phases B, C0)
+//   list phases  one thread per marked node of the batch: subtree sizes, post-order positions, schedule entries
+//                with JC69 edge terms (k_eval phases C, D)
+//   column phase one thread per pattern column walks its locus' schedule (columnWalk, shared with k_eval); the
+//                conditional vectors stay in HBM/L2 — a CTA re-reads what it wrote a few microseconds earlier
+//   root phase   phase-averaged root sums and per-locus log-likelihoods (k_eval phase F)
+// and nothing but the final state goes back to HBM.  One launch replaces 2(n-1) + 2(2n-1) + 1 launches of the
+// stepwise route (k_smp_age_propose / k_smp_spr_propose + k_eval per node), whose warp-per-locus proposal kernels left
+// half of their lanes idle and re-staged every genealogy twice per step.
+//
+// Same chain as the stepwise route, bit for bit: random streams are keyed by (locus, step) with the stepwise route's
+// step numbers; the column arithmetic is the same code; the coal statistic of a moved node's population is summed in
+// the order of the stepwise route's 32-lane shuffle tree (teamPopStat).  tests/test_gpu_sampler.py compares the two.
+#pragma once
+#include "sampler_kernels.cuh"
+
+namespace gphocs {
+
+constexpr int kTeam = 8;                        // threads per locus in the team phase
+constexpr int kTeamSlots = kThreads / kTeam;    // = kMaxBatchLoci
+static_assert(kTeamSlots == kMaxBatchLoci, "one team per locus of a CTA batch");
+constexpr int kSweepMaxNodes = 64;              // genealogies of up to 32 leaves (larger ones take the stepwise route)
+// A proposal of these sweeps dirties one path to the root (coalescence time) or two paths that join (SPR): at most one
+// result waits for its sibling's subtree, so ONE parking row per column is enough (k_eval keeps kStack for full
+// evaluations); anything deeper would be re-read from the record just written, as in k_eval.
+constexpr int kSweepStack = 1;
+constexpr uint32_t kSweepHi = kSweepStack * kRow;
+#ifndef GPHOCS_SWEEP_MINBLOCKS
+#define GPHOCS_SWEEP_MINBLOCKS 8
+#endif
+
+// what the sweeps read of the model (SmpModel carries 39 populations and 32 bands: 2.4 KB per CTA)
+struct SweepModel {
+  int Q;
+  int father[kSmpMaxPops], leavesBelow[kSmpMaxPops];
+  unsigned long long below[kSmpMaxPops];
+  double theta[kSmpMaxPops], tau[kSmpMaxPops], coalRate[kSmpMaxPops];
+};
+
+struct SweepSmem {
+  // per locus slot: what lives for the whole sweep ...
+  size_t offAge, offNode, offNeed, offPop, offCoal, offNcoal, perLocus;
+  // ... and the scheduling scratch of one step, which shares its space with the column stack (never live together)
+  size_t offSize, offWalk, perScratch;
+  size_t perSched;
+  // CTA regions
+  size_t offLoci, offSched, offStack, offWords, offList, offTerm, offMeta, offProp, offModel, total;
+  int W32;
+};
+__host__ __device__ inline SweepSmem sweepSmemLayout(int n, int maxLoci, int Q) {
+  const int N = 2 * n - 1, NI = n - 1;
+  SweepSmem m;
+  m.W32 = (n + 7) / 8;
+  m.offAge = 0;                                             // [N] double
+  m.offCoal = m.offAge + (size_t)N * 8;                     // [Q] double
+  m.offNode = m.offCoal + (size_t)Q * 8;                    // [N] NodeRec
+  m.offNcoal = m.offNode + (size_t)N * sizeof(NodeRec);     // [Q] int
+  m.offNeed = m.offNcoal + (size_t)Q * 4;                   // [N] uint8
+  m.offPop = m.offNeed + (size_t)N;                         // [N] uint8
+  m.perLocus = (m.offPop + (size_t)N + 15) & ~(size_t)15;
+  m.offSize = 0;                                            // [NI] int
+  m.offWalk = m.offSize + (size_t)NI * 4;                   // [N] uint32; the team phase keeps its lists here
+  m.perScratch = (m.offWalk + (size_t)N * 4 + 15) & ~(size_t)15;
+  m.perSched = (size_t)NI * sizeof(SchedEntryCompact);
+  m.offLoci = 0;
+  m.offSched = m.offLoci + m.perLocus * (size_t)maxLoci;
+  // column stack (one parking row: lo halves, hi halves) = the root vectors after the walk = the scheduling scratch
+  const size_t stackBytes = 2 * (size_t)kSweepHi, scratchBytes = m.perScratch * (size_t)maxLoci;
+  m.offStack = m.offSched + m.perSched * (size_t)maxLoci;
+  m.offWords = m.offStack + (stackBytes > scratchBytes ? stackBytes : scratchBytes);   // [W32][kThreads] uint32, whole sweep
+  m.offList = m.offWords + (size_t)m.W32 * kThreads * 4;    // [maxLoci*NI] uint32: marked nodes of the batch
+  m.offTerm = m.offList;                                    // [kThreads] double once the list is dead
+  const size_t listBytes = (size_t)maxLoci * NI * 4, termBytes = (size_t)kThreads * 8;
+  m.offMeta = (m.offList + (listBytes > termBytes ? listBytes : termBytes) + 15) & ~(size_t)15;   // per-slot scalars
+  m.offProp = m.offMeta + (size_t)kTeamSlots * 48;          // [slots] SmpProposal
+  m.offModel = (m.offProp + (size_t)kTeamSlots * sizeof(SmpProposal) + 15) & ~(size_t)15;
+  m.total = (m.offModel + sizeof(SweepModel) + 15) & ~(size_t)15;
+  return m;
+}
+__host__ __device__ inline size_t sweepSmemBytes(int n, int maxLoci, int Q) { return sweepSmemLayout(n, maxLoci, Q).total; }
+
+struct Team {
+  int j;           // 0..7 inside the team; 0 = leader
+  int leader;      // lane of the leader inside the warp
+  unsigned mask;   // the team's lanes
+};
+__device__ __forceinline__ double teamBcast(const Team& tm, double v) { return __shfl_sync(tm.mask, v, tm.leader); }
+__device__ __forceinline__ int teamBcast(const Team& tm, int v) { return __shfl_sync(tm.mask, v, tm.leader); }
+__device__ __forceinline__ int teamSumI(const Team& tm, int v) {
+#pragma unroll
+  for (int off = kTeam / 2; off > 0; off >>= 1) v += __shfl_xor_sync(tm.mask, v, off);
+  return v;
+}
+
+// What the 32 lanes of the stepwise route's warp hold is held here by 8 threads: thread j stands for the "virtual
+// lanes" j, j+8, j+16, j+24.  warpSumD's shuffle tree adds lanes that differ in bit 4, then bit 3, ..., bit 0; the first
+// two levels are thread-local here, the last three cross the team — same additions, same order, same bits.
+__device__ __forceinline__ double teamSumLikeWarp(const Team& tm, const double (&vl)[4]) {
+  const double a = vl[0] + vl[2], b = vl[1] + vl[3];
+  double v = a + b;
+#pragma unroll
+  for (int off = kTeam / 2; off > 0; off >>= 1) v += __shfl_xor_sync(tm.mask, v, off);
+  return v;
+}
+
+// members of a team append the items they hold (`mine` = one bit per item, item k of thread j = id(j, k)) to a list in
+// shared memory, densely; returns the list length.  Two rounds of ballots cover up to 8 items per thread.
+template <typename IdOf>
+__device__ __forceinline__ int teamCompact(const Team& tm, unsigned mine, int itemsPerThread, uint8_t* list, IdOf id) {
+  int count = 0;
+  for (int k = 0; k < itemsPerThread; k++) {
+    const bool in = (mine >> k) & 1u;
+    const unsigned ballot = (__ballot_sync(tm.mask, in) >> tm.leader) & ((1u << kTeam) - 1u);
+    if (in) list[count + __popc(ballot & ((1u << tm.j) - 1u))] = (uint8_t)id(tm.j, k);
+    count += __popc(ballot);
+  }
+  __syncwarp(tm.mask);
+  return count;
+}
+
+// wlPopStat (sampler_kernels.cuh) on a team: coal statistic of population `pop` from the coalescences assigned to it.
+// scratch: N bytes of the team's own shared memory (the ids of the population's coalescences).
+__device__ inline double teamPopStat(const Team& tm, const SweepModel& m, const double* age, const uint8_t* np, int n, int N, int pop,
+                                     int nStart, uint8_t* scratch) {
+  unsigned mine = 0;
+  const int per = (N - n + kTeam - 1) / kTeam;
+  for (int k = 0; k < per; k++) {
+    const int x = n + tm.j + kTeam * k;
+    if (x < N && np[x] == pop) mine |= 1u << k;
+  }
+  const int total = teamCompact(tm, mine, per, scratch, [&](int j, int k) { return n + j + kTeam * k; });
+  const double tau = m.tau[pop];
+  const double end = m.father[pop] >= 0 ? m.tau[m.father[pop]] : kOldAge;
+  if (total == 0) return (double)(nStart * (nStart - 1)) * (end - tau);
+  const int R = N <= 32 ? 1 : 2;   // nodes per lane of the stepwise route
+  double vl[4];
+#pragma unroll
+  for (int kk = 0; kk < 4; kk++) {
+    double v = 0.0;
+#pragma unroll 1
+    for (int r = 0; r < R; r++) {
+      const int x = tm.j + kTeam * kk + 32 * r;
+      if (x < n || x >= N || np[x] != pop) continue;
+      const double ax = age[x];
+      int cnt = 0;
+      double prev = tau;
+#pragma unroll 1
+      for (int i = 0; i < total; i++) {   // order-free: a count and a maximum
+        const int y = scratch[i];
+        const double ay = age[y];
+        if (ay < ax || (ay == ax && y < x)) { cnt++; prev = fmax(prev, ay); }
+      }
+      const int lin = nStart - cnt;
+      v += (double)(lin * (lin - 1)) * (ax - prev);
+      if (cnt == total - 1) {
+        const int restLin = lin - 1;
+        v += (double)(restLin * (restLin - 1)) * (end - ax);
+      }
+    }
+    vl[kk] = v;
+  }
+  return teamSumLikeWarp(tm, vl);
+}
+
+// smpAgeProposeBody on a team; the genealogy is the shared-memory copy behind `t`, np / coal / ncoal the slot's arrays
+__device__ inline SmpProposal teamAgePropose(const Team& tm, const SweepModel& m, const TreeView& t, const uint8_t* np, const double* coal,
+                                             const int* ncoal, int l, int n, int N, int inode, double finetune, unsigned long long seed,
+                                             unsigned long long step, uint8_t* scratch) {
+  SmpProposal pr = smpNoProposal();
+  pr.node = inode;
+  const int root = *t.root;
+  if (root < n) return pr;
+  double tnew = 0.0;
+  int valid = 0, pop = 0, nStart = 0;
+  if (tm.j == 0) {
+    pop = np[inode];
+    const double told = t.age[inode];
+    const NodeRec rec = t.node[inode];
+    const double lo = fmax(m.tau[pop], fmax(t.age[rec.left], t.age[rec.right]));
+    double hi = m.father[pop] >= 0 ? m.tau[m.father[pop]] : kOldAge;
+    if (inode != root) hi = fmin(hi, t.age[rec.father]);
+    SmpRng rng(seed, (unsigned long long)l, step);
+    tnew = smpReflect(told + finetune * rng.normal2(), lo, hi);
+    valid = fabs(tnew - told) >= 1e-15;   // GPhoCS.c:2354-2358
+    if (valid) {
+      adjustAge(t, inode, tnew);
+      nStart = m.leavesBelow[pop];
+      for (int q = 0; q < m.Q; q++)
+        if (q != pop && ((m.below[pop] >> q) & 1ull)) nStart -= ncoal[q];
+    }
+  }
+  valid = teamBcast(tm, valid);
+  if (!valid) return pr;
+  pop = teamBcast(tm, pop);
+  nStart = teamBcast(tm, nStart);
+  __syncwarp(tm.mask);   // the leader's new age is in shared memory
+  const double coalNew = teamPopStat(tm, m, t.age, np, n, N, pop, nStart, scratch);
+  pr.genDelta = -(coalNew - coal[pop]) / m.theta[pop];
+  pr.aux = coalNew;
+  pr.pop = pop;
+  pr.valid = 1;
+  return pr;
+}
+
+// smpSprProposeBody on a team: every thread rings the clocks of its share of the branches
+__device__ inline SmpProposal teamSprPropose(const Team& tm, const SweepModel& m, const TreeView& t, uint8_t* np, int l, int n, int N,
+                                             int node, unsigned long long seed, unsigned long long step) {
+  SmpProposal pr = smpNoProposal();
+  const int root = *t.root;
+  if (root < n || node == root) return pr;
+  const int F = t.node[node].father;
+  const NodeRec recF = t.node[F];
+  const int S = recF.left + recF.right - node;
+  const int G = recF.father;
+  const double t0 = t.age[node];
+  const int pop0 = np[node];
+  const double ageG = G >= 0 ? t.age[G] : kSmpInf;
+  double bestT = kSmpInf;
+  int bestX = -1, bestPop = -1;
+  const SmpRng rng(seed, (unsigned long long)l, step);
+#pragma unroll 1
+  for (int x = tm.j; x < N; x += kTeam) {
+    if (x == node || x == F) continue;
+    const int fx = t.node[x].father;
+    const double endx = x == S ? ageG : (fx >= 0 ? t.age[fx] : kSmpInf);
+    int q = np[x];   // first population in which the two lineages can meet: their common ancestor
+    while (!((m.below[q] >> pop0) & 1ull)) q = m.father[q];
+    double sNow = fmax(fmax(t0, t.age[x]), m.tau[q]);
+    if (sNow >= endx) continue;
+    while (m.father[q] >= 0 && m.tau[m.father[q]] <= sNow) q = m.father[q];
+    double need = rng.exponentialAt((unsigned long long)x);
+#pragma unroll 1
+    for (int it = 0; it < kSmpMaxPops; it++) {
+      const double popEnd = m.father[q] >= 0 ? m.tau[m.father[q]] : kSmpInf;
+      const double segEnd = fmin(endx, popEnd);
+      const double rate = m.coalRate[q];
+      if (rate * (segEnd - sNow) >= need) {
+        const double T = sNow + need / rate;
+        if (T < bestT) { bestT = T; bestX = x; bestPop = q; }
+        break;
+      }
+      need -= rate * (segEnd - sNow);
+      sNow = segEnd;
+      if (sNow >= endx) break;
+      q = m.father[q];
+    }
+  }
+#pragma unroll
+  for (int off = kTeam / 2; off > 0; off >>= 1) {   // earliest ring over the team (ties: lower node id)
+    const double oT = __shfl_xor_sync(tm.mask, bestT, off);
+    const int oX = __shfl_xor_sync(tm.mask, bestX, off);
+    const int oP = __shfl_xor_sync(tm.mask, bestPop, off);
+    if (oT < bestT || (oT == bestT && oX >= 0 && (bestX < 0 || oX < bestX))) { bestT = oT; bestX = oX; bestPop = oP; }
+  }
+  if (bestX >= 0) {
+    if (tm.j == 0) {
+      pr.pop = np[F];
+      pr.node = F;
+      spr(t, node, bestX, bestT);
+      np[F] = (uint8_t)bestPop;
+    }
+    pr.valid = 1;   // the statistics of accepted loci are refreshed once, after the sweep (k_smp_init_stats)
+  }
+  return pr;
+}
+
+// smpResolve on a team; returns 1 if the proposal counts as accepted
+__device__ inline int teamResolve(const Team& tm, const TreeView& t, uint8_t* np, double* coal, const SmpProposal& pr, int l, int N,
+                                  int kind, unsigned long long seed, unsigned long long step) {
+  int ok = 0;
+  if (pr.valid) {
+    if (tm.j == 0) {
+      const double lnacc = (*t.lnL - *t.savedLnL) + pr.genDelta;
+      ok = lnacc >= 0.0;
+      if (!ok) {
+        SmpRng rng(seed, (unsigned long long)l, step);
+        ok = rng.uniform() < exp(lnacc);
+      }
+    }
+    ok = teamBcast(tm, ok);
+    if (ok) {
+      for (int x = tm.j; x < N; x += kTeam)
+        if (t.node[x].flags & (F_RECALC | F_SAVED)) commitNode(t, x);   // both are no-ops on unmarked nodes
+      if (tm.j == 0) {
+        commitLocus(t);
+        if (kind == 0) coal[pr.pop] = pr.aux;
+      }
+    } else {
+      for (int x = tm.j; x < N; x += kTeam)
+        if (t.node[x].flags & (F_RECALC | F_SAVED)) revertNode(t, x);
+      if (tm.j == 0) {
+        revertLocus(t);
+        if (kind == 1) np[pr.node] = (uint8_t)pr.pop;
+      }
+    }
+  } else if (kind == 0) {
+    ok = 1;   // an unchanged age counts as accepted (GPhoCS.c:2354-2358)
+  }
+  __syncwarp(tm.mask);   // the proposal that follows reads what other threads of the team have just committed or reverted
+  return ok;
+}
+
+__global__ void __launch_bounds__(kThreads, GPHOCS_SWEEP_MINBLOCKS)
+k_sweep(StoreDev d, SmpDev sd, const SmpModel* __restrict__ mp, const Batch* __restrict__ batches, int maxLoci, double ftCoal,
+        unsigned long long seed, unsigned long long step0) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const Batch b = batches[blockIdx.x];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = d.n, N = d.N, NI = d.NI, nl = b.numLoci, Q = sd.Q;
+  const SweepSmem lay = sweepSmemLayout(n, maxLoci, Q);
+
+  // ---- carve shared memory
+  auto sAge = [&](int s) { return reinterpret_cast<double*>(smem + lay.offLoci + lay.perLocus * s + lay.offAge); };
+  auto sCoal = [&](int s) { return reinterpret_cast<double*>(smem + lay.offLoci + lay.perLocus * s + lay.offCoal); };
+  auto sNode = [&](int s) { return reinterpret_cast<NodeRec*>(smem + lay.offLoci + lay.perLocus * s + lay.offNode); };
+  auto sSize = [&](int s) { return reinterpret_cast<int*>(smem + lay.offStack + lay.perScratch * s + lay.offSize); };
+  auto sWalk = [&](int s) { return reinterpret_cast<uint32_t*>(smem + lay.offStack + lay.perScratch * s + lay.offWalk); };
+  auto sNcoal = [&](int s) { return reinterpret_cast<int*>(smem + lay.offLoci + lay.perLocus * s + lay.offNcoal); };
+  auto sNeed = [&](int s) { return reinterpret_cast<uint8_t*>(smem + lay.offLoci + lay.perLocus * s + lay.offNeed); };
+  auto sPop = [&](int s) { return reinterpret_cast<uint8_t*>(smem + lay.offLoci + lay.perLocus * s + lay.offPop); };
+  auto sSched = [&](int s) { return reinterpret_cast<SchedEntryCompact*>(smem + lay.offSched + lay.perSched * s); };
+  const uint32_t stackBase = smemAddr(smem + lay.offStack);
+  double* sRoot = reinterpret_cast<double*>(smem + lay.offStack);   // [kThreads][4], after the walk
+  double* sTerm = reinterpret_cast<double*>(smem + lay.offTerm);
+  double* mRate = reinterpret_cast<double*>(smem + lay.offMeta);    // per-slot scalars
+  double* mLnL = mRate + kTeamSlots;
+  double* mSavedLnL = mLnL + kTeamSlots;
+  int* mColStart = reinterpret_cast<int*>(mSavedLnL + kTeamSlots);
+  int* mP = mColStart + kTeamSlots;
+  int* mK = mP + kTeamSlots;
+  int* mRoot = mK + kTeamSlots;
+  int* mSavedRoot = mRoot + kTeamSlots;
+  int* mActive = mSavedRoot + kTeamSlots;
+  SmpProposal* sProp = reinterpret_cast<SmpProposal*>(smem + lay.offProp);
+  __shared__ int sListCountCell;   // not inside the list region: sTerm takes that over while the count is being reset
+  int* sListCount = &sListCountCell;
+  uint32_t* sList = reinterpret_cast<uint32_t*>(smem + lay.offList);
+  SweepModel& sModel = *reinterpret_cast<SweepModel*>(smem + lay.offModel);
+  __shared__ unsigned int sAccepted[2];
+
+  // ---- stage the batch: model, per-locus scalars, genealogies, population assignments, statistics, leaf codes
+  if (tid == 0) sModel.Q = Q;
+  for (int p = tid; p < Q; p += kThreads) {
+    sModel.father[p] = mp->father[p]; sModel.leavesBelow[p] = mp->leavesBelow[p]; sModel.below[p] = mp->below[p];
+    sModel.theta[p] = mp->theta[p]; sModel.tau[p] = mp->tau[p]; sModel.coalRate[p] = mp->coalRate[p];
+  }
+  unsigned long long w0 = 0ull, w1 = 0ull;
+  int ph = 0, cnt = 0;
+  if (tid < b.numCols) {
+    const int c = b.firstCol + tid;
+    w0 = d.leafWords[c];
+    if (d.W > 1) w1 = d.leafWords[(size_t)d.Ct + c];
+    ph = d.grpPhases[c];
+    cnt = d.grpCount[c];
+  }
+  if (tid < nl) {
+    const int l = b.firstLocus + tid;
+    const int c0 = d.colStart[l];
+    mColStart[tid] = c0;
+    mP[tid] = d.colStart[l + 1] - c0;
+    const int root = d.root[l];
+    mRoot[tid] = root;
+    mSavedRoot[tid] = d.savedRoot[l];
+    mRate[tid] = d.rate[l];
+    mActive[tid] = (mP[tid] > 0) && (root >= n);
+    mK[tid] = 0;
+    mLnL[tid] = d.lnL[l];
+    mSavedLnL[tid] = d.savedLnL[l];
+  }
+  if (tid < 2) sAccepted[tid] = 0u;
+  if (tid == 0) *sListCount = 0;
+  for (int s = warp; s < nl; s += kWarps) {
+    const int l = b.firstLocus + s;
+    const size_t g0 = (size_t)l * N;
+    NodeRec* nd = sNode(s);
+    double* age = sAge(s);
+    uint8_t* need = sNeed(s);
+    uint8_t* pop = sPop(s);
+    for (int v = lane; v < N; v += 32) {
+      nd[v] = d.node[g0 + v];
+      age[v] = d.age[g0 + v];
+      pop[v] = sd.nodePop[g0 + v];
+      need[v] = 0;
+    }
+    for (int p = lane; p < Q; p += 32) {
+      sCoal(s)[p] = sd.coal[(size_t)l * Q + p];
+      sNcoal(s)[p] = sd.ncoal[(size_t)l * Q + p];
+    }
+  }
+  const uint32_t myStack = stackBase + tid * 16;
+  const uint32_t myWords = smemAddr(smem + lay.offWords) + tid * 4;
+  const bool live = tid < b.numCols;
+  if (live) {   // this column's leaf masks, 8 leaves per 32-bit word
+    stsU32(myWords, (uint32_t)w0);
+    if (lay.W32 > 1) stsU32(myWords + kThreads * 4, (uint32_t)(w0 >> 32));
+    if (lay.W32 > 2) stsU32(myWords + 2 * kThreads * 4, (uint32_t)w1);
+    if (lay.W32 > 3) stsU32(myWords + 3 * kThreads * 4, (uint32_t)(w1 >> 32));
+  }
+  __syncthreads();
+  int colSlot = 0;   // the locus this thread's column belongs to
+  if (live) {
+    const int c = b.firstCol + tid;
+    while (colSlot + 1 < nl && c >= mColStart[colSlot + 1]) colSlot++;
+  }
+  char* const clvCol = reinterpret_cast<char*>(d.clv + (size_t)mColStart[colSlot] * NI * 8 +
+                                               (size_t)(live ? b.firstCol + tid - mColStart[colSlot] : 0) * 4);
+  const SweepModel& m = sModel;
+
+  // ---- the team of this thread and the genealogy it edits
+  Team tm;
+  tm.j = tid & (kTeam - 1);
+  tm.leader = lane & ~(kTeam - 1);
+  tm.mask = ((1u << kTeam) - 1u) << tm.leader;
+  const int slot = tid / kTeam;
+  const bool teamOn = slot < nl;
+  const int myLocus = b.firstLocus + slot;
+  TreeView t;
+  if (teamOn) {
+    const size_t o = (size_t)myLocus * N;
+    t.node = sNode(slot); t.saved = d.saved + o;
+    t.age = sAge(slot); t.svAge = d.svAge + o;
+    t.root = mRoot + slot; t.savedRoot = mSavedRoot + slot;
+    t.lnL = mLnL + slot; t.savedLnL = mSavedLnL + slot; t.rate = mRate + slot;
+    t.numLeaves = n;
+    t.numPatterns = mP[slot];
+  }
+  unsigned int accepted[2] = {0u, 0u};
+
+  const int numAge = ftCoal > 0.0 ? NI : 0, numSteps = numAge + N;
+  for (int it = 0; it <= numSteps; it++) {
+    // ---- team phase
+    if (teamOn) {
+      if (it > 0) {
+        const int kind = it - 1 < numAge ? 0 : 1;
+        const int ok = teamResolve(tm, t, sPop(slot), sCoal(slot), sProp[slot], myLocus, N, kind, seed, step0 + 2ull * (it - 1) + 1ull);
+        if (tm.j == 0) accepted[kind] += ok;
+      }
+      if (it < numSteps) {
+        const unsigned long long step = step0 + 2ull * it;
+        uint8_t* scratch = reinterpret_cast<uint8_t*>(sWalk(slot));   // the list phases have not started: N words free
+        const SmpProposal pr = it < numAge
+            ? teamAgePropose(tm, m, t, sPop(slot), sCoal(slot), sNcoal(slot), myLocus, n, N, n + it, ftCoal, seed, step, scratch)
+            : teamSprPropose(tm, m, t, sPop(slot), myLocus, n, N, it - numAge, seed, step);
+        if (tm.j == 0) {
+          sProp[slot] = pr;
+          mK[slot] = 0;
+          if (mActive[slot]) mSavedLnL[slot] = mLnL[slot];   // what every evaluation starts with (.c:440)
+        }
+        __syncwarp(tm.mask);
+        if (mActive[slot]) {
+          // k_eval phase B: dirty nodes and their ancestors (a moved leaf dirties its father, .c:1569-1575)
+          NodeRec* nd = t.node;
+          uint8_t* need = sNeed(slot);
+          for (int v = tm.j; v < N; v += kTeam)
+            if (nd[v].flags & F_RECALC) {
+              int u = v < n ? nd[v].father : v;
+              for (int k = 0; u >= 0 && !need[u] && k < N; k++) {   // concurrent walkers store the same 1 (see k_eval)
+                need[u] = 1;
+                u = nd[u].father;
+              }
+            }
+          __syncwarp(tm.mask);
+          // k_eval phase C0: marked nodes of the batch compacted into one list; their destination buffers flipped
+          for (int v0 = n; v0 < N; v0 += kTeam) {
+            const int v = v0 + tm.j;
+            const bool marked = v < N && need[v];
+            const unsigned ballot = (__ballot_sync(tm.mask, marked) >> tm.leader) & ((1u << kTeam) - 1u);
+            int base = 0;
+            if (tm.j == 0 && ballot) base = atomicAdd(sListCount, __popc(ballot));
+            base = teamBcast(tm, base);
+            if (marked) {
+              sSize(slot)[v - n] = 0;   // phase C counts into it (its space was the column stack a moment ago)
+              sList[base + __popc(ballot & ((1u << tm.j) - 1u))] = (uint32_t)(slot << 16 | v);
+              const uint8_t f = nd[v].flags;
+              if (!(f & F_RECALC)) nd[v].flags = (uint8_t)((f ^ F_SEL) | F_RECALC);
+            }
+          }
+        }
+      }
+    }
+    if (it == numSteps) break;
+    __syncthreads();
+    const int listCount = *sListCount;
+    // ---- k_eval phase C: marked nodes per subtree
+    for (int j = tid; j < listCount; j += kThreads) {
+      const int s = sList[j] >> 16, v = sList[j] & 0xffff;
+      const NodeRec* nd = sNode(s);
+      int* size = sSize(s);
+      int a = v;
+      for (int k = 0; a >= 0 && k < N; k++) {
+        atomicAdd(&size[a - n], 1);
+        a = nd[a].father;
+      }
+    }
+    __syncthreads();
+    // ---- k_eval phase D1: what a node adds to the post-order start of everything below it (heavier child first)
+    for (int j = tid; j < listCount; j += kThreads) {
+      const int s = sList[j] >> 16, v = sList[j] & 0xffff;
+      const NodeRec* nd = sNode(s);
+      const uint8_t* need = sNeed(s);
+      const int* size = sSize(s);
+      const int a = nd[v].father;
+      uint32_t contrib = 0;
+      if (a >= 0) {
+        const int l = nd[a].left, r = nd[a].right;
+        const int wl = (l >= n && need[l]) ? size[l - n] : 0;
+        const int wr = (r >= n && need[r]) ? size[r - n] : 0;
+        const int first = wl >= wr ? l : r;
+        if (v != first) contrib = (uint32_t)(v == l ? wr : wl);
+      }
+      sWalk(s)[v] = (uint32_t)(a + 1) | (contrib << 16);
+    }
+    __syncthreads();
+    // ---- k_eval phase D2: position, stack depth, child sources and JC69 edge terms of every marked node
+    for (int j = tid; j < listCount; j += kThreads) {
+      const int s = sList[j] >> 16, v = sList[j] & 0xffff;
+      const NodeRec* nd = sNode(s);
+      const uint8_t* need = sNeed(s);
+      const int* size = sSize(s);
+      const uint32_t* walk = sWalk(s);
+      const double* age = sAge(s);
+      const double rate = mRate[s];
+      int start = 0, depth = 0;
+      {
+        uint32_t w = walk[v];
+        for (int k = 0; k < N; k++) {
+          const uint32_t c = w >> 16;
+          start += c;
+          depth += c != 0;
+          const int a = (int)(w & 0xffffu) - 1;
+          if (a < 0) break;
+          w = walk[a];
+        }
+      }
+      const int l = nd[v].left, r = nd[v].right;
+      const int wl = (l >= n && need[l]) ? size[l - n] : 0;
+      const int wr = (r >= n && need[r]) ? size[r - n] : 0;
+      const bool leftFirst = wl >= wr;
+      const int A = leftFirst ? l : r, B = leftFirst ? r : l;
+      const int wA = leftFirst ? wl : wr, wB = leftFirst ? wr : wl;
+      const uint32_t strideBytes = (uint32_t)mP[s] * 32u;
+      auto record = [&](int x) { return (uint32_t)((x - n) * 2 + (nd[x].flags & F_SEL)) * strideBytes; };
+      auto leafRef = [&](int x) { return (uint32_t)(x >> 3) * (kThreads * 4u) | ((uint32_t)(x & 7) * 4u) << 16; };
+      uint32_t kindA, kindB, offA = 0, offB = 0;
+      if (A < n) { kindA = SRC_LEAF; offA = leafRef(A); }
+      else if (wA > 0 && wB == 0) { kindA = SRC_TOP; }
+      else if (wA > 0 && depth < kSweepStack) { kindA = SRC_STACK; offA = ((uint32_t)depth * kRow) << 16; }
+      else { kindA = SRC_GLOBAL; offA = record(A); }
+      if (B < n) { kindB = SRC_LEAF; offB = leafRef(B); }
+      else if (wB > 0) { kindB = SRC_TOP; }
+      else { kindB = SRC_GLOBAL; offB = record(B); }
+      SchedEntryCompact en;
+      const double av = age[v];
+      en.e0A = edgeProb(rate * (av - age[A]));
+      en.e0B = edgeProb(rate * (av - age[B]));
+      en.offA = offA; en.offB = offB;
+      en.dstOff = record(v);
+      uint32_t push = 0xffffu;
+      {
+        const int f = nd[v].father;
+        if (f >= 0 && v != mRoot[s] && depth < kSweepStack) {
+          const int fl = nd[f].left, fr = nd[f].right;
+          const int wfl = (fl >= n && need[fl]) ? size[fl - n] : 0;
+          const int wfr = (fr >= n && need[fr]) ? size[fr - n] : 0;
+          const int first = wfl >= wfr ? fl : fr;
+          const int wSibling = v == fl ? wfr : wfl;
+          if (v == first && wSibling > 0) push = (uint32_t)depth * kRow;
+        }
+      }
+      en.ctl = kindA | (kindB << 2) | (push << 16);
+      sSched(s)[start + size[v - n] - 1] = en;
+      if (v == mRoot[s]) mK[s] = size[v - n];
+    }
+    __syncthreads();
+    // ---- column phase (k_eval phase E)
+    double pv[4] = {0.0, 0.0, 0.0, 0.0};
+    const int k = (live && mActive[colSlot]) ? mK[colSlot] : 0;
+    if (k > 0) columnWalk<kSweepHi, true>(smemAddr(sSched(colSlot)), k, clvCol, myStack, myWords, true, pv);
+    __syncthreads();   // the stack is dead; its space takes the root vectors
+#pragma unroll
+    for (int q = 0; q < 4; q++) sRoot[tid * 4 + q] = pv[q];
+    for (int j = tid; j < listCount; j += kThreads) {   // dirty marks back to zero for the next step
+      const int s = sList[j] >> 16, v = sList[j] & 0xffff;
+      sNeed(s)[v] = 0;
+    }
+    __syncthreads();
+    // ---- root phase (k_eval phase F): 4*phases conditionals per phase group in the reference's order (.c:470-479)
+    double term = 0.0;
+    if (k > 0 && ph > 0) {
+      double prob = 0.0;
+      const int numConds = 4 * ph;
+      for (int j = 0; j < numConds; j++) prob += sRoot[tid * 4 + j];
+      term = log(prob / numConds) * cnt;
+    }
+    sTerm[tid] = term;
+    if (tid == 0) *sListCount = 0;
+    __syncthreads();
+    if (tid < nl && mActive[tid] && mK[tid] > 0) {   // per-locus sum in pattern order
+      const int P = mP[tid];
+      const double* tt = sTerm + (mColStart[tid] - b.firstCol);
+      double lnl = 0.0;
+      for (int j = 0; j < P; j++) lnl += tt[j];
+      mLnL[tid] = lnl;
+    }
+    __syncthreads();
+  }
+
+  // ---- the final state goes back: genealogies (every proposal is resolved: flags hold buffer selectors only),
+  //      population assignments, log-likelihoods, coal statistics
+  if (tm.j == 0 && teamOn) {
+    if (accepted[0]) atomicAdd(&sAccepted[0], accepted[0]);
+    if (accepted[1]) atomicAdd(&sAccepted[1], accepted[1]);
+  }
+  __syncthreads();
+  for (int s = warp; s < nl; s += kWarps) {
+    const int l = b.firstLocus + s;
+    const size_t g0 = (size_t)l * N;
+    const NodeRec* nd = sNode(s);
+    const double* age = sAge(s);
+    const uint8_t* pop = sPop(s);
+    for (int v = lane; v < N; v += 32) {
+      d.node[g0 + v] = nd[v];
+      d.age[g0 + v] = age[v];
+      sd.nodePop[g0 + v] = pop[v];
+    }
+    for (int p = lane; p < Q; p += 32) sd.coal[(size_t)l * Q + p] = sCoal(s)[p];
+  }
+  if (tid < nl) {
+    const int l = b.firstLocus + tid;
+    d.root[l] = mRoot[tid];
+    d.savedRoot[l] = mSavedRoot[tid];
+    d.lnL[l] = mLnL[tid];
+    d.savedLnL[l] = mSavedLnL[tid];
+    sd.prop[l] = smpNoProposal();
+  }
+  if (tid < 2 && sAccepted[tid]) atomicAdd(sd.accepted + tid, (unsigned long long)sAccepted[tid]);
+}
+
+}  // namespace gphocs

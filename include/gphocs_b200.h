@@ -278,19 +278,12 @@ int gphocsSamplerTraceWidth(const GphocsSampler *sm);
 int gphocsSamplerOpenTrace(GphocsSampler *sm, const char *path, const char *const *popNames, double thetaTauPrint,
                            double migRatePrint, int sampleSkip);
 int gphocsSamplerCloseTrace(GphocsSampler *sm);
-/* 1: the coalescence-time and SPR sweeps of a model without migration bands (<= 64 nodes) run as one launch that keeps
- * every locus on a warp (propose, incremental likelihood, accept per node); 0 (default): one proposal and one
- * evaluation launch per node.  Same random streams and arithmetic: both give the same chain bit for bit.  Measured
- * slower on B200, hence opt-in. */
-int gphocsSamplerSetFusedSweep(GphocsSampler *sm, int on);
-/* 1: the per-locus proposal kernels finish the tree-side half of the incremental evaluation (dirty nodes, buffer
- * flips, children-first order, JC69 edge terms) and a column-walk kernel does the rest; 0 (default): k_eval builds the
- * schedule from the flags.  Same arithmetic: the chain does not depend on the choice.  Measured slower on B200
- * (DESIGN.md 4b), hence opt-in. */
-int gphocsSamplerSetScheduledEval(GphocsSampler *sm, int on);
-/* CUDA streams the per-locus sweeps are spread over: loci are independent there, so the sweeps can be cut in two halves
- * that run side by side.  1 (default) or 2; the chain does not depend on it.  Measured: no gain on B200. */
-int gphocsSamplerSetSweepStreams(GphocsSampler *sm, int streams);
+/* The coalescence-time and SPR sweeps (UpdateGB_InternalNode GPhoCS.c:2287, UpdateGB_MigSPR :2598) of a model without
+ * migration bands run as ONE launch in which a CTA keeps its batch of loci for both sweeps (up to 32 leaves, no locus
+ * with more than 128 pattern columns); other models take the stepwise route: a proposal launch and an evaluation
+ * launch per node.  1 forces the stepwise route everywhere, 0 (default) restores the choice above.  Same random
+ * streams and arithmetic: both routes give the same chain bit for bit. */
+int gphocsSamplerSetStepwise(GphocsSampler *sm, int on);
 /* accepted[10], proposed[10] for {coalescence time, SPR, theta, tau, mixing, migration rate, migration time,
  * (proposed only) split-time moves rejected for a migration conflict, locus rate (pairs of loci), sample age} */
 int gphocsSamplerGetState(GphocsSampler *sm, double *theta, double *tau, long long *accepted, long long *proposed);

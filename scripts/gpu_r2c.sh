@@ -1,0 +1,9 @@
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_sampler.py -x -q -k "sweep_routes or stays_consistent" > gpurun_out/r2c_pytest.log 2>&1; echo "pytest rc=$?"; tail -5 gpurun_out/r2c_pytest.log
+rm -f gpurun_out/r2c_bench.log
+for L in 100000 12500; do
+  timeout 300 python scripts/sampler_bench.py --config hap16 --loci $L --iterations 30 >> gpurun_out/r2c_bench.log 2>&1
+done
+cut -c1-330 gpurun_out/r2c_bench.log
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 60 -c 20 --csv --log-file gpurun_out/r2c_launches.csv \
+    python scripts/sampler_bench.py --config hap16 --loci 100000 --iterations 4 > /dev/null 2>&1; grep k_sweep gpurun_out/r2c_launches.csv | head -2

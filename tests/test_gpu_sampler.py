@@ -87,52 +87,61 @@ def test_many_leaves_per_locus_stay_consistent(leaves):
     st.close()
 
 
-@pytest.mark.parametrize("cfg,L", [("hap16", 300), ("ancient", 200), ("pop6nomig", 150), ("dip8mig", 200), ("pop6mig4", 120)])
-def test_evaluation_routes_give_the_same_chain(cfg, L):
-    """Routes to the likelihood of a proposal — k_eval rebuilding its schedule from the flags ("plain"; the same with
-    the loci cut in two halves on two streams, "two_streams"), the
-    proposal kernel handing a schedule to k_eval_sched ("sched", default), whole sweeps on a warp with the warp-level
-    evaluation ("sweep", models without migration) — use the same random streams and the same arithmetic: identical
-    traces, statistics, genealogies, log-likelihoods and conditional vectors."""
-    if cfg == "pop6nomig":      # 24 leaves, 47 nodes: two nodes per lane
+@pytest.mark.parametrize("cfg,L", [("hap16", 300), ("ancient", 200), ("pop6nomig", 150), ("mid", 80), ("wide32", 60), ("tiny", 50)])
+def test_sweep_routes_give_the_same_chain(cfg, L):
+    """The one-launch sweep (sweep_kernels.cuh: a CTA keeps its batch of loci for both per-locus sweeps) and the stepwise
+    route (a proposal launch and a k_eval launch per node) use the same random streams and the same arithmetic:
+    identical traces, statistics, genealogies, population assignments, log-likelihoods and conditional vectors —
+    with a tenth of the launches.  Shapes: configs[1]; configs[4] (sample ages, locus rates); 24 leaves / 6
+    populations (two nodes per lane on the stepwise route); denser patterns (a few loci per CTA batch, loci wider
+    than a warp); 32 leaves (the largest the sweep takes); 3 leaves (fewer nodes than team threads)."""
+    if cfg == "pop6nomig":
         base = synth.config("pop6mig4")
         model = synth.Model("pop6nomig", base.cur, base.anc, diploid=base.diploid)
+    elif cfg == "mid":          # theta 5e-3: tens of patterns per locus, a few loci per CTA batch
+        model = synth.config("hap16")
+        model.theta = 5e-3
+        model.anc = [(a, b, c, t * 5) for a, b, c, t in model.anc]
+    elif cfg == "wide32":
+        model = synth.Model("wide32", [("A", 16), ("B", 16)], [("root", "A", "B", 1e-3)])
+    elif cfg == "tiny":
+        model = synth.Model("tiny", [("A", 2), ("B", 1)], [("root", "A", "B", 1e-3)])
     else:
         model = synth.config(cfg)
     w = synth.generate(model, L, seed=41)
-    mig = (w.mig_start, w.mig_branch, w.mig_band, w.mig_age) if len(w.pops["band_src"]) else None
+    assert not len(w.pops["band_src"])
     out = {}
-    for route in ("plain", "sched", "two_streams") + (() if mig else ("sweep",)):
+    for route in ("stepwise", "sweep"):
         st = gp.LociStore.from_workload(w)
         extra = {}
         if model.sample_age:
             st.set_rates(np.ones(w.L))
             extra = dict(estimate_sample_age=[1 if nm in model.sample_age else 0 for nm, _ in model.cur], locus_rate_finetune=0.3)
-        sm = gp.Sampler(st, w.pops, w.node_pop, seed=77, migration=mig, **extra)
-        sm.set_scheduled_eval(route == "sched")
-        sm.set_fused_sweep(route == "sweep")
-        sm.set_sweep_streams(2 if route == "two_streams" else 1)
+        sm = gp.Sampler(st, w.pops, w.node_pop, seed=77, **extra)
+        sm.set_stepwise(route == "stepwise")
         k0 = gp.lib().gphocsKernelLaunchCount()
         tr = sm.iterate(12)
         launches = gp.lib().gphocsKernelLaunchCount() - k0
         assert sm.check()[0] == 0
         stats = sm.stats()
+        state = sm.state()
         node_pop = sm.download()
         trees = st.get_trees()
-        clv = st.clv(0, st.n + 1, P=int(w.patt_start[1] - w.patt_start[0]))
-        out[route] = (tr, stats, node_pop, trees, st.lnl(), launches, clv)
+        clvs = [st.clv(l, st.n + k, P=int(w.patt_start[l + 1] - w.patt_start[l])) for l in (0, L // 2, L - 1) for k in (0, st.n - 2)]
+        out[route] = (tr, stats, node_pop, trees, st.lnl(), launches, clvs, state)
         sm.close(); st.close()
-    a = out["plain"]
-    for route, b in out.items():
-        assert np.array_equal(a[0], b[0]), route
-        assert np.array_equal(a[1]["coal"], b[1]["coal"]) and np.array_equal(a[1]["num_coals"], b[1]["num_coals"]), route
-        assert np.array_equal(a[1]["mig"], b[1]["mig"]) and np.array_equal(a[1]["num_migs"], b[1]["num_migs"]), route
-        assert np.array_equal(a[2], b[2]), route
-        for x, y in zip(a[3], b[3]):
-            assert np.array_equal(x, y), route
-        assert np.array_equal(a[4], b[4]) and np.array_equal(a[6], b[6]), route
-    if "sweep" in out:
-        assert out["sweep"][5] < a[5] / 3, (out["sweep"][5], a[5])
+    a, b = out["stepwise"], out["sweep"]
+    assert np.array_equal(a[0], b[0])
+    assert np.array_equal(a[1]["coal"], b[1]["coal"]) and np.array_equal(a[1]["num_coals"], b[1]["num_coals"])
+    assert np.array_equal(a[2], b[2])
+    for x, y in zip(a[3], b[3]):
+        assert np.array_equal(x, y)
+    assert np.array_equal(a[4], b[4])
+    for x, y in zip(a[6], b[6]):
+        assert np.array_equal(x, y)
+    for move in ("coal_time", "spr"):
+        assert a[7]["accepted"][move] == b[7]["accepted"][move] and a[7]["proposed"][move] == b[7]["proposed"][move], move
+    assert b[5] < a[5] / 2, (b[5], a[5])
 
 
 def test_uninformative_data_recovers_the_prior():
