@@ -16,6 +16,11 @@ Workload (config.workload): BASELINE.json configs[3] — 100k loci x 1 kb, 6-pop
 bands, 2 unphased diploids per population (24 leaves) — per GPU (weak scaling, loci sharded by rank with no
 data-path collective).  Synthetic alignments from g-phocs_b200/synth.py; per-step HBM working set is
 several GB (>> 126 MB L2), so no explicit L2 flush is needed.
+
+BASELINE.json's metric has a second half — MCMC iterations/s at 10k / 100k loci — which the JSON line carries inside
+the objects the driver keeps: `roofline.mcmc` (device-resident update steps, per configuration: iterations/s, kernel
+launches and algorithmic bytes per iteration, fraction of the HBM roofline; the 100k-locus configurations are sharded
+over all ranks = strong scaling) and `cpu_baseline.mcmc` (the reference's own OpenMP build on the host cores).
 """
 import argparse
 import importlib
@@ -140,7 +145,7 @@ def reference_sample(cfg, sample_loci, seed, reps, threads, quiet=True):
     sd, sg = C.c_double(), C.c_double()
     # bounded sample: passes per step sized from two calibration passes so that the whole run is ~20 s of CPU work
     t_pass = min(lib.refh_time_both_once(C.byref(sd), C.byref(sg)) for _ in range(2))
-    passes = int(max(1, min(PASSES_PER_STEP, round(20.0 / max(reps * t_pass, 1e-9)))))
+    passes = int(max(1, min(PASSES_PER_STEP, round(25.0 / max(reps * t_pass, 1e-9)))))
     for _ in range(reps):
         t = 0.0
         for _p in range(passes):
@@ -202,9 +207,11 @@ def reference_mcmc(threads, iterations=40, cfg=MCMC_CONFIG):
             "iters_per_s": (iterations - 1) / max(wall[iterations] - wall[1], 1e-9), "wall_s": wall[iterations], "setup_s": wall[1]}
 
 
-def device_mcmc(gp, synth, device, total_loci, iterations, rank=0, world=1, cfg=MCMC_CONFIG):
+def device_mcmc(gp, synth, device, total_loci, iterations, rank=0, world=1, cfg=MCMC_CONFIG, peak_gbs=None):
     """MCMC iterations/s of the device-resident update steps (gphocs_b200.h group D) on workload `cfg` with `total_loci`
-    loci sharded over `world` ranks; global decisions are taken on NCCL all-reduced sums."""
+    loci sharded over `world` ranks (strong scaling); global decisions are taken on NCCL all-reduced sums.
+    Iteration-level roofline: the algorithmic bytes of every incremental evaluation of the iteration, 32*P*(2k+1) with k
+    conditional vectors recomputed, counted by the kernels themselves, over the iteration time."""
     import torch
     import torch.distributed as dist
     shard = importlib.import_module("g-phocs_b200.shard")
@@ -222,6 +229,7 @@ def device_mcmc(gp, synth, device, total_loci, iterations, rank=0, world=1, cfg=
     if world > 1:
         sm.init_nccl(rank, world, locus_offset=lo)      # the library's own communicator: sums stay on the device
     sm.iterate(5, trace=False)
+    sm.eval_counters(reset=True)                        # switches the accounting on
     k0 = gp.lib().gphocsKernelLaunchCount()
     if world > 1:
         dist.barrier()
@@ -230,21 +238,58 @@ def device_mcmc(gp, synth, device, total_loci, iterations, rank=0, world=1, cfg=
     sm.iterate(iterations, trace=False)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
+    evals, ebytes = sm.eval_counters()
     if world > 1:
-        t = torch.tensor([dt], dtype=torch.float64, device=f"cuda:{device}")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dt = float(t.item())
+        t = torch.tensor([dt, -float(evals), -float(ebytes)], dtype=torch.float64, device=f"cuda:{device}")
+        dist.all_reduce(t[:1], op=dist.ReduceOp.MAX)
+        dist.all_reduce(t[1:], op=dist.ReduceOp.SUM)
+        dt, evals, ebytes = float(t[0].item()), -float(t[1].item()), -float(t[2].item())
     launches = gp.lib().gphocsKernelLaunchCount() - k0
     violations, stat_err, lnl_err = sm.check()
     s = sm.state()
+    gbs = ebytes / dt / 1e9
     out = {"config": f"{cfg}: {total_loci} loci over {world} GPU(s)", "iterations": iterations, "iters_per_s": iterations / dt,
+           "ms_per_iteration": 1e3 * dt / iterations,
            "kernel_launches_per_iteration": launches / iterations,
-           "accept_rates": {m: float(s["accepted"][m]) / max(1, int(s["proposed"][m])) for m in gp.Sampler.MOVES if m != "tau_conflicts"},
+           "incremental_evals_per_iteration": evals / iterations,
+           "algorithmic_bytes_per_iteration": ebytes / iterations,
+           "achieved_gbs_all_gpus": gbs, "frac_of_hbm_peak": (gbs / world / peak_gbs) if peak_gbs else None,
+           "accept_rates": {m: round(float(s["accepted"][m]) / max(1, int(s["proposed"][m])), 4) for m in gp.Sampler.MOVES if m != "tau_conflicts"},
            "check": {"violations": int(violations), "max_stat_rel_err_vs_recompute": stat_err,
                      "max_lnl_rel_err_vs_full_recompute": lnl_err}}
     sm.close()
     st.close()
     return out
+
+
+def evals_at_10k(gp, synth, device, cfg, steps=40):
+    """Device-resident evaluations/s of the same step (full data likelihood + genealogy likelihood of every locus) at
+    10k loci — BASELINE.json's smaller size.  The working set (tens of MB) would sit in the 126 MB L2, so a 512 MB
+    buffer is written between the timed steps."""
+    import torch
+    L = 10_000
+    w = synth.generate(synth.config(cfg), L, seed=4321)
+    stream = torch.cuda.Stream(device=device)
+    st = gp.LociStore.from_workload(w, device=device, stream=stream.cuda_stream)
+    gen = gp.Genealogy(L, w.pops, device=device, stream=stream.cuda_stream)
+    gen.set_events(w.ev_start, w.pop_start, w.ev_type, w.ev_id, w.ev_time)
+    flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=f"cuda:{device}")
+    ms = []
+    with torch.cuda.stream(stream):
+        for i in range(steps + 3):
+            flush.fill_(i & 0xff)
+            a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            st.evaluate_device(0)
+            gen.evaluate_device()
+            b.record(stream)
+            if i >= 3:
+                ms.append((a, b))
+    torch.cuda.synchronize()
+    t = sum(a.elapsed_time(b) for a, b in ms) / len(ms)
+    st.close(); gen.close()
+    return {"config": workload_name(cfg, L), "evals_per_s": L / (t * 1e-3), "ms_per_step": t, "steps": len(ms),
+            "l2": "512 MB written between timed steps (working set would otherwise stay in L2)"}
 
 
 class quiet_stdout:
@@ -349,11 +394,19 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(timed),
         "warmup": args.warmup, "ms_per_step": 1e3 * total / len(timed), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(args.config, args.loci) + " per GPU", "sample": sample},
+        "config": common_config(args.config, args.loci, args.gpus),
         "cpu_baseline": cb,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
+
+
+def common_config(cfg, L, gpus):
+    """`config` of the JSON line — the same object for both arms (what differs, e.g. the reference arm's bounded
+    sample, is described in `cpu_baseline.sample`)."""
+    return {"workload": workload_name(cfg, L) + " per GPU", "loci_per_gpu": L, "n_gpus": gpus, "host_cores": os.cpu_count() or 1,
+            "l2": "per-step HBM working set of several GB >> 126 MB L2 (no flush needed)",
+            "parallelism": f"loci sharded over {gpus} GPU(s), one all-reduce of a (2+2Q+2B)-double vector per step on a side stream"}
 
 
 def workload_name(cfg, L):
@@ -404,10 +457,14 @@ def run_b200(args):
     host_threads = lib.gphocsSetHostThreads(max(1, (os.cpu_count() or 1) // world))   # torchrun pins OMP_NUM_THREADS=1
     V = 1 + 2 * Q + 2 * B
     assert 1 + V == shard.payload_len(Q, B)
-    payload = torch.zeros(1 + V, dtype=torch.float64, device=dev)   # [sum data lnL | sum gen lnL, totals...]
+    # [sum data lnL | sum gen lnL, totals...] of step i is summed over ranks on a side stream while step i+1 computes
+    pipe = shard.PipelinedAllReduce(1 + V, dev, depth=2)
+    step_no = [0]
 
     def step(record=None):
         """device-resident pass; `record` = list to append (start, mid, end) events to"""
+        i = step_no[0]
+        step_no[0] += 1
         with torch.cuda.stream(stream):
             if record is not None:
                 e0 = torch.cuda.Event(enable_timing=True); e0.record(stream)
@@ -418,9 +475,10 @@ def run_b200(args):
             if record is not None:
                 e2 = torch.cuda.Event(enable_timing=True); e2.record(stream)
                 record.append((e0, e1, e2))
+            payload = pipe.buffer(i, stream)
             lib.gphocsCopyDeviceAsync(C.c_void_p(payload.data_ptr()), C.c_void_p(dsum), 8, C.c_void_p(stream.cuda_stream))
             lib.gphocsCopyDeviceAsync(C.c_void_p(payload.data_ptr() + 8), C.c_void_p(dtot), 8 * V, C.c_void_p(stream.cuda_stream))
-            shard.all_reduce_payload(payload)     # the only cross-GPU traffic: < 1 KB per step
+            pipe.submit(i, stream)                # the only cross-GPU traffic: < 1 KB per step
 
     def barrier():
         if world > 1:
@@ -443,6 +501,7 @@ def run_b200(args):
     for _ in range(args.steps):
         step(rec)
     with torch.cuda.stream(stream):
+        payload = pipe.result(step_no[0] - 1, stream)     # the last step's sums are in before the clock stops
         t_end.record(stream)
     barrier()
     launches = lib.gphocsKernelLaunchCount() - launches0
@@ -543,46 +602,56 @@ def run_b200(args):
     torch.cuda.synchronize()
     inc_ms = a.elapsed_time(b)
     st.apply_ops(rej)
-    # MCMC iterations/s of the device-resident steps: BASELINE.json configs[3] (100k loci, 6 populations + 4 bands) and
-    # the migration-free 100k-locus shape sharded over all ranks (strong scaling); configs[1] and [2] (10k loci) at N=1
-    mcmc = {} if args.no_mcmc else {"configs3_pop6mig4_100k_sharded": device_mcmc(gp, synth, local_rank, 100_000, 10, rank, world, cfg="pop6mig4"),
-            "configs4_ancient_50k_sharded": device_mcmc(gp, synth, local_rank, 50_000, 20, rank, world, cfg="ancient"),
-            "hap16_100k_sharded": device_mcmc(gp, synth, local_rank, 100_000, 30, rank, world)}
+    # MCMC iterations/s of the device-resident steps (BASELINE.json's second metric).  The 100k / 50k-locus
+    # configurations are sharded over all ranks (strong scaling: total loci fixed); the 10k-locus ones run at N = 1.
+    peak, peak_src = measured_peak()
+    mcmc = {}
+    if not args.no_mcmc:
+        mcmc["configs3_pop6mig4_100k_sharded"] = device_mcmc(gp, synth, local_rank, 100_000, 10, rank, world, cfg="pop6mig4", peak_gbs=peak)
+        mcmc["hap16_100k_sharded"] = device_mcmc(gp, synth, local_rank, 100_000, 40, rank, world, peak_gbs=peak)
+        mcmc["configs4_ancient_50k_sharded"] = device_mcmc(gp, synth, local_rank, 50_000, 20, rank, world, cfg="ancient", peak_gbs=peak)
+        if world == 1:
+            mcmc["configs1_hap16_10k"] = device_mcmc(gp, synth, local_rank, MCMC_LOCI, 100, peak_gbs=peak)
+            mcmc["configs2_dip8mig_10k"] = device_mcmc(gp, synth, local_rank, 10_000, 50, cfg="dip8mig", peak_gbs=peak)
+    small = None
     if world == 1 and not args.no_mcmc:
-        mcmc["configs1_hap16_10k"] = device_mcmc(gp, synth, local_rank, MCMC_LOCI, 100)
-        mcmc["configs2_dip8mig_10k"] = device_mcmc(gp, synth, local_rank, 10_000, 50, cfg="dip8mig")
+        small = {"configs1_hap16_10k": evals_at_10k(gp, synth, local_rank, "hap16"),
+                 "configs2_dip8mig_10k": evals_at_10k(gp, synth, local_rank, "dip8mig")}
     clocks = sampler.stop() if rank == 0 else None
     ingest = ingest_bench(gp, synth, local_rank) if (rank == 0 and not args.no_cpu_baseline) else None
 
     if rank == 0:
-        peak, peak_src = measured_peak()
-        achieved = bytes_data / (ms_data * 1e-3) / 1e9
-        traffic = None
+        survey_gbs = bytes_data / (ms_data * 1e-3) / 1e9
+        layout_gbs = bytes_layout / (ms_data * 1e-3) / 1e9
+        traffic, traffic_src = None, None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
             tj = json.load(open(tp))
             if tj.get("workload") == f"{args.config}:{L}":
-                traffic = tj.get("k_eval_dram_bytes_per_launch")   # ncu --set full: dram__bytes_read.sum + dram__bytes_write.sum
+                traffic = tj.get("k_eval_dram_bytes_per_launch")
+                traffic_src = ("stored figure, NOT measured in this run: dram__bytes_read.sum + dram__bytes_write.sum of one k_eval launch "
+                               "from the ncu --set full capture named in profiles/traffic.json")
         value = world * L * args.steps / (ms_total * 1e-3)
         cb = cpu_baseline_subprocess(args.config, args.sample_loci, 3) if (world == 1 and not args.no_cpu_baseline) else None
+        mcmc_head = mcmc.get("configs3_pop6mig4_100k_sharded")
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(args.config, L) + " per GPU", "loci_per_gpu": L, "leaves": n,
-                       "mean_phased_patterns": float(P.mean()), "mean_events": float(E.mean()),
-                       "l2": "per-step HBM working set %.2f GB >> 126 MB L2 (no flush needed)" % (bytes_data / 2e9),
-                       "parallelism": f"loci sharded over {world} GPU(s), all-reduce of a {8 * (1 + V)}-byte vector per step"},
+            "config": common_config(args.config, L, world),
+            # the fraction reported is the one on the bytes this layout really moves (== the ncu DRAM traffic); the
+            # SURVEY 8d formula, which also counts leaf vectors that are stored here as 4-bit masks, is kept beside it
             "roofline": {"bound": "hbm", "kernel": "k_eval (full data-likelihood evaluation, all loci)",
-                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_data,
-                         "algorithmic_bytes_formula": "SURVEY.md 8d: 32*P*(2n-1) + 24*(2n-1) + 8*P + 8 per locus, summed over loci",
-                         "layout_min_bytes_per_launch": bytes_layout,
-                         "frac_of_layout_min": bytes_layout / (ms_data * 1e-3) / 1e9 / peak,
-                         "note": "leaves are stored as 4-bit masks, not fp64 vectors, so the layout moves fewer bytes than "
-                                 "the survey formula counts; frac uses the formula, frac_of_layout_min the bytes this layout must move",
-                         "ms_per_launch": ms_data, "genealogy_kernel_ms": ms_gen,
-                         "genealogy_achieved_gbs": bytes_gen / (ms_gen * 1e-3) / 1e9},
+                         "achieved": layout_gbs, "peak": peak, "unit": "GB/s", "frac": layout_gbs / peak,
+                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                         "bytes_per_launch": bytes_layout,
+                         "bytes_formula": "this layout's minimum per locus: 32*P*(n-1) written + 8*P*ceil(n/16) + 8*P + 16*(2n-1) + 24 read",
+                         "survey_formula": {"bytes_per_launch": bytes_data, "achieved": survey_gbs, "frac": survey_gbs / peak,
+                                            "formula": "SURVEY.md 8d: 32*P*(2n-1) + 24*(2n-1) + 8*P + 8 per locus (counts 32-byte leaf "
+                                                       "vectors that do not exist here: a layout win, not bandwidth)"},
+                         "ms_per_launch": ms_data, "mean_phased_patterns": float(P.mean()), "mean_events": float(E.mean()),
+                         "genealogy_kernel_ms": ms_gen, "genealogy_achieved_gbs": bytes_gen / (ms_gen * 1e-3) / 1e9,
+                         "mcmc": mcmc, "evals_per_s_at_10k_loci": small},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "steps": e2e_steps, "host_threads_per_rank": host_threads,
                     "route": "gphocsStoreSetTreesPacked + gphocsGenSetEventsPacked (16-bit topology and event codes on the wire)",
@@ -590,12 +659,13 @@ def run_b200(args):
                                     "route": "gphocsStoreSetTrees + gphocsGenSetEvents (int32 arrays copied as they are)"}},
             "gpu_launches": int(launches),
             "clocks": clocks,
+            "mcmc_iters_per_s": mcmc_head["iters_per_s"] if mcmc_head else None,
+            "mcmc_config": mcmc_head["config"] if mcmc_head else None,
             "extra": {"sum_data_lnl": total_data_lnl, "sum_gen_lnl": total_gen_lnl,
                       "mcmc_cycle_proposals_per_sec_e2e": world * L * cyc / cyc_s,
                       "incremental_eval_ms_device": inc_ms,
                       "incremental_evals_per_sec_device": L / (inc_ms * 1e-3),
-                      "device_bytes_store": st.device_bytes,
-                      "mcmc_device_resident": mcmc, "ingest": ingest},
+                      "device_bytes_store": st.device_bytes, "ingest": ingest},
         }
         if cb is not None:
             line["cpu_baseline"] = cb
@@ -614,7 +684,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="pop6mig4")
     ap.add_argument("--loci", type=int, default=100_000, help="loci per GPU")
-    ap.add_argument("--sample-loci", type=int, default=2000, help="loci in the CPU-baseline sample")
+    ap.add_argument("--sample-loci", type=int, default=20000,
+                    help="loci in the reference arm's bounded sample (working set >> host last-level cache)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-mcmc", action="store_true", help="skip the device-resident MCMC extras (development runs)")
     ap.add_argument("--with-mcmc", action="store_true", help="reference arm: also time the reference's MCMC iterations/s")

@@ -127,6 +127,7 @@ def lib():
         "gphocsSamplerCloseTrace": (ci, [vp]),
         "gphocsSamplerSetStepwise": (ci, [vp, ci]),
         "gphocsSamplerGetState": (ci, [vp, c_dbl_p, c_dbl_p, c_ll_p, c_ll_p]),
+        "gphocsSamplerEvalCounters": (ci, [vp, C.POINTER(C.c_ulonglong), ci]),
         "gphocsSamplerCheck": (ci, [vp, c_dbl_p, c_dbl_p]),
         "gphocsSamplerDownload": (ci, [vp, c_int_p]),
         "gphocsSamplerGetStats": (ci, [vp, c_dbl_p, c_int_p, c_dbl_p, c_int_p]),
@@ -653,6 +654,14 @@ class Sampler:
         if self.lib.gphocsSamplerOpenTrace(self.h, str(path).encode(), arr, float(theta_tau_print), float(mig_rate_print),
                                            int(sample_skip)) != 0:
             raise RuntimeError("gphocsSamplerOpenTrace failed")
+
+    def eval_counters(self, reset=False):
+        """(incremental locus evaluations, their algorithmic bytes per SURVEY.md 8d) since the last reset; the first
+        call switches the accounting on."""
+        out = (C.c_ulonglong * 2)()
+        if self.lib.gphocsSamplerEvalCounters(self.h, out, int(bool(reset))) != 0:
+            raise RuntimeError("gphocsSamplerEvalCounters failed")
+        return int(out[0]), int(out[1])
 
     def set_stepwise(self, on):
         """1: per-node launches even where the one-launch sweep applies (same chain either way)."""

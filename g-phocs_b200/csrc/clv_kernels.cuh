@@ -75,6 +75,9 @@ struct StoreDev {
   double* rootScratch;
   const uint8_t* active;  // per-locus mask or nullptr
   double* ctaSum;         // one partial sum per batch
+  // optional accounting for the roofline of incremental evaluations (nullptr: off): [0] += loci re-evaluated,
+  // [1] += their algorithmic bytes 32*P*(2k+1), k = conditional vectors recomputed
+  unsigned long long* evalCounters;
 };
 
 // One schedule entry = one node to (re)compute; entries are ordered so that children precede parents.
@@ -639,6 +642,13 @@ k_eval(StoreDev d, const Batch* __restrict__ batches, int batchBase, int useOld,
         if (on) sum += x;
       }
       if (lane == 0) d.ctaSum[batchBase + blockIdx.x] = sum;
+      if (d.evalCounters && useOld) {
+        unsigned long long by = mine && mK[lane] > 0 ? 32ull * (unsigned long long)mP[lane] * (2ull * (unsigned long long)mK[lane] + 1ull) : 0ull;
+        unsigned cntEv = __popc(__ballot_sync(0xffffffffu, by != 0ull));
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) by += __shfl_xor_sync(0xffffffffu, by, off);
+        if (lane == 0 && cntEv) { atomicAdd(d.evalCounters, (unsigned long long)cntEv); atomicAdd(d.evalCounters + 1, by); }
+      }
     }
   } else {
     // oversized locus: groups may straddle chunks; reduce from scratch with a fixed-order block tree

@@ -302,7 +302,7 @@ extern "C" GphocsStore* gphocsStoreCreate(int device, int numLoci, int numLeaves
     delete s;
     return nullptr;
   }
-  d.colStart = dColStart; d.leafWords = dWords; d.grpPhases = dPh; d.grpCount = dCnt; d.active = nullptr;
+  d.colStart = dColStart; d.leafWords = dWords; d.grpPhases = dPh; d.grpCount = dCnt; d.active = nullptr; d.evalCounters = nullptr;
   s->deviceBytes = (long long)((size_t)Ct * NI * 64 + words.size() * 8 + (size_t)Ct * 8 + LN * (2 * 8 + 16) + (size_t)L * 36);
   cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
   s->ownStream = true;

@@ -83,7 +83,7 @@ __host__ __device__ inline SweepSmem sweepSmemLayout(int n, int maxLoci, int Q) 
   m.offTerm = m.offList;                                    // [kThreads] double once the list is dead
   const size_t listBytes = (size_t)maxLoci * NI * 4, termBytes = (size_t)kThreads * 8;
   m.offMeta = (m.offList + (listBytes > termBytes ? listBytes : termBytes) + 15) & ~(size_t)15;   // per-slot scalars
-  m.offProp = m.offMeta + (size_t)kTeamSlots * 48;          // [slots] SmpProposal
+  m.offProp = m.offMeta + (size_t)kTeamSlots * 64;          // [slots] SmpProposal
   m.offModel = (m.offProp + (size_t)kTeamSlots * sizeof(SmpProposal) + 15) & ~(size_t)15;
   m.total = (m.offModel + sizeof(SweepModel) + 15) & ~(size_t)15;
   return m;
@@ -336,7 +336,9 @@ k_sweep(StoreDev d, SmpDev sd, const SmpModel* __restrict__ mp, const Batch* __r
   double* mRate = reinterpret_cast<double*>(smem + lay.offMeta);    // per-slot scalars
   double* mLnL = mRate + kTeamSlots;
   double* mSavedLnL = mLnL + kTeamSlots;
-  int* mColStart = reinterpret_cast<int*>(mSavedLnL + kTeamSlots);
+  unsigned long long* mEvals = reinterpret_cast<unsigned long long*>(mSavedLnL + kTeamSlots);   // accounting, SURVEY.md 8d
+  unsigned long long* mEvalBytes = mEvals + kTeamSlots;
+  int* mColStart = reinterpret_cast<int*>(mEvalBytes + kTeamSlots);
   int* mP = mColStart + kTeamSlots;
   int* mK = mP + kTeamSlots;
   int* mRoot = mK + kTeamSlots;
@@ -377,6 +379,8 @@ k_sweep(StoreDev d, SmpDev sd, const SmpModel* __restrict__ mp, const Batch* __r
     mK[tid] = 0;
     mLnL[tid] = d.lnL[l];
     mSavedLnL[tid] = d.savedLnL[l];
+    mEvals[tid] = 0ull;
+    mEvalBytes[tid] = 0ull;
   }
   if (tid < 2) sAccepted[tid] = 0u;
   if (tid == 0) *sListCount = 0;
@@ -612,6 +616,8 @@ k_sweep(StoreDev d, SmpDev sd, const SmpModel* __restrict__ mp, const Batch* __r
       double lnl = 0.0;
       for (int j = 0; j < P; j++) lnl += tt[j];
       mLnL[tid] = lnl;
+      mEvals[tid]++;
+      mEvalBytes[tid] += 32ull * (unsigned long long)P * (2ull * (unsigned long long)mK[tid] + 1ull);
     }
     __syncthreads();
   }
@@ -645,6 +651,15 @@ k_sweep(StoreDev d, SmpDev sd, const SmpModel* __restrict__ mp, const Batch* __r
     sd.prop[l] = smpNoProposal();
   }
   if (tid < 2 && sAccepted[tid]) atomicAdd(sd.accepted + tid, (unsigned long long)sAccepted[tid]);
+  if (d.evalCounters && warp == 0) {
+    unsigned long long evals = lane < nl ? mEvals[lane] : 0ull, evalBytes = lane < nl ? mEvalBytes[lane] : 0ull;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      evals += __shfl_xor_sync(0xffffffffu, evals, off);
+      evalBytes += __shfl_xor_sync(0xffffffffu, evalBytes, off);
+    }
+    if (lane == 0 && evals) { atomicAdd(d.evalCounters, evals); atomicAdd(d.evalCounters + 1, evalBytes); }
+  }
 }
 
 }  // namespace gphocs

@@ -46,3 +46,64 @@ def all_reduce_payload(tensor):
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         dist.all_reduce(tensor, op=dist.ReduceOp.SUM)
     return tensor
+
+
+class PipelinedAllReduce:
+    """The per-step payload all-reduce taken off the evaluation stream.
+
+    The payload of step i is summed over ranks on a side stream while the kernels of step i+1 run: the evaluation stream
+    only records an event after it has written the payload and, `depth` steps later, waits for the event that marks
+    that buffer's all-reduce as finished (long since, in practice).  Results are therefore available one step late —
+    fine for what consumes them (running totals for the trace line, global proposals that are decided once per sweep).
+    CPU tensors (gloo) use asynchronous work handles instead of streams; same interface."""
+
+    def __init__(self, length, device, depth=2, dtype=None):
+        import torch
+        self.torch = torch
+        self.cuda = torch.device(device).type == "cuda"
+        self.buffers = [torch.zeros(length, dtype=dtype or torch.float64, device=device) for _ in range(depth)]
+        self.depth = depth
+        self.work = [None] * depth
+        if self.cuda:
+            self.side = torch.cuda.Stream(device=device)
+            self.ready = [torch.cuda.Event() for _ in range(depth)]     # payload written by the evaluation stream
+            self.done = [torch.cuda.Event() for _ in range(depth)]      # all-reduce finished on the side stream
+            self.used = [False] * depth
+
+    def buffer(self, step, stream=None):
+        """Buffer for this step's payload; the evaluation stream first waits for the all-reduce that used it last."""
+        k = step % self.depth
+        if self.cuda:
+            if self.used[k]:
+                (stream or self.torch.cuda.current_stream()).wait_event(self.done[k])
+        elif self.work[k] is not None:
+            self.work[k].wait()
+            self.work[k] = None
+        return self.buffers[k]
+
+    def submit(self, step, stream=None):
+        """Call after the payload of `step` has been enqueued on the evaluation stream."""
+        import torch.distributed as dist
+        k = step % self.depth
+        active = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        if self.cuda:
+            main = stream or self.torch.cuda.current_stream()
+            self.ready[k].record(main)
+            self.side.wait_event(self.ready[k])
+            if active:
+                with self.torch.cuda.stream(self.side):
+                    dist.all_reduce(self.buffers[k], op=dist.ReduceOp.SUM)
+            self.done[k].record(self.side)
+            self.used[k] = True
+        elif active:
+            self.work[k] = dist.all_reduce(self.buffers[k], op=dist.ReduceOp.SUM, async_op=True)
+
+    def result(self, step, stream=None):
+        """The all-reduced payload of `step` (the evaluation stream waits for it; CPU: blocks)."""
+        k = step % self.depth
+        if self.cuda:
+            (stream or self.torch.cuda.current_stream()).wait_event(self.done[k])
+        elif self.work[k] is not None:
+            self.work[k].wait()
+            self.work[k] = None
+        return self.buffers[k]

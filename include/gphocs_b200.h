@@ -287,6 +287,10 @@ int gphocsSamplerSetStepwise(GphocsSampler *sm, int on);
 /* accepted[10], proposed[10] for {coalescence time, SPR, theta, tau, mixing, migration rate, migration time,
  * (proposed only) split-time moves rejected for a migration conflict, locus rate (pairs of loci), sample age} */
 int gphocsSamplerGetState(GphocsSampler *sm, double *theta, double *tau, long long *accepted, long long *proposed);
+/* accounting for the roofline of an MCMC iteration: out2[0] = incremental locus evaluations, out2[1] = their algorithmic
+ * bytes (32 * P * (2k + 1) with k conditional vectors recomputed) since the previous call with reset != 0;
+ * the first call switches the accounting on */
+int gphocsSamplerEvalCounters(GphocsSampler *sm, unsigned long long *out2, int reset);
 /* checkAll (patch.c:2745) on the device: returns structural violations; largest relative deviation of the
  * incrementally maintained statistics / data log-likelihoods from a recomputation from scratch */
 int gphocsSamplerCheck(GphocsSampler *sm, double *maxStatErr, double *maxLnLErr);

@@ -55,6 +55,44 @@ def _worker(rank, world, port, L, out):
         dist.destroy_process_group()
 
 
+def _pipeline_worker(rank, world, port, out):
+    for p in (ROOT, os.path.join(ROOT, "tests")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        pipe = shard.PipelinedAllReduce(4, "cpu", depth=2)
+        got = []
+        for step in range(7):      # step i's payload is reduced while step i+1 is being "computed"
+            buf = pipe.buffer(step)
+            buf.copy_(torch.tensor([step, rank + 1.0, (rank + 1.0) * step, 1.0], dtype=torch.float64))
+            pipe.submit(step)
+            if step > 0:
+                got.append(pipe.result(step - 1).clone())
+        got.append(pipe.result(6).clone())
+        if rank == 0:
+            np.save(out, torch.stack(got).numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_pipelined_allreduce_returns_every_step_once(tmp_path):
+    """The side-stream all-reduce of bench.py's step, on gloo: with two buffers in flight every step's payload comes
+    back summed over both ranks, in order, one step late."""
+    world = 2
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    out = str(tmp_path / "pipe.npy")
+    mp.spawn(_pipeline_worker, args=(world, port, out), nprocs=world, join=True)
+    got = np.load(out)
+    want = np.array([[2.0 * i, 3.0, 3.0 * i, 2.0] for i in range(7)])
+    assert np.array_equal(got, want)
+
+
 def test_shard_ranges_cover_all_loci_once():
     for L in (1, 7, 100, 100_000):
         for world in (1, 2, 3, 8):
