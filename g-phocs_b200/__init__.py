@@ -126,6 +126,7 @@ def lib():
         "gphocsSamplerOpenTrace": (ci, [vp, C.c_char_p, C.POINTER(C.c_char_p), cd, cd, ci]),
         "gphocsSamplerCloseTrace": (ci, [vp]),
         "gphocsSamplerSetStepwise": (ci, [vp, ci]),
+        "gphocsSamplerSetMigRates": (ci, [vp, c_dbl_p]),
         "gphocsSamplerGetState": (ci, [vp, c_dbl_p, c_dbl_p, c_ll_p, c_ll_p]),
         "gphocsSamplerEvalCounters": (ci, [vp, C.POINTER(C.c_ulonglong), ci]),
         "gphocsSamplerCheck": (ci, [vp, c_dbl_p, c_dbl_p]),
@@ -662,6 +663,11 @@ class Sampler:
         if self.lib.gphocsSamplerEvalCounters(self.h, out, int(bool(reset))) != 0:
             raise RuntimeError("gphocsSamplerEvalCounters failed")
         return int(out[0]), int(out[1])
+
+    def set_mig_rates(self, rates):
+        r = np.ascontiguousarray(rates, np.float64)
+        if self.lib.gphocsSamplerSetMigRates(self.h, _dp(r)) != 0:
+            raise RuntimeError("gphocsSamplerSetMigRates failed")
 
     def set_stepwise(self, on):
         """1: per-node launches even where the one-launch sweep applies (same chain either way)."""

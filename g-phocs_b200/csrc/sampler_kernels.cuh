@@ -662,81 +662,84 @@ __global__ void __launch_bounds__(kSmpThreads) k_smp_init_stats(StoreDev d, SmpD
 // ------------------------------------------------------------------------------------------ locus-rate moves
 // UpdateLocusRate (GPhoCS.c:4598-4675) keeps the mean rate at 1 by moving rate between a locus and a reference locus,
 // one locus after the other.  Here the same move — rate shifted between TWO loci, their sum kept, Dirichlet(alpha)
-// prior ratio, both data likelihoods recomputed from scratch — is made on disjoint pairs (l, l + offset) for all
+// prior ratio, both data likelihoods recomputed from scratch — is made on disjoint pairs (g, g + offset) for all
 // pairs at once; the offset changes every iteration so rate can travel between any two loci.
-// Loci are first rotated by `shift` (so that every pair of loci can meet), then (l', l' + offset) pair up inside
+// Pairs are formed over the GLOBAL locus index (all ranks): the two loci of a pair may live on different GPUs.  Every
+// rank sees the gathered rates (before the move) and, after the evaluation, the gathered log-likelihood changes of all
+// loci, and computes proposal and decision of a pair from the same numbers with the same random stream (keyed by the
+// pair's lower global index): both owners act alike without talking to each other.
+// Loci are first rotated by `shift` (so that every pair of loci can meet), then (g', g' + offset) pair up inside
 // blocks of 2 * offset.  Returns the partner (-1: unpaired this round); *proposer = this locus is the lower of its pair.
-__device__ inline int smpRatePartner(int l, int L, int offset, int shift, bool* proposer) {
-  const int lp = (l + shift) % L;
-  const bool lower = ((lp / offset) & 1) == 0;
+__device__ inline long long smpRatePartner(long long g, long long Lg, long long offset, long long shift, bool* proposer) {
+  const long long gp = (g + shift) % Lg;
+  const bool lower = ((gp / offset) & 1) == 0;
   *proposer = lower;
-  const int pp = lower ? lp + offset : lp - offset;
-  if (pp >= L) return -1;
-  return (pp - shift + L) % L;
+  const long long pp = lower ? gp + offset : gp - offset;
+  if (pp >= Lg) return -1;
+  return (pp - shift + Lg) % Lg;
+}
+// gather[g] = rate of global locus g, negative if the locus has no genealogy (never moved); own segment only — the
+// all-reduce that follows fills in the other ranks' (their segments are zero here)
+__global__ void __launch_bounds__(kSmpThreads) k_smp_rate_gather(StoreDev d, double* __restrict__ gather, long long off) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l < d.L) gather[off + l] = d.root[l] >= d.n ? d.rate[l] : -d.rate[l];
+}
+// the pair's proposal, from the gathered rates: new rate of the lower locus; valid = both loci can move
+__device__ inline double smpRateProposal(const double* __restrict__ gather, long long lo, long long hi, double finetune,
+                                         unsigned long long seed, unsigned long long step, bool* valid) {
+  const double r0 = gather[lo], r1 = gather[hi];
+  *valid = r0 > 0.0 && r1 > 0.0;
+  if (!*valid) return 0.0;
+  SmpRng rng(seed, (unsigned long long)lo, step);
+  return smpReflect(r0 + finetune * rng.normal2(), 0.0, r0 + r1);
 }
 __global__ void __launch_bounds__(kSmpThreads)
-k_smp_rate_propose(StoreDev d, SmpDev sd, int offset, int shift, double finetune, unsigned long long seed, unsigned long long step) {
+k_smp_rate_propose(StoreDev d, const double* __restrict__ gather, long long off, long long Lg, long long offset, long long shift,
+                   double finetune, unsigned long long seed, unsigned long long step) {
   const int l = blockIdx.x * blockDim.x + threadIdx.x;
   if (l >= d.L) return;
-  SmpProposal pr = smpNoProposal();
-  bool proposer;
-  const int partner = smpRatePartner(l, d.L, offset, shift, &proposer);
-  if (partner >= 0 && proposer && d.root[l] >= d.n && d.root[partner] >= d.n) {
-    const double r0 = d.rate[l], r1 = d.rate[partner];
-    SmpRng rng(seed, (unsigned long long)l, step);
-    const double rn = smpReflect(r0 + finetune * rng.normal2(), 0.0, r0 + r1);
-    pr.genDelta = r0;        // old rates, for the prior ratio and for a rejection
-    pr.aux = r1;
-    pr.node = partner;
-    pr.valid = 1;
-    d.rate[l] = rn;
-    d.rate[partner] = r0 + r1 - rn;
-  }
-  sd.prop[l] = pr;
+  bool proposer, valid;
+  const long long g = off + l, partner = smpRatePartner(g, Lg, offset, shift, &proposer);
+  if (partner < 0) return;
+  const long long lo = proposer ? g : partner, hi = proposer ? partner : g;
+  const double rn = smpRateProposal(gather, lo, hi, finetune, seed, step, &valid);
+  if (valid) d.rate[l] = proposer ? rn : gather[lo] + gather[hi] - rn;
 }
-// after a full evaluation (useOld = 0) of every locus: both loci of a pair reach the same decision from the same
-// numbers; the decision is left in prop[l].ntj1 for k_smp_rate_restore (rates are restored in a second launch so
-// that no thread reads a rate its partner has already put back)
+// after a full evaluation (useOld = 0) of every locus: gather[g] = change of the locus' log-likelihood (own segment)
+__global__ void __launch_bounds__(kSmpThreads) k_smp_rate_delta(StoreDev d, double* __restrict__ gather, long long off) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l < d.L) gather[off + l] = d.lnL[l] - d.savedLnL[l];
+}
+// both owners of a pair reach the same decision from the same numbers, then commit or put the old rate back
 __global__ void __launch_bounds__(kSmpThreads)
-k_smp_rate_accept(StoreDev d, SmpDev sd, int offset, int shift, double alpha, unsigned long long seed, unsigned long long step) {
+k_smp_rate_resolve(StoreDev d, SmpDev sd, const double* __restrict__ rates, const double* __restrict__ delta, long long off, long long Lg,
+                   long long offset, long long shift, double finetune, double alpha, unsigned long long seed, unsigned long long step) {
   const int l = blockIdx.x * blockDim.x + threadIdx.x;
   if (l >= d.L) return;
-  bool proposer;
-  const int partner = smpRatePartner(l, d.L, offset, shift, &proposer);
+  bool proposer, valid = false;
+  const long long g = off + l, partner = smpRatePartner(g, Lg, offset, shift, &proposer);
   int ok = 0;
   if (partner >= 0) {
-    const int lo = proposer ? l : partner;
-    const SmpProposal pr = sd.prop[lo];
-    if (pr.valid) {
-      const int hi = pr.node;
-      const double r0 = pr.genDelta, r1 = pr.aux;
-      double lnacc = (d.lnL[lo] - d.savedLnL[lo]) + (d.lnL[hi] - d.savedLnL[hi]);
-      lnacc += (alpha - 1.0) * log((d.rate[lo] * d.rate[hi]) / (r0 * r1));
+    const long long lo = proposer ? g : partner, hi = proposer ? partner : g;
+    const double rn = smpRateProposal(rates, lo, hi, finetune, seed, step, &valid);
+    if (valid) {
+      const double r0 = rates[lo], r1 = rates[hi];
+      double lnacc = delta[lo] + delta[hi];
+      lnacc += (alpha - 1.0) * log((rn * (r0 + r1 - rn)) / (r0 * r1));
       ok = lnacc >= 0.0;
       if (!ok) {
-        SmpRng rng(seed, (unsigned long long)lo, step);
+        SmpRng rng(seed, (unsigned long long)lo, step + 1ull);
         ok = rng.uniform() < exp(lnacc);
       }
     }
   }
-  sd.prop[l].ntj1 = ok;
-}
-__global__ void __launch_bounds__(kSmpThreads) k_smp_rate_restore(StoreDev d, SmpDev sd, int offset, int shift) {
-  const int l = blockIdx.x * blockDim.x + threadIdx.x;
-  if (l >= d.L) return;
-  bool proposer;
-  const int partner = smpRatePartner(l, d.L, offset, shift, &proposer);
-  const int ok = sd.prop[l].ntj1;
   const TreeView t = deviceView(d, l);
   if (ok) {
     commit(t);
     if (proposer) atomicAdd(sd.accepted + 2, 1ull);
   } else {
     revert(t);   // also for unpaired loci: the full evaluation flipped their buffers
-    if (partner >= 0) {
-      const SmpProposal pr = sd.prop[proposer ? l : partner];
-      if (pr.valid) d.rate[l] = proposer ? pr.genDelta : pr.aux;
-    }
+    if (valid) d.rate[l] = rates[g];
   }
 }
 

@@ -254,6 +254,8 @@ int gphocsSamplerSetMigration(GphocsSampler *sm, int numBands, const int *bandSr
 int gphocsNcclUniqueId(char *out128);
 int gphocsSamplerInitNccl(GphocsSampler *sm, const char *uniqueId128, int rank, int worldSize, long long locusOffset);
 /* finetune-mig-time, finetune-mig-rate */
+/* new migration rates for all bands, e.g. the host's draw at iteration start-mig (GPhoCS.c:1738-1757) */
+int gphocsSamplerSetMigRates(GphocsSampler *sm, const double *migRate);
 int gphocsSamplerSetMigFinetunes(GphocsSampler *sm, double migTime, double migRate);
 /* Ancient samples and rate variation (BASELINE.json configs[4]).  tau[p < numCurPops] given at creation is the age of
  * population p's samples (pops[p]->sampleAge, PopulationTree.h:97; the leaves' ages in the store must agree).

@@ -1,0 +1,79 @@
+"""Shared by the GPU tests that compare a device chain with the reference's own chain: runs oracle/_ref/G-PhoCS-ref once
+per (shape, loci, iterations, finetunes, priors) and keeps the trace for the other tests of the session."""
+import hashlib
+import importlib
+import json
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.path.join(ROOT, "oracle", "_ref", "G-PhoCS-ref")
+DEVHOST = os.path.join(ROOT, "oracle", "_ref", "G-PhoCS-b200-dev")
+synth = importlib.import_module("g-phocs_b200.synth")
+CACHE = os.path.join(tempfile.gettempdir(), "gphocs_b200_refchains")
+
+FT = dict(coal_time=0.01, theta=0.3, tau=0.0002, mixing=0.05, mig_time=0.3, mig_rate=0.4)
+# Gamma(1, 0.005) on the migration rates: the control-file default Gamma(0.002, 1e-5) puts a spike at the 1e-5 cut-off
+# (GPhoCS.c:3159) that chains leave and enter only rarely, which makes means of short chains meaningless
+MIG_PRIOR = (1.0, 0.005)
+
+
+def read_trace(path):
+    with open(path) as f:
+        lines = [ln.rstrip("\n") for ln in f if ln.strip()]
+    names = lines[0].split()
+    rows = [[float(x) for x in ln.split()] for ln in lines[1:]]
+    width = min(len(r) for r in rows)
+    return names, np.array([r[:width] for r in rows])
+
+
+def batch_se(x, batches=20):
+    """Monte-Carlo standard error of the mean of a correlated series by batch means."""
+    x = np.asarray(x, float)
+    k = len(x) // batches
+    means = x[:k * batches].reshape(batches, k).mean(1)
+    return means.std(ddof=1) / np.sqrt(batches)
+
+
+def setup(cfg, L, iters, data_seed=99, finetunes=None, mig_prior=MIG_PRIOR):
+    """Directory with the alignment and a control file for `cfg`; returns (dir, model, workload, ctl path)."""
+    ft = dict(FT)
+    ft.update(finetunes or {})
+    key = hashlib.sha1(json.dumps([cfg, L, iters, data_seed, ft, mig_prior], sort_keys=True).encode()).hexdigest()[:16]
+    d = os.path.join(CACHE, key)
+    os.makedirs(d, exist_ok=True)
+    model = synth.config(cfg)
+    seq = os.path.join(d, "seqs.txt")
+    w = synth.generate(model, L, seed=data_seed, seqfile=seq)
+    return d, model, w, ft
+
+
+def chain(binary, tag, cfg, L, iters, data_seed=99, finetunes=None, mig_prior=MIG_PRIOR, threads=4, seed=4242, timeout=3000):
+    """Trace (names, rows) of `binary` on the shape; cached in the session's temp directory."""
+    d, model, w, ft = setup(cfg, L, iters, data_seed, finetunes, mig_prior)
+    ctl, trace = os.path.join(d, f"{tag}.ctl"), os.path.join(d, f"{tag}.trace")
+    done = os.path.join(d, f"{tag}.done")
+    if not os.path.exists(done):
+        synth.write_control_file(model, ctl, os.path.join(d, "seqs.txt"), trace, iterations=iters, seed=seed,
+                                 iterations_per_log=iters, finetunes=ft, mig_prior=mig_prior)
+        r = subprocess.run([binary, ctl, "-n", str(threads)], capture_output=True, text=True, timeout=timeout, cwd=d)
+        assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+        with open(done, "w") as f:
+            f.write(r.stdout[-4000:])
+    names, rows = read_trace(trace)
+    return names, rows, model, w, ft, open(done).read()
+
+
+def parameter_columns(model, rows):
+    """Trace rows -> parameter columns in natural units (print factors of the control files written by synth)."""
+    Q, C, B = model.numPops, model.numCurPops, len(model.bands)
+    K = 2 * Q - C + B + sum(1 for _ in model.sample_age) + (1 if model.rate_shape > 0 else 0)
+    x = rows[:, 1:1 + K].copy()
+    x[:, :2 * Q - C] /= 10000.0                                  # tau-theta-print
+    x[:, 2 * Q - C:2 * Q - C + B] /= 0.001                       # mig-rate-print
+    e0 = 2 * Q - C + B
+    x[:, e0:e0 + len(model.sample_age)] /= 10000.0               # estimated sample ages are taus
+    return x

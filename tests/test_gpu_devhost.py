@@ -1,0 +1,47 @@
+"""GPU: the fast-path host (oracle/_ref/G-PhoCS-b200-dev = the unmodified reference host through initializeMCMC +
+g-phocs_b200/host/gphocs_device_mcmc.c) runs the SAME control file as the reference program and
+writes the same trace format; its posterior means agree with the reference's own chain within Monte-Carlo error on
+all five shapes of BASELINE.json `configs`, and it is much faster than the reference on the box's host cores."""
+import os
+import time
+
+import numpy as np
+import pytest
+import torch
+
+import refchain as rc
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not torch.cuda.is_available(), reason="needs a CUDA device"),
+              pytest.mark.skipif(not (os.path.exists(rc.REF) and os.path.exists(rc.DEVHOST)), reason="oracle/_ref binaries not built")]
+
+SHAPES = [("hap16", 60, 30000), ("sample", 60, 30000), ("dip8mig", 40, 30000), ("ancient", 50, 30000), ("pop6mig4", 30, 30000)]
+
+
+@pytest.mark.parametrize("cfg,L,iters", SHAPES)
+def test_control_file_run_matches_reference_posterior(cfg, L, iters):
+    burn = iters // 5
+    names_r, ref, model, w, ft, _ = rc.chain(rc.REF, "ref", cfg, L, iters)
+    names_d, dev, _, _, _, log = rc.chain(rc.DEVHOST, "dev", cfg, L, iters, threads=2, seed=777)
+    assert names_r == names_d                      # same trace header, literally
+    assert ref.shape == dev.shape and dev.shape[0] == iters
+    assert "MCMC done" in log and "inconsistency" not in log
+    a, b = rc.parameter_columns(model, ref)[burn:], rc.parameter_columns(model, dev)[burn:]
+    for k in range(a.shape[1]):
+        se = np.hypot(rc.batch_se(a[:, k]), rc.batch_se(b[:, k]))
+        assert abs(a[:, k].mean() - b[:, k].mean()) < 3.0 * se + 0.01 * abs(a[:, k].mean()), \
+            (names_r[1 + k], a[:, k].mean(), b[:, k].mean(), se)
+    # the two log-likelihood columns (mean full lnL per locus, data lnL) describe the same posterior
+    for col in (-2, -1):
+        x, y = ref[burn:, col], dev[burn:, col]
+        se = np.hypot(rc.batch_se(x), rc.batch_se(y))
+        assert abs(x.mean() - y.mean()) < 3.0 * se + 2e-3 * abs(x.mean()), (names_r[col], x.mean(), y.mean(), se)
+
+
+def test_control_file_run_is_faster_than_the_reference(tmp_path):
+    """configs[1] at 2000 loci, 60 iterations: wall time of the whole program, ingest and set-up included."""
+    t = {}
+    for tag, binary, threads in (("ref", rc.REF, os.cpu_count() or 1), ("dev", rc.DEVHOST, os.cpu_count() or 1)):
+        t0 = time.perf_counter()
+        rc.chain(binary, tag + "_speed", "hap16", 2000, 60, threads=threads)
+        t[tag] = time.perf_counter() - t0
+    assert t["dev"] < t["ref"], t

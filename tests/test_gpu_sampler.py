@@ -166,7 +166,7 @@ def test_uninformative_data_recovers_the_prior():
     for col, name in [(0, "theta_A"), (1, "theta_B"), (2, "theta_root"), (3, "tau_root")]:
         x = tr[:, col]
         se = batch_se(x)
-        assert abs(x.mean() - mean) < 4.5 * se + 0.01 * mean, (name, x.mean(), mean, se)
+        assert abs(x.mean() - mean) < 3.5 * se + 0.01 * mean, (name, x.mean(), mean, se)
         assert abs(x.std() - sd) < 0.12 * sd, (name, x.std(), sd)
     assert np.all(tr[:, -2] == 0.0)                     # data log-likelihood is identically zero
     sm.close()
@@ -174,22 +174,16 @@ def test_uninformative_data_recovers_the_prior():
 
 
 @pytest.mark.skipif(not os.path.exists(REF), reason="oracle/_ref/G-PhoCS-ref not built")
-def test_posterior_means_match_the_reference_chain(tmp_path):
+def test_posterior_means_match_the_reference_chain():
     """BASELINE.json configs[1] shape (16 haplotypes, 4 populations, no migration) at 60 loci: posterior means of
-    every theta and tau from the device chain against the reference's own chain on the same alignment."""
-    import subprocess
-    model = synth.config("hap16")
-    L, iters, burn = 60, 12000, 2000
-    seq = str(tmp_path / "seqs.txt")
-    w = synth.generate(model, L, seed=99, seqfile=seq)
-    ft = dict(coal_time=0.01, theta=0.3, tau=0.0002, mixing=0.05)
-    ctl, trace = str(tmp_path / "ref.ctl"), str(tmp_path / "ref.trace")
-    synth.write_control_file(model, ctl, seq, trace, iterations=iters, seed=4242, iterations_per_log=iters, finetunes=ft)
-    r = subprocess.run([REF, ctl, "-n", "4"], capture_output=True, text=True, timeout=1500, cwd=str(tmp_path))
-    assert r.returncode == 0, r.stdout[-2000:]
-    names, ref = read_trace(trace)
+    every theta and tau from the device chain against the reference's own chain on the same alignment, within
+    3 Monte-Carlo standard errors (+ 1 %: the batch-means error estimate is itself uncertain)."""
+    import refchain as rc
+    L, iters = 60, 30000
+    burn = iters // 5
+    names, ref, model, w, ft, _ = rc.chain(rc.REF, "ref", "hap16", L, iters)
     Q, C = model.numPops, model.numCurPops
-    ref = ref[burn:, 1:1 + 2 * Q - C] / 10000.0        # tau-theta-print factor of the control file
+    ref = rc.parameter_columns(model, ref)[burn:]
     st = gp.LociStore.from_workload(w)
     sm = gp.Sampler(st, w.pops, w.node_pop, seed=2024, finetunes=(ft["coal_time"], ft["theta"], ft["tau"], ft["mixing"]))
     tr = sm.iterate(iters)[burn:, :2 * Q - C]
@@ -197,6 +191,6 @@ def test_posterior_means_match_the_reference_chain(tmp_path):
     for k in range(2 * Q - C):
         a, b = ref[:, k], tr[:, k]
         se = np.hypot(batch_se(a), batch_se(b))
-        assert abs(a.mean() - b.mean()) < 4.5 * se + 0.02 * abs(a.mean()), (names[1 + k], a.mean(), b.mean(), se)
+        assert abs(a.mean() - b.mean()) < 3.0 * se + 0.01 * abs(a.mean()), (names[1 + k], a.mean(), b.mean(), se)
     sm.close()
     st.close()

@@ -76,7 +76,7 @@ def test_uninformative_data_recovers_the_prior_of_sample_age_and_rates():
         x = tr[:, col]
         mean, sd = expect[name]
         se = batch_se(x)
-        assert abs(x.mean() - mean) < 4.5 * se + 0.01 * mean, (name, x.mean(), mean, se)
+        assert abs(x.mean() - mean) < 3.5 * se + 0.01 * mean, (name, x.mean(), mean, se)
         assert abs(x.std() - sd) < 0.12 * sd, (name, x.std(), sd)
     var = tr[:, 5] ** 2                                  # trace column = sqrt(mean (rate - 1)^2)
     want = (L - 1) / (ralpha * L + 1)
@@ -86,25 +86,18 @@ def test_uninformative_data_recovers_the_prior_of_sample_age_and_rates():
 
 
 @pytest.mark.skipif(not os.path.exists(REF), reason="oracle/_ref/G-PhoCS-ref not built")
-def test_posterior_means_match_the_reference_chain_with_ancient_samples(tmp_path):
-    """BASELINE.json configs[4] shape (ancient samples in B, `locus-mut-rate VAR 1.0`) at 60 loci: posterior means of
-    the thetas, taus, the sample age and the rate spread against the reference's own chain on the same alignment."""
-    import subprocess
-    model = synth.config("ancient")
-    L, iters, burn = 60, 12000, 2000
-    seq = str(tmp_path / "seqs.txt")
-    w = synth.generate(model, L, seed=77, seqfile=seq)
-    ft = dict(coal_time=0.01, theta=0.3, tau=0.0002, mixing=0.05)
-    ctl, trace = str(tmp_path / "ref.ctl"), str(tmp_path / "ref.trace")
-    synth.write_control_file(model, ctl, seq, trace, iterations=iters, seed=4242, iterations_per_log=iters, finetunes=ft)
-    r = subprocess.run([REF, ctl, "-n", "4"], capture_output=True, text=True, timeout=1500, cwd=str(tmp_path))
-    assert r.returncode == 0, r.stdout[-2000:]
-    names, ref = read_trace(trace)
+def test_posterior_means_match_the_reference_chain_with_ancient_samples():
+    """BASELINE.json configs[4] shape (ancient samples in B, `locus-mut-rate VAR 1.0`) at 50 loci: posterior means of
+    the thetas, taus, the sample age and the rate spread against the reference's own chain on the same alignment,
+    within 3 Monte-Carlo standard errors (+ 1 %)."""
+    import refchain as rc
+    L, iters = 50, 30000
+    burn = iters // 5
+    names, ref, model, w, ft, _ = rc.chain(rc.REF, "ref", "ancient", L, iters)
     Q, C = model.numPops, model.numCurPops
     K = 2 * Q - C
     assert names[1 + K].startswith("tau_") and names[2 + K] == "Variance-Mut", names
-    ref = ref[burn:, 1:3 + K]
-    ref[:, :K + 1] /= 10000.0                            # tau-theta-print factor of the control file
+    ref = rc.parameter_columns(model, ref)[burn:]
     st = gp.LociStore.from_workload(w)
     st.set_rates(np.ones(w.L))
     sm = gp.Sampler(st, w.pops, w.node_pop, seed=2024, finetunes=(ft["coal_time"], ft["theta"], ft["tau"], ft["mixing"]),
@@ -114,7 +107,7 @@ def test_posterior_means_match_the_reference_chain_with_ancient_samples(tmp_path
     for k in range(K + 2):
         a, b = ref[:, k], tr[:, k]
         se = np.hypot(batch_se(a), batch_se(b))
-        assert abs(a.mean() - b.mean()) < 4.5 * se + 0.02 * abs(a.mean()), (names[1 + k], a.mean(), b.mean(), se)
+        assert abs(a.mean() - b.mean()) < 3.0 * se + 0.01 * abs(a.mean()), (names[1 + k], a.mean(), b.mean(), se)
     sm.close(); st.close()
 
 

@@ -80,7 +80,7 @@ def test_uninformative_data_recovers_the_prior_with_migration():
                                 (4, "m_A->B", ma / mb, np.sqrt(ma) / mb)]:
         x = tr[:, col]
         se = batch_se(x)
-        assert abs(x.mean() - mean) < 4.5 * se + 0.01 * mean, (name, x.mean(), mean, se)
+        assert abs(x.mean() - mean) < 3.5 * se + 0.01 * mean, (name, x.mean(), mean, se)
         assert abs(x.std() - sd) < 0.15 * sd, (name, x.std(), sd)
     s = sm.state()
     assert s["accepted"]["mig_time"] > 0 and s["accepted"]["mig_rate"] > 0
@@ -88,37 +88,26 @@ def test_uninformative_data_recovers_the_prior_with_migration():
 
 
 @pytest.mark.skipif(not os.path.exists(REF), reason="oracle/_ref/G-PhoCS-ref not built")
-@pytest.mark.parametrize("cfg,L", [("sample", 60), ("dip8mig", 40)])
-def test_posterior_means_match_the_reference_chain_with_migration(tmp_path, cfg, L):
-    """Unphased diploids, migration bands: posterior means of every theta, tau and migration rate from the device
-    chain against the reference's own chain on the same alignment (same priors and finetunes)."""
-    import subprocess
-    model = synth.config(cfg)
-    iters, burn = 14000, 3000
-    seq = str(tmp_path / "seqs.txt")
-    w = synth.generate(model, L, seed=99, seqfile=seq)
-    ft = dict(coal_time=0.01, theta=0.3, tau=0.0002, mixing=0.05, mig_time=0.3, mig_rate=0.4)
-    ctl, trace = str(tmp_path / "ref.ctl"), str(tmp_path / "ref.trace")
-    # Gamma(1, 0.005) on the migration rates: the control-file default Gamma(0.002, 1e-5) puts a spike at the 1e-5
-    # cut-off (GPhoCS.c:3159) that chains leave and enter only rarely, which makes means of short chains meaningless
-    mig_prior = (1.0, 0.005)
-    synth.write_control_file(model, ctl, seq, trace, iterations=iters, seed=4242, iterations_per_log=iters, finetunes=ft,
-                             mig_prior=mig_prior)
-    r = subprocess.run([REF, ctl, "-n", "4"], capture_output=True, text=True, timeout=2400, cwd=str(tmp_path))
-    assert r.returncode == 0, r.stdout[-2000:]
-    names, ref = read_trace(trace)
+@pytest.mark.parametrize("cfg,L", [("sample", 60), ("dip8mig", 40), ("pop6mig4", 30)])
+def test_posterior_means_match_the_reference_chain_with_migration(cfg, L):
+    """Unphased diploids, migration bands — the sample shape, configs[2] and configs[3] (6 populations, 4 bands, the
+    shape of the bench headline): posterior means of every theta, tau and migration rate from the device chain against
+    the reference's own chain on the same alignment (same priors and finetunes), within 3 Monte-Carlo standard errors
+    (+ 1 %: the batch-means error estimate is itself uncertain)."""
+    import refchain as rc
+    iters = 30000
+    burn = iters // 5
+    names, ref, model, w, ft, _ = rc.chain(rc.REF, "ref", cfg, L, iters)
     Q, C, B = model.numPops, model.numCurPops, len(model.bands)
     K = 2 * Q - C + B
-    ref = ref[burn:, 1:1 + K].copy()
-    ref[:, :2 * Q - C] /= 10000.0          # tau-theta-print
-    ref[:, 2 * Q - C:] /= 0.001            # mig-rate-print
+    ref = rc.parameter_columns(model, ref)[burn:]
     st = gp.LociStore.from_workload(w)
     sm = gp.Sampler(st, w.pops, w.node_pop, seed=2024, finetunes=(ft["coal_time"], ft["theta"], ft["tau"], ft["mixing"]),
-                    migration=migration_of(w), mig_prior=mig_prior, mig_finetunes=(ft["mig_time"], ft["mig_rate"]))
+                    migration=migration_of(w), mig_prior=rc.MIG_PRIOR, mig_finetunes=(ft["mig_time"], ft["mig_rate"]))
     tr = sm.iterate(iters)[burn:, :K]
     assert sm.check()[0] == 0
     for k in range(K):
         a, b = ref[:, k], tr[:, k]
         se = np.hypot(batch_se(a), batch_se(b))
-        assert abs(a.mean() - b.mean()) < 4.5 * se + 0.03 * abs(a.mean()), (names[1 + k], a.mean(), b.mean(), se)
+        assert abs(a.mean() - b.mean()) < 3.0 * se + 0.01 * abs(a.mean()), (names[1 + k], a.mean(), b.mean(), se)
     sm.close(); st.close()
