@@ -108,6 +108,8 @@ def lib():
         "gphocsGenSetEventsPacked": (ci, [vp, c_int_p, C.POINTER(C.c_ushort), C.POINTER(C.c_ushort), c_dbl_p]),
         "gphocsGenEvaluate": (ci, [vp, c_dbl_p, c_dbl_p, c_int_p, c_dbl_p, c_int_p, c_dbl_p, c_ll_p, c_dbl_p, c_ll_p, c_dbl_p]),
         "gphocsGenEvaluateDevice": (ci, [vp, C.POINTER(vp), C.POINTER(vp)]),
+        "gphocsGenRecalc": (ci, [vp, ci, c_int_p, c_int_p, c_int_p, c_dbl_p, c_dbl_p]),
+        "gphocsGenGetStats": (ci, [vp, c_dbl_p, c_int_p, c_dbl_p, c_int_p]),
         "gphocsGenGetLineages": (ci, [vp, c_int_p]),
         "gphocsGenSync": (ci, [vp]),
         # D. device-resident MCMC steps
@@ -433,6 +435,26 @@ class Genealogy:
         if v < 0:
             raise RuntimeError("gphocsGenEvaluateDevice failed")
         return a.value, b.value, v
+
+    def recalc(self, locus, pop, times_start, times):
+        """recalcStats for the listed (locus, population) chains with new elapsed times; returns its return values."""
+        locus, pop, ts = _i32(locus), _i32(pop), _i32(times_start)
+        t = np.ascontiguousarray(times, np.float64)
+        out = np.zeros(len(locus))
+        if self.lib.gphocsGenRecalc(self.h, len(locus), _ip(locus), _ip(pop), _ip(ts), _dp(t), _dp(out)) != 0:
+            raise RuntimeError("gphocsGenRecalc failed")
+        return out
+
+    def stats_only(self):
+        """Per-locus statistics as stored on the device, without evaluating."""
+        L, Q, B = self.L, self.Q, self.B
+        coal, ncoal = np.zeros((L, Q)), np.zeros((L, Q), np.int32)
+        mig, nmig = np.zeros((L, max(B, 1))), np.zeros((L, max(B, 1)), np.int32)
+        if B:
+            mig, nmig = np.zeros((L, B)), np.zeros((L, B), np.int32)
+        if self.lib.gphocsGenGetStats(self.h, _dp(coal), _ip(ncoal), _dp(mig), _ip(nmig)) != 0:
+            raise RuntimeError("gphocsGenGetStats failed")
+        return dict(coal=coal, num_coals=ncoal, mig=mig[:, :B], num_migs=nmig[:, :B])
 
     def lineages(self):
         out = np.zeros(self.E, np.int32)

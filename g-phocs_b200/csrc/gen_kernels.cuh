@@ -53,6 +53,7 @@ struct GenDev {
   int* numCoals;             // [L][Q]
   double* mig;               // [L][B]
   int* numMigs;              // [L][B]
+  uint8_t* enter;            // [L][Q] lineages at the start of each chain (events[first].num_lineages, patch.c:2398)
   double* ctaTotals;         // [numCTAs][V], V = 1 + 2Q + 2B
   const GenParams* params;
 };
@@ -152,6 +153,7 @@ __global__ void __launch_bounds__(kGenThreads) k_gen_eval(GenDev d, int maxTileE
       }
       sEnd[tid * Q + p] = (uint8_t)(n0 + dl[p]);
       dl[p] = (int16_t)n0;
+      d.enter[(size_t)(l0 + tid) * Q + p] = (uint8_t)n0;   // what an incremental re-walk of one chain starts from
     }
   }
   __syncthreads();
@@ -250,6 +252,59 @@ __global__ void __launch_bounds__(kGenThreads) k_gen_eval(GenDev d, int maxTileE
     }
     d.ctaTotals[(size_t)blockIdx.x * V + v] = acc;
   }
+}
+
+// recalcStats (patch.c:2387-2513) for a list of (locus, population) chains whose events kept their order and number
+// but changed their elapsed times — what rubberBand (patch.c:596-801) does to the chains of a split-time proposal.
+// One thread per chain: the new times are copied over the old ones, the chain is re-walked in the reference's order of
+// operations from the lineage count it is entered with (same code path as pass B of k_gen_eval, so the statistics are
+// bit-identical to a full evaluation of the updated snapshot), the stored statistics are replaced and the change of the
+// log-density is returned as recalcStats returns it: minus (mig - old) * rate at every MIG_BAND_END, in chain order,
+// then minus (coal - old) / theta.  status[k] != 0: the chain has a different number of events (nothing is changed).
+__global__ void __launch_bounds__(128) k_gen_recalc(GenDev d, double* __restrict__ evTime, int nPairs, const int* __restrict__ pairLocus,
+                                                    const int* __restrict__ pairPop, const int* __restrict__ timesStart,
+                                                    const double* __restrict__ newTimes, double* __restrict__ delta,
+                                                    int* __restrict__ status, const __grid_constant__ GenParams prm) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nPairs) return;
+  const int l = pairLocus[k], p = pairPop[k], Q = d.Q, B = d.B;
+  const uint16_t* ps = d.popStart + (size_t)l * (Q + 1);
+  const int a = d.evStart[l] + ps[p], b = d.evStart[l] + ps[p + 1];
+  const int t0 = timesStart[k];
+  if (timesStart[k + 1] - t0 != b - a) { status[k] = 1; delta[k] = 0.0; return; }
+  status[k] = 0;
+  int n = d.enter[(size_t)l * Q + p];
+  const int smp = prm.samplesPerPop[p];
+  double coal = 0.0, dl = 0.0;
+  double* mg = d.mig + (size_t)l * B;
+  double acc[8];             // statistics of the bands that are live at this point of the chain (they may overlap)
+  int accId[8], nLive = 0;
+  for (int e = a; e < b; e++) {
+    const double t = newTimes[t0 + (e - a)];
+    evTime[e] = t;
+    const int code = d.evCode[e], type = code & 7, id = code >> 3;
+    coal = __dadd_rn(coal, __dmul_rn((double)(n * (n - 1)), t));
+    if (nLive) {
+      const double nt = __dmul_rn((double)n, t);
+      for (int i = 0; i < nLive; i++) acc[i] = __dadd_rn(acc[i], nt);
+    }
+    if (type == EV_BAND_START) {
+      if (nLive < 8) { acc[nLive] = 0.0; accId[nLive] = id; nLive++; } else status[k] = 2;
+    } else if (type == EV_BAND_END) {
+      for (int i = 0; i < nLive; i++)
+        if (accId[i] == id) {
+          dl = __dsub_rn(dl, __dmul_rn(__dsub_rn(acc[i], mg[id]), prm.migRate[id]));
+          mg[id] = acc[i];
+          acc[i] = acc[nLive - 1]; accId[i] = accId[nLive - 1]; nLive--;
+          break;
+        }
+    }
+    n += type == EV_SAMPLES_START ? smp : lineageStep(type);
+  }
+  double* cs = d.coal + (size_t)l * Q + p;
+  dl = __dsub_rn(dl, __ddiv_rn(__dsub_rn(coal, *cs), prm.theta[p]));
+  *cs = coal;
+  delta[k] = dl;
 }
 
 // event snapshot copied from page-locked caller arrays as it is: int32 type / id -> 16-bit code, int32 chain offsets

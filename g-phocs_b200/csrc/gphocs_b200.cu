@@ -967,6 +967,7 @@ struct GphocsGenealogy {
   bool ownStream = false;
   int L = 0, Q = 0, C = 0, B = 0, V = 0;
   long long totalEvents = 0;
+  bool evaluatedOnce = false;     // a full evaluation has left the lineage counts at the start of every chain (gphocsGenRecalc)
   int maxTileEvents = 0, numCtas = 0;
   GenParams hp{};
   GenDev d{};
@@ -985,6 +986,8 @@ struct GphocsGenealogy {
   long long* dRawStart = nullptr;
   int* dBadEvents = nullptr;
   size_t raw32Cap = 0;
+  Staging<int> rcInts;            // gphocsGenRecalc: locus ids, population ids, offsets of the new times, status
+  Staging<double> rcTimes, rcDelta;
   std::vector<int> postOrder;
 };
 
@@ -1030,7 +1033,8 @@ extern "C" GphocsGenealogy* gphocsGenCreate(int device, int numLoci, int numPops
   bool ok = devAlloc(&g->dParams, 1) == 0 && devAlloc(&g->dEvStart, numLoci + 1) == 0 &&
             devAlloc(&g->dPopStart, (size_t)numLoci * (numPops + 1)) == 0 && devAlloc(&g->d.lnL, numLoci) == 0 &&
             devAlloc(&g->d.coal, LQ) == 0 && devAlloc(&g->d.numCoals, LQ) == 0 && devAlloc(&g->d.mig, LB) == 0 &&
-            devAlloc(&g->d.numMigs, LB) == 0 && devAlloc(&g->d.ctaTotals, (size_t)g->numCtas * g->V) == 0 &&
+            devAlloc(&g->d.numMigs, LB) == 0 && devAlloc(&g->d.enter, LQ) == 0 &&
+            devAlloc(&g->d.ctaTotals, (size_t)g->numCtas * g->V) == 0 &&
             devAlloc(&g->dTotals, g->V) == 0;
   if (!ok) { delete g; return nullptr; }
   cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking);
@@ -1044,12 +1048,13 @@ extern "C" int gphocsGenDestroy(GphocsGenealogy* g) {
   cudaSetDevice(g->device);
   cudaDeviceSynchronize();
   void* ptrs[] = {g->dParams, g->dEvStart, g->dPopStart, g->dEvTime, g->dEvCode, g->dLineages, g->dTotals, g->d.lnL,
-                  g->d.coal, g->d.numCoals, g->d.mig, g->d.numMigs, g->d.ctaTotals};
+                  g->d.coal, g->d.numCoals, g->d.mig, g->d.numMigs, g->d.ctaTotals, g->d.enter};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (g->dRaw32) cudaFree(g->dRaw32);
   if (g->dRawStart) cudaFree(g->dRawStart);
   if (g->dBadEvents) cudaFree(g->dBadEvents);
   g->out.release(); g->sEs.release(); g->sPs.release(); g->sCode.release();
+  g->rcInts.release(); g->rcTimes.release(); g->rcDelta.release();
   if (g->ownStream && g->stream) cudaStreamDestroy(g->stream);
   delete g;
   return 0;
@@ -1107,6 +1112,7 @@ extern "C" int gphocsGenSetEvents(GphocsGenealogy* g, const long long* evStart, 
   const long long E = evStart[L] - evStart[0];
   if (E <= 0 || E >= (1ll << 31)) { fprintf(stderr, "gphocs_b200: bad event count %lld\n", E); return -1; }
   g->totalEvents = 0;   // the object holds no snapshot until this call has succeeded
+  g->evaluatedOnce = false;
   if (genReserveEvents(g, (size_t)E)) return -1;
   // Page-locked caller arrays: the DMA engine reads them where they are and k_gen_pack narrows them on the device;
   // the host only finds the largest tile (for the shared-memory size) while the copies are in flight.
@@ -1206,6 +1212,7 @@ extern "C" int gphocsGenSetEventsPacked(GphocsGenealogy* g, const int* evStart, 
   const long long E = evStart[L];
   if (evStart[0] != 0 || E <= 0 || E >= (1ll << 31)) { fprintf(stderr, "gphocs_b200: bad event count %lld\n", E); return -1; }
   g->totalEvents = 0;   // the object holds no snapshot until this call has succeeded
+  g->evaluatedOnce = false;
   if (genReserveEvents(g, (size_t)E)) return -1;
   if (!g->dBadEvents && devAlloc(&g->dBadEvents, 1)) return -1;
   const size_t nPs = (size_t)L * (Q + 1);
@@ -1249,6 +1256,7 @@ static int genLaunch(GphocsGenealogy* g, bool wantLineages) {
   k_gen_reduce<<<g->V, 256, 0, g->stream>>>(g->d.ctaTotals, g->numCtas, g->V, g->dTotals);
   g_launches += 2;
   CUDA_TRY(cudaGetLastError());
+  g->evaluatedOnce = true;
   return 0;
 }
 
@@ -1283,6 +1291,67 @@ extern "C" int gphocsGenEvaluate(GphocsGenealogy* g, double* lnL, double* coal, 
     if (totalMig) totalMig[b] = t[1 + 2 * Q + b];
     if (totalNumMigs) totalNumMigs[b] = (long long)llround(t[1 + 2 * Q + B + b]);
   }
+  return 0;
+}
+
+// recalcStats (patch.c:2387-2513) for nPairs (locus, population) chains of the resident snapshot whose events kept
+// their number and order but changed their elapsed times (rubberBand, patch.c:596-801): evTime holds the new times of
+// the listed chains one after the other, timesStart[nPairs + 1] where each chain's begin.  The chains' statistics are
+// recomputed as a full evaluation of the updated snapshot would (bit for bit), stored, and deltaLnL[k] is what
+// recalcStats returns.  Needs one full evaluation of the snapshot before (it leaves the lineage counts the chains are
+// entered with).  Per-locus log-densities and the totals are those of the last full evaluation until the next one.
+extern "C" int gphocsGenRecalc(GphocsGenealogy* g, int nPairs, const int* locus, const int* pop, const int* timesStart,
+                               const double* evTime, double* deltaLnL) {
+  cudaSetDevice(g->device);
+  if (g->totalEvents <= 0) { fprintf(stderr, "gphocs_b200: gphocsGenSetEvents has not been called\n"); return -1; }
+  if (!g->evaluatedOnce) { fprintf(stderr, "gphocs_b200: gphocsGenRecalc needs a full evaluation of the snapshot first\n"); return -1; }
+  if (nPairs <= 0) return 0;
+  const size_t nTimes = (size_t)timesStart[nPairs];
+  for (int k = 0; k < nPairs; k++)
+    if (locus[k] < 0 || locus[k] >= g->L || pop[k] < 0 || pop[k] >= g->Q || timesStart[k + 1] < timesStart[k]) {
+      fprintf(stderr, "gphocs_b200: chain %d (locus %d, population %d) is outside the snapshot\n", k, locus[k], pop[k]);
+      return -1;
+    }
+  if (g->rcInts.reserve(4 * (size_t)nPairs + 1) || g->rcTimes.reserve(nTimes) || g->rcDelta.reserve((size_t)nPairs)) return -1;
+  CUDA_TRY(cudaStreamSynchronize(g->stream));   // the staging buffers may still feed the previous call
+  int* hi = g->rcInts.host;
+  memcpy(hi, locus, sizeof(int) * nPairs);
+  memcpy(hi + nPairs, pop, sizeof(int) * nPairs);
+  memcpy(hi + 2 * nPairs, timesStart, sizeof(int) * ((size_t)nPairs + 1));
+  memcpy(g->rcTimes.host, evTime, sizeof(double) * nTimes);
+  CUDA_TRY(cudaMemcpyAsync(g->rcInts.dev, hi, sizeof(int) * (3 * (size_t)nPairs + 1), cudaMemcpyHostToDevice, g->stream));
+  CUDA_TRY(cudaMemcpyAsync(g->rcTimes.dev, g->rcTimes.host, sizeof(double) * nTimes, cudaMemcpyHostToDevice, g->stream));
+  GenDev d = g->d;
+  d.L = g->L; d.Q = g->Q; d.B = g->B;
+  d.evStart = g->dEvStart; d.popStart = g->dPopStart; d.evTime = g->dEvTime; d.evCode = g->dEvCode;
+  d.evLineages = nullptr; d.params = g->dParams;
+  int* dStatus = g->rcInts.dev + 3 * (size_t)nPairs + 1;
+  k_gen_recalc<<<(nPairs + 127) / 128, 128, 0, g->stream>>>(d, g->dEvTime, nPairs, g->rcInts.dev, g->rcInts.dev + nPairs,
+                                                            g->rcInts.dev + 2 * nPairs, g->rcTimes.dev, g->rcDelta.dev, dStatus, g->hp);
+  g_launches++;
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpyAsync(g->rcDelta.host, g->rcDelta.dev, sizeof(double) * nPairs, cudaMemcpyDeviceToHost, g->stream));
+  CUDA_TRY(cudaMemcpyAsync(hi + 3 * (size_t)nPairs + 1, dStatus, sizeof(int) * nPairs, cudaMemcpyDeviceToHost, g->stream));
+  CUDA_TRY(cudaStreamSynchronize(g->stream));
+  for (int k = 0; k < nPairs; k++)
+    if (hi[3 * (size_t)nPairs + 1 + k] != 0) {
+      fprintf(stderr, "gphocs_b200: chain %d (locus %d, population %d): %s\n", k, locus[k], pop[k],
+              hi[3 * (size_t)nPairs + 1 + k] == 1 ? "the number of events differs from the resident chain's" : "more than 8 overlapping migration bands");
+      return -1;
+    }
+  if (deltaLnL) memcpy(deltaLnL, g->rcDelta.host, sizeof(double) * nPairs);
+  return 0;
+}
+
+// per-locus statistics as they are stored on the device (after gphocsGenEvaluate / gphocsGenRecalc), without evaluating
+extern "C" int gphocsGenGetStats(GphocsGenealogy* g, double* coal, int* numCoals, double* mig, int* numMigs) {
+  cudaSetDevice(g->device);
+  const size_t LQ = (size_t)g->L * g->Q, LB = (size_t)g->L * g->B;
+  CUDA_TRY(cudaStreamSynchronize(g->stream));
+  if (coal) CUDA_TRY(cudaMemcpy(coal, g->d.coal, sizeof(double) * LQ, cudaMemcpyDeviceToHost));
+  if (numCoals) CUDA_TRY(cudaMemcpy(numCoals, g->d.numCoals, sizeof(int) * LQ, cudaMemcpyDeviceToHost));
+  if (mig && LB) CUDA_TRY(cudaMemcpy(mig, g->d.mig, sizeof(double) * LB, cudaMemcpyDeviceToHost));
+  if (numMigs && LB) CUDA_TRY(cudaMemcpy(numMigs, g->d.numMigs, sizeof(int) * LB, cudaMemcpyDeviceToHost));
   return 0;
 }
 

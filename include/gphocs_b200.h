@@ -213,6 +213,17 @@ int gphocsGenEvaluate(GphocsGenealogy *g, double *lnL, double *coal, int *numCoa
  * [sumLnL, totalCoal[numPops], totalNumCoals[numPops] (as exact doubles), totalMig[numBands], totalNumMigs[numBands]]
  * = the all-reduce payload of SURVEY.md §8e. Returns its length in doubles. */
 int gphocsGenEvaluateDevice(GphocsGenealogy *g, void **devLnL, void **devTotals);
+/* recalcStats (patch.c:2387-2513), the incremental half of the path: nPairs (locus, population) chains of the resident
+ * snapshot whose events kept their number and order but changed their elapsed times — what rubberBand (patch.c:596-801)
+ * does for every UpdateTau proposal.  evTime = the new elapsed times of the listed chains one after the other,
+ * timesStart[nPairs + 1] = where each chain's begin.  Statistics of the chains are recomputed bit for bit as a full
+ * evaluation of the updated snapshot would and stored; deltaLnL[k] = recalcStats' return value (minus (mig - old) * rate
+ * at every MIG_BAND_END in chain order, then minus (coal - old) / theta).  A rejected proposal sends the old times back,
+ * as rubberBandRipple(gen, 1) does.  Needs one gphocsGenEvaluate of the snapshot before. */
+int gphocsGenRecalc(GphocsGenealogy *g, int nPairs, const int *locus, const int *pop, const int *timesStart,
+                    const double *evTime, double *deltaLnL);
+/* per-locus statistics as stored on the device after gphocsGenEvaluate / gphocsGenRecalc (any pointer may be NULL) */
+int gphocsGenGetStats(GphocsGenealogy *g, double *coal, int *numCoals, double *mig, int *numMigs);
 /* num_lineages per event as recalcStats leaves it (patch.c:2405); host array [total events] */
 int gphocsGenGetLineages(GphocsGenealogy *g, int *numLineages);
 int gphocsGenSync(GphocsGenealogy *g);

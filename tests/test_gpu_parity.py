@@ -434,3 +434,149 @@ def test_packed_wire_formats_equal_the_plain_ones():
     with pytest.raises(RuntimeError):
         gb.set_events_packed(es, wrong, code, w.ev_time)
     ga.close(); gb.close()
+
+
+# ------------------------------------------------------------------------------------- edge lengths, full sizes
+def test_zero_tiny_and_negative_edge_lengths_through_the_kernel():
+    """computeEdgeConditionalJC (LocusDataLikelihood.c:1843-1845): an edge shorter than 1e-100 — zero (a child as old as
+    its father), denormal-small or NEGATIVE (a child older than its father, which proposals pass through before they
+    are rejected) — has transition probability exactly 0, i.e. the child's vector is copied.  Full and incremental
+    evaluation of such genealogies against the oracle, internal vectors included."""
+    w = synth.generate(synth.config("dip8mig"), 96, seed=23)
+    n, N = w.n, 2 * w.n - 1
+    age = w.age.copy()
+    kinds = []
+    for l in range(w.L):
+        v = n + (l % (n - 2))                      # an internal node that is not the root in most loci
+        f = int(w.father[l, v])
+        if f < 0:
+            v = int(w.left[l, v]) if int(w.left[l, v]) >= n else int(w.right[l, v])
+            f = int(w.father[l, v])
+        if f < 0 or v < n:
+            kinds.append(None)
+            continue
+        k = l % 4
+        if k == 0:
+            age[l, v] = age[l, f]                  # zero-length edge
+        elif k == 1:
+            age[l, v] = age[l, f] * (1.0 + 1e-3)   # negative edge length: t < 1e-100 holds as well
+        elif k == 2:
+            age[l, v] = np.nextafter(age[l, f], 0.0)    # one ulp below the father: ~1e-19 > 1e-100, NOT the branch
+        else:
+            age[l, f] = age[l, v]                  # father pulled down onto the child (both its edges change)
+        kinds.append((v, f, k))
+    w2 = w
+    st = gp.LociStore.from_workload(w2)
+    st.set_trees(w.father, w.left, w.right, age, w.root)
+    got = st.evaluate(0)
+    orc = oracle_loci(w)
+    for l, o in enumerate(orc):
+        o.set_tree(w.father[l], w.left[l], w.right[l], age[l], int(w.root[l]))
+    want = np.array([o.compute(0) for o in orc])
+    finite = np.isfinite(want)
+    assert finite.sum() > 0.9 * w.L
+    assert rel(got[finite], want[finite]) < RTOL
+    assert np.array_equal(np.isfinite(got), finite)            # a likelihood the reference loses, this path loses too
+    for l in range(0, w.L, 7):
+        P = int(w.patt_start[l + 1] - w.patt_start[l])
+        for node in range(n, N):
+            assert np.allclose(st.clv(l, node, P=P), orc[l].clv(node), rtol=1e-12, atol=0.0), (l, node, kinds[l])
+    # the same states reached by an incremental evaluation: back to the original ages, then the edit as a proposal
+    st.apply_ops(gp.make_ops(np.arange(w.L), gp.OP_COMMIT))
+    st.set_trees(w.father, w.left, w.right, w.age, w.root)
+    st.evaluate(0)
+    st.apply_ops(gp.make_ops(np.arange(w.L), gp.OP_COMMIT))
+    sel = [l for l, kd in enumerate(kinds) if kd is not None and kd[2] != 3]
+    nodes = np.array([kinds[l][0] for l in sel])
+    st.apply_ops(gp.make_ops(np.array(sel), gp.OP_ADJUST_AGE, a=nodes, x=age[sel, nodes]))
+    inc = st.evaluate(1)
+    assert rel(inc[sel][finite[sel]], want[sel][finite[sel]]) < RTOL
+    st.close()
+
+
+@pytest.mark.parametrize("cfg,L", [("pop6mig4", 100_000), ("ancient", 50_000)])
+def test_full_size_data_and_genealogy_likelihood_against_sampled_oracle(cfg, L):
+    """BASELINE.json configs[3] (100k loci x 24 leaves, 4 bands) and configs[4] (50k loci, ancient samples, per-locus
+    rates) at FULL size: every locus is evaluated on the device; a random sample of 600 loci is checked against the
+    oracle (data lnL to 1e-10, genealogy statistics and lnL bit for bit), and the device totals against the sum of
+    the per-locus values."""
+    w = synth.generate(synth.config(cfg), L, seed=2026)
+    st = gp.LociStore.from_workload(w)
+    lnl, total = st.evaluate(0, want_sum=True)
+    assert np.all(np.isfinite(lnl))
+    rng = np.random.default_rng(5)
+    ids = np.sort(rng.choice(L, 600, replace=False))
+    want = np.array([o.compute(0) for o in oracle_loci(w, ids)])
+    assert rel(lnl[ids], want) < RTOL
+    assert abs(total - lnl.sum()) <= 1e-11 * abs(total)
+    gen = gp.Genealogy(L, w.pops)
+    gen.set_events(w.ev_start, w.pop_start, w.ev_type, w.ev_id, w.ev_time)
+    r = gen.evaluate()
+    pt, keep = ob.make_poptree(w.pops, w.band_start, w.band_end)
+    B = len(w.pops["band_src"])
+    for l in ids:
+        e0, e1 = int(w.ev_start[l]), int(w.ev_start[l + 1])
+        _, cs, nc, ms, nm, glnl = ob.oracle_gen_locus(pt, w.pop_start[l], w.ev_type[e0:e1], w.ev_id[e0:e1], w.ev_time[e0:e1])
+        assert r["lnl"][l] == glnl and np.array_equal(r["coal"][l], cs) and np.array_equal(r["num_coals"][l], nc)
+        assert np.array_equal(r["mig"][l][:B], ms[:B]) and np.array_equal(r["num_migs"][l][:B], nm[:B])
+    assert np.array_equal(r["total_num_coals"], r["num_coals"].sum(0))
+    assert abs(r["sum_lnl"] - r["lnl"].sum()) <= 1e-11 * abs(r["sum_lnl"])
+    st.close(); gen.close()
+
+
+@pytest.mark.parametrize("cfg", ["pop6mig4", "dip8mig", "hap16"])
+def test_incremental_recalc_equals_full_evaluation(cfg):
+    """gphocsGenRecalc = recalcStats (patch.c:2387-2513) for single (locus, population) chains whose elapsed times
+    changed, as after rubberBand: the stored statistics become bit for bit those of a full evaluation of the updated
+    snapshot, the returned value is recalcStats' (the same operations in the same order), and sending the old times
+    back restores the old statistics exactly (what a rejected UpdateTau proposal does)."""
+    w = synth.generate(synth.config(cfg), 3000, seed=77)
+    Q, B = len(w.pops["father"]), len(w.pops["band_src"])
+    theta = np.full(Q, 1e-3) * (1 + 0.1 * np.arange(Q))
+    rate = np.array([150.0 + 30 * b for b in range(B)])
+    gen = gp.Genealogy(w.L, w.pops)
+    gen.set_params(theta, rate)
+    gen.set_events(w.ev_start, w.pop_start, w.ev_type, w.ev_id, w.ev_time)
+    before = gen.evaluate()
+    rng = np.random.default_rng(11)
+    loci = np.sort(rng.choice(w.L, 1200, replace=False))
+    pops = rng.integers(0, Q, len(loci))
+    new_time = w.ev_time.copy()
+    starts, chunks = [0], []
+    for l, p in zip(loci, pops):
+        a = int(w.ev_start[l] + w.pop_start[l][p]); b = int(w.ev_start[l] + w.pop_start[l][p + 1])
+        f = rng.uniform(0.6, 1.4, b - a)                       # every interval of the chain rescaled on its own
+        new_time[a:b] = w.ev_time[a:b] * f
+        chunks.append(new_time[a:b].copy())
+        starts.append(starts[-1] + (b - a))
+    delta = gen.recalc(loci, pops, starts, np.concatenate(chunks) if chunks else np.zeros(0))
+    after_inc = gen.stats_only()
+    # the same snapshot evaluated from scratch
+    gen2 = gp.Genealogy(w.L, w.pops)
+    gen2.set_params(theta, rate)
+    gen2.set_events(w.ev_start, w.pop_start, w.ev_type, w.ev_id, new_time)
+    full = gen2.evaluate()
+    assert np.array_equal(after_inc["coal"], full["coal"]) and np.array_equal(after_inc["mig"], full["mig"])
+    # recalcStats' return value from the stored statistics before and after, same operations in the same order
+    band_tgt = np.asarray(w.pops["band_tgt"])
+    for k, (l, p) in enumerate(zip(loci, pops)):
+        d = 0.0
+        a = int(w.ev_start[l] + w.pop_start[l][p]); b = int(w.ev_start[l] + w.pop_start[l][p + 1])
+        for e in range(a, b):                                  # MIG_BAND_END events in chain order
+            if w.ev_type[e] == 4:
+                bid = int(w.ev_id[e])
+                d = d - (full["mig"][l][bid] - before["mig"][l][bid]) * rate[bid]
+        d = d - (full["coal"][l][p] - before["coal"][l][p]) / theta[p]
+        assert delta[k] == d, (k, l, p, delta[k], d)
+        assert all(band_tgt[int(w.ev_id[e])] == p for e in range(a, b) if w.ev_type[e] == 4)
+    # the rejected proposal: old times back
+    old_chunks = [w.ev_time[int(w.ev_start[l] + w.pop_start[l][p]):int(w.ev_start[l] + w.pop_start[l][p + 1])] for l, p in zip(loci, pops)]
+    back = gen.recalc(loci, pops, starts, np.concatenate(old_chunks))
+    restored = gen.stats_only()
+    assert np.array_equal(restored["coal"], before["coal"]) and np.array_equal(restored["mig"], before["mig"])
+    assert np.allclose(back, -delta, rtol=1e-9, atol=1e-9)
+    # a chain of the wrong length is refused and nothing changes
+    with pytest.raises(RuntimeError):
+        gen.recalc(loci[:1], pops[:1], [0, starts[1] + 1], np.ones(starts[1] + 1))
+    assert np.array_equal(gen.stats_only()["coal"], before["coal"])
+    gen.close(); gen2.close()
