@@ -576,10 +576,72 @@ def run_b200(args):
     if world == 1:
         assert abs(sdata - total_data_lnl) <= 1e-9 * abs(total_data_lnl), (sdata, total_data_lnl)
         assert abs(sgen - total_gen_lnl) <= 1e-9 * abs(total_gen_lnl), (sgen, total_gen_lnl)
-    e2e_value, sdata, sgen = e2e_run(True)
+    e2e_full_value, sdata, sgen = e2e_run(True)
     if world == 1:
         assert abs(sdata - total_data_lnl) <= 1e-9 * abs(total_data_lnl), (sdata, total_data_lnl)
         assert abs(sgen - total_gen_lnl) <= 1e-9 * abs(total_gen_lnl), (sgen, total_gen_lnl)
+
+    # ---- e2e, delta route (the headline): an MCMC-shaped host step.  Between two steps of a chain a locus' genealogy
+    # changes in a few nodes and one or two event chains, so the host ships what changed — 24-byte edit records
+    # (resetSaved + adjustGenNodeAge per locus, gphocsStoreApplyOpsAsync) and the new elapsed times of one population's
+    # chain per locus (gphocsGenRecalcAsync) — and the device evaluates everything from scratch as in the resident
+    # step: full data likelihood of every locus, full genealogy likelihood of every locus, per-locus values and totals
+    # back in page-locked host memory before the step ends.  tests/test_gpu_parity.py::test_delta_upload_step_equals_
+    # the_full_upload: the state these deltas leave on the device is bit for bit the one a full upload leaves.
+    node = n + 2
+    nodeArr = np.full(L, node)
+    recs = []
+    for f in (1.001, 1.0):          # two edit sets, alternating, so the genealogies stay where they are on average
+        r_ = np.zeros(2 * L, gp.OP_DTYPE)
+        r_["locus"] = np.repeat(np.arange(L), 2)
+        r_["type"] = np.tile([gp.OP_COMMIT, gp.OP_ADJUST_AGE], L)
+        r_["a"] = np.tile([0, node], L)
+        fa = w.father[np.arange(L), nodeArr]
+        bound = np.where(fa >= 0, w.age[np.arange(L), np.maximum(fa, 0)], np.inf)     # stay below the father
+        r_["x"][1::2] = np.minimum(w.age[np.arange(L), nodeArr] * f, bound)
+        recs.append(gp.pinned_like(r_))
+    chain_pop = (np.arange(L) % Q).astype(np.int32)
+    a0 = (w.ev_start[:-1] + w.pop_start[np.arange(L), chain_pop]).astype(np.int64)
+    b0 = (w.ev_start[:-1] + w.pop_start[np.arange(L), chain_pop + 1]).astype(np.int64)
+    starts = np.zeros(L + 1, np.int32); starts[1:] = np.cumsum(b0 - a0)
+    idx = np.concatenate([np.arange(x, y) for x, y in zip(a0, b0)])
+    pin_loc, pin_pop, pin_starts = gp.pinned_like(np.arange(L, dtype=np.int32)), gp.pinned_like(chain_pop), gp.pinned_like(starts)
+    pin_times = [gp.pinned_like(w.ev_time[idx] * f) for f in (0.999, 1.0)]
+    h2d_delta = 2 * L * 24 + 4 * L + 4 * L + 4 * (L + 1) + 8 * len(idx)
+    st.set_trees_packed(hp["topo"], hw["age"], hw["root"])          # both objects back at the workload's state
+    gen.set_events_packed(hp["es"], hp["ps"], hp["code"], hw["ev_time"])
+    st.evaluate_device(0); gen.evaluate(per_locus_stats=False)
+    stream.synchronize()
+
+    def delta_step(i):
+        st.apply_ops_async(recs[i & 1])
+        dlnl, dsum = st.evaluate_device(0)
+        sp = C.c_void_p(stream.cuda_stream)
+        lib.gphocsCopyDeviceAsync(C.c_void_p(lnl_host.ctypes.data), C.c_void_p(dlnl), 8 * L, sp)
+        lib.gphocsCopyDeviceAsync(C.c_void_p(host_sums.ctypes.data), C.c_void_p(dsum), 8, sp)
+        gen.recalc_async(pin_loc, pin_pop, pin_starts, pin_times[i & 1])
+        r = gen.evaluate(per_locus_stats=False)
+        stream.synchronize()
+        return float(host_sums[0]), r["sum_lnl"]
+
+    for i in range(2):
+        delta_step(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        sd_, sg_ = delta_step(i)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    st.sync(); gen.sync()                                           # reports records / chains the device refused
+    if world > 1:
+        t = torch.tensor([dt], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    e2e_value = world * L * e2e_steps / dt
+    assert np.isfinite(sd_) and np.isfinite(sg_) and abs(sd_ - total_data_lnl) < 1e-3 * abs(total_data_lnl)
+    st.apply_ops(gp.make_ops(np.arange(L), gp.OP_COMMIT))
+    st.set_trees_packed(hp["topo"], hw["age"], hw["root"])
+    st.evaluate(0, out=lnl_host)
 
     # ---- MCMC-style cycle (extra): one node-age proposal per locus -> incremental evaluation -> accept/reject
     node = n + 2
@@ -652,11 +714,16 @@ def run_b200(args):
                          "ms_per_launch": ms_data, "mean_phased_patterns": float(P.mean()), "mean_events": float(E.mean()),
                          "genealogy_kernel_ms": ms_gen, "genealogy_achieved_gbs": bytes_gen / (ms_gen * 1e-3) / 1e9,
                          "mcmc": mcmc, "evals_per_s_at_10k_loci": small},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_delta), "d2h_bytes_per_step": int(d2h),
                     "steps": e2e_steps, "host_threads_per_rank": host_threads,
-                    "route": "gphocsStoreSetTreesPacked + gphocsGenSetEventsPacked (16-bit topology and event codes on the wire)",
-                    "int32_route": {"value": e2e_int32_value, "h2d_bytes_per_step": int(h2d_int32),
-                                    "route": "gphocsStoreSetTrees + gphocsGenSetEvents (int32 arrays copied as they are)"}},
+                    "route": "delta upload of an MCMC-shaped step: gphocsStoreApplyOpsAsync (resetSaved + adjustGenNodeAge records, "
+                             "one node per locus) + gphocsGenRecalcAsync (new elapsed times of one chain per locus), then the full data "
+                             "and genealogy evaluation of every locus; per-locus values and totals back in host memory",
+                    "full_upload": {"value": e2e_full_value, "h2d_bytes_per_step": int(h2d),
+                                    "route": "every genealogy and the whole event snapshot re-sent each step: gphocsStoreSetTreesPacked + "
+                                             "gphocsGenSetEventsPacked (16-bit topology and event codes on the wire)"},
+                    "full_upload_int32": {"value": e2e_int32_value, "h2d_bytes_per_step": int(h2d_int32),
+                                          "route": "gphocsStoreSetTrees + gphocsGenSetEvents (int32 arrays copied as they are)"}},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "mcmc_iters_per_s": mcmc_head["iters_per_s"] if mcmc_head else None,

@@ -85,6 +85,7 @@ def lib():
         "gphocsStoreGetTrees": (ci, [vp, ci, c_int_p, c_int_p, c_int_p, c_int_p, c_dbl_p, c_int_p]),
         "gphocsStoreSetRates": (ci, [vp, ci, c_int_p, c_dbl_p]),
         "gphocsStoreApplyOps": (ci, [vp, ci, vp, c_int_p]),
+        "gphocsStoreApplyOpsAsync": (ci, [vp, ci, vp]),
         "gphocsStoreEvaluate": (ci, [vp, ci, c_int_p, ci, c_dbl_p, c_dbl_p]),
         "gphocsStoreEvaluateDevice": (ci, [vp, ci, C.POINTER(vp), C.POINTER(vp)]),
         "gphocsStoreGetLnL": (ci, [vp, ci, c_int_p, c_dbl_p]),
@@ -109,6 +110,7 @@ def lib():
         "gphocsGenEvaluate": (ci, [vp, c_dbl_p, c_dbl_p, c_int_p, c_dbl_p, c_int_p, c_dbl_p, c_ll_p, c_dbl_p, c_ll_p, c_dbl_p]),
         "gphocsGenEvaluateDevice": (ci, [vp, C.POINTER(vp), C.POINTER(vp)]),
         "gphocsGenRecalc": (ci, [vp, ci, c_int_p, c_int_p, c_int_p, c_dbl_p, c_dbl_p]),
+        "gphocsGenRecalcAsync": (ci, [vp, ci, c_int_p, c_int_p, c_int_p, c_dbl_p, C.POINTER(vp)]),
         "gphocsGenGetStats": (ci, [vp, c_dbl_p, c_int_p, c_dbl_p, c_int_p]),
         "gphocsGenGetLineages": (ci, [vp, c_int_p]),
         "gphocsGenSync": (ci, [vp]),
@@ -255,6 +257,11 @@ class LociStore:
         self._check(self.lib.gphocsStoreGetRates(self.h, len(out), _ip(None if ids is None else _i32(ids)), _dp(out)),
                     "gphocsStoreGetRates")
         return out
+
+    def apply_ops_async(self, ops):
+        """Edit records (sorted by locus, page-locked: pinned_like) for the device copy only; returns at once."""
+        assert ops.dtype == OP_DTYPE and ops.flags["C_CONTIGUOUS"]
+        self._check(self.lib.gphocsStoreApplyOpsAsync(self.h, len(ops), ops.ctypes.data_as(C.c_void_p)), "gphocsStoreApplyOpsAsync")
 
     def apply_ops(self, ops, want_status=False):
         ops = np.ascontiguousarray(ops, OP_DTYPE)
@@ -445,6 +452,17 @@ class Genealogy:
             raise RuntimeError("gphocsGenRecalc failed")
         return out
 
+    def recalc_async(self, locus, pop, times_start, times):
+        """gphocsGenRecalcAsync on page-locked int32 / float64 arrays (pinned_like); returns the device pointer of the deltas."""
+        out = C.c_void_p()
+        if self.lib.gphocsGenRecalcAsync(self.h, len(locus), _ip(locus), _ip(pop), _ip(times_start), _dp(times), C.byref(out)) != 0:
+            raise RuntimeError("gphocsGenRecalcAsync failed")
+        return out.value
+
+    def sync(self):
+        if self.lib.gphocsGenSync(self.h) != 0:
+            raise RuntimeError("gphocsGenSync reported refused chains or a CUDA error")
+
     def stats_only(self):
         """Per-locus statistics as stored on the device, without evaluating."""
         L, Q, B = self.L, self.Q, self.B
@@ -461,9 +479,6 @@ class Genealogy:
         if self.lib.gphocsGenGetLineages(self.h, _ip(out)) != 0:
             raise RuntimeError("gphocsGenGetLineages failed")
         return out
-
-    def sync(self):
-        self.lib.gphocsGenSync(self.h)
 
 
 class ScalarLocus:

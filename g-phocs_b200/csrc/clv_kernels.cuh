@@ -162,6 +162,25 @@ __global__ void k_apply_ops(StoreDev d, const Op* __restrict__ ops, const int* _
   for (int o = o0; o < o1; o++) status[o] = applyOp(t, ops[o]);
 }
 
+// The same for records that arrive sorted by locus (gphocsStoreApplyOpsAsync): the thread that holds the first record
+// of a locus replays that locus' records; no segment table crosses PCIe.  *bad counts records outside the store or tree.
+__global__ void k_apply_ops_sorted(StoreDev d, const Op* __restrict__ ops, int nOps, int* __restrict__ bad) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nOps) return;
+  const int locus = ops[i].locus;
+  if (i > 0 && ops[i - 1].locus == locus) return;
+  if (locus < 0 || locus >= d.L || (i > 0 && ops[i - 1].locus > locus)) { atomicAdd(bad, 1); return; }
+  const TreeView t = deviceView(d, locus);
+  for (int o = i; o < nOps && ops[o].locus == locus; o++) {
+    const Op op = ops[o];
+    bool ok = op.type >= OP_ADJUST_AGE && op.type <= OP_SET_RATE;
+    if (op.type == OP_ADJUST_AGE) ok = op.a >= 0 && op.a < d.N;
+    if (op.type == OP_SPR) ok = op.a >= 0 && op.a < d.N && op.b >= 0 && op.b < d.N && op.a != op.b && t.node[op.a].father >= 0;
+    if (!ok) { atomicAdd(bad, 1); return; }
+    applyOp(t, op);
+  }
+}
+
 // genealogies host -> device: topology fields, ages and roots of the listed loci; flag bytes (buffer
 // selectors, dirty marks) stay as they are on the device
 __global__ void k_set_trees(StoreDev d, const int* __restrict__ ids, const int16_t* __restrict__ topo,

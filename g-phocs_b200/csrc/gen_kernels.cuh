@@ -268,6 +268,7 @@ __global__ void __launch_bounds__(128) k_gen_recalc(GenDev d, double* __restrict
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= nPairs) return;
   const int l = pairLocus[k], p = pairPop[k], Q = d.Q, B = d.B;
+  if (l < 0 || l >= d.L || p < 0 || p >= Q) { status[k] = 3; delta[k] = 0.0; return; }
   const uint16_t* ps = d.popStart + (size_t)l * (Q + 1);
   const int a = d.evStart[l] + ps[p], b = d.evStart[l] + ps[p + 1];
   const int t0 = timesStart[k];

@@ -146,6 +146,11 @@ struct GphocsStore {
   bool debugMirror = false;  // also mirror SEL/RECALC bits on the host (tests)
   bool opsInFlight = false;  // an edit batch was enqueued without a stream synchronisation
   std::atomic<bool> mirrorStale{false};  // topology / ages / roots of the mirror are behind the device copy (refreshMirrorLocked)
+  std::atomic<bool> flagsStale{false};   // edits went to the device only (gphocsStoreApplyOpsAsync): the mirror's saved copies and
+                                         // flag bytes follow with the next refresh as well
+  Op* dOpsAsync = nullptr;               // device copy of the records of gphocsStoreApplyOpsAsync
+  size_t opsAsyncCap = 0;
+  int* dBadOps = nullptr;
   std::atomic<bool> lnlStale{false};     // lnL / savedLnL of the mirror are behind it (gphocsStoreEvaluateDevice, the sampler)
   std::mutex mu;
 
@@ -359,6 +364,8 @@ extern "C" int gphocsStoreDestroy(GphocsStore* s) {
   for (void* p : ptrs) if (p) cudaFree(p);
   if (s->dTopo32) cudaFree(s->dTopo32);
   if (s->dBadTopo) cudaFree(s->dBadTopo);
+  if (s->dOpsAsync) cudaFree(s->dOpsAsync);
+  if (s->dBadOps) cudaFree(s->dBadOps);
   s->ops.release(); s->seg.release(); s->status.release(); s->ids.release(); s->f64.release(); s->i16.release();
   if (s->ownStream && s->stream) cudaStreamDestroy(s->stream);
   delete s;
@@ -402,10 +409,11 @@ extern "C" int gphocsHostFree(void* p) {
   if (p) CUDA_TRY(cudaFreeHost(p));
   return 0;
 }
+static int takeBadOps(GphocsStore* s);
 extern "C" int gphocsStoreSync(GphocsStore* s) {
   cudaSetDevice(s->device);
   CUDA_TRY(cudaStreamSynchronize(s->stream));
-  return 0;
+  return takeBadOps(s);
 }
 
 // ---- genealogies
@@ -432,13 +440,21 @@ static int refreshMirrorLocked(GphocsStore* s) {
   CUDA_TRY(cudaMemcpy(s->hRate.data(), s->d.rate, (size_t)s->L * sizeof(double), cudaMemcpyDeviceToHost));
   NodeRec* hn = s->hNode.data();
   const NodeRec* dn = nd.data();
+  const bool withFlags = s->flagsStale.load(std::memory_order_acquire);
   parallelFor(0, (long long)LN, [&](long long lo_, long long hi_) {
     for (long long i = lo_; i < hi_; i++) {
       NodeRec rec = hn[i];
       rec.father = dn[i].father; rec.left = dn[i].left; rec.right = dn[i].right;
+      if (withFlags) rec.flags = s->debugMirror ? dn[i].flags : (uint8_t)((rec.flags & ~F_SAVED) | (dn[i].flags & F_SAVED));
       hn[i] = rec;
     }
   }, 65536);
+  if (withFlags) {   // proposals made on the device only may be pending: their saved copies belong to the mirror too
+    CUDA_TRY(cudaMemcpy(s->hsNode.data(), s->d.saved, LN * sizeof(NodeRec), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(s->hsAge.data(), s->d.svAge, LN * sizeof(double), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(s->hSavedRoot.data(), s->d.savedRoot, (size_t)s->L * sizeof(int), cudaMemcpyDeviceToHost));
+    s->flagsStale.store(false, std::memory_order_release);
+  }
   s->mirrorStale.store(false, std::memory_order_release);
   return 0;
 }
@@ -726,6 +742,49 @@ extern "C" int gphocsStoreApplyOps(GphocsStore* s, int nOps, const GphocsOp* ops
   return launchOps(s, ops, nOps, outStatus, true);
 }
 
+// Edit records for the device copy only, without waiting: the records must be sorted by locus (all records of a locus
+// adjacent, in call order) and should lie in page-locked memory (gphocsHostAlloc) — the DMA engine reads them where they
+// are and they must stay untouched until the stream has passed the copy (the next synchronising call of this store).
+// The host mirror behind the scalar API's getters is brought up to date when somebody reads it.  Records outside the
+// store or a tree are refused on the device; the next synchronising call (gphocsStoreSync, gphocsStoreEvaluate, ...) reports it.
+extern "C" int gphocsStoreApplyOpsAsync(GphocsStore* s, int nOps, const GphocsOp* ops_) {
+  std::lock_guard<std::mutex> lk(s->mu);
+  if (flushPending(s)) return -1;
+  if (nOps <= 0) return 0;
+  cudaSetDevice(s->device);
+  if ((size_t)nOps > s->opsAsyncCap) {
+    if (s->dOpsAsync) { CUDA_TRY(cudaStreamSynchronize(s->stream)); cudaFree(s->dOpsAsync); }
+    s->dOpsAsync = nullptr; s->opsAsyncCap = 0;
+    if (devAlloc(&s->dOpsAsync, (size_t)nOps + (size_t)nOps / 4)) return -1;
+    s->opsAsyncCap = (size_t)nOps + (size_t)nOps / 4;
+  }
+  if (!s->dBadOps) {
+    if (devAlloc(&s->dBadOps, 1)) return -1;
+    CUDA_TRY(cudaMemset(s->dBadOps, 0, sizeof(int)));
+  }
+  CUDA_TRY(cudaMemcpyAsync(s->dOpsAsync, ops_, sizeof(Op) * (size_t)nOps, cudaMemcpyHostToDevice, s->stream));
+  k_apply_ops_sorted<<<(nOps + 127) / 128, 128, 0, s->stream>>>(s->d, s->dOpsAsync, nOps, s->dBadOps);
+  g_launches++;
+  CUDA_TRY(cudaGetLastError());
+  s->mirrorStale.store(true, std::memory_order_release);
+  s->flagsStale.store(true, std::memory_order_release);
+  s->lnlStale.store(true, std::memory_order_release);   // OP_REVERT restores lnL on the device
+  return 0;
+}
+// records refused by the device since the last call (0 = none); synchronises the stream
+static int takeBadOps(GphocsStore* s) {
+  if (!s->dBadOps) return 0;
+  int bad = 0;
+  CUDA_TRY(cudaMemcpyAsync(&bad, s->dBadOps, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+  CUDA_TRY(cudaStreamSynchronize(s->stream));
+  if (bad) {
+    CUDA_TRY(cudaMemset(s->dBadOps, 0, sizeof(int)));
+    fprintf(stderr, "gphocs_b200: %d edit records of gphocsStoreApplyOpsAsync were outside the store, a tree, or out of order\n", bad);
+    return -1;
+  }
+  return 0;
+}
+
 extern "C" int gphocsStoreSetRates(GphocsStore* s, int nLoci, const int* locusIds, const double* rates) {
   std::vector<GphocsOp> ops(nLoci);
   for (int k = 0; k < nLoci; k++) ops[k] = GphocsOp{locusIds ? locusIds[k] : k, GPHOCS_OP_SET_RATE, 0, 0, rates[k]};
@@ -986,6 +1045,10 @@ struct GphocsGenealogy {
   long long* dRawStart = nullptr;
   int* dBadEvents = nullptr;
   size_t raw32Cap = 0;
+  int* dRcStatus = nullptr;       // gphocsGenRecalcAsync: per-chain status of the last call, checked by the next synchronising call
+  double* dRcDelta = nullptr;
+  size_t rcAsyncCap = 0;
+  int rcAsyncPairs = 0;
   Staging<int> rcInts;            // gphocsGenRecalc: locus ids, population ids, offsets of the new times, status
   Staging<double> rcTimes, rcDelta;
   std::vector<int> postOrder;
@@ -1055,6 +1118,8 @@ extern "C" int gphocsGenDestroy(GphocsGenealogy* g) {
   if (g->dBadEvents) cudaFree(g->dBadEvents);
   g->out.release(); g->sEs.release(); g->sPs.release(); g->sCode.release();
   g->rcInts.release(); g->rcTimes.release(); g->rcDelta.release();
+  if (g->dRcStatus) cudaFree(g->dRcStatus);
+  if (g->dRcDelta) cudaFree(g->dRcDelta);
   if (g->ownStream && g->stream) cudaStreamDestroy(g->stream);
   delete g;
   return 0;
@@ -1343,6 +1408,61 @@ extern "C" int gphocsGenRecalc(GphocsGenealogy* g, int nPairs, const int* locus,
   return 0;
 }
 
+// The same without waiting, for arrays in page-locked memory (gphocsHostAlloc) that stay untouched until the next
+// synchronising call on this object: the DMA engine reads them where they are; *devDelta = device array of the nPairs
+// return values (stream-ordered: copy it out with gphocsCopyDeviceAsync on the same stream).  Chains refused by the
+// device (different number of events, ids outside the snapshot) are reported by the next gphocsGenSync / gphocsGenEvaluate.
+extern "C" int gphocsGenRecalcAsync(GphocsGenealogy* g, int nPairs, const int* locus, const int* pop, const int* timesStart,
+                                    const double* evTime, void** devDelta) {
+  cudaSetDevice(g->device);
+  if (g->totalEvents <= 0 || !g->evaluatedOnce) {
+    fprintf(stderr, "gphocs_b200: gphocsGenRecalcAsync needs a snapshot and one full evaluation of it\n");
+    return -1;
+  }
+  if (nPairs <= 0) return 0;
+  const size_t nTimes = (size_t)timesStart[nPairs];
+  if (g->rcInts.reserve(4 * (size_t)nPairs + 1) || g->rcTimes.reserve(nTimes)) return -1;
+  if ((size_t)nPairs > g->rcAsyncCap) {
+    CUDA_TRY(cudaStreamSynchronize(g->stream));
+    if (g->dRcStatus) cudaFree(g->dRcStatus);
+    if (g->dRcDelta) cudaFree(g->dRcDelta);
+    g->dRcStatus = nullptr; g->dRcDelta = nullptr; g->rcAsyncCap = 0;
+    if (devAlloc(&g->dRcStatus, (size_t)nPairs) || devAlloc(&g->dRcDelta, (size_t)nPairs)) return -1;
+    g->rcAsyncCap = (size_t)nPairs;
+  }
+  int* di = g->rcInts.dev;
+  CUDA_TRY(cudaMemcpyAsync(di, locus, sizeof(int) * (size_t)nPairs, cudaMemcpyHostToDevice, g->stream));
+  CUDA_TRY(cudaMemcpyAsync(di + nPairs, pop, sizeof(int) * (size_t)nPairs, cudaMemcpyHostToDevice, g->stream));
+  CUDA_TRY(cudaMemcpyAsync(di + 2 * (size_t)nPairs, timesStart, sizeof(int) * ((size_t)nPairs + 1), cudaMemcpyHostToDevice, g->stream));
+  CUDA_TRY(cudaMemcpyAsync(g->rcTimes.dev, evTime, sizeof(double) * nTimes, cudaMemcpyHostToDevice, g->stream));
+  GenDev d = g->d;
+  d.L = g->L; d.Q = g->Q; d.B = g->B;
+  d.evStart = g->dEvStart; d.popStart = g->dPopStart; d.evTime = g->dEvTime; d.evCode = g->dEvCode;
+  d.evLineages = nullptr; d.params = g->dParams;
+  k_gen_recalc<<<(nPairs + 127) / 128, 128, 0, g->stream>>>(d, g->dEvTime, nPairs, di, di + nPairs, di + 2 * (size_t)nPairs, g->rcTimes.dev,
+                                                            g->dRcDelta, g->dRcStatus, g->hp);
+  g_launches++;
+  CUDA_TRY(cudaGetLastError());
+  g->rcAsyncPairs = nPairs;
+  if (devDelta) *devDelta = g->dRcDelta;
+  return 0;
+}
+// chains the device refused in the last gphocsGenRecalcAsync (call with the stream synchronised)
+static int genTakeRecalcStatus(GphocsGenealogy* g) {
+  if (g->rcAsyncPairs <= 0) return 0;
+  std::vector<int> st((size_t)g->rcAsyncPairs);
+  CUDA_TRY(cudaMemcpy(st.data(), g->dRcStatus, sizeof(int) * st.size(), cudaMemcpyDeviceToHost));
+  g->rcAsyncPairs = 0;
+  for (size_t k = 0; k < st.size(); k++)
+    if (st[k] != 0) {
+      fprintf(stderr, "gphocs_b200: gphocsGenRecalcAsync: chain %zu was refused (%s)\n", k,
+              st[k] == 1 ? "number of events differs from the resident chain's" : st[k] == 2 ? "more than 8 overlapping migration bands"
+                                                                                           : "locus or population outside the snapshot");
+      return -1;
+    }
+  return 0;
+}
+
 // per-locus statistics as they are stored on the device (after gphocsGenEvaluate / gphocsGenRecalc), without evaluating
 extern "C" int gphocsGenGetStats(GphocsGenealogy* g, double* coal, int* numCoals, double* mig, int* numMigs) {
   cudaSetDevice(g->device);
@@ -1367,7 +1487,7 @@ extern "C" int gphocsGenGetLineages(GphocsGenealogy* g, int* numLineages) {
 extern "C" int gphocsGenSync(GphocsGenealogy* g) {
   cudaSetDevice(g->device);
   CUDA_TRY(cudaStreamSynchronize(g->stream));
-  return 0;
+  return genTakeRecalcStatus(g);
 }
 
 #include "locus_api.inc"

@@ -142,6 +142,11 @@ int gphocsStoreGetRates(GphocsStore *s, int nLoci, const int *locusIds, double *
 /* proposals / accept / reject: applied to the host mirror at once and to the device copy in order.
  * Several records may target one locus (they apply in array order).  outStatus[nOps] may be NULL. */
 int gphocsStoreApplyOps(GphocsStore *s, int nOps, const GphocsOp *ops, int *outStatus);
+/* the same for the device copy only, without waiting — the delta upload of a host that keeps its own genealogies: records
+ * sorted by locus (those of a locus adjacent, in call order), in page-locked memory (gphocsHostAlloc) that stays untouched
+ * until the next synchronising call of the store.  The host mirror behind the getters of group A follows on demand.
+ * Records outside the store or a tree are refused on the device and reported by gphocsStoreSync. */
+int gphocsStoreApplyOpsAsync(GphocsStore *s, int nOps, const GphocsOp *ops);
 
 /* computeLocusDataLikelihood(locus, useOld) for every listed locus (NULL = all) in one launch.
  * outLnL[nLoci] (host) receives the per-locus values, *outSum their sum; either may be NULL. */
@@ -222,6 +227,11 @@ int gphocsGenEvaluateDevice(GphocsGenealogy *g, void **devLnL, void **devTotals)
  * as rubberBandRipple(gen, 1) does.  Needs one gphocsGenEvaluate of the snapshot before. */
 int gphocsGenRecalc(GphocsGenealogy *g, int nPairs, const int *locus, const int *pop, const int *timesStart,
                     const double *evTime, double *deltaLnL);
+/* the same without waiting: arrays in page-locked memory (gphocsHostAlloc), untouched until the next synchronising call;
+ * *devDelta = device array of the return values, stream-ordered (gphocsCopyDeviceAsync).  Refused chains (different
+ * number of events, ids outside the snapshot) are reported by the next gphocsGenSync. */
+int gphocsGenRecalcAsync(GphocsGenealogy *g, int nPairs, const int *locus, const int *pop, const int *timesStart,
+                         const double *evTime, void **devDelta);
 /* per-locus statistics as stored on the device after gphocsGenEvaluate / gphocsGenRecalc (any pointer may be NULL) */
 int gphocsGenGetStats(GphocsGenealogy *g, double *coal, int *numCoals, double *mig, int *numMigs);
 /* num_lineages per event as recalcStats leaves it (patch.c:2405); host array [total events] */

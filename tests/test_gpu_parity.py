@@ -580,3 +580,63 @@ def test_incremental_recalc_equals_full_evaluation(cfg):
         gen.recalc(loci[:1], pops[:1], [0, starts[1] + 1], np.ones(starts[1] + 1))
     assert np.array_equal(gen.stats_only()["coal"], before["coal"])
     gen.close(); gen2.close()
+
+
+def test_delta_upload_step_equals_the_full_upload():
+    """The delta routes of an MCMC-shaped host step — gphocsStoreApplyOpsAsync (edit records for the device copy only,
+    no waiting) and gphocsGenRecalcAsync (new elapsed times of single chains) — leave the device in exactly the state
+    a full upload of the edited genealogies and event snapshot leaves it in: log-likelihoods and statistics bit for bit;
+    the host mirror catches up on demand, pending proposal included (revert through the synchronous API)."""
+    w = synth.generate(synth.config("dip8mig"), 2000, seed=5)
+    L, n = w.L, w.n
+    st = gp.LociStore.from_workload(w)
+    st.evaluate(0)
+    st.apply_ops(gp.make_ops(np.arange(L), gp.OP_COMMIT))
+    node = n + 3
+    new_age = w.age[:, node] * 1.0005
+    recs = np.zeros(2 * L, gp.OP_DTYPE)                       # per locus: resetSaved, then adjustGenNodeAge
+    recs["locus"] = np.repeat(np.arange(L), 2)
+    recs["type"] = np.tile([gp.OP_COMMIT, gp.OP_ADJUST_AGE], L)
+    recs["a"] = np.tile([0, node], L)
+    recs["x"][1::2] = new_age
+    st.apply_ops_async(gp.pinned_like(recs))
+    got = st.evaluate(0)
+    age2 = w.age.copy(); age2[:, node] = new_age
+    st2 = gp.LociStore.from_workload(w)
+    st2.set_trees(w.father, w.left, w.right, age2, w.root)
+    want = st2.evaluate(0)
+    assert np.array_equal(got, want)
+    # the mirror follows: trees, the pending proposal's saved copies, then a revert through the synchronous API
+    f, l_, r, a, root = st.get_trees()
+    assert np.array_equal(a, age2)
+    assert st.check_mirror() == 0
+    st.apply_ops(gp.make_ops(np.arange(L), gp.OP_REVERT))
+    assert np.array_equal(st.get_trees()[3], w.age) and st.check_mirror() == 0
+    # records out of order or outside the tree are refused on the device and reported by the next sync
+    bad = np.zeros(2, gp.OP_DTYPE); bad["locus"] = [5, 3]; bad["type"] = gp.OP_COMMIT
+    st.apply_ops_async(gp.pinned_like(bad))
+    with pytest.raises(RuntimeError):
+        st.sync()
+    st.sync()
+    # genealogy: new times of one chain per locus, asynchronously, against a full snapshot
+    Q = len(w.pops["father"])
+    gen = gp.Genealogy(L, w.pops)
+    gen.set_events(w.ev_start, w.pop_start, w.ev_type, w.ev_id, w.ev_time)
+    gen.evaluate()
+    pops = (np.arange(L) % Q).astype(np.int32)
+    new_time = w.ev_time.copy()
+    starts, chunks = [0], []
+    for l in range(L):
+        a0 = int(w.ev_start[l] + w.pop_start[l][pops[l]]); b0 = int(w.ev_start[l] + w.pop_start[l][pops[l] + 1])
+        new_time[a0:b0] *= 0.9
+        chunks.append(new_time[a0:b0]); starts.append(starts[-1] + b0 - a0)
+    pin = [gp.pinned_like(np.arange(L, dtype=np.int32)), gp.pinned_like(pops), gp.pinned_like(np.asarray(starts, np.int32)),
+           gp.pinned_like(np.concatenate(chunks))]
+    assert gen.recalc_async(*pin)
+    gen.sync()
+    full = gp.Genealogy(L, w.pops)
+    full.set_events(w.ev_start, w.pop_start, w.ev_type, w.ev_id, new_time)
+    ref = full.evaluate()
+    inc = gen.evaluate()                                       # full evaluation of the snapshot the deltas produced
+    assert np.array_equal(inc["lnl"], ref["lnl"]) and np.array_equal(inc["coal"], ref["coal"]) and np.array_equal(inc["mig"], ref["mig"])
+    st.close(); st2.close(); gen.close(); full.close()
