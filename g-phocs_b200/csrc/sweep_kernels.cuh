@@ -40,55 +40,82 @@ constexpr uint32_t kSweepHi = kSweepStack * kRow;
 #define GPHOCS_SWEEP_MINBLOCKS 8
 #endif
 
-// what the sweeps read of the model (SmpModel carries 39 populations and 32 bands: 2.4 KB per CTA)
+// what the sweeps read of the model (SmpModel carries 39 populations and 32 bands: 2.7 KB per CTA)
 struct SweepModel {
-  int Q;
+  int Q, B;
   int father[kSmpMaxPops], leavesBelow[kSmpMaxPops];
   unsigned long long below[kSmpMaxPops];
   double theta[kSmpMaxPops], tau[kSmpMaxPops], coalRate[kSmpMaxPops];
 };
+// ... plus the bands, for models that have them (staged right behind the SweepModel)
+struct SweepBands {
+  int C;
+  int src[kSmpMaxBands], tgt[kSmpMaxBands];
+  double rate[kSmpMaxBands];
+};
 
 struct SweepSmem {
   // per locus slot: what lives for the whole sweep ...
-  size_t offAge, offNode, offNeed, offPop, offCoal, offNcoal, perLocus;
+  uint32_t offAge, offNode, offNeed, offPop, offCoal, offNcoal, perLocus;
+  // ... with migration bands also the migration events (current and saved), band statistics and the branch segments
+  uint32_t offMigAge, offSvMigAge, offMigStat, offPendMig, offNmig, offMigInts, offMigBranch, offMigBand, offSegT0, offSegT1,
+      offSegBranch, offSegPop;
   // ... and the scheduling scratch of one step, which shares its space with the column stack (never live together)
-  size_t offSize, offWalk, perScratch;
-  size_t perSched;
+  uint32_t offSize, offWalk, perScratch;
+  uint32_t perSched;
   // CTA regions
-  size_t offLoci, offSched, offStack, offWords, offList, offTerm, offMeta, offProp, offModel, total;
-  int W32;
+  uint32_t offLoci, offSched, offStack, offWords, offList, offTerm, offMeta, offProp, offCells, offModel, total;
+  int W32, maxSegs;
 };
-__host__ __device__ inline SweepSmem sweepSmemLayout(int n, int maxLoci, int Q) {
+// B = 0: a model without migration bands (maxSegs ignored)
+__host__ __device__ inline SweepSmem sweepSmemLayout(int n, int maxLoci, int Q, int B = 0, int maxSegs = 0) {
   const int N = 2 * n - 1, NI = n - 1;
   SweepSmem m;
   m.W32 = (n + 7) / 8;
+  m.maxSegs = B > 0 ? maxSegs : 0;
+  const uint32_t S = (uint32_t)m.maxSegs, nb = (uint32_t)B, M = B > 0 ? (uint32_t)kSmpMaxMigs : 0u;
   m.offAge = 0;                                             // [N] double
-  m.offCoal = m.offAge + (size_t)N * 8;                     // [Q] double
-  m.offNode = m.offCoal + (size_t)Q * 8;                    // [N] NodeRec
-  m.offNcoal = m.offNode + (size_t)N * sizeof(NodeRec);     // [Q] int
-  m.offNeed = m.offNcoal + (size_t)Q * 4;                   // [N] uint8
-  m.offPop = m.offNeed + (size_t)N;                         // [N] uint8
-  m.perLocus = (m.offPop + (size_t)N + 15) & ~(size_t)15;
+  m.offCoal = m.offAge + (uint32_t)N * 8;                   // [Q] double
+  m.offMigAge = m.offCoal + (uint32_t)Q * 8;                // [M] double
+  m.offSvMigAge = m.offMigAge + M * 8;                      // [M] double
+  m.offMigStat = m.offSvMigAge + M * 8;                     // [B] double mig_stats
+  m.offPendMig = m.offMigStat + nb * 8;                     // [B + 1] double: statistics of the pending proposal (bands, then coal)
+  m.offSegT0 = m.offPendMig + (B > 0 ? (nb + 1) * 8 : 0);   // [S] double
+  m.offSegT1 = m.offSegT0 + S * 8;                          // [S] double
+  m.offNode = m.offSegT1 + S * 8;                           // [N] NodeRec
+  m.offNcoal = m.offNode + (uint32_t)N * sizeof(NodeRec);   // [Q] int
+  m.offNmig = m.offNcoal + (uint32_t)Q * 4;                 // [B] int
+  m.offMigInts = m.offNmig + nb * 4;                        // numMigs, saved numMigs, segment count, inconsistency flag
+  m.offMigBranch = m.offMigInts + (B > 0 ? 16u : 0u);       // [2][M] uint8: current, saved
+  m.offMigBand = m.offMigBranch + 2 * M;                    // [2][M] uint8
+  m.offSegBranch = m.offMigBand + 2 * M;                    // [S] uint8
+  m.offSegPop = m.offSegBranch + S;                         // [S] uint8
+  m.offNeed = m.offSegPop + S;                              // [N] uint8
+  m.offPop = m.offNeed + (uint32_t)N;                       // [N] uint8
+  m.perLocus = (m.offPop + (uint32_t)N + 15) & ~15u;
   m.offSize = 0;                                            // [NI] int
-  m.offWalk = m.offSize + (size_t)NI * 4;                   // [N] uint32; the team phase keeps its lists here
-  m.perScratch = (m.offWalk + (size_t)N * 4 + 15) & ~(size_t)15;
-  m.perSched = (size_t)NI * sizeof(SchedEntryCompact);
+  m.offWalk = m.offSize + (uint32_t)NI * 4;                 // [N] uint32; the team phase keeps its lists here
+  m.perScratch = (m.offWalk + (uint32_t)N * 4 + S + 15) & ~15u;   // (+ S bytes: a list of segment indices)
+  m.perSched = (uint32_t)NI * sizeof(SchedEntryCompact);
   m.offLoci = 0;
-  m.offSched = m.offLoci + m.perLocus * (size_t)maxLoci;
+  m.offSched = m.offLoci + m.perLocus * (uint32_t)maxLoci;
   // column stack (one parking row: lo halves, hi halves) = the root vectors after the walk = the scheduling scratch
-  const size_t stackBytes = 2 * (size_t)kSweepHi, scratchBytes = m.perScratch * (size_t)maxLoci;
-  m.offStack = m.offSched + m.perSched * (size_t)maxLoci;
+  const uint32_t stackBytes = 2 * (uint32_t)kSweepHi, scratchBytes = m.perScratch * (uint32_t)maxLoci;
+  m.offStack = m.offSched + m.perSched * (uint32_t)maxLoci;
   m.offWords = m.offStack + (stackBytes > scratchBytes ? stackBytes : scratchBytes);   // [W32][kThreads] uint32, whole sweep
-  m.offList = m.offWords + (size_t)m.W32 * kThreads * 4;    // [maxLoci*NI] uint32: marked nodes of the batch
+  m.offList = m.offWords + (uint32_t)m.W32 * kThreads * 4;  // [maxLoci*NI] uint32: marked nodes of the batch
   m.offTerm = m.offList;                                    // [kThreads] double once the list is dead
-  const size_t listBytes = (size_t)maxLoci * NI * 4, termBytes = (size_t)kThreads * 8;
-  m.offMeta = (m.offList + (listBytes > termBytes ? listBytes : termBytes) + 15) & ~(size_t)15;   // per-slot scalars
-  m.offProp = m.offMeta + (size_t)kTeamSlots * 64;          // [slots] SmpProposal
-  m.offModel = (m.offProp + (size_t)kTeamSlots * sizeof(SmpProposal) + 15) & ~(size_t)15;
-  m.total = (m.offModel + sizeof(SweepModel) + 15) & ~(size_t)15;
+  const uint32_t listBytes = (uint32_t)maxLoci * NI * 4, termBytes = (uint32_t)kThreads * 8;
+  m.offMeta = (m.offList + (listBytes > termBytes ? listBytes : termBytes) + 15) & ~15u;   // per-slot scalars
+  m.offProp = m.offMeta + (uint32_t)kTeamSlots * 64;        // [slots] SmpProposal
+  m.offCells = (m.offProp + (uint32_t)kTeamSlots * sizeof(SmpProposal) + 15) & ~15u;   // list count, acceptance counters
+  m.offModel = m.offCells + 16;
+  m.total = (m.offModel + sizeof(SweepModel) + (B > 0 ? sizeof(SweepBands) : 0) + 15) & ~15u;
   return m;
 }
-__host__ __device__ inline size_t sweepSmemBytes(int n, int maxLoci, int Q) { return sweepSmemLayout(n, maxLoci, Q).total; }
+__host__ __device__ inline size_t sweepSmemBytes(int n, int maxLoci, int Q, int B = 0, int maxSegs = 0) {
+  return sweepSmemLayout(n, maxLoci, Q, B, maxSegs).total;
+}
 
 struct Team {
   int j;           // 0..7 inside the team; 0 = leader
@@ -311,355 +338,410 @@ __device__ inline int teamResolve(const Team& tm, const TreeView& t, uint8_t* np
   return ok;
 }
 
-__global__ void __launch_bounds__(kThreads, GPHOCS_SWEEP_MINBLOCKS)
-k_sweep(StoreDev d, SmpDev sd, const SmpModel* __restrict__ mp, const Batch* __restrict__ batches, int maxLoci, double ftCoal,
-        unsigned long long seed, unsigned long long step0) {
-  extern __shared__ __align__(16) unsigned char smem[];
-  const Batch b = batches[blockIdx.x];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int n = d.n, N = d.N, NI = d.NI, nl = b.numLoci, Q = sd.Q;
-  const SweepSmem lay = sweepSmemLayout(n, maxLoci, Q);
+// ------------------------------------------------------------------------------------------ what the sweep kernels share
+// Shared-memory views, the column state of this thread and the phases every step runs after its team phase.
+struct SweepCtx {
+  unsigned char* smem;
+  SweepSmem lay;
+  Batch b;
+  int tid, lane, warp, n, N, NI, nl, Q;
+  // this thread's pattern column
+  bool live;
+  int colSlot, ph, cnt;
+  char* clvCol;
+  uint32_t myStack, myWords;
 
-  // ---- carve shared memory
-  auto sAge = [&](int s) { return reinterpret_cast<double*>(smem + lay.offLoci + lay.perLocus * s + lay.offAge); };
-  auto sCoal = [&](int s) { return reinterpret_cast<double*>(smem + lay.offLoci + lay.perLocus * s + lay.offCoal); };
-  auto sNode = [&](int s) { return reinterpret_cast<NodeRec*>(smem + lay.offLoci + lay.perLocus * s + lay.offNode); };
-  auto sSize = [&](int s) { return reinterpret_cast<int*>(smem + lay.offStack + lay.perScratch * s + lay.offSize); };
-  auto sWalk = [&](int s) { return reinterpret_cast<uint32_t*>(smem + lay.offStack + lay.perScratch * s + lay.offWalk); };
-  auto sNcoal = [&](int s) { return reinterpret_cast<int*>(smem + lay.offLoci + lay.perLocus * s + lay.offNcoal); };
-  auto sNeed = [&](int s) { return reinterpret_cast<uint8_t*>(smem + lay.offLoci + lay.perLocus * s + lay.offNeed); };
-  auto sPop = [&](int s) { return reinterpret_cast<uint8_t*>(smem + lay.offLoci + lay.perLocus * s + lay.offPop); };
-  auto sSched = [&](int s) { return reinterpret_cast<SchedEntryCompact*>(smem + lay.offSched + lay.perSched * s); };
-  const uint32_t stackBase = smemAddr(smem + lay.offStack);
-  double* sRoot = reinterpret_cast<double*>(smem + lay.offStack);   // [kThreads][4], after the walk
-  double* sTerm = reinterpret_cast<double*>(smem + lay.offTerm);
-  double* mRate = reinterpret_cast<double*>(smem + lay.offMeta);    // per-slot scalars
-  double* mLnL = mRate + kTeamSlots;
-  double* mSavedLnL = mLnL + kTeamSlots;
-  unsigned long long* mEvals = reinterpret_cast<unsigned long long*>(mSavedLnL + kTeamSlots);   // accounting, SURVEY.md 8d
-  unsigned long long* mEvalBytes = mEvals + kTeamSlots;
-  int* mColStart = reinterpret_cast<int*>(mEvalBytes + kTeamSlots);
-  int* mP = mColStart + kTeamSlots;
-  int* mK = mP + kTeamSlots;
-  int* mRoot = mK + kTeamSlots;
-  int* mSavedRoot = mRoot + kTeamSlots;
-  int* mActive = mSavedRoot + kTeamSlots;
-  SmpProposal* sProp = reinterpret_cast<SmpProposal*>(smem + lay.offProp);
-  __shared__ int sListCountCell;   // not inside the list region: sTerm takes that over while the count is being reset
-  int* sListCount = &sListCountCell;
-  uint32_t* sList = reinterpret_cast<uint32_t*>(smem + lay.offList);
-  SweepModel& sModel = *reinterpret_cast<SweepModel*>(smem + lay.offModel);
-  __shared__ unsigned int sAccepted[2];
+  __device__ __forceinline__ unsigned char* locus(int s) const { return smem + lay.offLoci + lay.perLocus * s; }
+  __device__ __forceinline__ unsigned char* scratch(int s) const { return smem + lay.offStack + lay.perScratch * s; }
+  __device__ __forceinline__ double* age(int s) const { return reinterpret_cast<double*>(locus(s) + lay.offAge); }
+  __device__ __forceinline__ double* coal(int s) const { return reinterpret_cast<double*>(locus(s) + lay.offCoal); }
+  __device__ __forceinline__ NodeRec* node(int s) const { return reinterpret_cast<NodeRec*>(locus(s) + lay.offNode); }
+  __device__ __forceinline__ int* ncoal(int s) const { return reinterpret_cast<int*>(locus(s) + lay.offNcoal); }
+  __device__ __forceinline__ uint8_t* need(int s) const { return locus(s) + lay.offNeed; }
+  __device__ __forceinline__ uint8_t* pop(int s) const { return locus(s) + lay.offPop; }
+  __device__ __forceinline__ int* size(int s) const { return reinterpret_cast<int*>(scratch(s) + lay.offSize); }
+  __device__ __forceinline__ uint32_t* walk(int s) const { return reinterpret_cast<uint32_t*>(scratch(s) + lay.offWalk); }
+  __device__ __forceinline__ SchedEntryCompact* sched(int s) const {
+    return reinterpret_cast<SchedEntryCompact*>(smem + lay.offSched + lay.perSched * s);
+  }
+  __device__ __forceinline__ double* root4() const { return reinterpret_cast<double*>(smem + lay.offStack); }   // after the walk
+  __device__ __forceinline__ double* term() const { return reinterpret_cast<double*>(smem + lay.offTerm); }
+  // per-slot scalars
+  __device__ __forceinline__ double* mRate() const { return reinterpret_cast<double*>(smem + lay.offMeta); }
+  __device__ __forceinline__ double* mLnL() const { return mRate() + kTeamSlots; }
+  __device__ __forceinline__ double* mSavedLnL() const { return mLnL() + kTeamSlots; }
+  __device__ __forceinline__ unsigned long long* mEvals() const { return reinterpret_cast<unsigned long long*>(mSavedLnL() + kTeamSlots); }
+  __device__ __forceinline__ unsigned long long* mEvalBytes() const { return mEvals() + kTeamSlots; }
+  __device__ __forceinline__ int* mColStart() const { return reinterpret_cast<int*>(mEvalBytes() + kTeamSlots); }
+  __device__ __forceinline__ int* mP() const { return mColStart() + kTeamSlots; }
+  __device__ __forceinline__ int* mK() const { return mP() + kTeamSlots; }
+  __device__ __forceinline__ int* mRoot() const { return mK() + kTeamSlots; }
+  __device__ __forceinline__ int* mSavedRoot() const { return mRoot() + kTeamSlots; }
+  __device__ __forceinline__ int* mActive() const { return mSavedRoot() + kTeamSlots; }
+  __device__ __forceinline__ SmpProposal* prop() const { return reinterpret_cast<SmpProposal*>(smem + lay.offProp); }
+  // not inside the list region: the root terms take that over while the count is being reset
+  __device__ __forceinline__ int* listCount() const { return reinterpret_cast<int*>(smem + lay.offCells); }
+  __device__ __forceinline__ unsigned int* accepted() const { return reinterpret_cast<unsigned int*>(smem + lay.offCells) + 1; }   // [2]
+  __device__ __forceinline__ uint32_t* list() const { return reinterpret_cast<uint32_t*>(smem + lay.offList); }
+  __device__ __forceinline__ SweepModel& model() const { return *reinterpret_cast<SweepModel*>(smem + lay.offModel); }
+  __device__ __forceinline__ SweepBands& bands() const { return *reinterpret_cast<SweepBands*>(smem + lay.offModel + sizeof(SweepModel)); }
+};
 
-  // ---- stage the batch: model, per-locus scalars, genealogies, population assignments, statistics, leaf codes
-  if (tid == 0) sModel.Q = Q;
+// stage the batch: model, per-locus scalars, genealogies, population assignments, coal statistics, leaf codes; ends
+// with a barrier.  The caller stages what else its model needs before calling (no barrier in between is needed).
+__device__ inline void sweepStage(SweepCtx& c, unsigned char* smem, const SweepSmem& lay, const StoreDev& d, const SmpDev& sd,
+                                  const SmpModel* __restrict__ mp, const Batch& b) {
+  c.smem = smem; c.lay = lay; c.b = b;
+  c.tid = threadIdx.x; c.lane = c.tid & 31; c.warp = c.tid >> 5;
+  c.n = d.n; c.N = d.N; c.NI = d.NI; c.nl = b.numLoci; c.Q = sd.Q;
+  const int tid = c.tid, Q = c.Q, N = c.N, nl = c.nl;
+  SweepModel& sModel = c.model();
+  if (tid == 0) { sModel.Q = Q; sModel.B = mp->B; }
   for (int p = tid; p < Q; p += kThreads) {
     sModel.father[p] = mp->father[p]; sModel.leavesBelow[p] = mp->leavesBelow[p]; sModel.below[p] = mp->below[p];
     sModel.theta[p] = mp->theta[p]; sModel.tau[p] = mp->tau[p]; sModel.coalRate[p] = mp->coalRate[p];
   }
   unsigned long long w0 = 0ull, w1 = 0ull;
-  int ph = 0, cnt = 0;
-  if (tid < b.numCols) {
-    const int c = b.firstCol + tid;
-    w0 = d.leafWords[c];
-    if (d.W > 1) w1 = d.leafWords[(size_t)d.Ct + c];
-    ph = d.grpPhases[c];
-    cnt = d.grpCount[c];
+  c.ph = 0; c.cnt = 0;
+  c.live = tid < b.numCols;
+  if (c.live) {
+    const int col = b.firstCol + tid;
+    w0 = d.leafWords[col];
+    if (d.W > 1) w1 = d.leafWords[(size_t)d.Ct + col];
+    c.ph = d.grpPhases[col];
+    c.cnt = d.grpCount[col];
   }
   if (tid < nl) {
     const int l = b.firstLocus + tid;
     const int c0 = d.colStart[l];
-    mColStart[tid] = c0;
-    mP[tid] = d.colStart[l + 1] - c0;
+    c.mColStart()[tid] = c0;
+    c.mP()[tid] = d.colStart[l + 1] - c0;
     const int root = d.root[l];
-    mRoot[tid] = root;
-    mSavedRoot[tid] = d.savedRoot[l];
-    mRate[tid] = d.rate[l];
-    mActive[tid] = (mP[tid] > 0) && (root >= n);
-    mK[tid] = 0;
-    mLnL[tid] = d.lnL[l];
-    mSavedLnL[tid] = d.savedLnL[l];
-    mEvals[tid] = 0ull;
-    mEvalBytes[tid] = 0ull;
+    c.mRoot()[tid] = root;
+    c.mSavedRoot()[tid] = d.savedRoot[l];
+    c.mRate()[tid] = d.rate[l];
+    c.mActive()[tid] = (c.mP()[tid] > 0) && (root >= c.n);
+    c.mK()[tid] = 0;
+    c.mLnL()[tid] = d.lnL[l];
+    c.mSavedLnL()[tid] = d.savedLnL[l];
+    c.mEvals()[tid] = 0ull;
+    c.mEvalBytes()[tid] = 0ull;
   }
-  if (tid < 2) sAccepted[tid] = 0u;
-  if (tid == 0) *sListCount = 0;
-  for (int s = warp; s < nl; s += kWarps) {
+  if (tid < 2) c.accepted()[tid] = 0u;
+  if (tid == 0) *c.listCount() = 0;
+  for (int s = c.warp; s < nl; s += kWarps) {
     const int l = b.firstLocus + s;
     const size_t g0 = (size_t)l * N;
-    NodeRec* nd = sNode(s);
-    double* age = sAge(s);
-    uint8_t* need = sNeed(s);
-    uint8_t* pop = sPop(s);
-    for (int v = lane; v < N; v += 32) {
+    NodeRec* nd = c.node(s);
+    double* age = c.age(s);
+    uint8_t* need = c.need(s);
+    uint8_t* pop = c.pop(s);
+    for (int v = c.lane; v < N; v += 32) {
       nd[v] = d.node[g0 + v];
       age[v] = d.age[g0 + v];
       pop[v] = sd.nodePop[g0 + v];
       need[v] = 0;
     }
-    for (int p = lane; p < Q; p += 32) {
-      sCoal(s)[p] = sd.coal[(size_t)l * Q + p];
-      sNcoal(s)[p] = sd.ncoal[(size_t)l * Q + p];
+    for (int p = c.lane; p < Q; p += 32) {
+      c.coal(s)[p] = sd.coal[(size_t)l * Q + p];
+      c.ncoal(s)[p] = sd.ncoal[(size_t)l * Q + p];
     }
   }
-  const uint32_t myStack = stackBase + tid * 16;
-  const uint32_t myWords = smemAddr(smem + lay.offWords) + tid * 4;
-  const bool live = tid < b.numCols;
-  if (live) {   // this column's leaf masks, 8 leaves per 32-bit word
-    stsU32(myWords, (uint32_t)w0);
-    if (lay.W32 > 1) stsU32(myWords + kThreads * 4, (uint32_t)(w0 >> 32));
-    if (lay.W32 > 2) stsU32(myWords + 2 * kThreads * 4, (uint32_t)w1);
-    if (lay.W32 > 3) stsU32(myWords + 3 * kThreads * 4, (uint32_t)(w1 >> 32));
+  c.myStack = smemAddr(smem + lay.offStack) + tid * 16;
+  c.myWords = smemAddr(smem + lay.offWords) + tid * 4;
+  if (c.live) {   // this column's leaf masks, 8 leaves per 32-bit word
+    stsU32(c.myWords, (uint32_t)w0);
+    if (lay.W32 > 1) stsU32(c.myWords + kThreads * 4, (uint32_t)(w0 >> 32));
+    if (lay.W32 > 2) stsU32(c.myWords + 2 * kThreads * 4, (uint32_t)w1);
+    if (lay.W32 > 3) stsU32(c.myWords + 3 * kThreads * 4, (uint32_t)(w1 >> 32));
   }
   __syncthreads();
-  int colSlot = 0;   // the locus this thread's column belongs to
-  if (live) {
-    const int c = b.firstCol + tid;
-    while (colSlot + 1 < nl && c >= mColStart[colSlot + 1]) colSlot++;
+  c.colSlot = 0;   // the locus this thread's column belongs to
+  if (c.live) {
+    const int col = b.firstCol + tid;
+    while (c.colSlot + 1 < nl && col >= c.mColStart()[c.colSlot + 1]) c.colSlot++;
   }
-  char* const clvCol = reinterpret_cast<char*>(d.clv + (size_t)mColStart[colSlot] * NI * 8 +
-                                               (size_t)(live ? b.firstCol + tid - mColStart[colSlot] : 0) * 4);
-  const SweepModel& m = sModel;
+  c.clvCol = reinterpret_cast<char*>(d.clv + (size_t)c.mColStart()[c.colSlot] * c.NI * 8 +
+                                     (size_t)(c.live ? b.firstCol + tid - c.mColStart()[c.colSlot] : 0) * 4);
+}
 
-  // ---- the team of this thread and the genealogy it edits
-  Team tm;
-  tm.j = tid & (kTeam - 1);
-  tm.leader = lane & ~(kTeam - 1);
-  tm.mask = ((1u << kTeam) - 1u) << tm.leader;
-  const int slot = tid / kTeam;
-  const bool teamOn = slot < nl;
-  const int myLocus = b.firstLocus + slot;
+// the genealogy of a slot as the edit protocol sees it: current arrays in shared memory, saved copies in HBM
+__device__ __forceinline__ TreeView sweepTreeView(const SweepCtx& c, const StoreDev& d, int slot) {
   TreeView t;
-  if (teamOn) {
-    const size_t o = (size_t)myLocus * N;
-    t.node = sNode(slot); t.saved = d.saved + o;
-    t.age = sAge(slot); t.svAge = d.svAge + o;
-    t.root = mRoot + slot; t.savedRoot = mSavedRoot + slot;
-    t.lnL = mLnL + slot; t.savedLnL = mSavedLnL + slot; t.rate = mRate + slot;
-    t.numLeaves = n;
-    t.numPatterns = mP[slot];
-  }
-  unsigned int accepted[2] = {0u, 0u};
+  const size_t o = (size_t)(c.b.firstLocus + slot) * c.N;
+  t.node = c.node(slot); t.saved = d.saved + o;
+  t.age = c.age(slot); t.svAge = d.svAge + o;
+  t.root = c.mRoot() + slot; t.savedRoot = c.mSavedRoot() + slot;
+  t.lnL = c.mLnL() + slot; t.savedLnL = c.mSavedLnL() + slot; t.rate = c.mRate() + slot;
+  t.numLeaves = c.n;
+  t.numPatterns = c.mP()[slot];
+  return t;
+}
 
-  const int numAge = ftCoal > 0.0 ? NI : 0, numSteps = numAge + N;
-  for (int it = 0; it <= numSteps; it++) {
-    // ---- team phase
-    if (teamOn) {
-      if (it > 0) {
-        const int kind = it - 1 < numAge ? 0 : 1;
-        const int ok = teamResolve(tm, t, sPop(slot), sCoal(slot), sProp[slot], myLocus, N, kind, seed, step0 + 2ull * (it - 1) + 1ull);
-        if (tm.j == 0) accepted[kind] += ok;
-      }
-      if (it < numSteps) {
-        const unsigned long long step = step0 + 2ull * it;
-        uint8_t* scratch = reinterpret_cast<uint8_t*>(sWalk(slot));   // the list phases have not started: N words free
-        const SmpProposal pr = it < numAge
-            ? teamAgePropose(tm, m, t, sPop(slot), sCoal(slot), sNcoal(slot), myLocus, n, N, n + it, ftCoal, seed, step, scratch)
-            : teamSprPropose(tm, m, t, sPop(slot), myLocus, n, N, it - numAge, seed, step);
-        if (tm.j == 0) {
-          sProp[slot] = pr;
-          mK[slot] = 0;
-          if (mActive[slot]) mSavedLnL[slot] = mLnL[slot];   // what every evaluation starts with (.c:440)
-        }
-        __syncwarp(tm.mask);
-        if (mActive[slot]) {
-          // k_eval phase B: dirty nodes and their ancestors (a moved leaf dirties its father, .c:1569-1575)
-          NodeRec* nd = t.node;
-          uint8_t* need = sNeed(slot);
-          for (int v = tm.j; v < N; v += kTeam)
-            if (nd[v].flags & F_RECALC) {
-              int u = v < n ? nd[v].father : v;
-              for (int k = 0; u >= 0 && !need[u] && k < N; k++) {   // concurrent walkers store the same 1 (see k_eval)
-                need[u] = 1;
-                u = nd[u].father;
-              }
-            }
-          __syncwarp(tm.mask);
-          // k_eval phase C0: marked nodes of the batch compacted into one list; their destination buffers flipped
-          for (int v0 = n; v0 < N; v0 += kTeam) {
-            const int v = v0 + tm.j;
-            const bool marked = v < N && need[v];
-            const unsigned ballot = (__ballot_sync(tm.mask, marked) >> tm.leader) & ((1u << kTeam) - 1u);
-            int base = 0;
-            if (tm.j == 0 && ballot) base = atomicAdd(sListCount, __popc(ballot));
-            base = teamBcast(tm, base);
-            if (marked) {
-              sSize(slot)[v - n] = 0;   // phase C counts into it (its space was the column stack a moment ago)
-              sList[base + __popc(ballot & ((1u << tm.j) - 1u))] = (uint32_t)(slot << 16 | v);
-              const uint8_t f = nd[v].flags;
-              if (!(f & F_RECALC)) nd[v].flags = (uint8_t)((f ^ F_SEL) | F_RECALC);
-            }
-          }
-        }
+// end of a team phase that has made a proposal for `slot`: k_eval phases B (dirty nodes and their ancestors; a moved
+// leaf dirties its father, .c:1569-1575) and C0 (marked nodes of the batch compacted into one list, their destination
+// buffers flipped)
+__device__ inline void sweepMarkAndCompact(const SweepCtx& c, const Team& tm, int slot) {
+  const int n = c.n, N = c.N;
+  if (tm.j == 0) {
+    c.mK()[slot] = 0;
+    if (c.mActive()[slot]) c.mSavedLnL()[slot] = c.mLnL()[slot];   // what every evaluation starts with (.c:440)
+  }
+  __syncwarp(tm.mask);
+  if (!c.mActive()[slot]) return;
+  NodeRec* nd = c.node(slot);
+  uint8_t* need = c.need(slot);
+  for (int v = tm.j; v < N; v += kTeam)
+    if (nd[v].flags & F_RECALC) {
+      int u = v < n ? nd[v].father : v;
+      for (int k = 0; u >= 0 && !need[u] && k < N; k++) {   // concurrent walkers store the same 1 (see k_eval)
+        need[u] = 1;
+        u = nd[u].father;
       }
     }
-    if (it == numSteps) break;
-    __syncthreads();
-    const int listCount = *sListCount;
-    // ---- k_eval phase C: marked nodes per subtree
-    for (int j = tid; j < listCount; j += kThreads) {
-      const int s = sList[j] >> 16, v = sList[j] & 0xffff;
-      const NodeRec* nd = sNode(s);
-      int* size = sSize(s);
-      int a = v;
-      for (int k = 0; a >= 0 && k < N; k++) {
-        atomicAdd(&size[a - n], 1);
-        a = nd[a].father;
-      }
+  __syncwarp(tm.mask);
+  for (int v0 = n; v0 < N; v0 += kTeam) {
+    const int v = v0 + tm.j;
+    const bool marked = v < N && need[v];
+    const unsigned ballot = (__ballot_sync(tm.mask, marked) >> tm.leader) & ((1u << kTeam) - 1u);
+    int base = 0;
+    if (tm.j == 0 && ballot) base = atomicAdd(c.listCount(), __popc(ballot));
+    base = teamBcast(tm, base);
+    if (marked) {
+      c.size(slot)[v - n] = 0;   // phase C counts into it (its space was the column stack a moment ago)
+      c.list()[base + __popc(ballot & ((1u << tm.j) - 1u))] = (uint32_t)(slot << 16 | v);
+      const uint8_t f = nd[v].flags;
+      if (!(f & F_RECALC)) nd[v].flags = (uint8_t)((f ^ F_SEL) | F_RECALC);
     }
-    __syncthreads();
-    // ---- k_eval phase D1: what a node adds to the post-order start of everything below it (heavier child first)
-    for (int j = tid; j < listCount; j += kThreads) {
-      const int s = sList[j] >> 16, v = sList[j] & 0xffff;
-      const NodeRec* nd = sNode(s);
-      const uint8_t* need = sNeed(s);
-      const int* size = sSize(s);
-      const int a = nd[v].father;
-      uint32_t contrib = 0;
-      if (a >= 0) {
-        const int l = nd[a].left, r = nd[a].right;
-        const int wl = (l >= n && need[l]) ? size[l - n] : 0;
-        const int wr = (r >= n && need[r]) ? size[r - n] : 0;
-        const int first = wl >= wr ? l : r;
-        if (v != first) contrib = (uint32_t)(v == l ? wr : wl);
-      }
-      sWalk(s)[v] = (uint32_t)(a + 1) | (contrib << 16);
+  }
+}
+
+// the rest of a step, for the whole CTA: k_eval phases C, D (list phases), E (column walk), F (root); leaves the new
+// log-likelihoods in mLnL and ends with a barrier
+__device__ inline void sweepEvaluate(const SweepCtx& c) {
+  const int tid = c.tid, n = c.n, N = c.N;
+  __syncthreads();
+  const int listCount = *c.listCount();
+  const uint32_t* sList = c.list();
+  // ---- k_eval phase C: marked nodes per subtree
+  for (int j = tid; j < listCount; j += kThreads) {
+    const int s = sList[j] >> 16, v = sList[j] & 0xffff;
+    const NodeRec* nd = c.node(s);
+    int* size = c.size(s);
+    int a = v;
+    for (int k = 0; a >= 0 && k < N; k++) {
+      atomicAdd(&size[a - n], 1);
+      a = nd[a].father;
     }
-    __syncthreads();
-    // ---- k_eval phase D2: position, stack depth, child sources and JC69 edge terms of every marked node
-    for (int j = tid; j < listCount; j += kThreads) {
-      const int s = sList[j] >> 16, v = sList[j] & 0xffff;
-      const NodeRec* nd = sNode(s);
-      const uint8_t* need = sNeed(s);
-      const int* size = sSize(s);
-      const uint32_t* walk = sWalk(s);
-      const double* age = sAge(s);
-      const double rate = mRate[s];
-      int start = 0, depth = 0;
-      {
-        uint32_t w = walk[v];
-        for (int k = 0; k < N; k++) {
-          const uint32_t c = w >> 16;
-          start += c;
-          depth += c != 0;
-          const int a = (int)(w & 0xffffu) - 1;
-          if (a < 0) break;
-          w = walk[a];
-        }
-      }
-      const int l = nd[v].left, r = nd[v].right;
+  }
+  __syncthreads();
+  // ---- k_eval phase D1: what a node adds to the post-order start of everything below it (heavier child first)
+  for (int j = tid; j < listCount; j += kThreads) {
+    const int s = sList[j] >> 16, v = sList[j] & 0xffff;
+    const NodeRec* nd = c.node(s);
+    const uint8_t* need = c.need(s);
+    const int* size = c.size(s);
+    const int a = nd[v].father;
+    uint32_t contrib = 0;
+    if (a >= 0) {
+      const int l = nd[a].left, r = nd[a].right;
       const int wl = (l >= n && need[l]) ? size[l - n] : 0;
       const int wr = (r >= n && need[r]) ? size[r - n] : 0;
-      const bool leftFirst = wl >= wr;
-      const int A = leftFirst ? l : r, B = leftFirst ? r : l;
-      const int wA = leftFirst ? wl : wr, wB = leftFirst ? wr : wl;
-      const uint32_t strideBytes = (uint32_t)mP[s] * 32u;
-      auto record = [&](int x) { return (uint32_t)((x - n) * 2 + (nd[x].flags & F_SEL)) * strideBytes; };
-      auto leafRef = [&](int x) { return (uint32_t)(x >> 3) * (kThreads * 4u) | ((uint32_t)(x & 7) * 4u) << 16; };
-      uint32_t kindA, kindB, offA = 0, offB = 0;
-      if (A < n) { kindA = SRC_LEAF; offA = leafRef(A); }
-      else if (wA > 0 && wB == 0) { kindA = SRC_TOP; }
-      else if (wA > 0 && depth < kSweepStack) { kindA = SRC_STACK; offA = ((uint32_t)depth * kRow) << 16; }
-      else { kindA = SRC_GLOBAL; offA = record(A); }
-      if (B < n) { kindB = SRC_LEAF; offB = leafRef(B); }
-      else if (wB > 0) { kindB = SRC_TOP; }
-      else { kindB = SRC_GLOBAL; offB = record(B); }
-      SchedEntryCompact en;
-      const double av = age[v];
-      en.e0A = edgeProb(rate * (av - age[A]));
-      en.e0B = edgeProb(rate * (av - age[B]));
-      en.offA = offA; en.offB = offB;
-      en.dstOff = record(v);
-      uint32_t push = 0xffffu;
-      {
-        const int f = nd[v].father;
-        if (f >= 0 && v != mRoot[s] && depth < kSweepStack) {
-          const int fl = nd[f].left, fr = nd[f].right;
-          const int wfl = (fl >= n && need[fl]) ? size[fl - n] : 0;
-          const int wfr = (fr >= n && need[fr]) ? size[fr - n] : 0;
-          const int first = wfl >= wfr ? fl : fr;
-          const int wSibling = v == fl ? wfr : wfl;
-          if (v == first && wSibling > 0) push = (uint32_t)depth * kRow;
-        }
-      }
-      en.ctl = kindA | (kindB << 2) | (push << 16);
-      sSched(s)[start + size[v - n] - 1] = en;
-      if (v == mRoot[s]) mK[s] = size[v - n];
+      const int first = wl >= wr ? l : r;
+      if (v != first) contrib = (uint32_t)(v == l ? wr : wl);
     }
-    __syncthreads();
-    // ---- column phase (k_eval phase E)
-    double pv[4] = {0.0, 0.0, 0.0, 0.0};
-    const int k = (live && mActive[colSlot]) ? mK[colSlot] : 0;
-    if (k > 0) columnWalk<kSweepHi, true>(smemAddr(sSched(colSlot)), k, clvCol, myStack, myWords, true, pv);
-    __syncthreads();   // the stack is dead; its space takes the root vectors
-#pragma unroll
-    for (int q = 0; q < 4; q++) sRoot[tid * 4 + q] = pv[q];
-    for (int j = tid; j < listCount; j += kThreads) {   // dirty marks back to zero for the next step
-      const int s = sList[j] >> 16, v = sList[j] & 0xffff;
-      sNeed(s)[v] = 0;
-    }
-    __syncthreads();
-    // ---- root phase (k_eval phase F): 4*phases conditionals per phase group in the reference's order (.c:470-479)
-    double term = 0.0;
-    if (k > 0 && ph > 0) {
-      double prob = 0.0;
-      const int numConds = 4 * ph;
-      for (int j = 0; j < numConds; j++) prob += sRoot[tid * 4 + j];
-      term = log(prob / numConds) * cnt;
-    }
-    sTerm[tid] = term;
-    if (tid == 0) *sListCount = 0;
-    __syncthreads();
-    if (tid < nl && mActive[tid] && mK[tid] > 0) {   // per-locus sum in pattern order
-      const int P = mP[tid];
-      const double* tt = sTerm + (mColStart[tid] - b.firstCol);
-      double lnl = 0.0;
-      for (int j = 0; j < P; j++) lnl += tt[j];
-      mLnL[tid] = lnl;
-      mEvals[tid]++;
-      mEvalBytes[tid] += 32ull * (unsigned long long)P * (2ull * (unsigned long long)mK[tid] + 1ull);
-    }
-    __syncthreads();
-  }
-
-  // ---- the final state goes back: genealogies (every proposal is resolved: flags hold buffer selectors only),
-  //      population assignments, log-likelihoods, coal statistics
-  if (tm.j == 0 && teamOn) {
-    if (accepted[0]) atomicAdd(&sAccepted[0], accepted[0]);
-    if (accepted[1]) atomicAdd(&sAccepted[1], accepted[1]);
+    c.walk(s)[v] = (uint32_t)(a + 1) | (contrib << 16);
   }
   __syncthreads();
-  for (int s = warp; s < nl; s += kWarps) {
-    const int l = b.firstLocus + s;
+  // ---- k_eval phase D2: position, stack depth, child sources and JC69 edge terms of every marked node
+  for (int j = tid; j < listCount; j += kThreads) {
+    const int s = sList[j] >> 16, v = sList[j] & 0xffff;
+    const NodeRec* nd = c.node(s);
+    const uint8_t* need = c.need(s);
+    const int* size = c.size(s);
+    const uint32_t* walk = c.walk(s);
+    const double* age = c.age(s);
+    const double rate = c.mRate()[s];
+    const int rootId = c.mRoot()[s];
+    int start = 0, depth = 0;
+    {
+      uint32_t w = walk[v];
+      for (int k = 0; k < N; k++) {
+        const uint32_t cc = w >> 16;
+        start += cc;
+        depth += cc != 0;
+        const int a = (int)(w & 0xffffu) - 1;
+        if (a < 0) break;
+        w = walk[a];
+      }
+    }
+    const int l = nd[v].left, r = nd[v].right;
+    const int wl = (l >= n && need[l]) ? size[l - n] : 0;
+    const int wr = (r >= n && need[r]) ? size[r - n] : 0;
+    const bool leftFirst = wl >= wr;
+    const int A = leftFirst ? l : r, B = leftFirst ? r : l;
+    const int wA = leftFirst ? wl : wr, wB = leftFirst ? wr : wl;
+    const uint32_t strideBytes = (uint32_t)c.mP()[s] * 32u;
+    auto record = [&](int x) { return (uint32_t)((x - n) * 2 + (nd[x].flags & F_SEL)) * strideBytes; };
+    auto leafRef = [&](int x) { return (uint32_t)(x >> 3) * (kThreads * 4u) | ((uint32_t)(x & 7) * 4u) << 16; };
+    uint32_t kindA, kindB, offA = 0, offB = 0;
+    if (A < n) { kindA = SRC_LEAF; offA = leafRef(A); }
+    else if (wA > 0 && wB == 0) { kindA = SRC_TOP; }
+    else if (wA > 0 && depth < kSweepStack) { kindA = SRC_STACK; offA = ((uint32_t)depth * kRow) << 16; }
+    else { kindA = SRC_GLOBAL; offA = record(A); }
+    if (B < n) { kindB = SRC_LEAF; offB = leafRef(B); }
+    else if (wB > 0) { kindB = SRC_TOP; }
+    else { kindB = SRC_GLOBAL; offB = record(B); }
+    SchedEntryCompact en;
+    const double av = age[v];
+    en.e0A = edgeProb(rate * (av - age[A]));
+    en.e0B = edgeProb(rate * (av - age[B]));
+    en.offA = offA; en.offB = offB;
+    en.dstOff = record(v);
+    uint32_t push = 0xffffu;
+    {
+      const int f = nd[v].father;
+      if (f >= 0 && v != rootId && depth < kSweepStack) {
+        const int fl = nd[f].left, fr = nd[f].right;
+        const int wfl = (fl >= n && need[fl]) ? size[fl - n] : 0;
+        const int wfr = (fr >= n && need[fr]) ? size[fr - n] : 0;
+        const int first = wfl >= wfr ? fl : fr;
+        const int wSibling = v == fl ? wfr : wfl;
+        if (v == first && wSibling > 0) push = (uint32_t)depth * kRow;
+      }
+    }
+    en.ctl = kindA | (kindB << 2) | (push << 16);
+    c.sched(s)[start + size[v - n] - 1] = en;
+    if (v == rootId) c.mK()[s] = size[v - n];
+  }
+  __syncthreads();
+  // ---- column phase (k_eval phase E)
+  double pv[4] = {0.0, 0.0, 0.0, 0.0};
+  const int k = (c.live && c.mActive()[c.colSlot]) ? c.mK()[c.colSlot] : 0;
+  if (k > 0) columnWalk<kSweepHi, true>(smemAddr(c.sched(c.colSlot)), k, c.clvCol, c.myStack, c.myWords, true, pv);
+  __syncthreads();   // the stack is dead; its space takes the root vectors
+  double* sRoot = c.root4();
+#pragma unroll
+  for (int q = 0; q < 4; q++) sRoot[tid * 4 + q] = pv[q];
+  for (int j = tid; j < listCount; j += kThreads) {   // dirty marks back to zero for the next step
+    const int s = sList[j] >> 16, v = sList[j] & 0xffff;
+    c.need(s)[v] = 0;
+  }
+  __syncthreads();
+  // ---- root phase (k_eval phase F): 4*phases conditionals per phase group in the reference's order (.c:470-479)
+  double term = 0.0;
+  if (k > 0 && c.ph > 0) {
+    double prob = 0.0;
+    const int numConds = 4 * c.ph;
+    for (int j = 0; j < numConds; j++) prob += sRoot[tid * 4 + j];
+    term = log(prob / numConds) * c.cnt;
+  }
+  c.term()[tid] = term;
+  if (tid == 0) *c.listCount() = 0;
+  __syncthreads();
+  if (tid < c.nl && c.mActive()[tid] && c.mK()[tid] > 0) {   // per-locus sum in pattern order
+    const int P = c.mP()[tid];
+    const double* tt = c.term() + (c.mColStart()[tid] - c.b.firstCol);
+    double lnl = 0.0;
+    for (int j = 0; j < P; j++) lnl += tt[j];
+    c.mLnL()[tid] = lnl;
+    c.mEvals()[tid]++;
+    c.mEvalBytes()[tid] += 32ull * (unsigned long long)P * (2ull * (unsigned long long)c.mK()[tid] + 1ull);
+  }
+  __syncthreads();
+}
+
+// the final state goes back: genealogies (every proposal is resolved: flags hold buffer selectors only), population
+// assignments, log-likelihoods, coal statistics, acceptance counters (kinds 0 and 1), evaluation accounting
+__device__ inline void sweepWriteBack(const SweepCtx& c, const StoreDev& d, const SmpDev& sd, const unsigned int (&acceptedMine)[2],
+                                      bool leaderOn) {
+  const int tid = c.tid, N = c.N, Q = c.Q, nl = c.nl;
+  if (leaderOn) {
+    if (acceptedMine[0]) atomicAdd(&c.accepted()[0], acceptedMine[0]);
+    if (acceptedMine[1]) atomicAdd(&c.accepted()[1], acceptedMine[1]);
+  }
+  __syncthreads();
+  for (int s = c.warp; s < nl; s += kWarps) {
+    const int l = c.b.firstLocus + s;
     const size_t g0 = (size_t)l * N;
-    const NodeRec* nd = sNode(s);
-    const double* age = sAge(s);
-    const uint8_t* pop = sPop(s);
-    for (int v = lane; v < N; v += 32) {
+    const NodeRec* nd = c.node(s);
+    const double* age = c.age(s);
+    const uint8_t* pop = c.pop(s);
+    for (int v = c.lane; v < N; v += 32) {
       d.node[g0 + v] = nd[v];
       d.age[g0 + v] = age[v];
       sd.nodePop[g0 + v] = pop[v];
     }
-    for (int p = lane; p < Q; p += 32) sd.coal[(size_t)l * Q + p] = sCoal(s)[p];
+    for (int p = c.lane; p < Q; p += 32) sd.coal[(size_t)l * Q + p] = c.coal(s)[p];
   }
   if (tid < nl) {
-    const int l = b.firstLocus + tid;
-    d.root[l] = mRoot[tid];
-    d.savedRoot[l] = mSavedRoot[tid];
-    d.lnL[l] = mLnL[tid];
-    d.savedLnL[l] = mSavedLnL[tid];
+    const int l = c.b.firstLocus + tid;
+    d.root[l] = c.mRoot()[tid];
+    d.savedRoot[l] = c.mSavedRoot()[tid];
+    d.lnL[l] = c.mLnL()[tid];
+    d.savedLnL[l] = c.mSavedLnL()[tid];
     sd.prop[l] = smpNoProposal();
   }
-  if (tid < 2 && sAccepted[tid]) atomicAdd(sd.accepted + tid, (unsigned long long)sAccepted[tid]);
-  if (d.evalCounters && warp == 0) {
-    unsigned long long evals = lane < nl ? mEvals[lane] : 0ull, evalBytes = lane < nl ? mEvalBytes[lane] : 0ull;
+  if (tid < 2 && c.accepted()[tid]) atomicAdd(sd.accepted + tid, (unsigned long long)c.accepted()[tid]);
+  if (d.evalCounters && c.warp == 0) {
+    unsigned long long evals = c.lane < nl ? c.mEvals()[c.lane] : 0ull, evalBytes = c.lane < nl ? c.mEvalBytes()[c.lane] : 0ull;
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
       evals += __shfl_xor_sync(0xffffffffu, evals, off);
       evalBytes += __shfl_xor_sync(0xffffffffu, evalBytes, off);
     }
-    if (lane == 0 && evals) { atomicAdd(d.evalCounters, evals); atomicAdd(d.evalCounters + 1, evalBytes); }
+    if (c.lane == 0 && evals) { atomicAdd(d.evalCounters, evals); atomicAdd(d.evalCounters + 1, evalBytes); }
   }
+}
+
+__device__ __forceinline__ Team sweepTeam(int tid) {
+  Team tm;
+  tm.j = tid & (kTeam - 1);
+  tm.leader = (tid & 31) & ~(kTeam - 1);
+  tm.mask = ((1u << kTeam) - 1u) << tm.leader;
+  return tm;
+}
+
+// ------------------------------------------------------------------------------------------ models without migration bands
+__global__ void __launch_bounds__(kThreads, GPHOCS_SWEEP_MINBLOCKS)
+k_sweep(StoreDev d, SmpDev sd, const SmpModel* __restrict__ mp, const Batch* __restrict__ batches, int maxLoci, double ftCoal,
+        unsigned long long seed, unsigned long long step0) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  SweepCtx c;
+  sweepStage(c, smem, sweepSmemLayout(d.n, maxLoci, sd.Q), d, sd, mp, batches[blockIdx.x]);
+  const SweepModel& m = c.model();
+  const int n = c.n, N = c.N;
+  const Team tm = sweepTeam(c.tid);
+  const int slot = c.tid / kTeam;
+  const bool teamOn = slot < c.nl;
+  const int myLocus = c.b.firstLocus + slot;
+  TreeView t;
+  if (teamOn) t = sweepTreeView(c, d, slot);
+  unsigned int accepted[2] = {0u, 0u};
+
+  const int numAge = ftCoal > 0.0 ? c.NI : 0, numSteps = numAge + N;
+  for (int it = 0; it <= numSteps; it++) {
+    // ---- team phase: the previous proposal is resolved, the next one made
+    if (teamOn) {
+      if (it > 0) {
+        const int kind = it - 1 < numAge ? 0 : 1;
+        const int ok = teamResolve(tm, t, c.pop(slot), c.coal(slot), c.prop()[slot], myLocus, N, kind, seed, step0 + 2ull * (it - 1) + 1ull);
+        if (tm.j == 0) accepted[kind] += ok;
+      }
+      if (it < numSteps) {
+        const unsigned long long step = step0 + 2ull * it;
+        uint8_t* scratch = reinterpret_cast<uint8_t*>(c.walk(slot));   // the list phases have not started: N words free
+        const SmpProposal pr = it < numAge
+            ? teamAgePropose(tm, m, t, c.pop(slot), c.coal(slot), c.ncoal(slot), myLocus, n, N, n + it, ftCoal, seed, step, scratch)
+            : teamSprPropose(tm, m, t, c.pop(slot), myLocus, n, N, it - numAge, seed, step);
+        if (tm.j == 0) c.prop()[slot] = pr;
+        sweepMarkAndCompact(c, tm, slot);
+      }
+    }
+    if (it == numSteps) break;
+    sweepEvaluate(c);
+  }
+  sweepWriteBack(c, d, sd, accepted, teamOn && tm.j == 0);
 }
 
 }  // namespace gphocs

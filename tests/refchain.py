@@ -77,3 +77,17 @@ def parameter_columns(model, rows):
     e0 = 2 * Q - C + B
     x[:, e0:e0 + len(model.sample_age)] /= 10000.0               # estimated sample ages are taus
     return x
+
+
+def pooled_between_chain_se(group_a, group_b):
+    """Standard error of (mean of group a's chain means - mean of group b's) from the spread BETWEEN independent chains:
+    each group is [chains][parameters] of per-chain posterior means.  For parameters that mix slowly (the configs[3]
+    shape: two reference chains that differ only in their seed disagree by 8 batch-means standard errors on theta_B)
+    batch means inside one chain underestimate the error; independent chains do not."""
+    a, b = np.asarray(group_a, float), np.asarray(group_b, float)
+    dof = max(1, len(a) + len(b) - 2)
+    ss = ((a - a.mean(0)) ** 2).sum(0) + ((b - b.mean(0)) ** 2).sum(0)
+    return np.sqrt(ss / dof * (1.0 / len(a) + 1.0 / len(b)))
+
+
+REF_SEEDS = (4242, 999, 31337)
