@@ -42,60 +42,36 @@ constexpr uint32_t kSweepHi = kSweepStack * kRow;
 
 // what the sweeps read of the model (SmpModel carries 39 populations and 32 bands: 2.7 KB per CTA)
 struct SweepModel {
-  int Q, B;
+  int Q;
   int father[kSmpMaxPops], leavesBelow[kSmpMaxPops];
   unsigned long long below[kSmpMaxPops];
   double theta[kSmpMaxPops], tau[kSmpMaxPops], coalRate[kSmpMaxPops];
-};
-// ... plus the bands, for models that have them (staged right behind the SweepModel)
-struct SweepBands {
-  int C;
-  int src[kSmpMaxBands], tgt[kSmpMaxBands];
-  double rate[kSmpMaxBands];
 };
 
 struct SweepSmem {
   // per locus slot: what lives for the whole sweep ...
   uint32_t offAge, offNode, offNeed, offPop, offCoal, offNcoal, perLocus;
-  // ... with migration bands also the migration events (current and saved), band statistics and the branch segments
-  uint32_t offMigAge, offSvMigAge, offMigStat, offPendMig, offNmig, offMigInts, offMigBranch, offMigBand, offSegT0, offSegT1,
-      offSegBranch, offSegPop;
   // ... and the scheduling scratch of one step, which shares its space with the column stack (never live together)
   uint32_t offSize, offWalk, perScratch;
   uint32_t perSched;
   // CTA regions
   uint32_t offLoci, offSched, offStack, offWords, offList, offTerm, offMeta, offProp, offCells, offModel, total;
-  int W32, maxSegs;
+  int W32;
 };
-// B = 0: a model without migration bands (maxSegs ignored)
-__host__ __device__ inline SweepSmem sweepSmemLayout(int n, int maxLoci, int Q, int B = 0, int maxSegs = 0) {
+__host__ __device__ inline SweepSmem sweepSmemLayout(int n, int maxLoci, int Q) {
   const int N = 2 * n - 1, NI = n - 1;
   SweepSmem m;
   m.W32 = (n + 7) / 8;
-  m.maxSegs = B > 0 ? maxSegs : 0;
-  const uint32_t S = (uint32_t)m.maxSegs, nb = (uint32_t)B, M = B > 0 ? (uint32_t)kSmpMaxMigs : 0u;
   m.offAge = 0;                                             // [N] double
   m.offCoal = m.offAge + (uint32_t)N * 8;                   // [Q] double
-  m.offMigAge = m.offCoal + (uint32_t)Q * 8;                // [M] double
-  m.offSvMigAge = m.offMigAge + M * 8;                      // [M] double
-  m.offMigStat = m.offSvMigAge + M * 8;                     // [B] double mig_stats
-  m.offPendMig = m.offMigStat + nb * 8;                     // [B + 1] double: statistics of the pending proposal (bands, then coal)
-  m.offSegT0 = m.offPendMig + (B > 0 ? (nb + 1) * 8 : 0);   // [S] double
-  m.offSegT1 = m.offSegT0 + S * 8;                          // [S] double
-  m.offNode = m.offSegT1 + S * 8;                           // [N] NodeRec
+  m.offNode = m.offCoal + (uint32_t)Q * 8;                  // [N] NodeRec
   m.offNcoal = m.offNode + (uint32_t)N * sizeof(NodeRec);   // [Q] int
-  m.offNmig = m.offNcoal + (uint32_t)Q * 4;                 // [B] int
-  m.offMigInts = m.offNmig + nb * 4;                        // numMigs, saved numMigs, segment count, inconsistency flag
-  m.offMigBranch = m.offMigInts + (B > 0 ? 16u : 0u);       // [2][M] uint8: current, saved
-  m.offMigBand = m.offMigBranch + 2 * M;                    // [2][M] uint8
-  m.offSegBranch = m.offMigBand + 2 * M;                    // [S] uint8
-  m.offSegPop = m.offSegBranch + S;                         // [S] uint8
-  m.offNeed = m.offSegPop + S;                              // [N] uint8
+  m.offNeed = m.offNcoal + (uint32_t)Q * 4;                 // [N] uint8
   m.offPop = m.offNeed + (uint32_t)N;                       // [N] uint8
   m.perLocus = (m.offPop + (uint32_t)N + 15) & ~15u;
   m.offSize = 0;                                            // [NI] int
   m.offWalk = m.offSize + (uint32_t)NI * 4;                 // [N] uint32; the team phase keeps its lists here
-  m.perScratch = (m.offWalk + (uint32_t)N * 4 + S + 15) & ~15u;   // (+ S bytes: a list of segment indices)
+  m.perScratch = (m.offWalk + (uint32_t)N * 4 + 15) & ~15u;
   m.perSched = (uint32_t)NI * sizeof(SchedEntryCompact);
   m.offLoci = 0;
   m.offSched = m.offLoci + m.perLocus * (uint32_t)maxLoci;
@@ -110,12 +86,10 @@ __host__ __device__ inline SweepSmem sweepSmemLayout(int n, int maxLoci, int Q, 
   m.offProp = m.offMeta + (uint32_t)kTeamSlots * 64;        // [slots] SmpProposal
   m.offCells = (m.offProp + (uint32_t)kTeamSlots * sizeof(SmpProposal) + 15) & ~15u;   // list count, acceptance counters
   m.offModel = m.offCells + 16;
-  m.total = (m.offModel + sizeof(SweepModel) + (B > 0 ? sizeof(SweepBands) : 0) + 15) & ~15u;
+  m.total = (m.offModel + sizeof(SweepModel) + 15) & ~15u;
   return m;
 }
-__host__ __device__ inline size_t sweepSmemBytes(int n, int maxLoci, int Q, int B = 0, int maxSegs = 0) {
-  return sweepSmemLayout(n, maxLoci, Q, B, maxSegs).total;
-}
+__host__ __device__ inline size_t sweepSmemBytes(int n, int maxLoci, int Q) { return sweepSmemLayout(n, maxLoci, Q).total; }
 
 struct Team {
   int j;           // 0..7 inside the team; 0 = leader
@@ -345,7 +319,8 @@ struct SweepCtx {
   SweepSmem lay;
   Batch b;
   int tid, lane, warp, n, N, NI, nl, Q;
-  // this thread's pattern column
+  // this thread's pattern column (of the first chunk, when the batch is one locus wider than the CTA)
+  bool oversized;
   bool live;
   int colSlot, ph, cnt;
   char* clvCol;
@@ -384,11 +359,10 @@ struct SweepCtx {
   __device__ __forceinline__ unsigned int* accepted() const { return reinterpret_cast<unsigned int*>(smem + lay.offCells) + 1; }   // [2]
   __device__ __forceinline__ uint32_t* list() const { return reinterpret_cast<uint32_t*>(smem + lay.offList); }
   __device__ __forceinline__ SweepModel& model() const { return *reinterpret_cast<SweepModel*>(smem + lay.offModel); }
-  __device__ __forceinline__ SweepBands& bands() const { return *reinterpret_cast<SweepBands*>(smem + lay.offModel + sizeof(SweepModel)); }
 };
 
 // stage the batch: model, per-locus scalars, genealogies, population assignments, coal statistics, leaf codes; ends
-// with a barrier.  The caller stages what else its model needs before calling (no barrier in between is needed).
+// with a barrier
 __device__ inline void sweepStage(SweepCtx& c, unsigned char* smem, const SweepSmem& lay, const StoreDev& d, const SmpDev& sd,
                                   const SmpModel* __restrict__ mp, const Batch& b) {
   c.smem = smem; c.lay = lay; c.b = b;
@@ -396,20 +370,20 @@ __device__ inline void sweepStage(SweepCtx& c, unsigned char* smem, const SweepS
   c.n = d.n; c.N = d.N; c.NI = d.NI; c.nl = b.numLoci; c.Q = sd.Q;
   const int tid = c.tid, Q = c.Q, N = c.N, nl = c.nl;
   SweepModel& sModel = c.model();
-  if (tid == 0) { sModel.Q = Q; sModel.B = mp->B; }
+  if (tid == 0) sModel.Q = Q;
   for (int p = tid; p < Q; p += kThreads) {
     sModel.father[p] = mp->father[p]; sModel.leavesBelow[p] = mp->leavesBelow[p]; sModel.below[p] = mp->below[p];
     sModel.theta[p] = mp->theta[p]; sModel.tau[p] = mp->tau[p]; sModel.coalRate[p] = mp->coalRate[p];
   }
   unsigned long long w0 = 0ull, w1 = 0ull;
   c.ph = 0; c.cnt = 0;
+  c.oversized = b.scratchOff >= 0;
   c.live = tid < b.numCols;
   if (c.live) {
     const int col = b.firstCol + tid;
     w0 = d.leafWords[col];
     if (d.W > 1) w1 = d.leafWords[(size_t)d.Ct + col];
-    c.ph = d.grpPhases[col];
-    c.cnt = d.grpCount[col];
+    if (!c.oversized) { c.ph = d.grpPhases[col]; c.cnt = d.grpCount[col]; }
   }
   if (tid < nl) {
     const int l = b.firstLocus + tid;
@@ -516,9 +490,69 @@ __device__ inline void sweepMarkAndCompact(const SweepCtx& c, const Team& tm, in
   }
 }
 
+// Column and root phases for a batch that is ONE locus with more pattern columns than the CTA has threads: the columns
+// are walked in chunks of kThreads, root vectors go through rootScratch, the terms are reduced by the fixed-order block
+// tree of k_eval's oversized path (same bits).  Ends with a barrier.
+__device__ inline void sweepEvaluateWide(const SweepCtx& c, const StoreDev& d, int listCount) {
+  const int tid = c.tid;
+  const uint32_t* sList = c.list();
+  const int k = c.mActive()[0] ? c.mK()[0] : 0;
+  const int P = c.mP()[0], c0 = c.mColStart()[0];
+  if (k > 0) {
+    const int numChunks = (c.b.numCols + kThreads - 1) / kThreads;
+    for (int chunk = 0; chunk < numChunks; chunk++) {
+      const int p = chunk * kThreads + tid;
+      if (p >= c.b.numCols) break;
+      const int col = c.b.firstCol + p;
+      const unsigned long long w0 = d.leafWords[col];
+      const unsigned long long w1 = d.W > 1 ? d.leafWords[(size_t)d.Ct + col] : 0ull;
+      stsU32(c.myWords, (uint32_t)w0);
+      if (c.lay.W32 > 1) stsU32(c.myWords + kThreads * 4, (uint32_t)(w0 >> 32));
+      if (c.lay.W32 > 2) stsU32(c.myWords + 2 * kThreads * 4, (uint32_t)w1);
+      if (c.lay.W32 > 3) stsU32(c.myWords + 3 * kThreads * 4, (uint32_t)(w1 >> 32));
+      char* clvCol = reinterpret_cast<char*>(d.clv + (size_t)c0 * c.NI * 8 + (size_t)p * 4);
+      double pv[4] = {0.0, 0.0, 0.0, 0.0};
+      columnWalk<kSweepHi, true>(smemAddr(c.sched(0)), k, clvCol, c.myStack, c.myWords, true, pv);
+      double* dst = d.rootScratch + ((size_t)c.b.scratchOff + p) * 4;
+#pragma unroll
+      for (int q = 0; q < 4; q++) dst[q] = pv[q];
+    }
+  }
+  __syncthreads();
+  for (int j = tid; j < listCount; j += kThreads) c.need(sList[j] >> 16)[sList[j] & 0xffff] = 0;
+  __syncthreads();   // the list is dead: its space takes the terms
+  double acc = 0.0;
+  if (k > 0) {
+    const double* src = d.rootScratch + (size_t)c.b.scratchOff * 4;
+    for (int p = tid; p < P; p += kThreads) {
+      const int phs = d.grpPhases[c0 + p];
+      if (phs > 0) {
+        double prob = 0.0;
+        const int numConds = 4 * phs;
+        for (int j = 0; j < numConds; j++) prob += src[(size_t)p * 4 + j];
+        acc += log(prob / numConds) * d.grpCount[c0 + p];
+      }
+    }
+  }
+  double* sTerm = c.term();
+  sTerm[tid] = acc;
+  if (tid == 0) *c.listCount() = 0;
+  __syncthreads();
+  for (int off = kThreads / 2; off > 0; off >>= 1) {
+    if (tid < off) sTerm[tid] += sTerm[tid + off];
+    __syncthreads();
+  }
+  if (tid == 0 && k > 0) {
+    c.mLnL()[0] = sTerm[0];
+    c.mEvals()[0]++;
+    c.mEvalBytes()[0] += 32ull * (unsigned long long)P * (2ull * (unsigned long long)k + 1ull);
+  }
+  __syncthreads();
+}
+
 // the rest of a step, for the whole CTA: k_eval phases C, D (list phases), E (column walk), F (root); leaves the new
 // log-likelihoods in mLnL and ends with a barrier
-__device__ inline void sweepEvaluate(const SweepCtx& c) {
+__device__ inline void sweepEvaluate(const SweepCtx& c, const StoreDev& d) {
   const int tid = c.tid, n = c.n, N = c.N;
   __syncthreads();
   const int listCount = *c.listCount();
@@ -615,6 +649,7 @@ __device__ inline void sweepEvaluate(const SweepCtx& c) {
     if (v == rootId) c.mK()[s] = size[v - n];
   }
   __syncthreads();
+  if (c.oversized) { sweepEvaluateWide(c, d, listCount); return; }
   // ---- column phase (k_eval phase E)
   double pv[4] = {0.0, 0.0, 0.0, 0.0};
   const int k = (c.live && c.mActive()[c.colSlot]) ? c.mK()[c.colSlot] : 0;
@@ -739,7 +774,7 @@ k_sweep(StoreDev d, SmpDev sd, const SmpModel* __restrict__ mp, const Batch* __r
       }
     }
     if (it == numSteps) break;
-    sweepEvaluate(c);
+    sweepEvaluate(c, d);
   }
   sweepWriteBack(c, d, sd, accepted, teamOn && tm.j == 0);
 }

@@ -302,10 +302,10 @@ int gphocsSamplerOpenTrace(GphocsSampler *sm, const char *path, const char *cons
                            double migRatePrint, int sampleSkip);
 int gphocsSamplerCloseTrace(GphocsSampler *sm);
 /* The coalescence-time and SPR sweeps (UpdateGB_InternalNode GPhoCS.c:2287, UpdateGB_MigSPR :2598) of a model without
- * migration bands run as ONE launch in which a CTA keeps its batch of loci for both sweeps (up to 32 leaves, no locus
- * with more than 128 pattern columns); other models take the stepwise route: a proposal launch and an evaluation
- * launch per node.  1 forces the stepwise route everywhere, 0 (default) restores the choice above.  Same random
- * streams and arithmetic: both routes give the same chain bit for bit. */
+ * migration bands run as ONE launch in which a CTA keeps its batch of loci for both sweeps (up to 32 leaves); models
+ * with migration bands and larger genealogies take the stepwise route: a proposal launch and an evaluation launch per
+ * node.  1 forces the stepwise route everywhere, 0 (default) restores the choice above.  Same random streams and
+ * arithmetic: both routes give the same chain bit for bit. */
 int gphocsSamplerSetStepwise(GphocsSampler *sm, int on);
 /* accepted[10], proposed[10] for {coalescence time, SPR, theta, tau, mixing, migration rate, migration time,
  * (proposed only) split-time moves rejected for a migration conflict, locus rate (pairs of loci), sample age} */

@@ -87,14 +87,15 @@ def test_many_leaves_per_locus_stay_consistent(leaves):
     st.close()
 
 
-@pytest.mark.parametrize("cfg,L", [("hap16", 300), ("ancient", 200), ("pop6nomig", 150), ("mid", 80), ("wide32", 60), ("tiny", 50)])
+@pytest.mark.parametrize("cfg,L", [("hap16", 300), ("ancient", 200), ("pop6nomig", 150), ("mid", 80), ("dense", 24), ("wide32", 60), ("tiny", 50)])
 def test_sweep_routes_give_the_same_chain(cfg, L):
     """The one-launch sweep (sweep_kernels.cuh: a CTA keeps its batch of loci for both per-locus sweeps) and the stepwise
     route (a proposal launch and a k_eval launch per node) use the same random streams and the same arithmetic:
     identical traces, statistics, genealogies, population assignments, log-likelihoods and conditional vectors —
     with a tenth of the launches.  Shapes: configs[1]; configs[4] (sample ages, locus rates); 24 leaves / 6
     populations (two nodes per lane on the stepwise route); denser patterns (a few loci per CTA batch, loci wider
-    than a warp); 32 leaves (the largest the sweep takes); 3 leaves (fewer nodes than team threads)."""
+    than a warp); dense patterns (every locus wider than a CTA: walked in chunks, root terms through HBM scratch);
+    32 leaves (the largest the sweep takes); 3 leaves (fewer nodes than team threads)."""
     if cfg == "pop6nomig":
         base = synth.config("pop6mig4")
         model = synth.Model("pop6nomig", base.cur, base.anc, diploid=base.diploid)
