@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libgphocs_b200.so")
+LIB_PATH = os.environ.get("GPHOCS_B200_LIB") or os.path.join(_HERE, "csrc", "libgphocs_b200.so")   # the variable: development builds
 
 c_int_p = C.POINTER(C.c_int)
 c_dbl_p = C.POINTER(C.c_double)

@@ -144,12 +144,15 @@ __device__ inline int smgWalkBranch(const SmpModel& m, const SmgWarp& w, int x, 
   const double tEnd = fa >= 0 ? w.age[fa] : kSmpInf;
   const int nm = *w.numMigs;
   int bad = (fa >= 0 && tEnd < t) || (fa < 0 && x != root);
-  unsigned used = 0;
+  unsigned used = 0, mine = 0;   // mine: the events that sit on this branch (most branches carry none: no scan per step then)
+  for (int k = 0; k < nm; k++) mine |= (unsigned)(w.migBranch[k] == x) << k;
   for (int it = 0; it < 2 * kSmpMaxPops + kSmpMaxMigs + 2; it++) {
     int mi = -1;   // earliest migration event of this branch not yet passed
     double mAge = kSmpInf;
-    for (int k = 0; k < nm; k++)
-      if (w.migBranch[k] == x && !((used >> k) & 1u) && w.migAge[k] < mAge) { mi = k; mAge = w.migAge[k]; }
+    for (unsigned rest = mine & ~used; rest; rest &= rest - 1) {
+      const int k = __ffs(rest) - 1;
+      if (w.migAge[k] < mAge) { mi = k; mAge = w.migAge[k]; }
+    }
     const double popEnd = m.father[pop] >= 0 ? smpTau(m, m.father[pop], ovPop, ovTau) : kSmpInf;
     const double tNext = fmin(tEnd, fmin(popEnd, mAge));
     emit(pop, t, tNext);
@@ -494,6 +497,8 @@ __device__ inline void smgSprProposeBody(const StoreDev& d, const SmpDev& sd, co
   int numNew = 0, target = -1, fail = *w.bad;
   int kept = 0;   // events of the genealogy that survive the pruning
   for (int k = 0; k < *w.numMigs; k++) kept += w.migBranch[k] != node;
+  // one clock per (sojourn, segment) and per (sojourn, band): draws of one family of streams under (locus, step)
+  const SmpRng rng(seed, (unsigned long long)l, step);
   for (int it = 0; it < 4 * kSmpMaxPops + 2 * kSmpMaxMigs && target < 0 && !fail; it++) {
     const double popEnd = m.father[pop] >= 0 ? m.tau[m.father[pop]] : kSmpInf;
     double bestT = kSmpInf;
@@ -502,16 +507,14 @@ __device__ inline void smgSprProposeBody(const StoreDev& d, const SmpDev& sd, co
       if (w.segPop[i] != pop) continue;
       const double a = fmax(now, w.segT0[i]), b = fmin(popEnd, w.segT1[i]);
       if (b <= a) continue;
-      SmpRng rng(seed, (unsigned long long)l * 4096ull + (unsigned long long)i, step * 64ull + (unsigned long long)it);
-      const double T = a + rng.exponential() * m.theta[pop] * 0.5;
+      const double T = a + rng.exponentialAt((unsigned long long)it * 8192ull + (unsigned long long)i) * m.theta[pop] * 0.5;
       if (T < b && T < bestT) { bestT = T; bestKind = 0; bestId = i; }
     }
     for (int b = lane; b < m.B; b += 32) {
       if (m.bandTgt[b] != pop || !(m.migRate[b] > 0.0)) continue;
       const double a = fmax(now, smgBandStart(m, b, -1, 0.0)), e = fmin(popEnd, smgBandEnd(m, b, -1, 0.0));
       if (e <= a) continue;
-      SmpRng rng(seed, (unsigned long long)l * 4096ull + 2048ull + (unsigned long long)b, step * 64ull + (unsigned long long)it);
-      const double T = a + rng.exponential() / m.migRate[b];
+      const double T = a + rng.exponentialAt((unsigned long long)it * 8192ull + 4096ull + (unsigned long long)b) / m.migRate[b];
       if (T < e && T < bestT) { bestT = T; bestKind = 1; bestId = b; }
     }
 #pragma unroll

@@ -316,7 +316,7 @@ __device__ inline int teamResolve(const Team& tm, const TreeView& t, uint8_t* np
 // Shared-memory views, the column state of this thread and the phases every step runs after its team phase.
 struct SweepCtx {
   unsigned char* smem;
-  SweepSmem lay;
+  const SweepSmem* layp;   // the kernel's __grid_constant__ parameter: its fields are constant-bank operands
   Batch b;
   int tid, lane, warp, n, N, NI, nl, Q;
   // this thread's pattern column (of the first chunk, when the batch is one locus wider than the CTA)
@@ -326,23 +326,23 @@ struct SweepCtx {
   char* clvCol;
   uint32_t myStack, myWords;
 
-  __device__ __forceinline__ unsigned char* locus(int s) const { return smem + lay.offLoci + lay.perLocus * s; }
-  __device__ __forceinline__ unsigned char* scratch(int s) const { return smem + lay.offStack + lay.perScratch * s; }
-  __device__ __forceinline__ double* age(int s) const { return reinterpret_cast<double*>(locus(s) + lay.offAge); }
-  __device__ __forceinline__ double* coal(int s) const { return reinterpret_cast<double*>(locus(s) + lay.offCoal); }
-  __device__ __forceinline__ NodeRec* node(int s) const { return reinterpret_cast<NodeRec*>(locus(s) + lay.offNode); }
-  __device__ __forceinline__ int* ncoal(int s) const { return reinterpret_cast<int*>(locus(s) + lay.offNcoal); }
-  __device__ __forceinline__ uint8_t* need(int s) const { return locus(s) + lay.offNeed; }
-  __device__ __forceinline__ uint8_t* pop(int s) const { return locus(s) + lay.offPop; }
-  __device__ __forceinline__ int* size(int s) const { return reinterpret_cast<int*>(scratch(s) + lay.offSize); }
-  __device__ __forceinline__ uint32_t* walk(int s) const { return reinterpret_cast<uint32_t*>(scratch(s) + lay.offWalk); }
+  __device__ __forceinline__ unsigned char* locus(int s) const { return smem + layp->offLoci + layp->perLocus * s; }
+  __device__ __forceinline__ unsigned char* scratch(int s) const { return smem + layp->offStack + layp->perScratch * s; }
+  __device__ __forceinline__ double* age(int s) const { return reinterpret_cast<double*>(locus(s) + layp->offAge); }
+  __device__ __forceinline__ double* coal(int s) const { return reinterpret_cast<double*>(locus(s) + layp->offCoal); }
+  __device__ __forceinline__ NodeRec* node(int s) const { return reinterpret_cast<NodeRec*>(locus(s) + layp->offNode); }
+  __device__ __forceinline__ int* ncoal(int s) const { return reinterpret_cast<int*>(locus(s) + layp->offNcoal); }
+  __device__ __forceinline__ uint8_t* need(int s) const { return locus(s) + layp->offNeed; }
+  __device__ __forceinline__ uint8_t* pop(int s) const { return locus(s) + layp->offPop; }
+  __device__ __forceinline__ int* size(int s) const { return reinterpret_cast<int*>(scratch(s) + layp->offSize); }
+  __device__ __forceinline__ uint32_t* walk(int s) const { return reinterpret_cast<uint32_t*>(scratch(s) + layp->offWalk); }
   __device__ __forceinline__ SchedEntryCompact* sched(int s) const {
-    return reinterpret_cast<SchedEntryCompact*>(smem + lay.offSched + lay.perSched * s);
+    return reinterpret_cast<SchedEntryCompact*>(smem + layp->offSched + layp->perSched * s);
   }
-  __device__ __forceinline__ double* root4() const { return reinterpret_cast<double*>(smem + lay.offStack); }   // after the walk
-  __device__ __forceinline__ double* term() const { return reinterpret_cast<double*>(smem + lay.offTerm); }
+  __device__ __forceinline__ double* root4() const { return reinterpret_cast<double*>(smem + layp->offStack); }   // after the walk
+  __device__ __forceinline__ double* term() const { return reinterpret_cast<double*>(smem + layp->offTerm); }
   // per-slot scalars
-  __device__ __forceinline__ double* mRate() const { return reinterpret_cast<double*>(smem + lay.offMeta); }
+  __device__ __forceinline__ double* mRate() const { return reinterpret_cast<double*>(smem + layp->offMeta); }
   __device__ __forceinline__ double* mLnL() const { return mRate() + kTeamSlots; }
   __device__ __forceinline__ double* mSavedLnL() const { return mLnL() + kTeamSlots; }
   __device__ __forceinline__ unsigned long long* mEvals() const { return reinterpret_cast<unsigned long long*>(mSavedLnL() + kTeamSlots); }
@@ -353,19 +353,19 @@ struct SweepCtx {
   __device__ __forceinline__ int* mRoot() const { return mK() + kTeamSlots; }
   __device__ __forceinline__ int* mSavedRoot() const { return mRoot() + kTeamSlots; }
   __device__ __forceinline__ int* mActive() const { return mSavedRoot() + kTeamSlots; }
-  __device__ __forceinline__ SmpProposal* prop() const { return reinterpret_cast<SmpProposal*>(smem + lay.offProp); }
+  __device__ __forceinline__ SmpProposal* prop() const { return reinterpret_cast<SmpProposal*>(smem + layp->offProp); }
   // not inside the list region: the root terms take that over while the count is being reset
-  __device__ __forceinline__ int* listCount() const { return reinterpret_cast<int*>(smem + lay.offCells); }
-  __device__ __forceinline__ unsigned int* accepted() const { return reinterpret_cast<unsigned int*>(smem + lay.offCells) + 1; }   // [2]
-  __device__ __forceinline__ uint32_t* list() const { return reinterpret_cast<uint32_t*>(smem + lay.offList); }
-  __device__ __forceinline__ SweepModel& model() const { return *reinterpret_cast<SweepModel*>(smem + lay.offModel); }
+  __device__ __forceinline__ int* listCount() const { return reinterpret_cast<int*>(smem + layp->offCells); }
+  __device__ __forceinline__ unsigned int* accepted() const { return reinterpret_cast<unsigned int*>(smem + layp->offCells) + 1; }   // [2]
+  __device__ __forceinline__ uint32_t* list() const { return reinterpret_cast<uint32_t*>(smem + layp->offList); }
+  __device__ __forceinline__ SweepModel& model() const { return *reinterpret_cast<SweepModel*>(smem + layp->offModel); }
 };
 
 // stage the batch: model, per-locus scalars, genealogies, population assignments, coal statistics, leaf codes; ends
 // with a barrier
 __device__ inline void sweepStage(SweepCtx& c, unsigned char* smem, const SweepSmem& lay, const StoreDev& d, const SmpDev& sd,
                                   const SmpModel* __restrict__ mp, const Batch& b) {
-  c.smem = smem; c.lay = lay; c.b = b;
+  c.smem = smem; c.layp = &lay; c.b = b;
   c.tid = threadIdx.x; c.lane = c.tid & 31; c.warp = c.tid >> 5;
   c.n = d.n; c.N = d.N; c.NI = d.NI; c.nl = b.numLoci; c.Q = sd.Q;
   const int tid = c.tid, Q = c.Q, N = c.N, nl = c.nl;
@@ -507,9 +507,9 @@ __device__ inline void sweepEvaluateWide(const SweepCtx& c, const StoreDev& d, i
       const unsigned long long w0 = d.leafWords[col];
       const unsigned long long w1 = d.W > 1 ? d.leafWords[(size_t)d.Ct + col] : 0ull;
       stsU32(c.myWords, (uint32_t)w0);
-      if (c.lay.W32 > 1) stsU32(c.myWords + kThreads * 4, (uint32_t)(w0 >> 32));
-      if (c.lay.W32 > 2) stsU32(c.myWords + 2 * kThreads * 4, (uint32_t)w1);
-      if (c.lay.W32 > 3) stsU32(c.myWords + 3 * kThreads * 4, (uint32_t)(w1 >> 32));
+      if (c.layp->W32 > 1) stsU32(c.myWords + kThreads * 4, (uint32_t)(w0 >> 32));
+      if (c.layp->W32 > 2) stsU32(c.myWords + 2 * kThreads * 4, (uint32_t)w1);
+      if (c.layp->W32 > 3) stsU32(c.myWords + 3 * kThreads * 4, (uint32_t)(w1 >> 32));
       char* clvCol = reinterpret_cast<char*>(d.clv + (size_t)c0 * c.NI * 8 + (size_t)p * 4);
       double pv[4] = {0.0, 0.0, 0.0, 0.0};
       columnWalk<kSweepHi, true>(smemAddr(c.sched(0)), k, clvCol, c.myStack, c.myWords, true, pv);
@@ -739,11 +739,11 @@ __device__ __forceinline__ Team sweepTeam(int tid) {
 
 // ------------------------------------------------------------------------------------------ models without migration bands
 __global__ void __launch_bounds__(kThreads, GPHOCS_SWEEP_MINBLOCKS)
-k_sweep(StoreDev d, SmpDev sd, const SmpModel* __restrict__ mp, const Batch* __restrict__ batches, int maxLoci, double ftCoal,
-        unsigned long long seed, unsigned long long step0) {
+k_sweep(StoreDev d, SmpDev sd, const SmpModel* __restrict__ mp, const Batch* __restrict__ batches, const __grid_constant__ SweepSmem lay,
+        double ftCoal, unsigned long long seed, unsigned long long step0) {
   extern __shared__ __align__(16) unsigned char smem[];
   SweepCtx c;
-  sweepStage(c, smem, sweepSmemLayout(d.n, maxLoci, sd.Q), d, sd, mp, batches[blockIdx.x]);
+  sweepStage(c, smem, lay, d, sd, mp, batches[blockIdx.x]);
   const SweepModel& m = c.model();
   const int n = c.n, N = c.N;
   const Team tm = sweepTeam(c.tid);

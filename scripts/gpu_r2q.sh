@@ -1,0 +1,5 @@
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_sampler_mig.py tests/test_gpu_sampler.py -x -q -k "consistent or segment or sweep_routes" > gpurun_out/r2q_pytest.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/r2q_pytest.log | cut -c1-300
+timeout 300 python scripts/sampler_bench.py --config pop6mig4 --loci 100000 --iterations 10 2>&1 | cut -c1-240
+timeout 300 python scripts/sampler_bench.py --config dip8mig --loci 10000 --iterations 20 2>&1 | cut -c1-240
+timeout 300 python scripts/sampler_bench.py --config hap16 --loci 100000 --iterations 30 2>&1 | cut -c1-240
