@@ -638,7 +638,9 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt = float(t.item())
     e2e_value = world * L * e2e_steps / dt
-    assert np.isfinite(sd_) and np.isfinite(sg_) and abs(sd_ - total_data_lnl) < 1e-3 * abs(total_data_lnl)
+    assert np.isfinite(sd_) and np.isfinite(sg_)
+    if world == 1:      # (with several ranks total_data_lnl is the all-reduced sum, sd_ this rank's)
+        assert abs(sd_ - total_data_lnl) < 1e-3 * abs(total_data_lnl), (sd_, total_data_lnl)
     st.apply_ops(gp.make_ops(np.arange(L), gp.OP_COMMIT))
     st.set_trees_packed(hp["topo"], hw["age"], hw["root"])
     st.evaluate(0, out=lnl_host)
