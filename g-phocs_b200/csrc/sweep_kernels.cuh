@@ -689,7 +689,7 @@ __device__ inline void sweepEvaluate(const SweepCtx& c, const StoreDev& d) {
 // the final state goes back: genealogies (every proposal is resolved: flags hold buffer selectors only), population
 // assignments, log-likelihoods, coal statistics, acceptance counters (kinds 0 and 1), evaluation accounting
 __device__ inline void sweepWriteBack(const SweepCtx& c, const StoreDev& d, const SmpDev& sd, const unsigned int (&acceptedMine)[2],
-                                      bool leaderOn) {
+                                      bool leaderOn, bool keepProposals = false) {
   const int tid = c.tid, N = c.N, Q = c.Q, nl = c.nl;
   if (leaderOn) {
     if (acceptedMine[0]) atomicAdd(&c.accepted()[0], acceptedMine[0]);
@@ -715,7 +715,7 @@ __device__ inline void sweepWriteBack(const SweepCtx& c, const StoreDev& d, cons
     d.savedRoot[l] = c.mSavedRoot()[tid];
     d.lnL[l] = c.mLnL()[tid];
     d.savedLnL[l] = c.mSavedLnL()[tid];
-    sd.prop[l] = smpNoProposal();
+    sd.prop[l] = keepProposals ? c.prop()[tid] : smpNoProposal();   // (a global move stays pending until the next launch)
   }
   if (tid < 2 && c.accepted()[tid]) atomicAdd(sd.accepted + tid, (unsigned long long)c.accepted()[tid]);
   if (d.evalCounters && c.warp == 0) {
@@ -777,6 +777,188 @@ k_sweep(StoreDev d, SmpDev sd, const SmpModel* __restrict__ mp, const Batch* __r
     sweepEvaluate(c, d);
   }
   sweepWriteBack(c, d, sd, accepted, teamOn && tm.j == 0);
+}
+
+// ------------------------------------------------------------------------------------------ global moves, one launch each
+// UpdateTau (GPhoCS.c:3224-3990, with the rubber band of patch.c:596-801), UpdateSampleAge (GPhoCS.c:4006) and mixing
+// (GPhoCS.c:4688) propose one change for ALL loci and are accepted or rejected as a whole, from sums over the loci.  On
+// the stepwise route that is five launches per move (resolve the previous move, propose, evaluate, reduce, reduce).
+// Here one launch does it with the machinery of k_sweep: the CTA stages its batch, a team per locus first resolves
+// the PREVIOUS global move (the host knows its outcome by now and passes it in), then makes this move's proposal —
+// rubber band + the statistics under the proposed split time, or the rescaling of every age — the list / column /
+// root phases evaluate it.  The proposal records and log-likelihoods go back per locus and k_smp_reduce sums them
+// exactly as on the stepwise route: two launches per move, and the same chain bit for bit.  Models without migration
+// bands.
+struct GlobalMove {
+  int prevKind;       // -1: nothing pending; 0: a split-time / sample-age move; 1: mixing
+  int prevAccept;
+  double prevC;       // mixing: the factor of the pending move
+  int kind;           // -1: resolve only; 0: split-time / sample-age move of population A; 1: mixing by c
+  int A;
+  double tauOld, tauNew, lb, ub, f0, f1, c;
+};
+
+// wlStats (sampler_kernels.cuh) on a team, with population A's split time overridden: coalT[p], ncoalT[p] for every p.
+// terms: NI doubles of team scratch.  Per-population sums are formed in the order of wlStats' 32-lane shuffle tree
+// (teamSumLikeWarp), so the statistics are those of the stepwise route bit for bit.
+__device__ inline void teamStatsAll(const Team& tm, const SweepModel& m, const double* age, const uint8_t* np, int n, int N, int ovPop,
+                                    double ovTau, double* terms, double* coalT, int* ncoalT) {
+  const int Q = m.Q;
+  auto tauOf = [&](int p) { return p == ovPop ? ovTau : m.tau[p]; };
+  auto endOf = [&](int p) { return m.father[p] >= 0 ? tauOf(m.father[p]) : kOldAge; };
+  auto entering = [&](int p) {   // lineages entering p = samples below it minus coalescences strictly below it
+    int lin = m.leavesBelow[p];
+    for (int q = 0; q < Q; q++)
+      if (q != p && ((m.below[p] >> q) & 1ull)) lin -= ncoalT[q];
+    return lin;
+  };
+  for (int p = tm.j; p < Q; p += kTeam) {   // coalescences per population
+    int k = 0;
+    for (int x = n; x < N; x++) k += np[x] == p;
+    ncoalT[p] = k;
+  }
+  __syncwarp(tm.mask);
+#pragma unroll 1
+  for (int x = n + tm.j; x < N; x += kTeam) {
+    const int p = np[x];
+    const double ax = age[x];
+    int cnt = 0;
+    double prev = tauOf(p);
+#pragma unroll 1
+    for (int y = n; y < N; y++) {
+      if (np[y] != p) continue;
+      const double ay = age[y];
+      if (ay < ax || (ay == ax && y < x)) { cnt++; prev = fmax(prev, ay); }
+    }
+    const int lin = entering(p) - cnt;
+    double term = (double)(lin * (lin - 1)) * (ax - prev);
+    if (cnt == ncoalT[p] - 1) {   // last coalescence of its population: the interval up to the population's end
+      const int rest = lin - 1;
+      term += (double)(rest * (rest - 1)) * (endOf(p) - ax);
+    }
+    terms[x - n] = term;
+  }
+  __syncwarp(tm.mask);
+  const int R = N <= 32 ? 1 : 2;   // nodes per lane of the stepwise route
+#pragma unroll 1
+  for (int p = 0; p < Q; p++) {
+    double vl[4];
+#pragma unroll
+    for (int kk = 0; kk < 4; kk++) {
+      double v = 0.0;
+      for (int r = 0; r < R; r++) {
+        const int x = tm.j + kTeam * kk + 32 * r;
+        v += (x >= n && x < N && np[x] == p) ? terms[x - n] : 0.0;
+      }
+      vl[kk] = v;
+    }
+    double v = teamSumLikeWarp(tm, vl);
+    if (ncoalT[p] == 0) {
+      const int lin = entering(p);
+      v = (double)(lin * (lin - 1)) * (endOf(p) - tauOf(p));
+    }
+    if (tm.j == 0) coalT[p] = v;
+  }
+  __syncwarp(tm.mask);
+}
+
+__global__ void __launch_bounds__(kThreads, GPHOCS_SWEEP_MINBLOCKS)
+k_global_move(StoreDev d, SmpDev sd, const SmpModel* __restrict__ mp, const Batch* __restrict__ batches, const __grid_constant__ SweepSmem lay,
+              const __grid_constant__ GlobalMove gm) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  SweepCtx c;
+  sweepStage(c, smem, lay, d, sd, mp, batches[blockIdx.x]);
+  const SweepModel& m = c.model();
+  const int n = c.n, N = c.N, Q = c.Q;
+  const Team tm = sweepTeam(c.tid);
+  const int slot = c.tid / kTeam;
+  const bool teamOn = slot < c.nl;
+  const int myLocus = c.b.firstLocus + slot;
+  unsigned int none[2] = {0u, 0u};
+  if (teamOn) {
+    TreeView t = sweepTreeView(c, d, slot);
+    double* coal = c.coal(slot);
+    uint8_t* np = c.pop(slot);
+    // ---- the previous global move of this locus: k_smp_global_resolve
+    const SmpProposal prev = sd.prop[myLocus];
+    if (gm.prevKind >= 0 && prev.valid) {
+      if (gm.prevAccept) {
+        for (int x = tm.j; x < N; x += kTeam) commitNode(t, x);
+        for (int p = tm.j; p < Q; p += kTeam) coal[p] = gm.prevKind == 0 ? sd.coalT[(size_t)myLocus * Q + p] : coal[p] * gm.prevC;
+        if (tm.j == 0) commitLocus(t);
+      } else {
+        for (int x = tm.j; x < N; x += kTeam) revertNode(t, x);
+        if (tm.j == 0) revertLocus(t);
+      }
+    }
+    __syncwarp(tm.mask);
+    // ---- this move's proposal
+    SmpProposal pr = smpNoProposal();
+    if (gm.kind == 0) {   // k_smp_tau_propose
+      const int A = gm.A;
+      pr.pop = A;
+      if (*t.root >= n) {
+        // the model this launch sees still holds the old split time of A unless the previous move changed it: the host
+        // uploads the model after every accepted move, so m.tau is current
+        const bool isRoot = m.father[A] < 0;
+        int s0 = -1, s1 = -1;   // A's sons (none for a current population: then its SAMPLE AGE moves, GPhoCS.c:4006)
+        for (int p = 0; p < Q; p++)
+          if (m.father[p] == A) { if (s0 < 0) s0 = p; else s1 = p; }
+        int n0 = 0, n1 = 0;
+        for (int x = tm.j; x < N; x += kTeam) {
+          int which = 0;   // 1: lower band, 2: upper band, 3: sample of A
+          const int q = np[x];
+          const double a = t.age[x];
+          if (x >= n) {
+            if (q == A) { if (isRoot || (a > gm.tauOld && a < gm.ub)) which = 2; }
+            else if ((q == s0 || q == s1) && a > gm.lb && a < gm.tauOld) which = 1;
+          } else if (s0 < 0 && q == A) {
+            which = 3;
+          }
+          if (which) {
+            const double an = which == 3 ? gm.tauNew : (which == 1 || isRoot ? gm.lb + (a - gm.lb) * gm.f0 : gm.ub + (a - gm.ub) * gm.f1);
+            adjustAge(t, x, an);
+          }
+          n0 += which == 1;
+          n1 += which == 2;
+        }
+        n0 = teamSumI(tm, n0);
+        n1 = teamSumI(tm, n1);
+        __syncwarp(tm.mask);
+        // statistics under the proposed split time -> the pending arrays in HBM (committed by the next launch if accepted)
+        double* terms = reinterpret_cast<double*>(c.sched(slot));         // team scratch (the schedule is built later):
+        double* coalT = terms + c.NI;                                      // NI + Q doubles fit NI 32-byte entries,
+        int* ncoalT = reinterpret_cast<int*>(c.walk(slot));                // Q ints the walk words
+        teamStatsAll(tm, m, t.age, np, n, N, A, gm.tauNew, terms, coalT, ncoalT);
+        for (int p = tm.j; p < Q; p += kTeam) {
+          sd.coalT[(size_t)myLocus * Q + p] = coalT[p];
+          sd.ncoalT[(size_t)myLocus * Q + p] = ncoalT[p];
+        }
+        double delta = 0.0;   // smpGenDelta, by the leader (population order)
+        if (tm.j == 0) {
+          const int* ncoal = c.ncoal(slot);
+          for (int p = 0; p < Q; p++) {
+            delta -= (coalT[p] - coal[p]) / m.theta[p];
+            if (ncoalT[p] != ncoal[p]) delta += (double)(ncoalT[p] - ncoal[p]) * log(2.0 / m.theta[p]);
+          }
+        }
+        pr.genDelta = delta;
+        pr.ntj0 = n0;
+        pr.ntj1 = n1;
+        pr.valid = 1;
+        __syncwarp(tm.mask);
+      }
+    } else if (gm.kind == 1) {   // k_smp_scale_propose
+      if (*t.root >= n) {
+        for (int x = tm.j; x < N; x += kTeam) adjustAge(t, x, gm.c * t.age[x]);
+        pr.valid = 1;
+      }
+    }
+    if (tm.j == 0) c.prop()[slot] = pr;
+    if (gm.kind >= 0) sweepMarkAndCompact(c, tm, slot);
+  }
+  if (gm.kind >= 0) sweepEvaluate(c, d);
+  sweepWriteBack(c, d, sd, none, false, true);
 }
 
 }  // namespace gphocs
