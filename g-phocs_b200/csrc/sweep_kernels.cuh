@@ -215,15 +215,18 @@ __device__ inline SmpProposal teamAgePropose(const Team& tm, const SweepModel& m
 }
 
 // smpSprProposeBody on a team: every thread rings the clocks of its share of the branches
+// (*oldGrandpa = the pruned father's father before the move, -1 if none: the second path of nodes to recompute starts there)
 __device__ inline SmpProposal teamSprPropose(const Team& tm, const SweepModel& m, const TreeView& t, uint8_t* np, int l, int n, int N,
-                                             int node, unsigned long long seed, unsigned long long step) {
+                                             int node, unsigned long long seed, unsigned long long step, int* oldGrandpa) {
   SmpProposal pr = smpNoProposal();
+  *oldGrandpa = -1;
   const int root = *t.root;
   if (root < n || node == root) return pr;
   const int F = t.node[node].father;
   const NodeRec recF = t.node[F];
   const int S = recF.left + recF.right - node;
   const int G = recF.father;
+  *oldGrandpa = G;
   const double t0 = t.age[node];
   const int pop0 = np[node];
   const double ageG = G >= 0 ? t.age[G] : kSmpInf;
@@ -550,9 +553,9 @@ __device__ inline void sweepEvaluateWide(const SweepCtx& c, const StoreDev& d, i
   __syncthreads();
 }
 
-// the rest of a step, for the whole CTA: k_eval phases C, D (list phases), E (column walk), F (root); leaves the new
-// log-likelihoods in mLnL and ends with a barrier
-__device__ inline void sweepEvaluate(const SweepCtx& c, const StoreDev& d) {
+// schedules for arbitrary sets of marked nodes (k_global_move): k_eval phases C, D over the list sweepMarkAndCompact left;
+// returns the list length
+__device__ inline int sweepListSchedule(const SweepCtx& c) {
   const int tid = c.tid, n = c.n, N = c.N;
   __syncthreads();
   const int listCount = *c.listCount();
@@ -648,6 +651,15 @@ __device__ inline void sweepEvaluate(const SweepCtx& c, const StoreDev& d) {
     c.sched(s)[start + size[v - n] - 1] = en;
     if (v == rootId) c.mK()[s] = size[v - n];
   }
+  return listCount;
+}
+
+// the rest of a step, for the whole CTA, once every locus' schedule stands: k_eval phases E (column walk) and F (root);
+// leaves the new log-likelihoods in mLnL and ends with a barrier.  listCount: entries of the marked-node list whose
+// dirty marks are to be cleared (0 when the schedules were built without the list).
+__device__ inline void sweepWalkAndRoot(const SweepCtx& c, const StoreDev& d, int listCount) {
+  const int tid = c.tid;
+  const uint32_t* sList = c.list();
   __syncthreads();
   if (c.oversized) { sweepEvaluateWide(c, d, listCount); return; }
   // ---- column phase (k_eval phase E)
@@ -729,6 +741,92 @@ __device__ inline void sweepWriteBack(const SweepCtx& c, const StoreDev& d, cons
   }
 }
 
+// Schedule of a node move, built by the locus' team without the batch-wide list phases.  What a coalescence-time move or
+// an SPR dirties is a path to the root (from `first`) or two paths that join (the second from `second`, the pruned
+// father's old father): tail A = path 1 below the junction, tail B = path 2 below it, stem = junction to root.  The
+// longer tail goes first and parks its top on the column stack's one row; every other recomputed child is the entry
+// right before its father's (register top).  Children first, same arithmetic per node as k_eval's schedule — the
+// product of the two children's factors does not depend on which of them is visited first — so the conditional vectors
+// are k_eval's bit for bit.  Also flips the destination buffers of the path nodes (k_eval phase C0).
+__device__ inline void sweepPathSchedule(const SweepCtx& c, const Team& tm, int slot, int first, int second) {
+  const int n = c.n, N = c.N;
+  if (tm.j == 0) {
+    c.mK()[slot] = 0;
+    if (c.mActive()[slot]) c.mSavedLnL()[slot] = c.mLnL()[slot];   // what every evaluation starts with (.c:440)
+  }
+  NodeRec* nd = c.node(slot);
+  uint8_t* need = c.need(slot);
+  uint8_t* ord = reinterpret_cast<uint8_t*>(c.walk(slot));   // team scratch: the nodes in schedule order
+  int k = 0, lenFirst = 0, lenA = 0, lenB = 0;
+  if (tm.j == 0 && c.mActive()[slot] && first >= n) {
+    // path 1: first .. root (written from ord[NI] downwards for now: tail B may have to go in front of it)
+    uint8_t* tmpA = ord + c.NI;
+    int a = 0;
+    for (int u = first; u >= 0 && a < c.NI; u = nd[u].father) { tmpA[a++] = (uint8_t)u; need[u] = 1; }
+    // path 2: second .. the first node that is on path 1 (exclusive)
+    uint8_t* tmpB = tmpA + c.NI;
+    int bLen = 0;
+    for (int u = second; u >= n && !need[u] && bLen < c.NI; u = nd[u].father) tmpB[bLen++] = (uint8_t)u;
+    int j = a;   // index on path 1 of the junction (a: no second path joins)
+    if (bLen > 0) {
+      const int top = nd[tmpB[bLen - 1]].father;
+      for (j = 0; j < a && tmpA[j] != top; j++) {}
+    }
+    lenA = bLen > 0 ? j : 0;
+    lenB = bLen;
+    // order: longer tail, other tail, then the rest of path 1
+    const bool aFirst = lenA >= lenB;
+    int o = 0;
+    if (aFirst) { for (int i = 0; i < lenA; i++) ord[o++] = tmpA[i]; for (int i = 0; i < lenB; i++) ord[o++] = tmpB[i]; }
+    else { for (int i = 0; i < lenB; i++) ord[o++] = tmpB[i]; for (int i = 0; i < lenA; i++) ord[o++] = tmpA[i]; }
+    for (int i = lenA; i < a; i++) ord[o++] = tmpA[i];
+    lenFirst = aFirst ? lenA : lenB;
+    k = o;
+    for (int i = 0; i < lenB; i++) need[tmpB[i]] = 1;
+    for (int i = 0; i < k; i++) {   // destination buffers of the nodes to recompute (once per proposal)
+      const uint8_t f = nd[ord[i]].flags;
+      if (!(f & F_RECALC)) nd[ord[i]].flags = (uint8_t)((f ^ F_SEL) | F_RECALC);
+    }
+    c.mK()[slot] = k;
+  }
+  k = teamBcast(tm, k);
+  lenFirst = teamBcast(tm, lenFirst);
+  const int bothTails = teamBcast(tm, (int)(lenA > 0 && lenB > 0));
+  __syncwarp(tm.mask);
+  if (k == 0) return;
+  const double* age = c.age(slot);
+  const double rate = c.mRate()[slot];
+  const uint32_t strideBytes = (uint32_t)c.mP()[slot] * 32u;
+  auto record = [&](int x) { return (uint32_t)((x - n) * 2 + (nd[x].flags & F_SEL)) * strideBytes; };
+  auto leafRef = [&](int x) { return (uint32_t)(x >> 3) * (kThreads * 4u) | ((uint32_t)(x & 7) * 4u) << 16; };
+  for (int i = tm.j; i < k; i += kTeam) {
+    const int v = ord[i];
+    const int prevNode = i > 0 ? ord[i - 1] : -1;
+    uint32_t kind[2], off[2];
+    int child[2] = {nd[v].left, nd[v].right};
+#pragma unroll
+    for (int s = 0; s < 2; s++) {
+      const int x = child[s];
+      off[s] = 0;
+      if (x < n) { kind[s] = SRC_LEAF; off[s] = leafRef(x); }
+      else if (!need[x]) { kind[s] = SRC_GLOBAL; off[s] = record(x); }   // clean child: its current buffer
+      else if (x == prevNode) { kind[s] = SRC_TOP; }
+      else { kind[s] = SRC_STACK; off[s] = 0u; }                          // the first tail's top, parked in row 0
+    }
+    SchedEntryCompact en;
+    const double av = age[v];
+    en.e0A = edgeProb(rate * (av - age[child[0]]));
+    en.e0B = edgeProb(rate * (av - age[child[1]]));
+    en.offA = off[0]; en.offB = off[1];
+    en.dstOff = record(v);
+    const uint32_t push = (bothTails && i == lenFirst - 1) ? 0u : 0xffffu;
+    en.ctl = kind[0] | (kind[1] << 2) | (push << 16);
+    c.sched(slot)[i] = en;
+  }
+  __syncwarp(tm.mask);
+  for (int i = tm.j; i < k; i += kTeam) need[ord[i]] = 0;   // marks back to zero for the next step
+}
+
 __device__ __forceinline__ Team sweepTeam(int tid) {
   Team tm;
   tm.j = tid & (kTeam - 1);
@@ -765,16 +863,20 @@ k_sweep(StoreDev d, SmpDev sd, const SmpModel* __restrict__ mp, const Batch* __r
       }
       if (it < numSteps) {
         const unsigned long long step = step0 + 2ull * it;
-        uint8_t* scratch = reinterpret_cast<uint8_t*>(c.walk(slot));   // the list phases have not started: N words free
+        uint8_t* scratch = reinterpret_cast<uint8_t*>(c.walk(slot));   // team scratch: N words
+        int second = -1;
         const SmpProposal pr = it < numAge
             ? teamAgePropose(tm, m, t, c.pop(slot), c.coal(slot), c.ncoal(slot), myLocus, n, N, n + it, ftCoal, seed, step, scratch)
-            : teamSprPropose(tm, m, t, c.pop(slot), myLocus, n, N, it - numAge, seed, step);
+            : teamSprPropose(tm, m, t, c.pop(slot), myLocus, n, N, it - numAge, seed, step, &second);
         if (tm.j == 0) c.prop()[slot] = pr;
-        sweepMarkAndCompact(c, tm, slot);
+        // nodes to recompute: the moved node (coalescence time) or the moved father and its old father (SPR), and
+        // their ancestors; nothing if no proposal was made
+        const int first = pr.valid ? (it < numAge ? n + it : teamBcast(tm, pr.node)) : -1;
+        sweepPathSchedule(c, tm, slot, first, pr.valid ? second : -1);
       }
     }
     if (it == numSteps) break;
-    sweepEvaluate(c, d);
+    sweepWalkAndRoot(c, d, 0);
   }
   sweepWriteBack(c, d, sd, accepted, teamOn && tm.j == 0);
 }
@@ -957,7 +1059,7 @@ k_global_move(StoreDev d, SmpDev sd, const SmpModel* __restrict__ mp, const Batc
     if (tm.j == 0) c.prop()[slot] = pr;
     if (gm.kind >= 0) sweepMarkAndCompact(c, tm, slot);
   }
-  if (gm.kind >= 0) sweepEvaluate(c, d);
+  if (gm.kind >= 0) sweepWalkAndRoot(c, d, sweepListSchedule(c));
   sweepWriteBack(c, d, sd, none, false, true);
 }
 
