@@ -104,9 +104,13 @@ struct SmpRng {
   __device__ double exponential() { return -log(uniform()); }
   // draw `idx` of a family of independent streams under this (seed, stream, step): one hash per draw, for loops that
   // need one exponential per branch or segment (the competing clocks of the SPR proposal)
+  // The clocks of a proposal only have to be exponential to proposal accuracy: the logarithm is taken in single
+  // precision (relative error 1e-7 of the waiting time), through log1p of u - 1 above one half so that short waiting
+  // times keep that relative accuracy; the uniform itself has its 53 bits.
   __device__ double exponentialAt(unsigned long long idx) const {
     const unsigned long long r = mix(key + (idx + 0x1000ull) * 0x9E3779B97F4A7C15ull);
-    return -log(((double)(r >> 11) + 0.5) * (1.0 / 9007199254740992.0));
+    const double u = ((double)(r >> 11) + 0.5) * (1.0 / 9007199254740992.0);
+    return u > 0.5 ? -(double)log1pf((float)(u - 1.0)) : -(double)logf((float)u);
   }
 };
 

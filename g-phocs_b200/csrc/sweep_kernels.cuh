@@ -719,7 +719,7 @@ __device__ inline void sweepWriteBack(const SweepCtx& c, const StoreDev& d, cons
       d.age[g0 + v] = age[v];
       sd.nodePop[g0 + v] = pop[v];
     }
-    for (int p = c.lane; p < Q; p += 32) sd.coal[(size_t)l * Q + p] = c.coal(s)[p];
+    for (int p = c.lane; p < Q; p += 32) { sd.coal[(size_t)l * Q + p] = c.coal(s)[p]; sd.ncoal[(size_t)l * Q + p] = c.ncoal(s)[p]; }
   }
   if (tid < nl) {
     const int l = c.b.firstLocus + tid;
@@ -757,51 +757,51 @@ __device__ inline void sweepPathSchedule(const SweepCtx& c, const Team& tm, int 
   NodeRec* nd = c.node(slot);
   uint8_t* need = c.need(slot);
   uint8_t* ord = reinterpret_cast<uint8_t*>(c.walk(slot));   // team scratch: the nodes in schedule order
-  int k = 0, lenFirst = 0, lenA = 0, lenB = 0;
+  // the leader walks the two paths (tmpA: first .. root; tmpB: second .. below the first node on path 1) ...
+  uint8_t* tmpA = ord;
+  uint8_t* tmpB = ord + c.NI;
+  int a = 0, lenA = 0, lenB = 0;
   if (tm.j == 0 && c.mActive()[slot] && first >= n) {
-    // path 1: first .. root (written from ord[NI] downwards for now: tail B may have to go in front of it)
-    uint8_t* tmpA = ord + c.NI;
-    int a = 0;
     for (int u = first; u >= 0 && a < c.NI; u = nd[u].father) { tmpA[a++] = (uint8_t)u; need[u] = 1; }
-    // path 2: second .. the first node that is on path 1 (exclusive)
-    uint8_t* tmpB = tmpA + c.NI;
     int bLen = 0;
     for (int u = second; u >= n && !need[u] && bLen < c.NI; u = nd[u].father) tmpB[bLen++] = (uint8_t)u;
-    int j = a;   // index on path 1 of the junction (a: no second path joins)
     if (bLen > 0) {
-      const int top = nd[tmpB[bLen - 1]].father;
-      for (j = 0; j < a && tmpA[j] != top; j++) {}
+      const int top = nd[tmpB[bLen - 1]].father;   // the junction: on path 1
+      for (lenA = 0; lenA < a && tmpA[lenA] != top; lenA++) {}
     }
-    lenA = bLen > 0 ? j : 0;
     lenB = bLen;
-    // order: longer tail, other tail, then the rest of path 1
-    const bool aFirst = lenA >= lenB;
-    int o = 0;
-    if (aFirst) { for (int i = 0; i < lenA; i++) ord[o++] = tmpA[i]; for (int i = 0; i < lenB; i++) ord[o++] = tmpB[i]; }
-    else { for (int i = 0; i < lenB; i++) ord[o++] = tmpB[i]; for (int i = 0; i < lenA; i++) ord[o++] = tmpA[i]; }
-    for (int i = lenA; i < a; i++) ord[o++] = tmpA[i];
-    lenFirst = aFirst ? lenA : lenB;
-    k = o;
-    for (int i = 0; i < lenB; i++) need[tmpB[i]] = 1;
-    for (int i = 0; i < k; i++) {   // destination buffers of the nodes to recompute (once per proposal)
-      const uint8_t f = nd[ord[i]].flags;
-      if (!(f & F_RECALC)) nd[ord[i]].flags = (uint8_t)((f ^ F_SEL) | F_RECALC);
-    }
-    c.mK()[slot] = k;
+    c.mK()[slot] = a + bLen;
   }
-  k = teamBcast(tm, k);
-  lenFirst = teamBcast(tm, lenFirst);
-  const int bothTails = teamBcast(tm, (int)(lenA > 0 && lenB > 0));
+  a = teamBcast(tm, a);
+  lenA = teamBcast(tm, lenA);
+  lenB = teamBcast(tm, lenB);
+  const int k = a + lenB;
   __syncwarp(tm.mask);
   if (k == 0) return;
+  // ... the team does the rest.  Order: longer tail, other tail, then the rest of path 1.
+  const bool aFirst = lenA >= lenB;
+  const int lenFirst = aFirst ? lenA : lenB;
+  const bool bothTails = lenA > 0 && lenB > 0;
+  auto nodeAt = [&](int i) -> int {
+    if (i < lenFirst) return aFirst ? tmpA[i] : tmpB[i];
+    if (i < lenA + lenB) return aFirst ? tmpB[i - lenA] : tmpA[i - lenB];
+    return tmpA[i - lenB];
+  };
+  for (int i = tm.j; i < k; i += kTeam) {   // marks of path 2, destination buffers of every node to recompute
+    const int v = nodeAt(i);
+    need[v] = 1;
+    const uint8_t f = nd[v].flags;
+    if (!(f & F_RECALC)) nd[v].flags = (uint8_t)((f ^ F_SEL) | F_RECALC);
+  }
+  __syncwarp(tm.mask);
   const double* age = c.age(slot);
   const double rate = c.mRate()[slot];
   const uint32_t strideBytes = (uint32_t)c.mP()[slot] * 32u;
   auto record = [&](int x) { return (uint32_t)((x - n) * 2 + (nd[x].flags & F_SEL)) * strideBytes; };
   auto leafRef = [&](int x) { return (uint32_t)(x >> 3) * (kThreads * 4u) | ((uint32_t)(x & 7) * 4u) << 16; };
   for (int i = tm.j; i < k; i += kTeam) {
-    const int v = ord[i];
-    const int prevNode = i > 0 ? ord[i - 1] : -1;
+    const int v = nodeAt(i);
+    const int prevNode = i > 0 ? nodeAt(i - 1) : -1;
     uint32_t kind[2], off[2];
     int child[2] = {nd[v].left, nd[v].right};
 #pragma unroll
@@ -824,7 +824,7 @@ __device__ inline void sweepPathSchedule(const SweepCtx& c, const Team& tm, int 
     c.sched(slot)[i] = en;
   }
   __syncwarp(tm.mask);
-  for (int i = tm.j; i < k; i += kTeam) need[ord[i]] = 0;   // marks back to zero for the next step
+  for (int i = tm.j; i < k; i += kTeam) need[nodeAt(i)] = 0;   // marks back to zero for the next step
 }
 
 __device__ __forceinline__ Team sweepTeam(int tid) {
@@ -834,71 +834,6 @@ __device__ __forceinline__ Team sweepTeam(int tid) {
   tm.mask = ((1u << kTeam) - 1u) << tm.leader;
   return tm;
 }
-
-// ------------------------------------------------------------------------------------------ models without migration bands
-__global__ void __launch_bounds__(kThreads, GPHOCS_SWEEP_MINBLOCKS)
-k_sweep(StoreDev d, SmpDev sd, const SmpModel* __restrict__ mp, const Batch* __restrict__ batches, const __grid_constant__ SweepSmem lay,
-        double ftCoal, unsigned long long seed, unsigned long long step0) {
-  extern __shared__ __align__(16) unsigned char smem[];
-  SweepCtx c;
-  sweepStage(c, smem, lay, d, sd, mp, batches[blockIdx.x]);
-  const SweepModel& m = c.model();
-  const int n = c.n, N = c.N;
-  const Team tm = sweepTeam(c.tid);
-  const int slot = c.tid / kTeam;
-  const bool teamOn = slot < c.nl;
-  const int myLocus = c.b.firstLocus + slot;
-  TreeView t;
-  if (teamOn) t = sweepTreeView(c, d, slot);
-  unsigned int accepted[2] = {0u, 0u};
-
-  const int numAge = ftCoal > 0.0 ? c.NI : 0, numSteps = numAge + N;
-  for (int it = 0; it <= numSteps; it++) {
-    // ---- team phase: the previous proposal is resolved, the next one made
-    if (teamOn) {
-      if (it > 0) {
-        const int kind = it - 1 < numAge ? 0 : 1;
-        const int ok = teamResolve(tm, t, c.pop(slot), c.coal(slot), c.prop()[slot], myLocus, N, kind, seed, step0 + 2ull * (it - 1) + 1ull);
-        if (tm.j == 0) accepted[kind] += ok;
-      }
-      if (it < numSteps) {
-        const unsigned long long step = step0 + 2ull * it;
-        uint8_t* scratch = reinterpret_cast<uint8_t*>(c.walk(slot));   // team scratch: N words
-        int second = -1;
-        const SmpProposal pr = it < numAge
-            ? teamAgePropose(tm, m, t, c.pop(slot), c.coal(slot), c.ncoal(slot), myLocus, n, N, n + it, ftCoal, seed, step, scratch)
-            : teamSprPropose(tm, m, t, c.pop(slot), myLocus, n, N, it - numAge, seed, step, &second);
-        if (tm.j == 0) c.prop()[slot] = pr;
-        // nodes to recompute: the moved node (coalescence time) or the moved father and its old father (SPR), and
-        // their ancestors; nothing if no proposal was made
-        const int first = pr.valid ? (it < numAge ? n + it : teamBcast(tm, pr.node)) : -1;
-        sweepPathSchedule(c, tm, slot, first, pr.valid ? second : -1);
-      }
-    }
-    if (it == numSteps) break;
-    sweepWalkAndRoot(c, d, 0);
-  }
-  sweepWriteBack(c, d, sd, accepted, teamOn && tm.j == 0);
-}
-
-// ------------------------------------------------------------------------------------------ global moves, one launch each
-// UpdateTau (GPhoCS.c:3224-3990, with the rubber band of patch.c:596-801), UpdateSampleAge (GPhoCS.c:4006) and mixing
-// (GPhoCS.c:4688) propose one change for ALL loci and are accepted or rejected as a whole, from sums over the loci.  On
-// the stepwise route that is five launches per move (resolve the previous move, propose, evaluate, reduce, reduce).
-// Here one launch does it with the machinery of k_sweep: the CTA stages its batch, a team per locus first resolves
-// the PREVIOUS global move (the host knows its outcome by now and passes it in), then makes this move's proposal —
-// rubber band + the statistics under the proposed split time, or the rescaling of every age — the list / column /
-// root phases evaluate it.  The proposal records and log-likelihoods go back per locus and k_smp_reduce sums them
-// exactly as on the stepwise route: two launches per move, and the same chain bit for bit.  Models without migration
-// bands.
-struct GlobalMove {
-  int prevKind;       // -1: nothing pending; 0: a split-time / sample-age move; 1: mixing
-  int prevAccept;
-  double prevC;       // mixing: the factor of the pending move
-  int kind;           // -1: resolve only; 0: split-time / sample-age move of population A; 1: mixing by c
-  int A;
-  double tauOld, tauNew, lb, ub, f0, f1, c;
-};
 
 // wlStats (sampler_kernels.cuh) on a team, with population A's split time overridden: coalT[p], ncoalT[p] for every p.
 // terms: NI doubles of team scratch.  Per-population sums are formed in the order of wlStats' 32-lane shuffle tree
@@ -963,6 +898,79 @@ __device__ inline void teamStatsAll(const Team& tm, const SweepModel& m, const d
   }
   __syncwarp(tm.mask);
 }
+
+// ------------------------------------------------------------------------------------------ models without migration bands
+__global__ void __launch_bounds__(kThreads, GPHOCS_SWEEP_MINBLOCKS)
+k_sweep(StoreDev d, SmpDev sd, const SmpModel* __restrict__ mp, const Batch* __restrict__ batches, const __grid_constant__ SweepSmem lay,
+        double ftCoal, unsigned long long seed, unsigned long long step0) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  SweepCtx c;
+  sweepStage(c, smem, lay, d, sd, mp, batches[blockIdx.x]);
+  const SweepModel& m = c.model();
+  const int n = c.n, N = c.N;
+  const Team tm = sweepTeam(c.tid);
+  const int slot = c.tid / kTeam;
+  const bool teamOn = slot < c.nl;
+  const int myLocus = c.b.firstLocus + slot;
+  TreeView t;
+  if (teamOn) t = sweepTreeView(c, d, slot);
+  unsigned int accepted[2] = {0u, 0u};
+
+  const int numAge = ftCoal > 0.0 ? c.NI : 0, numSteps = numAge + N;
+  for (int it = 0; it <= numSteps; it++) {
+    // ---- team phase: the previous proposal is resolved, the next one made
+    if (teamOn) {
+      if (it > 0) {
+        const int kind = it - 1 < numAge ? 0 : 1;
+        const int ok = teamResolve(tm, t, c.pop(slot), c.coal(slot), c.prop()[slot], myLocus, N, kind, seed, step0 + 2ull * (it - 1) + 1ull);
+        if (tm.j == 0) accepted[kind] += ok;
+      }
+      if (it < numSteps) {
+        const unsigned long long step = step0 + 2ull * it;
+        uint8_t* scratch = reinterpret_cast<uint8_t*>(c.walk(slot));   // team scratch: N words
+        int second = -1;
+        const SmpProposal pr = it < numAge
+            ? teamAgePropose(tm, m, t, c.pop(slot), c.coal(slot), c.ncoal(slot), myLocus, n, N, n + it, ftCoal, seed, step, scratch)
+            : teamSprPropose(tm, m, t, c.pop(slot), myLocus, n, N, it - numAge, seed, step, &second);
+        if (tm.j == 0) c.prop()[slot] = pr;
+        // nodes to recompute: the moved node (coalescence time) or the moved father and its old father (SPR), and
+        // their ancestors; nothing if no proposal was made
+        const int first = pr.valid ? (it < numAge ? n + it : teamBcast(tm, pr.node)) : -1;
+        sweepPathSchedule(c, tm, slot, first, pr.valid ? second : -1);
+      }
+    }
+    if (it == numSteps) break;
+    sweepWalkAndRoot(c, d, 0);
+  }
+  // ---- statistics of the final genealogy (the SPR sweep moved coalescences between populations): k_smp_init_stats
+  if (teamOn && *t.root >= n) {
+    double* terms = reinterpret_cast<double*>(c.sched(slot));   // team scratch, as in k_global_move
+    double* coalT = terms + c.NI;
+    int* ncoalT = reinterpret_cast<int*>(c.walk(slot));
+    teamStatsAll(tm, m, t.age, c.pop(slot), n, N, -1, 0.0, terms, coalT, ncoalT);
+    for (int p = tm.j; p < c.Q; p += kTeam) { c.coal(slot)[p] = coalT[p]; c.ncoal(slot)[p] = ncoalT[p]; }
+  }
+  sweepWriteBack(c, d, sd, accepted, teamOn && tm.j == 0);
+}
+
+// ------------------------------------------------------------------------------------------ global moves, one launch each
+// UpdateTau (GPhoCS.c:3224-3990, with the rubber band of patch.c:596-801), UpdateSampleAge (GPhoCS.c:4006) and mixing
+// (GPhoCS.c:4688) propose one change for ALL loci and are accepted or rejected as a whole, from sums over the loci.  On
+// the stepwise route that is five launches per move (resolve the previous move, propose, evaluate, reduce, reduce).
+// Here one launch does it with the machinery of k_sweep: the CTA stages its batch, a team per locus first resolves
+// the PREVIOUS global move (the host knows its outcome by now and passes it in), then makes this move's proposal —
+// rubber band + the statistics under the proposed split time, or the rescaling of every age — the list / column /
+// root phases evaluate it.  The proposal records and log-likelihoods go back per locus and k_smp_reduce sums them
+// exactly as on the stepwise route: two launches per move, and the same chain bit for bit.  Models without migration
+// bands.
+struct GlobalMove {
+  int prevKind;       // -1: nothing pending; 0: a split-time / sample-age move; 1: mixing
+  int prevAccept;
+  double prevC;       // mixing: the factor of the pending move
+  int kind;           // -1: resolve only; 0: split-time / sample-age move of population A; 1: mixing by c
+  int A;
+  double tauOld, tauNew, lb, ub, f0, f1, c;
+};
 
 __global__ void __launch_bounds__(kThreads, GPHOCS_SWEEP_MINBLOCKS)
 k_global_move(StoreDev d, SmpDev sd, const SmpModel* __restrict__ mp, const Batch* __restrict__ batches, const __grid_constant__ SweepSmem lay,
