@@ -268,13 +268,14 @@ __device__ inline SmpProposal teamSprPropose(const Team& tm, const SweepModel& m
     if (oT < bestT || (oT == bestT && oX >= 0 && (bestX < 0 || oX < bestX))) { bestT = oT; bestX = oX; bestPop = oP; }
   }
   if (bestX >= 0) {
+    __syncwarp(tm.mask);   // every thread of the team has read the genealogy it is about to see rewired
     if (tm.j == 0) {
       pr.pop = np[F];
       pr.node = F;
       spr(t, node, bestX, bestT);
       np[F] = (uint8_t)bestPop;
     }
-    pr.valid = 1;   // the statistics of accepted loci are refreshed once, after the sweep (k_smp_init_stats)
+    pr.valid = 1;   // the statistics are refreshed once, after the sweep (teamStatsAll at the end of k_sweep)
   }
   return pr;
 }
@@ -749,7 +750,8 @@ __device__ inline void sweepWriteBack(const SweepCtx& c, const StoreDev& d, cons
 // product of the two children's factors does not depend on which of them is visited first — so the conditional vectors
 // are k_eval's bit for bit.  Also flips the destination buffers of the path nodes (k_eval phase C0).
 __device__ inline void sweepPathSchedule(const SweepCtx& c, const Team& tm, int slot, int first, int second) {
-  const int n = c.n, N = c.N;
+  const int n = c.n;
+  __syncwarp(tm.mask);   // the team is done with what it kept in its scratch during the proposal
   if (tm.j == 0) {
     c.mK()[slot] = 0;
     if (c.mActive()[slot]) c.mSavedLnL()[slot] = c.mLnL()[slot];   // what every evaluation starts with (.c:440)
