@@ -55,7 +55,7 @@ struct SweepSmem {
   uint32_t offSize, offWalk, perScratch;
   uint32_t perSched;
   // CTA regions
-  uint32_t offLoci, offSched, offStack, offWords, offList, offTerm, offMeta, offProp, offCells, offModel, total;
+  uint32_t offLoci, offSched, offStack, offWords, offList, offTerm, offMeta, offProp, offCells, offModel, offLca, total;
   int W32;
 };
 __host__ __device__ inline SweepSmem sweepSmemLayout(int n, int maxLoci, int Q) {
@@ -86,7 +86,8 @@ __host__ __device__ inline SweepSmem sweepSmemLayout(int n, int maxLoci, int Q) 
   m.offProp = m.offMeta + (uint32_t)kTeamSlots * 64;        // [slots] SmpProposal
   m.offCells = (m.offProp + (uint32_t)kTeamSlots * sizeof(SmpProposal) + 15) & ~15u;   // list count, acceptance counters
   m.offModel = m.offCells + 16;
-  m.total = (m.offModel + sizeof(SweepModel) + 15) & ~15u;
+  m.offLca = m.offModel + (uint32_t)sizeof(SweepModel);     // [Q][Q] uint8: lowest population above (or equal to) both
+  m.total = (m.offLca + (uint32_t)(Q * Q) + 15) & ~15u;
   return m;
 }
 __host__ __device__ inline size_t sweepSmemBytes(int n, int maxLoci, int Q) { return sweepSmemLayout(n, maxLoci, Q).total; }
@@ -217,7 +218,8 @@ __device__ inline SmpProposal teamAgePropose(const Team& tm, const SweepModel& m
 // smpSprProposeBody on a team: every thread rings the clocks of its share of the branches
 // (*oldGrandpa = the pruned father's father before the move, -1 if none: the second path of nodes to recompute starts there)
 __device__ inline SmpProposal teamSprPropose(const Team& tm, const SweepModel& m, const TreeView& t, uint8_t* np, int l, int n, int N,
-                                             int node, unsigned long long seed, unsigned long long step, int* oldGrandpa) {
+                                             int node, unsigned long long seed, unsigned long long step, int* oldGrandpa,
+                                             const uint8_t* lca) {
   SmpProposal pr = smpNoProposal();
   *oldGrandpa = -1;
   const int root = *t.root;
@@ -230,6 +232,8 @@ __device__ inline SmpProposal teamSprPropose(const Team& tm, const SweepModel& m
   const double t0 = t.age[node];
   const int pop0 = np[node];
   const double ageG = G >= 0 ? t.age[G] : kSmpInf;
+  // (compacting the branches that can meet the pruned lineage before ringing their clocks was measured twice — with the
+  // population walk repeated and with this table — and lost both times to the ballots it needs: 7.3 vs 7.0 ms)
   double bestT = kSmpInf;
   int bestX = -1, bestPop = -1;
   const SmpRng rng(seed, (unsigned long long)l, step);
@@ -238,8 +242,7 @@ __device__ inline SmpProposal teamSprPropose(const Team& tm, const SweepModel& m
     if (x == node || x == F) continue;
     const int fx = t.node[x].father;
     const double endx = x == S ? ageG : (fx >= 0 ? t.age[fx] : kSmpInf);
-    int q = np[x];   // first population in which the two lineages can meet: their common ancestor
-    while (!((m.below[q] >> pop0) & 1ull)) q = m.father[q];
+    int q = lca[np[x] * m.Q + pop0];   // first population in which the two lineages can meet: their common ancestor
     double sNow = fmax(fmax(t0, t.age[x]), m.tau[q]);
     if (sNow >= endx) continue;
     while (m.father[q] >= 0 && m.tau[m.father[q]] <= sNow) q = m.father[q];
@@ -363,6 +366,7 @@ struct SweepCtx {
   __device__ __forceinline__ unsigned int* accepted() const { return reinterpret_cast<unsigned int*>(smem + layp->offCells) + 1; }   // [2]
   __device__ __forceinline__ uint32_t* list() const { return reinterpret_cast<uint32_t*>(smem + layp->offList); }
   __device__ __forceinline__ SweepModel& model() const { return *reinterpret_cast<SweepModel*>(smem + layp->offModel); }
+  __device__ __forceinline__ uint8_t* lca() const { return smem + layp->offLca; }
 };
 
 // stage the batch: model, per-locus scalars, genealogies, population assignments, coal statistics, leaf codes; ends
@@ -378,6 +382,12 @@ __device__ inline void sweepStage(SweepCtx& c, unsigned char* smem, const SweepS
   for (int p = tid; p < Q; p += kThreads) {
     sModel.father[p] = mp->father[p]; sModel.leavesBelow[p] = mp->leavesBelow[p]; sModel.below[p] = mp->below[p];
     sModel.theta[p] = mp->theta[p]; sModel.tau[p] = mp->tau[p]; sModel.coalRate[p] = mp->coalRate[p];
+  }
+  for (int i = tid; i < Q * Q; i += kThreads) {   // lowest common population of every pair (the SPR proposal asks per branch)
+    const int pa = i / Q, pb = i - pa * Q;
+    int q = pa;
+    while (!((mp->below[q] >> pb) & 1ull)) q = mp->father[q];
+    c.lca()[i] = (uint8_t)q;
   }
   unsigned long long w0 = 0ull, w1 = 0ull;
   c.ph = 0; c.cnt = 0;
@@ -933,7 +943,7 @@ k_sweep(StoreDev d, SmpDev sd, const SmpModel* __restrict__ mp, const Batch* __r
         int second = -1;
         const SmpProposal pr = it < numAge
             ? teamAgePropose(tm, m, t, c.pop(slot), c.coal(slot), c.ncoal(slot), myLocus, n, N, n + it, ftCoal, seed, step, scratch)
-            : teamSprPropose(tm, m, t, c.pop(slot), myLocus, n, N, it - numAge, seed, step, &second);
+            : teamSprPropose(tm, m, t, c.pop(slot), myLocus, n, N, it - numAge, seed, step, &second, c.lca());
         if (tm.j == 0) c.prop()[slot] = pr;
         // nodes to recompute: the moved node (coalescence time) or the moved father and its old father (SPR), and
         // their ancestors; nothing if no proposal was made
