@@ -91,3 +91,16 @@ def pooled_between_chain_se(group_a, group_b):
 
 
 REF_SEEDS = (4242, 999, 31337)
+
+
+def sample_age_columns(model):
+    """Columns of parameter_columns() that hold ESTIMATED SAMPLE AGES.  The reference gives them the improper prior
+    Gamma(0, 0) ~ 1/x (PopulationTree.c:121), which makes the posterior non-integrable at 0: chains — the reference's as
+    much as the device's — wander off towards 0 for long stretches (three reference seeds give 1.5e-5, 2.3e-5 and 3.5e-5
+    for tau_B of the configs[4] shape; additive proposals of size 2e-4 are almost never accepted from 1e-8), so their
+    "posterior mean" has no Monte-Carlo error worth the name.  The move itself is checked with a proper prior in
+    tests/test_gpu_sampler_ancient.py::test_uninformative_data_recovers_the_prior_of_sample_age_and_rates; here these
+    columns only have to agree in order of magnitude."""
+    Q, C, B = model.numPops, model.numCurPops, len(model.bands)
+    e0 = 2 * Q - C + B
+    return set(range(e0, e0 + len(model.sample_age)))

