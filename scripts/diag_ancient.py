@@ -1,3 +1,5 @@
+"""configs[4] shape (50 loci): the same table for three reference seeds, two runs of the fast-path host program and two seeds of the device sampler - the run that showed the estimated sample age (improper prior) wandering in every chain.
+    python scripts/diag_ancient.py      (GPU box; needs oracle/_ref)"""
 import importlib, os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

@@ -1,3 +1,5 @@
+"""configs[3] shape (30 loci): posterior means of every parameter from two reference seeds, the fast-path host program and two seeds of the device sampler side by side, with batch-means standard errors - the run that showed theta_B / theta_AB / m_A->B mixing slowly in the reference itself.
+    python scripts/diag_pop6.py      (GPU box; needs oracle/_ref)"""
 import importlib, os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
