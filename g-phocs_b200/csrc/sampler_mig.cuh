@@ -253,7 +253,7 @@ __device__ inline void smgStats(const SmpModel& m, const SmgWarp& w, int n, int 
 // Statistics that a move inside population p can change: coal[p] and mig[b] of the bands whose target is p.  The
 // segments of p are compacted (their indices go to the front of w.segC's storage, reused as an int list) and only
 // they are paired.  Leaves the results in w.coal[p] / w.mig[b]; ncoal / nmig are unchanged by such a move.
-__device__ inline void smgPopStats(const SmpModel& m, const SmgWarp& w, int lane, int p) {
+__device__ inline void smgPopStats(const SmpModel& m, const SmgWarp& w, int lane, int p, int ovPop = -1, double ovTau = 0.0) {
   const int S = *w.segCount;
   int* list = reinterpret_cast<int*>(w.segC);
   int count = 0;
@@ -279,7 +279,7 @@ __device__ inline void smgPopStats(const SmpModel& m, const SmgWarp& w, int lane
   if (lane == 0) w.coal[p] = c;
   for (int b = 0; b < m.B; b++) {
     if (m.bandTgt[b] != p) continue;
-    const double s0 = smgBandStart(m, b, -1, 0.0), s1 = smgBandEnd(m, b, -1, 0.0);
+    const double s0 = smgBandStart(m, b, ovPop, ovTau), s1 = smgBandEnd(m, b, ovPop, ovTau);
     double g = 0.0;
     for (int a = lane; a < count; a += 32) {
       const int i = list[a];
@@ -640,7 +640,20 @@ k_smg_tau_propose(StoreDev d, SmpDev sd, const SmpModel* __restrict__ mp, int A,
   }
   __syncwarp();
   smgBuildSegments(m, w, N, root, lane, A, tauNew, -1, -1, -1);
-  smgStats(m, w, n, N, lane, A, tauNew);
+  // The rubber band moves events of A and its two sons only, and only bands that touch one of the three change their
+  // live interval: statistics of every other population and band keep their stored values.  (Pairing the segments of
+  // one population at a time — a few of the ~70 — instead of all of them at once is what makes this kernel 2x faster.)
+  for (int p = lane; p < m.Q; p += 32) { w.coal[p] = sd.coal[(size_t)l * m.Q + p]; w.ncoal[p] = sd.ncoal[(size_t)l * m.Q + p]; }
+  for (int b = lane; b < m.B; b += 32) { w.mig[b] = sd.mig[(size_t)l * m.B + b]; w.nmig[b] = sd.nmig[(size_t)l * m.B + b]; }
+  __syncwarp();
+  unsigned long long touched = 1ull << A;
+  if (s0 >= 0) touched |= (1ull << s0) | (1ull << s1);
+  // + both ends of every band that touches one of them: its live interval moves, and its rescaled migration events
+  // end a segment in the target population and begin one in the source population
+  unsigned long long redo = touched;
+  for (int b = 0; b < m.B; b++)
+    if (((touched >> m.bandSrc[b]) | (touched >> m.bandTgt[b])) & 1ull) redo |= (1ull << m.bandTgt[b]) | (1ull << m.bandSrc[b]);
+  for (unsigned long long rest = redo; rest; rest &= rest - 1) smgPopStats(m, w, lane, __ffsll((long long)rest) - 1, A, tauNew);
   smgWriteStats(m, w, sd, l, lane, 1);
   smgStoreMigs(w, sd, l, lane);
   if (lane == 0) {
