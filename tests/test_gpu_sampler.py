@@ -120,12 +120,15 @@ def test_sweep_routes_give_the_same_chain(cfg, L):
             extra = dict(estimate_sample_age=[1 if nm in model.sample_age else 0 for nm, _ in model.cur], locus_rate_finetune=0.3)
         sm = gp.Sampler(st, w.pops, w.node_pop, seed=77, **extra)
         sm.set_stepwise(route == "stepwise")
+        sm.eval_counters(reset=True)           # switches the roofline accounting on
         k0 = gp.lib().gphocsKernelLaunchCount()
         tr = sm.iterate(12)
         launches = gp.lib().gphocsKernelLaunchCount() - k0
+        counters = sm.eval_counters()
         assert sm.check()[0] == 0
         stats = sm.stats()
         state = sm.state()
+        state["eval_counters"] = counters
         node_pop = sm.download()
         trees = st.get_trees()
         clvs = [st.clv(l, st.n + k, P=int(w.patt_start[l + 1] - w.patt_start[l])) for l in (0, L // 2, L - 1) for k in (0, st.n - 2)]
@@ -142,6 +145,11 @@ def test_sweep_routes_give_the_same_chain(cfg, L):
         assert np.array_equal(x, y)
     for move in ("coal_time", "spr"):
         assert a[7]["accepted"][move] == b[7]["accepted"][move] and a[7]["proposed"][move] == b[7]["proposed"][move], move
+    # both routes count the same incremental evaluations and the same algorithmic bytes, 32 * P * (2k + 1) each
+    evals, nbytes = a[7]["eval_counters"]
+    assert a[7]["eval_counters"] == b[7]["eval_counters"] and evals > 0
+    P = np.diff(w.patt_start)
+    assert 32 * P.min() * 3 * evals <= nbytes <= 32 * P.max() * (2 * (w.n - 1) + 1) * evals
     assert b[5] < a[5] / 2, (b[5], a[5])
 
 
