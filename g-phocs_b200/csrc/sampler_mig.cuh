@@ -16,7 +16,7 @@ namespace gphocs {
 
 struct SmgWarp {      // per-warp shared-memory view (carved by smgCarve)
   double* age;        // [N]
-  int16_t* father;    // [N]
+  NodeRec* node;      // [N] topology + flag bytes (the proposal kernels edit this copy and write it back once)
   uint8_t* pop;       // [N]
   double* migAge;     // [kSmpMaxMigs]
   int16_t* migBranch; // [kSmpMaxMigs]
@@ -39,9 +39,9 @@ struct SmgWarp {      // per-warp shared-memory view (carved by smgCarve)
 __host__ __device__ inline int smgMaxSegs(int N) { return 4 * N + 2 * kSmpMaxMigs + 8; }
 __host__ __device__ inline size_t smgWarpBytes(int N, int Q, int B) {
   const size_t S = (size_t)smgMaxSegs(N);
-  size_t b = (size_t)N * 8 + kSmpMaxMigs * 8 + S * 24 + (size_t)Q * 8 + (size_t)B * 8;   // doubles first
+  size_t b = (size_t)N * 16 + kSmpMaxMigs * 8 + S * 24 + (size_t)Q * 8 + (size_t)B * 8;  // doubles and node records first
   b += 3 * 4 + (size_t)Q * 4 + (size_t)B * 4;                                            // ints
-  b += (size_t)N * 2 + kSmpMaxMigs * 2 + S * 2;                                          // int16
+  b += kSmpMaxMigs * 2 + S * 2;                                                          // int16
   b += (size_t)N + kSmpMaxMigs + S;                                                      // bytes
   return (b + 15) & ~(size_t)15;
 }
@@ -51,6 +51,7 @@ __device__ inline SmgWarp smgCarve(unsigned char* base, int N, int Q, int B) {
   w.maxSegs = S;
   double* dp = reinterpret_cast<double*>(base);
   w.age = dp; dp += N;
+  w.node = reinterpret_cast<NodeRec*>(dp); dp += N;
   w.migAge = dp; dp += kSmpMaxMigs;
   w.segT0 = dp; dp += S;
   w.segT1 = dp; dp += S;
@@ -62,7 +63,6 @@ __device__ inline SmgWarp smgCarve(unsigned char* base, int N, int Q, int B) {
   w.ncoal = ip; ip += Q;
   w.nmig = ip; ip += B;
   int16_t* sp = reinterpret_cast<int16_t*>(ip);
-  w.father = sp; sp += N;
   w.migBranch = sp; sp += kSmpMaxMigs;
   w.segBranch = sp; sp += S;
   uint8_t* bp = reinterpret_cast<uint8_t*>(sp);
@@ -88,7 +88,7 @@ __device__ inline void smgLoad(const SmgWarp& w, const StoreDev& d, const SmpDev
   for (int x = lane; x < N; x += 32) {
     const size_t o = (size_t)l * N + x;
     w.age[x] = d.age[o];
-    w.father[x] = d.node[o].father;
+    w.node[x] = d.node[o];
     w.pop[x] = sd.nodePop[o];
   }
   if (lane < kSmpMaxMigs) {
@@ -112,7 +112,17 @@ __device__ inline void smgStoreMigs(const SmgWarp& w, const SmpDev& sd, int l, i
   }
   if (lane == 0) sd.numMigs[l] = *w.numMigs;
 }
-// current events -> saved copy (restored if the proposal is rejected)
+// current events -> saved copy (restored if the proposal is rejected); `w` still holds the events as smgLoad read them
+__device__ inline void smgSaveMigs(const SmgWarp& w, const SmpDev& sd, int l, int lane) {
+  if (lane < kSmpMaxMigs) {
+    const size_t o = (size_t)l * kSmpMaxMigs + lane;
+    sd.svMigAge[o] = w.migAge[lane];
+    sd.svMigBranch[o] = w.migBranch[lane];
+    sd.svMigBand[o] = w.migBand[lane];
+  }
+  if (lane == 0) sd.svNumMigs[l] = *w.numMigs;
+}
+// the same from the HBM copy, for kernels that do not stage the locus
 __device__ inline void smgSaveMigs(const SmpDev& sd, int l, int lane) {
   if (lane < kSmpMaxMigs) {
     const size_t o = (size_t)l * kSmpMaxMigs + lane;
@@ -131,82 +141,110 @@ __device__ inline void smgRestoreMigs(const SmpDev& sd, int l, int lane) {
   }
   if (lane == 0) sd.numMigs[l] = sd.svNumMigs[l];
 }
-
-// Walks branch x (from its node up to its father, or for ever above the root) through the populations it visits:
-// up at population ends, sideways (target -> source) at its migration events.  emit(pop, from, to) per segment.
-// Returns 0 if the path is consistent: every migration event happens in its band's target population inside the
-// band's live interval, and the branch ends in the population of the father's coalescence.
-template <typename Emit>
-__device__ inline int smgWalkBranch(const SmpModel& m, const SmgWarp& w, int x, int root, int ovPop, double ovTau, Emit emit) {
-  int pop = w.pop[x];
-  double t = w.age[x];
-  const int fa = w.father[x];
-  const double tEnd = fa >= 0 ? w.age[fa] : kSmpInf;
-  const int nm = *w.numMigs;
-  int bad = (fa >= 0 && tEnd < t) || (fa < 0 && x != root);
-  unsigned used = 0, mine = 0;   // mine: the events that sit on this branch (most branches carry none: no scan per step then)
-  for (int k = 0; k < nm; k++) mine |= (unsigned)(w.migBranch[k] == x) << k;
-  for (int it = 0; it < 2 * kSmpMaxPops + kSmpMaxMigs + 2; it++) {
-    int mi = -1;   // earliest migration event of this branch not yet passed
-    double mAge = kSmpInf;
-    for (unsigned rest = mine & ~used; rest; rest &= rest - 1) {
-      const int k = __ffs(rest) - 1;
-      if (w.migAge[k] < mAge) { mi = k; mAge = w.migAge[k]; }
-    }
-    const double popEnd = m.father[pop] >= 0 ? smpTau(m, m.father[pop], ovPop, ovTau) : kSmpInf;
-    const double tNext = fmin(tEnd, fmin(popEnd, mAge));
-    emit(pop, t, tNext);
-    if (mi >= 0 && mAge <= tEnd && mAge <= popEnd) {   // sideways: target -> source of the band
-      const int b = w.migBand[mi];
-      if (pop != m.bandTgt[b] || mAge < t || mAge < smgBandStart(m, b, ovPop, ovTau) || mAge > smgBandEnd(m, b, ovPop, ovTau)) bad = 1;
-      pop = m.bandSrc[b];
-      t = mAge;
-      used |= 1u << mi;
-      continue;
-    }
-    if (mi >= 0 && tEnd <= popEnd) bad = 1;   // an event of this branch lies beyond the branch
-    if (tEnd <= popEnd) break;                // reached the father
-    if (m.father[pop] < 0) break;             // the root population never ends
-    pop = m.father[pop];
-    t = tNext;
+// saved copy -> the current events in HBM and their staged copy
+__device__ inline void smgRestoreMigs(const SmgWarp& w, const SmpDev& sd, int l, int lane) {
+  if (lane < kSmpMaxMigs) {
+    const size_t o = (size_t)l * kSmpMaxMigs + lane;
+    const double a = sd.svMigAge[o];
+    const int16_t br = sd.svMigBranch[o];
+    const uint8_t bd = sd.svMigBand[o];
+    sd.migAge[o] = a; sd.migBranch[o] = br; sd.migBand[o] = bd;
+    w.migAge[lane] = a; w.migBranch[lane] = br; w.migBand[lane] = bd;
   }
-  if (fa >= 0 && pop != w.pop[fa]) bad = 1;
-  return bad;
+  if (lane == 0) { const int k = sd.svNumMigs[l]; sd.numMigs[l] = k; *w.numMigs = k; }
 }
 
-// Segment list of the genealogy.  skipBranch: a branch left out (the pruned lineage of an SPR, -1: none);
-// relabelFrom/relabelTo: segments of branch relabelFrom are reported as belonging to relabelTo (the pruned father's
-// upper branch continues its remaining child's lineage).  Raises *w.bad on inconsistency or overflow.
+// The proposal kernels of the per-locus sweeps edit the genealogy in this warp's shared memory: node records and ages
+// of the view are the staged copies (one coalesced load by smgLoad, one coalesced store by smgStoreTree), the saved
+// copies, the root and the log-likelihoods stay where they are in HBM (written, hardly ever read).  A tree edit by one
+// lane is then a handful of shared-memory accesses instead of a chain of dependent HBM round trips.
+__device__ inline TreeView smgStagedView(const TreeView& t, const SmgWarp& w) {
+  TreeView s = t;
+  s.node = w.node;
+  s.age = w.age;
+  return s;
+}
+__device__ inline void smgStoreTree(const SmgWarp& w, const StoreDev& d, int l, int lane) {
+  __syncwarp();
+  const int N = d.N;
+  for (int x = lane; x < N; x += 32) {
+    const size_t o = (size_t)l * N + x;
+    d.node[o] = w.node[x];
+    d.age[o] = w.age[x];
+  }
+}
+
+// Segment list of the genealogy.  Every lane walks one branch (from its node up to its father, or for ever above the
+// root) through the populations it visits — up at population ends, sideways (target -> source) at its migration
+// events — one segment per round; the lanes that still have a segment to report in a round take consecutive slots
+// (one ballot), so every branch is walked exactly once and the list needs no prefix pass.  The order of the list is
+// (round of 32 branches, step of the walk, branch); nothing depends on it but the order of the sums taken over it.
+// skipBranch: a branch left out (the pruned lineage of an SPR, -1: none); relabelFrom/relabelTo: segments of branch
+// relabelFrom are reported as belonging to relabelTo (the pruned father's upper branch continues its remaining
+// child's lineage).  Raises *w.bad if a path is inconsistent — a migration event outside its band's target population
+// or live interval, an event beyond its branch, a branch that does not end in the population of the father's
+// coalescence — or if the list overflows.
 __device__ inline void smgBuildSegments(const SmpModel& m, const SmgWarp& w, int N, int root, int lane, int ovPop, double ovTau,
                                         int skipBranch, int relabelFrom, int relabelTo) {
-  if (lane == 0) *w.segCount = 0;
-  __syncwarp();
+  const int nm = *w.numMigs;
+  const unsigned below = (1u << lane) - 1u;
+  int base = 0, bad = 0;
   for (int x0 = 0; x0 < N; x0 += 32) {
     const int x = x0 + lane;
-    int cnt = 0, bad = 0;
-    if (x < N && x != skipBranch) bad = smgWalkBranch(m, w, x, root, ovPop, ovTau, [&](int, double, double) { cnt++; });
-    // exclusive prefix of the counts over the lanes
-    int incl = cnt;
-#pragma unroll
-    for (int off = 1; off < 32; off <<= 1) {
-      const int v = __shfl_up_sync(0xffffffffu, incl, off);
-      if (lane >= off) incl += v;
+    bool live = x < N && x != skipBranch;
+    int pop = 0, fa = -1;
+    double t = 0.0, tEnd = kSmpInf;
+    unsigned used = 0, mine = 0;   // mine: the events that sit on this branch (most branches carry none: no scan per step then)
+    if (live) {
+      pop = w.pop[x];
+      t = w.age[x];
+      fa = w.node[x].father;
+      if (fa >= 0) tEnd = w.age[fa];
+      bad |= (fa >= 0 && tEnd < t) || (fa < 0 && x != root);
+      for (int k = 0; k < nm; k++) mine |= (unsigned)(w.migBranch[k] == x) << k;
     }
-    const int base = *w.segCount;
-    const int total = __shfl_sync(0xffffffffu, incl, 31);
-    __syncwarp();
-    if (base + total > w.maxSegs) { if (lane == 0) *w.bad = 1; __syncwarp(); return; }
-    if (x < N && x != skipBranch) {
-      int k = base + incl - cnt;
-      const int label = x == relabelFrom ? relabelTo : x;
-      smgWalkBranch(m, w, x, root, ovPop, ovTau, [&](int pop, double a, double b) {
-        w.segPop[k] = (uint8_t)pop; w.segT0[k] = a; w.segT1[k] = b; w.segBranch[k] = (int16_t)label; k++;
-      });
+    const int label = x == relabelFrom ? relabelTo : x;
+    for (int it = 0; it < 2 * kSmpMaxPops + kSmpMaxMigs + 2; it++) {
+      const unsigned ballot = __ballot_sync(0xffffffffu, live);
+      if (!ballot) break;
+      if (live) {
+        int mi = -1;   // earliest migration event of this branch not yet passed
+        double mAge = kSmpInf;
+        for (unsigned rest = mine & ~used; rest; rest &= rest - 1) {
+          const int k = __ffs(rest) - 1;
+          if (w.migAge[k] < mAge) { mi = k; mAge = w.migAge[k]; }
+        }
+        const double popEnd = m.father[pop] >= 0 ? smpTau(m, m.father[pop], ovPop, ovTau) : kSmpInf;
+        const double tNext = fmin(tEnd, fmin(popEnd, mAge));
+        const int k = base + __popc(ballot & below);
+        if (k < w.maxSegs) { w.segPop[k] = (uint8_t)pop; w.segT0[k] = t; w.segT1[k] = tNext; w.segBranch[k] = (int16_t)label; }
+        if (mi >= 0 && mAge <= tEnd && mAge <= popEnd) {   // sideways: target -> source of the band
+          const int b = w.migBand[mi];
+          if (pop != m.bandTgt[b] || mAge < t || mAge < smgBandStart(m, b, ovPop, ovTau) || mAge > smgBandEnd(m, b, ovPop, ovTau)) bad = 1;
+          pop = m.bandSrc[b];
+          t = mAge;
+          used |= 1u << mi;
+        } else {
+          if (mi >= 0 && tEnd <= popEnd) bad = 1;   // an event of this branch lies beyond the branch
+          if (tEnd <= popEnd || m.father[pop] < 0) {   // reached the father / the root population never ends
+            if (fa >= 0 && pop != w.pop[fa]) bad = 1;
+            live = false;
+          } else {
+            pop = m.father[pop];
+            t = tNext;
+          }
+        }
+      }
+      base += __popc(ballot);
     }
-    if (bad) *w.bad = 1;
-    if (lane == 0) *w.segCount = base + total;
-    __syncwarp();
   }
+  if (base > w.maxSegs) { bad = 1; base = w.maxSegs; }
+  bad = __any_sync(0xffffffffu, bad);
+  if (lane == 0) {
+    *w.segCount = base;
+    if (bad) *w.bad = 1;
+  }
+  __syncwarp();
 }
 
 // statistics of the locus from its segments -> w.coal / w.ncoal / w.mig / w.nmig (deterministic summation order)
@@ -340,8 +378,8 @@ __global__ void __launch_bounds__(kSmpThreads) k_smg_stats(StoreDev d, SmpDev sd
   if (bad && lane == 0) bad[l] += *w.bad;
 }
 
-__device__ inline void smgResolve(const StoreDev& d, const SmpDev& sd, const SmpModel& m, const TreeView& t, int l, int lane, int N,
-                                  int kind, unsigned long long seed, unsigned long long step);
+__device__ inline void smgResolve(const StoreDev& d, const SmpDev& sd, const SmpModel& m, const TreeView& t, const SmgWarp* w, int l,
+                                  int lane, int N, int kind, unsigned long long seed, unsigned long long step);
 
 // ------------------------------------------------------------------------------------------ coalescence-time move
 // UpdateGB_InternalNode with migration: the node stays in its population and between the events next to it on
@@ -353,7 +391,6 @@ __device__ inline void smgAgeProposeBody(const StoreDev& d, const SmpDev& sd, co
   pr.node = inode;
   const int root = *t.root;
   if (root < n) { if (lane == 0) sd.prop[l] = pr; return; }
-  smgLoad(w, d, sd, l, lane);
   double tnew = 0.0;
   int valid = 0;
   if (lane == 0) {
@@ -375,12 +412,10 @@ __device__ inline void smgAgeProposeBody(const StoreDev& d, const SmpDev& sd, co
     SmpRng rng(seed, (unsigned long long)l, step);
     tnew = smpReflect(told + finetune * rng.normal2(), lo, hi);
     valid = fabs(tnew - told) >= 1e-15;
-    if (valid) adjustAge(t, inode, tnew);
+    if (valid) adjustAge(t, inode, tnew);   // t.age is w.age: the staged copy takes the new age
   }
   valid = __shfl_sync(0xffffffffu, valid, 0);
-  tnew = __shfl_sync(0xffffffffu, tnew, 0);
   if (valid) {
-    if (lane == 0) w.age[inode] = tnew;
     __syncwarp();
     const int p = w.pop[inode];
     smgBuildSegments(m, w, N, root, lane, -1, 0.0, -1, -1, -1);
@@ -402,12 +437,17 @@ __device__ inline void smgAgeProposeBody(const StoreDev& d, const SmpDev& sd, co
   }
   if (lane == 0) sd.prop[l] = pr;
 }
+// The proposal kernels of a sweep: stage the locus, settle the previous proposal of the sweep on the staged copy,
+// propose, write the genealogy back.
 __global__ void __launch_bounds__(kSmpThreads)
 k_smg_age_propose(StoreDev d, SmpDev sd, const SmpModel* __restrict__ mp, int inode, double finetune, unsigned long long seed,
                   unsigned long long step, int pendKind, unsigned long long pendStep) {
   SMG_PROLOGUE
-  if (pendKind >= 0) smgResolve(d, sd, m, t, l, lane, N, pendKind, seed, pendStep);   // the previous proposal of this locus
-  smgAgeProposeBody(d, sd, m, w, t, l, lane, n, N, inode, finetune, seed, step);
+  smgLoad(w, d, sd, l, lane);
+  const TreeView ts = smgStagedView(t, w);
+  if (pendKind >= 0) smgResolve(d, sd, m, ts, &w, l, lane, N, pendKind, seed, pendStep);   // the previous proposal of this locus
+  smgAgeProposeBody(d, sd, m, w, ts, l, lane, n, N, inode, finetune, seed, step);
+  smgStoreTree(w, d, l, lane);
 }
 
 // ------------------------------------------------------------------------------------------ migration-time moves
@@ -431,7 +471,7 @@ k_smg_mignode_sweep(StoreDev d, SmpDev sd, const SmpModel* __restrict__ mp, doub
       const int br = w.migBranch[k], b = w.migBand[k];
       told = w.migAge[k];
       double lo = fmax(smgBandStart(m, b, -1, 0.0), w.age[br]);
-      double hi = fmin(smgBandEnd(m, b, -1, 0.0), w.father[br] >= 0 ? w.age[w.father[br]] : kOldAge);
+      double hi = fmin(smgBandEnd(m, b, -1, 0.0), w.node[br].father >= 0 ? w.age[w.node[br].father] : kOldAge);
       for (int j = 0; j < nm; j++)
         if (j != k && w.migBranch[j] == br) {
           if (w.migAge[j] < told) lo = fmax(lo, w.migAge[j]);
@@ -483,8 +523,7 @@ __device__ inline void smgSprProposeBody(const StoreDev& d, const SmpDev& sd, co
   SmpProposal pr = smpNoProposal();
   const int root = *t.root;
   if (root < n || node == root) { if (lane == 0) sd.prop[l] = pr; return; }
-  smgLoad(w, d, sd, l, lane);
-  const int F = w.father[node];
+  const int F = w.node[node].father;
   const NodeRec recF = t.node[F];
   const int S = recF.left + recF.right - node;
   // pruned genealogy: without the branch of `node`; the father's upper branch continues the sibling's lineage
@@ -543,7 +582,7 @@ __device__ inline void smgSprProposeBody(const StoreDev& d, const SmpDev& sd, co
     }
   }
   if (target >= 0 && !fail) {
-    smgSaveMigs(sd, l, lane);
+    smgSaveMigs(w, sd, l, lane);
     __syncwarp();
     if (lane == 0) {
       // events of the genealogy after the move: the old lineage's go, the pruned father's upper branch joins the
@@ -578,8 +617,11 @@ __global__ void __launch_bounds__(kSmpThreads)
 k_smg_spr_propose(StoreDev d, SmpDev sd, const SmpModel* __restrict__ mp, int node, unsigned long long seed,
                   unsigned long long step, int pendKind, unsigned long long pendStep) {
   SMG_PROLOGUE
-  if (pendKind >= 0) smgResolve(d, sd, m, t, l, lane, N, pendKind, seed, pendStep);
-  smgSprProposeBody(d, sd, m, w, t, l, lane, n, N, node, seed, step);
+  smgLoad(w, d, sd, l, lane);
+  const TreeView ts = smgStagedView(t, w);
+  if (pendKind >= 0) smgResolve(d, sd, m, ts, &w, l, lane, N, pendKind, seed, pendStep);
+  smgSprProposeBody(d, sd, m, w, ts, l, lane, n, N, node, seed, step);
+  smgStoreTree(w, d, l, lane);
 }
 
 // ------------------------------------------------------------------------------------------ split-time move
@@ -595,7 +637,7 @@ k_smg_tau_propose(StoreDev d, SmpDev sd, const SmpModel* __restrict__ mp, int A,
   const int root = *t.root;
   if (root < n) { if (lane == 0) sd.prop[l] = pr; return; }
   smgLoad(w, d, sd, l, lane);
-  smgSaveMigs(sd, l, lane);
+  smgSaveMigs(w, sd, l, lane);
   const bool isRoot = A == m.rootPop;
   // A current population: its SAMPLE AGE moves (UpdateSampleAge, GPhoCS.c:4006-4590): the leaves of A take the new age
   const int s0 = A >= m.C ? m.son0[A] : -1, s1 = A >= m.C ? m.son1[A] : -1;
@@ -681,9 +723,10 @@ __global__ void __launch_bounds__(kSmpThreads) k_smg_scale_propose(StoreDev d, S
   if (lane == 0) sd.prop[l] = pr;
 }
 
-// per-locus accept / reject for models with migration (kind as in k_smp_accept)
-__device__ inline void smgResolve(const StoreDev& d, const SmpDev& sd, const SmpModel& m, const TreeView& t, int l, int lane, int N,
-                                  int kind, unsigned long long seed, unsigned long long step) {
+// per-locus accept / reject for models with migration (kind as in k_smp_accept).  t: the genealogy to settle — the HBM
+// view, or the staged view of a proposal kernel (w != NULL: what a rejection restores goes to the staged copy as well)
+__device__ inline void smgResolve(const StoreDev& d, const SmpDev& sd, const SmpModel& m, const TreeView& t, const SmgWarp* w, int l,
+                                  int lane, int N, int kind, unsigned long long seed, unsigned long long step) {
   const SmpProposal pr = sd.prop[l];
   int ok = 0;
   if (pr.valid) {
@@ -705,11 +748,18 @@ __device__ inline void smgResolve(const StoreDev& d, const SmpDev& sd, const Smp
       }
       if (lane == 0) commitLocus(t);
     } else {
-      for (int x = lane; x < N; x += 32) revertNode(t, x);
-      if (kind == 1) smgRestoreMigs(sd, l, lane);
+      for (int x = lane; x < N; x += 32)
+        if (t.node[x].flags & (F_RECALC | F_SAVED)) revertNode(t, x);   // a no-op on unmarked nodes
+      if (kind == 1) {
+        if (w) smgRestoreMigs(*w, sd, l, lane);
+        else smgRestoreMigs(sd, l, lane);
+      }
       if (lane == 0) {
         revertLocus(t);
-        if (kind == 1) sd.nodePop[(size_t)l * N + pr.node] = (uint8_t)pr.pop;
+        if (kind == 1) {
+          sd.nodePop[(size_t)l * N + pr.node] = (uint8_t)pr.pop;
+          if (w) w->pop[pr.node] = (uint8_t)pr.pop;
+        }
       }
     }
   } else if (kind == 0) {
@@ -722,7 +772,7 @@ __global__ void __launch_bounds__(kSmpThreads)
 k_smg_accept(StoreDev d, SmpDev sd, const SmpModel* __restrict__ mp, int kind, unsigned long long seed, unsigned long long step) {
   SMG_PROLOGUE
   (void)w;
-  smgResolve(d, sd, m, t, l, lane, N, kind, seed, step);
+  smgResolve(d, sd, m, t, nullptr, l, lane, N, kind, seed, step);
 }
 
 // one global accept / reject for every locus; how: 0 tau move (statistics <- pending), 1 rescaling (statistics *= c)
