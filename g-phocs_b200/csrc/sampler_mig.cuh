@@ -26,8 +26,8 @@ struct SmgWarp {      // per-warp shared-memory view (carved by smgCarve)
   int* bad;           // [1] inconsistency flag raised while cutting branches into segments
   double* segT0;      // [S]
   double* segT1;      // [S]
-  double* segC;       // [S] partial pair sums
   int16_t* segBranch; // [S]
+  uint16_t* list;     // [S] segments of one population, compacted (smgPopStats)
   uint8_t* segPop;    // [S]
   double* coal;       // [Q]
   double* mig;        // [B]
@@ -39,9 +39,9 @@ struct SmgWarp {      // per-warp shared-memory view (carved by smgCarve)
 __host__ __device__ inline int smgMaxSegs(int N) { return 4 * N + 2 * kSmpMaxMigs + 8; }
 __host__ __device__ inline size_t smgWarpBytes(int N, int Q, int B) {
   const size_t S = (size_t)smgMaxSegs(N);
-  size_t b = (size_t)N * 16 + kSmpMaxMigs * 8 + S * 24 + (size_t)Q * 8 + (size_t)B * 8;  // doubles and node records first
+  size_t b = (size_t)N * 16 + kSmpMaxMigs * 8 + S * 16 + (size_t)Q * 8 + (size_t)B * 8;  // doubles and node records first
   b += 3 * 4 + (size_t)Q * 4 + (size_t)B * 4;                                            // ints
-  b += kSmpMaxMigs * 2 + S * 2;                                                          // int16
+  b += kSmpMaxMigs * 2 + S * 4;                                                          // int16
   b += (size_t)N + kSmpMaxMigs + S;                                                      // bytes
   return (b + 15) & ~(size_t)15;
 }
@@ -55,7 +55,6 @@ __device__ inline SmgWarp smgCarve(unsigned char* base, int N, int Q, int B) {
   w.migAge = dp; dp += kSmpMaxMigs;
   w.segT0 = dp; dp += S;
   w.segT1 = dp; dp += S;
-  w.segC = dp; dp += S;
   w.coal = dp; dp += Q;
   w.mig = dp; dp += B;
   int* ip = reinterpret_cast<int*>(dp);
@@ -65,6 +64,7 @@ __device__ inline SmgWarp smgCarve(unsigned char* base, int N, int Q, int B) {
   int16_t* sp = reinterpret_cast<int16_t*>(ip);
   w.migBranch = sp; sp += kSmpMaxMigs;
   w.segBranch = sp; sp += S;
+  w.list = reinterpret_cast<uint16_t*>(sp); sp += S;
   uint8_t* bp = reinterpret_cast<uint8_t*>(sp);
   w.pop = bp; bp += N;
   w.migBand = bp; bp += kSmpMaxMigs;
@@ -247,67 +247,32 @@ __device__ inline void smgBuildSegments(const SmpModel& m, const SmgWarp& w, int
   __syncwarp();
 }
 
-// statistics of the locus from its segments -> w.coal / w.ncoal / w.mig / w.nmig (deterministic summation order)
-__device__ inline void smgStats(const SmpModel& m, const SmgWarp& w, int n, int N, int lane, int ovPop, double ovTau) {
-  const int S = *w.segCount, Q = m.Q, B = m.B;
-  for (int i = lane; i < S; i += 32) {   // pairs (i, j > i) in the same population
-    const int p = w.segPop[i];
-    const double a0 = w.segT0[i], a1 = w.segT1[i];
-    double c = 0.0;
-    for (int j = i + 1; j < S; j++)
-      if (w.segPop[j] == p) {
-        const double ov = fmin(a1, w.segT1[j]) - fmax(a0, w.segT0[j]);
-        if (ov > 0.0) c += ov;
-      }
-    w.segC[i] = 2.0 * c;
-  }
-  __syncwarp();
-  for (int p = lane; p < Q; p += 32) {
-    double c = 0.0;
-    for (int i = 0; i < S; i++)
-      if (w.segPop[i] == p) c += w.segC[i];
-    int k = 0;
-    for (int x = n; x < N; x++) k += w.pop[x] == p;
-    w.coal[p] = c;
-    w.ncoal[p] = k;
-  }
-  for (int b = lane; b < B; b += 32) {
-    const int tgt = m.bandTgt[b];
-    const double s0 = smgBandStart(m, b, ovPop, ovTau), s1 = smgBandEnd(m, b, ovPop, ovTau);
-    double c = 0.0;
-    for (int i = 0; i < S; i++)
-      if (w.segPop[i] == tgt) {
-        const double ov = fmin(s1, w.segT1[i]) - fmax(s0, w.segT0[i]);
-        if (ov > 0.0) c += ov;
-      }
-    int k = 0;
-    for (int e = 0; e < *w.numMigs; e++) k += w.migBand[e] == b;
-    w.mig[b] = c;
-    w.nmig[b] = k;
-  }
-  __syncwarp();
-}
-
 // Statistics that a move inside population p can change: coal[p] and mig[b] of the bands whose target is p.  The
-// segments of p are compacted (their indices go to the front of w.segC's storage, reused as an int list) and only
-// they are paired.  Leaves the results in w.coal[p] / w.mig[b]; ncoal / nmig are unchanged by such a move.
+// segments of p are compacted into w.list and only they are paired.  Leaves the results in w.coal[p] / w.mig[b];
+// ncoal / nmig are unchanged by such a move.
 __device__ inline void smgPopStats(const SmpModel& m, const SmgWarp& w, int lane, int p, int ovPop = -1, double ovTau = 0.0) {
   const int S = *w.segCount;
-  int* list = reinterpret_cast<int*>(w.segC);
+  uint16_t* list = w.list;
   int count = 0;
   for (int i0 = 0; i0 < S; i0 += 32) {
     const int i = i0 + lane;
     const bool in = i < S && w.segPop[i] == p;
     const unsigned ballot = __ballot_sync(0xffffffffu, in);
-    if (in) list[count + __popc(ballot & ((1u << lane) - 1u))] = i;
+    if (in) list[count + __popc(ballot & ((1u << lane) - 1u))] = (uint16_t)i;
     count += __popc(ballot);
   }
   __syncwarp();
+  // every unordered pair once, the same number of partners for every lane: entry a meets the (count-1)/2 entries that
+  // follow it around the circle and, for an even count, the entry opposite if a is in the first half
   double c = 0.0;
+  const int half = (count - 1) >> 1;
   for (int a = lane; a < count; a += 32) {
     const int i = list[a];
     const double a0 = w.segT0[i], a1 = w.segT1[i];
-    for (int bq = a + 1; bq < count; bq++) {
+    const int partners = half + (((count & 1) == 0 && a < (count >> 1)) ? 1 : 0);
+    int bq = a;
+    for (int k = 0; k < partners; k++) {
+      bq = bq + 1 == count ? 0 : bq + 1;
       const int j = list[bq];
       const double ov = fmin(a1, w.segT1[j]) - fmax(a0, w.segT0[j]);
       if (ov > 0.0) c += ov;
@@ -326,6 +291,24 @@ __device__ inline void smgPopStats(const SmpModel& m, const SmgWarp& w, int lane
     }
     g = warpSumD(g);
     if (lane == 0) w.mig[b] = g;
+  }
+  __syncwarp();
+}
+
+// statistics of the locus from its segments -> w.coal / w.ncoal / w.mig / w.nmig (deterministic summation order):
+// population by population (pairing the segments of one population at a time instead of filtering all pairs)
+__device__ inline void smgStats(const SmpModel& m, const SmgWarp& w, int n, int N, int lane, int ovPop, double ovTau) {
+  const int Q = m.Q, B = m.B;
+  for (int p = 0; p < Q; p++) smgPopStats(m, w, lane, p, ovPop, ovTau);
+  for (int p = lane; p < Q; p += 32) {
+    int k = 0;
+    for (int x = n; x < N; x++) k += w.pop[x] == p;
+    w.ncoal[p] = k;
+  }
+  for (int b = lane; b < B; b += 32) {
+    int k = 0;
+    for (int e = 0; e < *w.numMigs; e++) k += w.migBand[e] == b;
+    w.nmig[b] = k;
   }
   __syncwarp();
 }
@@ -349,6 +332,12 @@ __device__ inline void smgWriteStats(const SmpModel& m, const SmgWarp& w, const 
     (pending ? sd.migT : sd.mig)[(size_t)l * m.B + b] = w.mig[b];
     (pending ? sd.nmigT : sd.nmig)[(size_t)l * m.B + b] = w.nmig[b];
   }
+}
+// the locus' stored statistics -> w.*
+__device__ inline void smgLoadStats(const SmpModel& m, const SmgWarp& w, const SmpDev& sd, int l, int lane) {
+  for (int p = lane; p < m.Q; p += 32) { w.coal[p] = sd.coal[(size_t)l * m.Q + p]; w.ncoal[p] = sd.ncoal[(size_t)l * m.Q + p]; }
+  for (int b = lane; b < m.B; b += 32) { w.mig[b] = sd.mig[(size_t)l * m.B + b]; w.nmig[b] = sd.nmig[(size_t)l * m.B + b]; }
+  __syncwarp();
 }
 __device__ inline double smgStoredLnL(const SmpModel& m, const SmpDev& sd, int l) {
   return smgLnL(m, sd.coal + (size_t)l * m.Q, sd.ncoal + (size_t)l * m.Q, sd.mig + (size_t)l * m.B, sd.nmig + (size_t)l * m.B);
@@ -464,6 +453,7 @@ k_smg_mignode_sweep(StoreDev d, SmpDev sd, const SmpModel* __restrict__ mp, doub
   const int nm = *w.numMigs;
   unsigned long long acc = 0, tried = 0;
   double cur = smgStoredLnL(m, sd, l);
+  smgLoadStats(m, w, sd, l, lane);
   for (int k = 0; k < nm; k++) {
     double told = 0.0, tnew = 0.0;
     int valid = 0;
@@ -488,7 +478,11 @@ k_smg_mignode_sweep(StoreDev d, SmpDev sd, const SmpModel* __restrict__ mp, doub
     told = __shfl_sync(0xffffffffu, told, 0);
     __syncwarp();
     smgBuildSegments(m, w, N, root, lane, -1, 0.0, -1, -1, -1);
-    smgStats(m, w, n, N, lane, -1, 0.0);
+    // the event ends a segment in its band's target population and begins one in the source population: only the
+    // statistics of these two populations and of the bands into them can change
+    const int band = w.migBand[k];
+    smgPopStats(m, w, lane, m.bandTgt[band]);
+    smgPopStats(m, w, lane, m.bandSrc[band]);
     int ok = 0;
     if (lane == 0) {
       const double next = smgLnL(m, w.coal, w.ncoal, w.mig, w.nmig);
@@ -504,6 +498,7 @@ k_smg_mignode_sweep(StoreDev d, SmpDev sd, const SmpModel* __restrict__ mp, doub
     ok = __shfl_sync(0xffffffffu, ok, 0);
     cur = __shfl_sync(0xffffffffu, cur, 0);
     if (ok) { smgWriteStats(m, w, sd, l, lane, 0); acc++; }
+    else smgLoadStats(m, w, sd, l, lane);   // rejected (one proposal in ten): back to the stored statistics
     __syncwarp();
   }
   smgStoreMigs(w, sd, l, lane);
@@ -685,9 +680,7 @@ k_smg_tau_propose(StoreDev d, SmpDev sd, const SmpModel* __restrict__ mp, int A,
   // The rubber band moves events of A and its two sons only, and only bands that touch one of the three change their
   // live interval: statistics of every other population and band keep their stored values.  (Pairing the segments of
   // one population at a time — a few of the ~70 — instead of all of them at once is what makes this kernel 2x faster.)
-  for (int p = lane; p < m.Q; p += 32) { w.coal[p] = sd.coal[(size_t)l * m.Q + p]; w.ncoal[p] = sd.ncoal[(size_t)l * m.Q + p]; }
-  for (int b = lane; b < m.B; b += 32) { w.mig[b] = sd.mig[(size_t)l * m.B + b]; w.nmig[b] = sd.nmig[(size_t)l * m.B + b]; }
-  __syncwarp();
+  smgLoadStats(m, w, sd, l, lane);
   unsigned long long touched = 1ull << A;
   if (s0 >= 0) touched |= (1ull << s0) | (1ull << s1);
   // + both ends of every band that touches one of them: its live interval moves, and its rescaled migration events
