@@ -608,7 +608,7 @@ __device__ inline void smgSprProposeBody(const StoreDev& d, const SmpDev& sd, co
   }
   if (lane == 0) sd.prop[l] = pr;
 }
-__global__ void __launch_bounds__(kSmpThreads)
+__global__ void __launch_bounds__(kSmpThreads, 8)
 k_smg_spr_propose(StoreDev d, SmpDev sd, const SmpModel* __restrict__ mp, int node, unsigned long long seed,
                   unsigned long long step, int pendKind, unsigned long long pendStep) {
   SMG_PROLOGUE
@@ -633,6 +633,7 @@ k_smg_tau_propose(StoreDev d, SmpDev sd, const SmpModel* __restrict__ mp, int A,
   if (root < n) { if (lane == 0) sd.prop[l] = pr; return; }
   smgLoad(w, d, sd, l, lane);
   smgSaveMigs(w, sd, l, lane);
+  const TreeView ts = smgStagedView(t, w);
   const bool isRoot = A == m.rootPop;
   // A current population: its SAMPLE AGE moves (UpdateSampleAge, GPhoCS.c:4006-4590): the leaves of A take the new age
   const int s0 = A >= m.C ? m.son0[A] : -1, s1 = A >= m.C ? m.son1[A] : -1;
@@ -653,8 +654,7 @@ k_smg_tau_propose(StoreDev d, SmpDev sd, const SmpModel* __restrict__ mp, int A,
       }
       if (which) {
         const double an = which == 3 ? tauNew : (which == 1 || isRoot ? lb + (a - lb) * f0 : ub + (a - ub) * f1);
-        adjustAge(t, x, an);
-        w.age[x] = an;
+        adjustAge(ts, x, an);   // ts.age is w.age
       }
     }
     n0 += __popc(__ballot_sync(0xffffffffu, which == 1));
@@ -691,6 +691,7 @@ k_smg_tau_propose(StoreDev d, SmpDev sd, const SmpModel* __restrict__ mp, int A,
   for (unsigned long long rest = redo; rest; rest &= rest - 1) smgPopStats(m, w, lane, __ffsll((long long)rest) - 1, A, tauNew);
   smgWriteStats(m, w, sd, l, lane, 1);
   smgStoreMigs(w, sd, l, lane);
+  smgStoreTree(w, d, l, lane);
   if (lane == 0) {
     // log-density of the pending state under the proposed split time: theta and rates are unchanged
     pr.genDelta = smgLnL(m, w.coal, w.ncoal, w.mig, w.nmig) - smgStoredLnL(m, sd, l);
