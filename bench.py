@@ -437,7 +437,10 @@ def run_b200(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        opts = None
+        if args.nccl_high_priority:   # NCCL's kernels on a high-priority stream: they start when issued, not after the
+            opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)   # evaluation kernel's last wave of CTAs
+        dist.init_process_group("nccl", device_id=dev, pg_options=opts)
 
     L = args.loci
     model = synth.config(args.config)
@@ -458,7 +461,7 @@ def run_b200(args):
     V = 1 + 2 * Q + 2 * B
     assert 1 + V == shard.payload_len(Q, B)
     # [sum data lnL | sum gen lnL, totals...] of step i is summed over ranks on a side stream while step i+1 computes
-    pipe = shard.PipelinedAllReduce(1 + V, dev, depth=2)
+    pipe = shard.PipelinedAllReduce(1 + V, dev, depth=args.pipe_depth)
     step_no = [0]
 
     def step(record=None):
@@ -513,6 +516,14 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total = float(t.item())
     total_data_lnl, total_gen_lnl = float(payload[0].item()), float(payload[1].item())
+    if args.step_only:   # development: the device-resident step alone (scaling experiments)
+        if rank == 0:
+            print(json.dumps({"step_only": True, "n_gpus": world, "steps": args.steps, "ms_per_step": ms_total / args.steps,
+                              "ms_data": ms_data, "ms_gen": ms_gen, "pipe_depth": args.pipe_depth,
+                              "nccl_high_priority": bool(args.nccl_high_priority)}))
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     # ---- e2e: the same pass through the C ABI with HOST buffers (H2D of genealogies + event snapshots, D2H of
     # per-locus log-likelihoods and totals inside the timed region)
@@ -756,6 +767,9 @@ def main():
     ap.add_argument("--sample-loci", type=int, default=20000,
                     help="loci in the reference arm's bounded sample (working set >> host last-level cache)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--step-only", action="store_true", help="development: time the device-resident step, print it, stop")
+    ap.add_argument("--pipe-depth", type=int, default=2, help="steps the per-step all-reduce may lag behind the evaluation")
+    ap.add_argument("--nccl-high-priority", type=int, default=0, help="1: NCCL's stream gets high priority")
     ap.add_argument("--no-mcmc", action="store_true", help="skip the device-resident MCMC extras (development runs)")
     ap.add_argument("--with-mcmc", action="store_true", help="reference arm: also time the reference's MCMC iterations/s")
     args = ap.parse_args()

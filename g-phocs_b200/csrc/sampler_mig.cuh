@@ -497,6 +497,7 @@ k_smg_mignode_sweep(StoreDev d, SmpDev sd, const SmpModel* __restrict__ mp, doub
     }
     ok = __shfl_sync(0xffffffffu, ok, 0);
     cur = __shfl_sync(0xffffffffu, cur, 0);
+    __syncwarp();   // lane 0 has read the proposed statistics
     if (ok) { smgWriteStats(m, w, sd, l, lane, 0); acc++; }
     else smgLoadStats(m, w, sd, l, lane);   // rejected (one proposal in ten): back to the stored statistics
     __syncwarp();
