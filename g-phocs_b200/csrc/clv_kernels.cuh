@@ -698,6 +698,10 @@ k_eval(StoreDev d, const Batch* __restrict__ batches, int batchBase, int useOld,
         mLnL[0] = sTerm[0];
       }
       d.ctaSum[batchBase + blockIdx.x] = mActive[0] ? mLnL[0] : 0.0;
+      if (d.evalCounters && useOld && changed) {   // the roofline accounting of the sampler (as for the loci of a shared batch above)
+        atomicAdd(d.evalCounters, 1ull);
+        atomicAdd(d.evalCounters + 1, 32ull * (unsigned long long)mP[0] * (2ull * (unsigned long long)mK[0] + 1ull));
+      }
     }
   }
 }
