@@ -464,7 +464,7 @@ def run_b200(args):
     pipe = shard.PipelinedAllReduce(1 + V, dev, depth=args.pipe_depth)
     step_no = [0]
 
-    def step(record=None):
+    def step(record=None, pipe=pipe):
         """device-resident pass; `record` = list to append (start, mid, end) events to"""
         i = step_no[0]
         step_no[0] += 1
@@ -516,11 +516,39 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total = float(t.item())
     total_data_lnl, total_gen_lnl = float(payload[0].item()), float(payload[1].item())
-    if args.step_only:   # development: the device-resident step alone (scaling experiments)
+    if args.step_only:   # development: the device-resident step alone (scaling experiments), a few variants in one process
+        def timed(pipe_v, nsteps):
+            for _ in range(5):
+                step(None, pipe_v)
+            barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            with torch.cuda.stream(stream):
+                a.record(stream)
+            for _ in range(nsteps):
+                step(None, pipe_v)
+            with torch.cuda.stream(stream):
+                pipe_v.result(step_no[0] - 1, stream)
+                b.record(stream)
+            barrier()
+            ms = a.elapsed_time(b)
+            if world > 1:
+                tt = torch.tensor([ms], dtype=torch.float64, device=dev)
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                ms = float(tt.item())
+            return ms / nsteps
+        out = {"step_only": True, "n_gpus": world, "steps": args.steps, "ms_per_step": ms_total / args.steps,
+               "ms_data": ms_data, "ms_gen": ms_gen, "variants": {}}
+        groups = {"default": None}
+        if world > 1:
+            groups["nccl_high_priority"] = dist.new_group(pg_options=dist.ProcessGroupNCCL.Options(is_high_priority_stream=True))
+        for gname, grp in groups.items():
+            for depth in (2, 4):
+                pv = shard.PipelinedAllReduce(1 + V, dev, depth=depth, group=grp)
+                for nsteps in (20, 200):
+                    out["variants"][f"{gname}/depth{depth}/steps{nsteps}"] = timed(pv, nsteps)
         if rank == 0:
-            print(json.dumps({"step_only": True, "n_gpus": world, "steps": args.steps, "ms_per_step": ms_total / args.steps,
-                              "ms_data": ms_data, "ms_gen": ms_gen, "pipe_depth": args.pipe_depth,
-                              "nccl_high_priority": bool(args.nccl_high_priority)}))
+            print(json.dumps(out))
         if world > 1:
             dist.destroy_process_group()
         return

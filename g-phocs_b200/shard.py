@@ -57,9 +57,10 @@ class PipelinedAllReduce:
     fine for what consumes them (running totals for the trace line, global proposals that are decided once per sweep).
     CPU tensors (gloo) use asynchronous work handles instead of streams; same interface."""
 
-    def __init__(self, length, device, depth=2, dtype=None):
+    def __init__(self, length, device, depth=2, dtype=None, group=None):
         import torch
         self.torch = torch
+        self.group = group   # process group of the all-reduce (None: the default group)
         self.cuda = torch.device(device).type == "cuda"
         self.buffers = [torch.zeros(length, dtype=dtype or torch.float64, device=device) for _ in range(depth)]
         self.depth = depth
@@ -92,11 +93,11 @@ class PipelinedAllReduce:
             self.side.wait_event(self.ready[k])
             if active:
                 with self.torch.cuda.stream(self.side):
-                    dist.all_reduce(self.buffers[k], op=dist.ReduceOp.SUM)
+                    dist.all_reduce(self.buffers[k], op=dist.ReduceOp.SUM, group=self.group)
             self.done[k].record(self.side)
             self.used[k] = True
         elif active:
-            self.work[k] = dist.all_reduce(self.buffers[k], op=dist.ReduceOp.SUM, async_op=True)
+            self.work[k] = dist.all_reduce(self.buffers[k], op=dist.ReduceOp.SUM, async_op=True, group=self.group)
 
     def result(self, step, stream=None):
         """The all-reduced payload of `step` (the evaluation stream waits for it; CPU: blocks)."""

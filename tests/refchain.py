@@ -90,6 +90,21 @@ def pooled_between_chain_se(group_a, group_b):
     return np.sqrt(ss / dof * (1.0 / len(a) + 1.0 / len(b)))
 
 
+def group_difference(group_a, group_b):
+    """(difference of the two groups' means, its standard error) per parameter; each group is a list of chains
+    [iterations][parameters].  The error is the LARGER of two estimates: the spread between independent chains
+    (pooled_between_chain_se: right when chains mix slowly, but with two or three chains per group it is itself a noisy
+    estimate — by chance three chains can agree much better than their own batch-means errors say) and the batch-means
+    errors inside the chains combined (right when they mix well)."""
+    ma, mb = np.array([c.mean(0) for c in group_a]), np.array([c.mean(0) for c in group_b])
+    between = pooled_between_chain_se(ma, mb)
+
+    def within(group):
+        se = np.array([[batch_se(c[:, k]) for k in range(c.shape[1])] for c in group])
+        return np.sqrt((se ** 2).sum(0)) / len(group)
+    return ma.mean(0) - mb.mean(0), np.maximum(between, np.hypot(within(group_a), within(group_b))), ma, mb
+
+
 REF_SEEDS = (4242, 999, 31337)
 
 
