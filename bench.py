@@ -464,24 +464,27 @@ def run_b200(args):
     pipe = shard.PipelinedAllReduce(1 + V, dev, depth=args.pipe_depth)
     step_no = [0]
 
+    sp_main = C.c_void_p(stream.cuda_stream)
+
     def step(record=None, pipe=pipe):
-        """device-resident pass; `record` = list to append (start, mid, end) events to"""
+        """device-resident pass; `record` = (e0, e1, e2) timing events to record around the two evaluations.  Everything
+        here names its stream explicitly (no stream context per step: at eight ranks the host side of a step is what
+        the 0.5 ms of kernels have to hide)."""
         i = step_no[0]
         step_no[0] += 1
-        with torch.cuda.stream(stream):
-            if record is not None:
-                e0 = torch.cuda.Event(enable_timing=True); e0.record(stream)
-            _, dsum = st.evaluate_device(0)
-            if record is not None:
-                e1 = torch.cuda.Event(enable_timing=True); e1.record(stream)
-            _, dtot, v = gen.evaluate_device()
-            if record is not None:
-                e2 = torch.cuda.Event(enable_timing=True); e2.record(stream)
-                record.append((e0, e1, e2))
-            payload = pipe.buffer(i, stream)
-            lib.gphocsCopyDeviceAsync(C.c_void_p(payload.data_ptr()), C.c_void_p(dsum), 8, C.c_void_p(stream.cuda_stream))
-            lib.gphocsCopyDeviceAsync(C.c_void_p(payload.data_ptr() + 8), C.c_void_p(dtot), 8 * V, C.c_void_p(stream.cuda_stream))
-            pipe.submit(i, stream)                # the only cross-GPU traffic: < 1 KB per step (SURVEY.md §8e)
+        if record is not None:
+            record[0].record(stream)
+        _, dsum = st.evaluate_device(0)
+        if record is not None:
+            record[1].record(stream)
+        _, dtot, v = gen.evaluate_device()
+        if record is not None:
+            record[2].record(stream)
+        payload = pipe.buffer(i, stream)
+        base = payload.data_ptr()
+        lib.gphocsCopyDeviceAsync(C.c_void_p(base), C.c_void_p(dsum), 8, sp_main)
+        lib.gphocsCopyDeviceAsync(C.c_void_p(base + 8), C.c_void_p(dtot), 8 * V, sp_main)
+        pipe.submit(i, stream)                # the only cross-GPU traffic: < 1 KB per step (SURVEY.md §8e)
 
     def barrier():
         if world > 1:
@@ -495,14 +498,14 @@ def run_b200(args):
     if rank == 0:
         sampler.start()
     launches0 = lib.gphocsKernelLaunchCount()
-    rec = []
+    rec = [tuple(torch.cuda.Event(enable_timing=True) for _ in range(3)) for _ in range(args.steps)]   # created up front
     t_start = torch.cuda.Event(enable_timing=True)
     t_end = torch.cuda.Event(enable_timing=True)
     barrier()
     with torch.cuda.stream(stream):
         t_start.record(stream)
-    for _ in range(args.steps):
-        step(rec)
+    for k_step in range(args.steps):
+        step(rec[k_step])
     with torch.cuda.stream(stream):
         payload = pipe.result(step_no[0] - 1, stream)     # the last step's sums are in before the clock stops
         t_end.record(stream)
